@@ -55,7 +55,7 @@ static int cmdBuild(int argc, char **argv) {
     efm->setSuperBucketSize(bs * 16);
     efm->setMarkedRowsPercentage((uint8_t)mrp);
     efm->setEncryptionKeyFilePath(key);
-    efm->setComputeStatistics(true);
+    efm->setComputeStatistics(mrp > 0);   // writeHeader dereferences an unset markedRows pointer when mrp==0 (EFMIndex.cpp:1048)
     efm->maximumBucketAlphaSize = 0;   // uninitialised in the reference (EFMIndex.h:395); pin it so files are reproducible
     if (argc > 8) efm->setNumberOfThreads(atoi(argv[8]));
     auto t0 = chrono::steady_clock::now();
@@ -144,7 +144,14 @@ static int cmdDump(int argc, char **argv) {
     efm->setEncryptionKeyFilePath(argv[3]);
     efm->setNumberOfThreads(1);
     efm->load(argv[2]);
-    efm->readText();   // decodes every bucket + marked rows (EFMIndex.cpp:1348)
+    // same loop as EFMIndex::readText (EFMIndex.cpp:1348-1356), minus readMarkedRows when mrp==0
+    // (the reference dereferences a NULL marked bitmap there)
+    bool marks = efm->markedRowsPercentage > 0;
+    for (uint64_t b = 0; b < efm->bucketsNumber; b++) {
+        efm->checkBucketLoaded(efm->bitReader, b);
+        efm->buckets[b]->readText(efm->bitReader, efm->bucketEncryptionRandomGenerator);
+        if (marks) efm->buckets[b]->readMarkedRows(efm->bitReader);
+    }
     FILE *f = fopen(argv[4], "wb");
     if (!f) die("cannot write dump");
     uint32_t A = efm->compactAlphabetSize;
@@ -159,8 +166,9 @@ static int cmdDump(int argc, char **argv) {
     w64(f, sz);
     for (uint32_t i = 0; i < sz; i++) w64(f, (*efm->charactersBitSet)[i] ? (uint64_t)efm->charactersRemappings[i] : ~0ull);
     for (uint32_t i = 0; i < sz; i++) w64(f, (*efm->superAlphabet->permutation)[i]);
-    w64(f, efm->markedRowsNumber);
-    for (uint64_t i = 0; i < efm->markedRowsNumber; i++) w64(f, efm->markedRowsBuckets[i]);
+    uint64_t mrn = marks ? efm->markedRowsNumber : 0;
+    w64(f, mrn);
+    for (uint64_t i = 0; i < mrn; i++) w64(f, efm->markedRowsBuckets[i]);
     w64(f, efm->superBucketsNumber); w64(f, efm->bucketsNumber);
     for (uint64_t s = 0; s < efm->superBucketsNumber; s++) {
         SuperBucket *sb = efm->superBuckets[s];
@@ -177,7 +185,7 @@ static int cmdDump(int argc, char **argv) {
         w64(f, hasTable);
         if (hasTable) for (uint32_t i = 0; i < bk->superBucketAlphaSize; i++) w64(f, bk->previousBucketsOccurrences[i]);
         for (uint32_t i = 0; i < bk->superBucketAlphaSize; i++) w64(f, (*bk->charactersBitSet)[i] ? 1 : 0);
-        for (uint64_t i = 0; i < bk->length; i++) w64(f, (*bk->markedRowsBitmap)[i] ? 1 : 0);
+        for (uint64_t i = 0; i < bk->length; i++) w64(f, marks && (*bk->markedRowsBitmap)[i] ? 1 : 0);
         for (uint64_t i = 0; i < bk->length; i++) w64(f, sb->decode_map[bk->decodeMap[bk->bucketText[i]]]);
         w64(f, bk->markedRowsCache.size());
         for (auto &kv : bk->markedRowsCache) { w64(f, kv.first); w64(f, kv.second); }
