@@ -1,0 +1,315 @@
+"""ctypes binding of libe2fm_b200.so — the C ABI declared in include/e2fm_b200.h.
+
+This is plumbing for the tests and bench.py: every call goes straight to the CUDA library. There is no
+fallback: if the library has not been built, or no CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libe2fm_b200.so")
+
+E2FM_OK = 0
+MODE_COUNT = 0
+MODE_LOCATE = 1
+OPT_CHUNK = 2
+OPT_WINDOW = 3
+
+# every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
+EXPORTS = [
+    "e2fm_index_open", "e2fm_index_close", "e2fm_index_info", "e2fm_index_terminators", "e2fm_index_fasta_headers",
+    "e2fm_index_stream", "e2fm_search_batch", "e2fm_search_batch_fixed", "e2fm_search_batch_device",
+    "e2fm_search_batch_device_fixed", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
+    "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
+    "e2fm_result_free", "e2fm_last_batch_ms", "e2fm_last_batch_counters", "e2fm_set_option",
+    "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
+    "e2fm_debug_rank", "e2fm_last_error", "e2fm_version",
+]
+
+
+class E2FMError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+class Info(C.Structure):
+    _fields_ = [("text_length", C.c_uint64), ("bucket_size", C.c_uint64), ("superbucket_size", C.c_uint64),
+                ("n_buckets", C.c_uint64), ("n_superbuckets", C.c_uint64), ("n_sequences", C.c_uint64),
+                ("initial_n", C.c_uint64), ("device_bytes", C.c_uint64), ("k", C.c_uint32), ("n_symbols", C.c_uint32),
+                ("compact_alphabet", C.c_uint32), ("marked_rows_percentage", C.c_uint32), ("marking_rate", C.c_uint32),
+                ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("reserved", C.c_uint32), ("load_ms", C.c_float * 8)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C e2fm_b200/csrc). e2fm_b200 has no CPU search path.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.e2fm_last_error.restype = C.c_char_p
+    L.e2fm_version.restype = C.c_char_p
+    L.e2fm_device_count.restype = i32
+    L.e2fm_host_alloc.restype = vp
+    L.e2fm_host_alloc.argtypes = [C.c_size_t]
+    L.e2fm_host_free.argtypes = [vp]
+    L.e2fm_index_open.argtypes = [vp, C.c_size_t, C.c_char_p, i32, C.POINTER(vp)]
+    L.e2fm_index_close.argtypes = [vp]
+    L.e2fm_index_close.restype = None
+    L.e2fm_index_info.argtypes = [vp, C.POINTER(Info)]
+    L.e2fm_index_terminators.argtypes = [vp, vp, u64]
+    L.e2fm_index_fasta_headers.restype = u64
+    L.e2fm_index_fasta_headers.argtypes = [vp, vp, u64]
+    L.e2fm_index_stream.restype = vp
+    L.e2fm_index_stream.argtypes = [vp]
+    L.e2fm_search_batch.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp)]
+    L.e2fm_search_batch_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_search_batch_device.argtypes = [vp, vp, vp, u64, u64, i32, C.POINTER(vp)]
+    L.e2fm_search_batch_device_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_result_patterns.restype = u64
+    L.e2fm_result_patterns.argtypes = [vp]
+    L.e2fm_result_total_positions.restype = u64
+    L.e2fm_result_total_positions.argtypes = [vp]
+    L.e2fm_result_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.e2fm_result_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 5
+    L.e2fm_result_free.argtypes = [vp]
+    L.e2fm_result_free.restype = None
+    L.e2fm_last_batch_ms.argtypes = [vp, C.POINTER(C.c_float * 8)]
+    L.e2fm_last_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
+    L.e2fm_set_option.argtypes = [vp, i32, u64]
+    L.e2fm_debug_keystream.argtypes = [i32, C.c_char_p, u64, u32, u64, u64, vp]
+    L.e2fm_debug_salsa20.argtypes = [i32, C.c_char_p, u64, u64, u64, vp]
+    L.e2fm_debug_bwt.argtypes = [vp, u64, u64, vp]
+    L.e2fm_debug_marks.argtypes = [vp, u64, u64, vp]
+    L.e2fm_debug_lf.argtypes = [vp, vp, u64, vp]
+    L.e2fm_debug_rank.argtypes = [vp, vp, vp, u64, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != E2FM_OK:
+        raise E2FMError(rc, lib().e2fm_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib().e2fm_device_count()
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from e2fm_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._ptr = lib().e2fm_host_alloc(max(nbytes, 1))
+        if not self._ptr:
+            raise MemoryError("e2fm_host_alloc failed: " + lib().e2fm_last_error().decode())
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().e2fm_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    """Device-resident result of one batch (e2fm_result)."""
+
+    def __init__(self, handle, locate: bool):
+        self._h = handle
+        self.locate = locate
+        self.n = int(lib().e2fm_result_patterns(handle))
+        self.total = int(lib().e2fm_result_total_positions(handle))
+
+    def fetch(self, counts=None, pos_offsets=None, positions=None, seq_index=None, seq_offset=None, want_seq=True):
+        """D2H copy. Pass preallocated (pinned) arrays or leave None to allocate. Returns a dict."""
+        if counts is None:
+            counts = np.empty(self.n, dtype=np.uint64)
+        out = {"counts": counts}
+        p = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
+        if self.locate:
+            if pos_offsets is None:
+                pos_offsets = np.empty(self.n + 1, dtype=np.uint64)
+            if positions is None:
+                positions = np.empty(self.total, dtype=np.uint64)
+            if want_seq:
+                if seq_index is None:
+                    seq_index = np.empty(self.total, dtype=np.uint32)
+                if seq_offset is None:
+                    seq_offset = np.empty(self.total, dtype=np.uint64)
+            out.update(pos_offsets=pos_offsets, positions=positions, seq=seq_index, off=seq_offset)
+        check(lib().e2fm_result_fetch(self._h, p(counts), pos_offsets.ctypes.data if pos_offsets is not None else None,
+                                      p(positions), p(seq_index), p(seq_offset)))
+        return out
+
+    def device_ptrs(self):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        check(lib().e2fm_result_device_ptrs(self._h, *[C.byref(x) for x in ptrs]))
+        return {k: (v.value or 0) for k, v in zip(["counts", "pos_offsets", "positions", "seq", "off"], ptrs)}
+
+    def free(self):
+        if self._h:
+            lib().e2fm_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceIndex:
+    """An E2FM index flattened into the HBM of one GPU (e2fm_index)."""
+
+    def __init__(self, index_bytes: bytes, key64: bytes, device: int = 0):
+        if len(key64) != 64:
+            raise ValueError("the encryption key must be 64 bytes")   # EncryptionManager.cpp:25-36
+        h = C.c_void_p()
+        buf = np.frombuffer(index_bytes, dtype=np.uint8)
+        check(lib().e2fm_index_open(buf.ctypes.data, len(buf), key64, device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.info = Info()
+        check(lib().e2fm_index_info(self._h, C.byref(self.info)))
+
+    @classmethod
+    def from_file(cls, path: str, key64: bytes, device: int = 0):
+        with open(path, "rb") as f:
+            return cls(f.read(), key64, device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().e2fm_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- metadata
+    def terminators(self) -> np.ndarray:
+        out = np.zeros(int(self.info.n_sequences), dtype=np.int64)
+        check(lib().e2fm_index_terminators(self._h, out.ctypes.data, len(out)))
+        return out
+
+    def fasta_headers(self) -> bytes:
+        n = lib().e2fm_index_fasta_headers(self._h, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        lib().e2fm_index_fasta_headers(self._h, buf, n)
+        return buf.raw[:n]
+
+    def stream(self) -> int:
+        return lib().e2fm_index_stream(self._h) or 0
+
+    def set_option(self, opt: int, value: int):
+        check(lib().e2fm_set_option(self._h, opt, value))
+
+    # ---- search
+    def search_fixed(self, pats: np.ndarray, locate: bool) -> Result:
+        """pats: (n, L) uint8 host array (pinned or not)."""
+        assert pats.dtype == np.uint8 and pats.ndim == 2 and pats.flags.c_contiguous
+        h = C.c_void_p()
+        n, L = pats.shape
+        check(lib().e2fm_search_batch_fixed(self._h, pats.ctypes.data if pats.size else None, n, L,
+                                            MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
+        return Result(h, locate)
+
+    def search(self, data: np.ndarray, offsets: np.ndarray, locate: bool) -> Result:
+        """Ragged batch: pattern i = data[offsets[i]:offsets[i+1]]."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        n = len(offsets) - 1
+        check(lib().e2fm_search_batch(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, n,
+                                      MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
+        return Result(h, locate)
+
+    def search_list(self, patterns, locate: bool) -> Result:
+        """patterns: iterable of bytes objects."""
+        patterns = [bytes(p) for p in patterns]
+        offs = np.zeros(len(patterns) + 1, dtype=np.uint64)
+        if patterns:
+            offs[1:] = np.cumsum([len(p) for p in patterns])
+        data = np.frombuffer(b"".join(patterns), dtype=np.uint8)
+        return self.search(data, offs, locate)
+
+    def search_device_fixed(self, d_ptr: int, n: int, length: int, locate: bool) -> Result:
+        h = C.c_void_p()
+        check(lib().e2fm_search_batch_device_fixed(self._h, d_ptr, n, length, MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
+        return Result(h, locate)
+
+    def last_batch_ms(self):
+        a = (C.c_float * 8)()
+        check(lib().e2fm_last_batch_ms(self._h, C.byref(a)))
+        return dict(zip(["h2d", "backward_search", "expand", "walk", "r4", "results", "total", "r7"], [float(x) for x in a]))
+
+    def last_batch_counters(self):
+        a = (C.c_uint64 * 8)()
+        check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
+        return dict(zip(["rank", "lf", "mark", "tasks", "dups", "launches", "occurrences", "r7"], [int(x) for x in a]))
+
+    # ---- test hooks
+    def debug_bwt(self, row0: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint32)
+        check(lib().e2fm_debug_bwt(self._h, row0, count, out.ctypes.data))
+        return out
+
+    def debug_marks(self, row0: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint64)
+        check(lib().e2fm_debug_marks(self._h, row0, count, out.ctypes.data))
+        return out
+
+    def debug_lf(self, rows) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(len(rows), dtype=np.uint64)
+        check(lib().e2fm_debug_lf(self._h, rows.ctypes.data, len(rows), out.ctypes.data))
+        return out
+
+    def debug_rank(self, codes, rows) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(len(rows), dtype=np.uint64)
+        check(lib().e2fm_debug_rank(self._h, codes.ctypes.data, rows.ctypes.data, len(rows), out.ctypes.data))
+        return out
+
+
+def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count: int, device: int = 0) -> np.ndarray:
+    out = np.zeros(count, dtype=np.uint32)
+    check(lib().e2fm_debug_keystream(device, key64, nonce, max_value, start, count, out.ctypes.data))
+    return out
+
+
+def debug_salsa20(key32: bytes, nonce: int, first_block: int, n_blocks: int, device: int = 0) -> bytes:
+    out = np.zeros(n_blocks * 64, dtype=np.uint8)
+    check(lib().e2fm_debug_salsa20(device, key32, nonce, first_block, n_blocks, out.ctypes.data))
+    return out.tobytes()

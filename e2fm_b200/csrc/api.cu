@@ -1,0 +1,841 @@
+// api.cu — the C ABI of libe2fm_b200.so (include/e2fm_b200.h): index load pipeline, batched search,
+// result hand-over and the per-kernel test hooks. Everything below the ABI is CUDA; there is no CPU
+// search path in this library.
+#include "../../include/e2fm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bits.h"
+#include "device_index.cuh"
+#include "host_format.h"
+#include "index_build.cuh"
+#include "search.cuh"
+
+using namespace e2fm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Stream-ordered device buffer (default memory pool; the pool keeps freed blocks, see e2fm_index_open).
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DBuf() = default;
+    DBuf(size_t count, cudaStream_t st) { alloc(count, st); }
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    void alloc(size_t count, cudaStream_t st) {
+        release();
+        s = st;
+        n = count;
+        if (count) CK(cudaMallocAsync((void **)&p, count * sizeof(T), st));
+    }
+    void zero() { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    T *take() { T *q = p; p = nullptr; n = 0; return q; }
+    ~DBuf() { release(); }
+};
+
+struct EventTimer {
+    struct Span { cudaEvent_t a, b; int slot; };
+    std::vector<Span> spans;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) {}
+    int begin(int slot) {
+        Span sp;
+        sp.slot = slot;
+        CK(cudaEventCreate(&sp.a));
+        CK(cudaEventCreate(&sp.b));
+        CK(cudaEventRecord(sp.a, s));
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void end(int h) { CK(cudaEventRecord(spans[h].b, s)); }
+    // after the stream has been synchronised
+    void collect(float *out, int n_slots) {
+        for (auto &sp : spans) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.slot < n_slots) out[sp.slot] += ms;
+        }
+    }
+    ~EventTimer() {
+        for (auto &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    }
+};
+
+uint32_t floor_pow2(uint32_t v) {
+    uint32_t r = 1;
+    while (r * 2 <= v) r *= 2;
+    return r;
+}
+
+}  // namespace
+
+struct e2fm_index {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    HostImage img;              // header fields (the per-row vectors stay small: terminators, C, tables)
+    DevIndex dix{};
+    std::vector<void *> owned;  // device allocations that live as long as the index
+    uint64_t device_bytes = 0;
+    float load_ms[8] = {0};
+    float batch_ms[8] = {0};
+    uint64_t batch_ctr[8] = {0};
+    uint64_t chunk_patterns = 1u << 20;
+    uint64_t window_tasks = 64u << 20;
+    unsigned long long *d_stats = nullptr;
+    unsigned long long *h_stats = nullptr;   // pinned
+};
+
+struct e2fm_result {
+    e2fm_index *ix = nullptr;
+    uint64_t n = 0, total = 0;
+    bool located = false;
+    unsigned long long *d_counts = nullptr;
+    uint64_t *d_off = nullptr, *d_pos = nullptr, *d_seqoff = nullptr;
+    uint32_t *d_seq = nullptr;
+};
+
+namespace {
+
+template <class T>
+T *dev_keep(e2fm_index *ix, size_t count) {
+    T *p = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)&p, count * sizeof(T)));
+    ix->owned.push_back(p);
+    ix->device_bytes += count * sizeof(T);
+    return p;
+}
+
+template <class T>
+T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
+    T *p = dev_keep<T>(ix, count);
+    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, ix->stream));
+    return p;
+}
+
+void read_stats(e2fm_index *ix) {
+    CK(cudaMemcpyAsync(ix->h_stats, ix->d_stats, ST_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+}
+
+void check_build_status(e2fm_index *ix, const uint32_t *d_status, const char *stage) {
+    uint32_t st = 0;
+    CK(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    CK(cudaGetLastError());
+    if (st == 0) return;
+    std::string m = std::string("index decode failed in ") + stage + ":";
+    if (st & BUILD_ERR_BOUNDS) m += " field outside the file;";
+    if (st & BUILD_ERR_LENGTH) m += " decoded text disagrees with the header (wrong encryption key or corrupt index);";
+    if (st & BUILD_ERR_ALPHABET) m += " alphabet bitset mismatch;";
+    if (st & BUILD_ERR_MARKS) m += " marked-row value out of range;";
+    throw std::runtime_error(m);
+}
+
+// The one-time device pipeline: raw image -> flattened layout (device_index.cuh).
+void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
+    HostImage &img = ix->img;
+    cudaStream_t s = ix->stream;
+    EventTimer tm(s);
+
+    // ---- raw image + start tables to the device (temporary: freed once every bucket is decoded)
+    int h = tm.begin(1);
+    const size_t padded = (size + 15) / 16 * 16 + 64;
+    DBuf<uint8_t> d_file(padded, s);
+    CK(cudaMemsetAsync(d_file.p + (padded - 80), 0, 80, s));
+    CK(cudaMemcpyAsync(d_file.p, file, size, cudaMemcpyHostToDevice, s));
+    DBuf<uint64_t> d_bstart(img.B, s), d_sbstart(img.S, s);
+    CK(cudaMemcpyAsync(d_bstart.p, img.b_start.data(), img.B * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_sbstart.p, img.sb_start.data(), img.S * 8, cudaMemcpyHostToDevice, s));
+    tm.end(h);
+
+    DBuf<uint32_t> d_status(1, s);
+    d_status.zero();
+    DBuf<uint16_t> d_sbdecode((size_t)img.S * img.A, s);
+    DBuf<uint32_t> d_sbalpha(img.S, s);
+    uint64_t *rec = dev_keep<uint64_t>(ix, img.n);
+    const uint64_t mrn = img.mrp ? img.mrn : 0;
+    uint2 *mark_tab = dev_keep<uint2>(ix, mrn);
+    CK(cudaMemsetAsync(mark_tab, 0xFF, std::max<uint64_t>(mrn, 1) * sizeof(uint2), s));
+
+    BuildParams bp{};
+    bp.file = d_file.p;
+    bp.file_bytes = size;
+    bp.b_start = d_bstart.p;
+    bp.sb_start = d_sbstart.p;
+    bp.n = img.n;
+    bp.B = img.B;
+    bp.S = img.S;
+    bp.b_size = img.b_size;
+    bp.per = img.sb_size / img.b_size;
+    bp.mrn = mrn;
+    bp.A = img.A;
+    bp.mrp = img.mrp;
+    bp.rate = img.rate;
+    bp.val_bits = img.val_bits;
+    memcpy(bp.poly_key, img.poly_key, sizeof(bp.poly_key));
+    bp.sb_decode = d_sbdecode.p;
+    bp.sb_alpha = d_sbalpha.p;
+    bp.rec = rec;
+    bp.mark_tab = mark_tab;
+    bp.status = d_status.p;
+    bp.list_elems = (img.A + 1) / 2 * 2;
+    bp.mark_words = (uint32_t)((img.b_size + 31) / 32);
+
+    // ---- K2a: super-bucket alphabets
+    h = tm.begin(2);
+    launch_sb_parse(bp, s);
+    tm.end(h);
+
+    // ---- K1 + K2: key stream, then decrypt + RLE0^-1 + MTF^-1 of every bucket, in batches of buckets
+    h = tm.begin(3);
+    const uint32_t kbits_max = int_log2((uint64_t)img.A + 1);
+    const uint32_t blocks_per_bucket = (uint32_t)((img.b_size * kbits_max + 511) / 512 + 2);
+    const uint32_t ks_stride = blocks_per_bucket * 64;
+    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(img.B, (256ull << 20) / ks_stride));
+    DBuf<uint8_t> d_ks((size_t)batch * ks_stride + 64, s);
+    const int wpc = 4;
+    const size_t per_warp = (size_t)bp.list_elems * 4 + (size_t)bp.mark_words * 4;
+    const size_t smem = per_warp * wpc;
+    if (smem > 200 * 1024) throw std::runtime_error("unsupported index: bucket size / alphabet too large for the decode kernel");
+    CK(configure_bucket_decode(smem));
+    for (uint64_t b0 = 0; b0 < img.B; b0 += batch) {
+        const uint64_t nb = std::min(batch, img.B - b0);
+        launch_keystream(img.poly_key, b0, nb, blocks_per_bucket, 0, reinterpret_cast<uint4 *>(d_ks.p), s);
+        launch_bucket_decode(bp, b0, nb, d_ks.p, ks_stride, wpc, smem, s);
+    }
+    tm.end(h);
+    check_build_status(ix, d_status.p, "bucket decode");
+    d_ks.release();
+    d_file.release();
+    d_sbdecode.release();
+
+    // ---- rank sectors + LF
+    const uint32_t blk = std::min<uint32_t>(16384, std::max<uint32_t>(64, floor_pow2(8 * img.A)));
+    uint32_t blk_shift = 0;
+    while ((1u << blk_shift) < blk) blk_shift++;
+    const uint32_t n_blk = (uint32_t)((img.n + blk - 1) / blk);
+    uint4 *occ = dev_keep<uint4>(ix, (size_t)n_blk * img.A * 2);
+    uint64_t *d_C = dev_keep_copy<uint64_t>(ix, img.C.data(), img.C.size());
+    DBuf<unsigned long long> d_cursor(2, s);
+    d_cursor.zero();
+
+    RankBuildParams rp{};
+    rp.n = img.n;
+    rp.A = img.A;
+    rp.blk_shift = blk_shift;
+    rp.n_blk = n_blk;
+    rp.rec = rec;
+    rp.occ = occ;
+    rp.ovf = nullptr;
+    rp.ovf_cursor = d_cursor.p;
+    rp.C = d_C;
+    rp.mark_tab = mark_tab;
+    rp.mrn = mrn;
+    rp.status = d_status.p;
+    CK(configure_rank_hist((size_t)img.A * 4));
+    CK(configure_rank_fill((size_t)2 << blk_shift));
+    h = tm.begin(4);
+    launch_rank_hist(rp, s);
+    tm.end(h);
+    unsigned long long need = 0;
+    CK(cudaMemcpyAsync(&need, d_cursor.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (need >= (1ull << 32)) throw std::runtime_error("unsupported index: rank overflow pool exceeds 2^32 entries");
+    rp.ovf = dev_keep<uint16_t>(ix, need + 16);
+    h = tm.begin(5);
+    const uint32_t chunk_blocks = 256;
+    const uint32_t n_chunks = (n_blk + chunk_blocks - 1) / chunk_blocks;
+    DBuf<uint32_t> d_tot((size_t)n_chunks * img.A, s);
+    launch_rank_scan(rp, d_tot.p, n_chunks, chunk_blocks, s);
+    tm.end(h);
+    h = tm.begin(6);
+    launch_rank_fill(rp, s);
+    tm.end(h);
+    check_build_status(ix, d_status.p, "rank build");
+
+    // ---- small tables
+    uint8_t sym_index[256];
+    memset(sym_index, 0xFF, sizeof(sym_index));
+    for (uint32_t i = 0; i < img.n_sym; i++) sym_index[img.syms[i]] = (uint8_t)i;
+    DevIndex &d = ix->dix;
+    d.n = img.n;
+    d.initial_n = img.initial_n;
+    d.mrn = mrn;
+    d.k = img.k;
+    d.n_sym = img.n_sym;
+    d.A = img.A;
+    d.rate = img.rate;
+    d.blk_shift = blk_shift;
+    d.n_blk = n_blk;
+    d.sigma_k = img.sigma_k;
+    d.n_term = (uint32_t)img.terminators.size();
+    d.rec = rec;
+    d.occ = occ;
+    d.ovf = rp.ovf;
+    d.mark_tab = mark_tab;
+    d.C = d_C;
+    d.compact_of_natural = dev_keep_copy<uint16_t>(ix, img.compact_of_natural.data(), img.compact_of_natural.size());
+    d.natural_of_compact = dev_keep_copy<uint32_t>(ix, img.natural_of_compact.data(), img.natural_of_compact.size());
+    d.sym_index = dev_keep_copy<uint8_t>(ix, sym_index, 256);
+    d.terminators = dev_keep_copy<int64_t>(ix, img.terminators.data(), img.terminators.size());
+    CK(cudaStreamSynchronize(s));
+    tm.collect(ix->load_ms, 7);
+    for (int i = 1; i < 7; i++) ix->load_ms[7] += ix->load_ms[i];
+}
+
+struct Batch {
+    const uint8_t *d_bytes;
+    const uint64_t *d_off;
+    uint32_t fixed_len;
+    uint64_t n;
+};
+
+void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, EventTimer &tm) {
+    cudaStream_t s = ix->stream;
+    const DevIndex &dix = ix->dix;
+    const uint32_t k = dix.k;
+    uint64_t launches = 0;
+    res->n = b.n;
+    res->located = mode == E2FM_MODE_LOCATE;
+    DBuf<unsigned long long> counts(std::max<uint64_t>(b.n, 1), s);
+    counts.zero();
+    CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
+
+    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ix->chunk_patterns, (1ull << 31) / k));
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
+    const uint64_t items_cap = chunk * k;
+    DBuf<uint2> iv(items_cap, s);
+    DBuf<uint64_t> task_off(items_cap + 1, s);
+    DBuf<uint64_t> scratch(scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
+    DBuf<uint2> tasks;
+    DBuf<uint32_t> res_pat;
+    DBuf<uint64_t> res_pos;
+    uint64_t n_results = 0, total_tasks = 0;
+
+    for (uint64_t first = 0; first < b.n; first += chunk) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
+        PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
+        CK(cudaMemsetAsync(ix->d_stats + ST_TASKS, 0, 8, s));
+        CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
+        int h = tm.begin(1);
+        SearchArgs sa{dix, pv, mode, iv.p, counts.p, ix->d_stats};
+        launch_backward_search(sa, ix->n_sm, s);
+        launches++;
+        tm.end(h);
+        read_stats(ix);
+        const uint64_t n_tasks = ix->h_stats[ST_TASKS];
+        if (n_tasks == 0) continue;
+        total_tasks += n_tasks;
+        h = tm.begin(2);
+        launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
+        launches += 3;
+        tm.end(h);
+        const uint64_t win = std::min<uint64_t>(n_tasks, ix->window_tasks);
+        if (tasks.n < win) tasks.alloc(win, s);
+        for (uint64_t w0 = 0; w0 < n_tasks; w0 += win) {
+            const uint64_t w1 = std::min(n_tasks, w0 + win);
+            h = tm.begin(2);
+            launch_expand(iv.p, task_off.p, cnt * k, w0, w1, tasks.p, s);
+            launches++;
+            tm.end(h);
+            if (mode == E2FM_MODE_LOCATE && res_pos.n < n_results + (w1 - w0)) {
+                // grow the result store: every row task yields at most one occurrence
+                const uint64_t cap = std::max<uint64_t>(n_results + (w1 - w0), res_pos.n + res_pos.n / 2);
+                DBuf<uint32_t> np(cap, s);
+                DBuf<uint64_t> nq(cap, s);
+                if (n_results) {
+                    CK(cudaMemcpyAsync(np.p, res_pat.p, n_results * 4, cudaMemcpyDeviceToDevice, s));
+                    CK(cudaMemcpyAsync(nq.p, res_pos.p, n_results * 8, cudaMemcpyDeviceToDevice, s));
+                }
+                std::swap(res_pat.p, np.p); std::swap(res_pat.n, np.n); res_pat.s = s;
+                std::swap(res_pos.p, nq.p); std::swap(res_pos.n, nq.n); res_pos.s = s;
+            }
+            CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
+            h = tm.begin(3);
+            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), counts.p, res_pat.p, res_pos.p, ix->d_stats};
+            launch_walk(wa, ix->n_sm, s);
+            launches++;
+            tm.end(h);
+            read_stats(ix);
+            n_results = ix->h_stats[ST_RESULTS];
+        }
+    }
+
+    // ---- result pipeline (locate): CSR offsets, scatter, segmented sort + de-duplication, sequence mapping
+    uint64_t dups = 0;
+    if (mode == E2FM_MODE_LOCATE) {
+        int h = tm.begin(5);
+        DBuf<uint64_t> off(b.n + 1, s);
+        launch_scan_u64(counts.p, off.p, b.n, scratch.p, s);
+        launches += 3;
+        DBuf<uint64_t> pos(std::max<uint64_t>(n_results, 1), s);
+        DBuf<uint32_t> cursor(std::max<uint64_t>(b.n, 1), s);
+        cursor.zero();
+        launch_scatter(res_pat.p, res_pos.p, n_results, off.p, cursor.p, pos.p, s);
+        launches++;
+        DBuf<uint32_t> big_list(n_results / 24 + 1, s);
+        uint32_t *ulen = cursor.p;   // the cursors are dead after the scatter
+        launch_segment_sort(pos.p, off.p, b.n, big_list.p, ulen, ix->d_stats, s);
+        launches++;
+        tm.end(h);
+        read_stats(ix);
+        const uint64_t n_big = ix->h_stats[ST_BIGSEG];
+        if (n_big) {
+            h = tm.begin(5);
+            launch_segment_sort_big(pos.p, off.p, big_list.p, (uint32_t)n_big, ulen, ix->d_stats, s);
+            launches++;
+            tm.end(h);
+            read_stats(ix);
+        }
+        dups = ix->h_stats[ST_DUPS];
+        h = tm.begin(5);
+        if (dups) {
+            // EFMIndex::locateOccurrences erased adjacent duplicates (:2296-2299): rebuild the CSR around the unique heads
+            DBuf<unsigned long long> wide(b.n, s);
+            launch_ulen_widen(ulen, wide.p, b.n, s);
+            DBuf<uint64_t> noff(b.n + 1, s);
+            launch_scan_u64(wide.p, noff.p, b.n, scratch.p, s);
+            DBuf<uint64_t> npos(std::max<uint64_t>(n_results - dups, 1), s);
+            launch_repack(pos.p, off.p, noff.p, b.n, npos.p, s);
+            launches += 5;
+            std::swap(pos.p, npos.p); std::swap(pos.n, npos.n);
+            std::swap(off.p, noff.p); std::swap(off.n, noff.n);
+            n_results -= dups;
+        }
+        DBuf<uint32_t> seq(std::max<uint64_t>(n_results, 1), s);
+        DBuf<uint64_t> seqoff(std::max<uint64_t>(n_results, 1), s);
+        launch_map_positions(dix, pos.p, n_results, seq.p, seqoff.p, s);
+        launches++;
+        tm.end(h);
+        res->total = n_results;
+        res->d_off = off.take();
+        res->d_pos = pos.take();
+        res->d_seq = seq.take();
+        res->d_seqoff = seqoff.take();
+    }
+    res->d_counts = counts.take();
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    read_stats(ix);
+    ix->batch_ctr[0] = ix->h_stats[ST_RANK];
+    ix->batch_ctr[1] = ix->h_stats[ST_LF];
+    ix->batch_ctr[2] = ix->h_stats[ST_MARK];
+    ix->batch_ctr[3] = total_tasks;
+    ix->batch_ctr[4] = dups;
+    ix->batch_ctr[5] = launches;
+    ix->batch_ctr[6] = n_results;
+    ix->batch_ctr[7] = 0;
+}
+
+int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
+                  bool on_device, int mode, e2fm_result **out) {
+    if (!ix || !out || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
+    if (n && !bytes && total_bytes) return fail(E2FM_ERR_ARG, "pattern bytes missing");
+    if (n >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 patterns in one batch");
+    // EFMIndex.cpp:2305-2306 throws this for locate; count needs the marked rows as well (hat verification walks to
+    // them, :1862-1899 — the reference crashes there), so both modes are refused.
+    if (ix->img.mrp == 0)
+        return fail(E2FM_ERR_UNSUPPORTED, "The index doesn't contain marked rows: locate operation not supported");
+    *out = nullptr;
+    e2fm_result *res = new (std::nothrow) e2fm_result();
+    if (!res) return fail(E2FM_ERR_OOM, "out of host memory");
+    res->ix = ix;
+    try {
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t s = ix->stream;
+        memset(ix->batch_ms, 0, sizeof(ix->batch_ms));
+        EventTimer tm(s);
+        const int whole = tm.begin(6);
+        DBuf<uint8_t> d_bytes;
+        DBuf<uint64_t> d_off;
+        Batch b{bytes, offsets, fixed_len, n};
+        if (!on_device) {
+            const int h = tm.begin(0);
+            d_bytes.alloc(total_bytes + 16, s);
+            if (total_bytes) CK(cudaMemcpyAsync(d_bytes.p, bytes, total_bytes, cudaMemcpyHostToDevice, s));
+            b.d_bytes = d_bytes.p;
+            if (offsets) {
+                d_off.alloc(n + 1, s);
+                CK(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+                b.d_off = d_off.p;
+            }
+            tm.end(h);
+        }
+        run_batch(ix, b, mode, res, tm);
+        tm.end(whole);
+        CK(cudaStreamSynchronize(s));
+        tm.collect(ix->batch_ms, 8);
+    } catch (const CudaError &e) {
+        e2fm_result_free(res);
+        return fail(E2FM_ERR_CUDA, e.what());
+    } catch (const std::bad_alloc &) {
+        e2fm_result_free(res);
+        return fail(E2FM_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+        e2fm_result_free(res);
+        return fail(E2FM_ERR_FORMAT, e.what());
+    }
+    *out = res;
+    return E2FM_OK;
+}
+
+static int with_device(int device, cudaStream_t *s) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(E2FM_ERR_CUDA, "no CUDA device: e2fm_b200 has no CPU search path");
+    }
+    if (device < 0 || device >= n_dev) return fail(E2FM_ERR_ARG, "no such CUDA device");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(E2FM_ERR_CUDA, "cudaSetDevice failed");
+    *s = nullptr;
+    return E2FM_OK;
+}
+
+static void key_words(const uint8_t *k32, uint32_t w[8]) {
+    for (int i = 0; i < 8; i++)
+        w[i] = (uint32_t)k32[4 * i] | ((uint32_t)k32[4 * i + 1] << 8) | ((uint32_t)k32[4 * i + 2] << 16) | ((uint32_t)k32[4 * i + 3] << 24);
+}
+
+template <class F>
+static int debug_call(const e2fm_index *ix, F f) {
+    if (!ix) return fail(E2FM_ERR_ARG, "bad argument");
+    try {
+        CK(cudaSetDevice(ix->device));
+        f(ix->stream);
+        CK(cudaStreamSynchronize(ix->stream));
+        CK(cudaGetLastError());
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *e2fm_last_error(void) { return g_err.c_str(); }
+const char *e2fm_version(void) { return "e2fm_b200 0.1 (sm_100a)"; }
+
+int e2fm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void *e2fm_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "cudaHostAlloc failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void e2fm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], int device, e2fm_index **out) {
+    if (!file || !key64 || !out) return fail(E2FM_ERR_ARG, "bad argument");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(E2FM_ERR_CUDA, "no CUDA device: e2fm_b200 has no CPU search path");
+    }
+    if (device < 0 || device >= n_dev) return fail(E2FM_ERR_ARG, "no such CUDA device");
+    e2fm_index *ix = new (std::nothrow) e2fm_index();
+    if (!ix) return fail(E2FM_ERR_OOM, "out of host memory");
+    ix->device = device;
+    int rc = E2FM_OK;
+    try {
+        const double t0 = now_ms();
+        parse_index_header(file, size, key64, ix->img);
+        ix->load_ms[0] = (float)(now_ms() - t0);
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        ix->n_sm = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;   // keep freed blocks in the pool: batches reuse their work buffers
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        CK(cudaMalloc((void **)&ix->d_stats, ST_N * sizeof(unsigned long long)));
+        CK(cudaHostAlloc((void **)&ix->h_stats, ST_N * sizeof(unsigned long long), cudaHostAllocDefault));
+        build_device_index(ix, file, size);
+    } catch (const CudaError &e) {
+        rc = fail(E2FM_ERR_CUDA, e.what());
+    } catch (const std::bad_alloc &) {
+        rc = fail(E2FM_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+        rc = fail(E2FM_ERR_FORMAT, e.what());
+    }
+    if (rc != E2FM_OK) {
+        e2fm_index_close(ix);
+        return rc;
+    }
+    *out = ix;
+    return E2FM_OK;
+}
+
+void e2fm_index_close(e2fm_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (void *p : ix->owned) cudaFree(p);
+    if (ix->d_stats) cudaFree(ix->d_stats);
+    if (ix->h_stats) cudaFreeHost(ix->h_stats);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    cudaGetLastError();
+    delete ix;
+}
+
+int e2fm_index_info(const e2fm_index *ix, e2fm_info *o) {
+    if (!ix || !o) return fail(E2FM_ERR_ARG, "bad argument");
+    memset(o, 0, sizeof(*o));
+    const HostImage &g = ix->img;
+    o->text_length = g.n;
+    o->bucket_size = g.b_size;
+    o->superbucket_size = g.sb_size;
+    o->n_buckets = g.B;
+    o->n_superbuckets = g.S;
+    o->n_sequences = g.terminators.size();
+    o->initial_n = g.initial_n;
+    o->device_bytes = ix->device_bytes;
+    o->k = g.k;
+    o->n_symbols = g.n_sym;
+    o->compact_alphabet = g.A;
+    o->marked_rows_percentage = g.mrp;
+    o->marking_rate = g.rate;
+    o->rank_block = 1u << ix->dix.blk_shift;
+    o->quirks = g.quirks;
+    memcpy(o->load_ms, ix->load_ms, sizeof(o->load_ms));
+    return E2FM_OK;
+}
+
+int e2fm_index_terminators(const e2fm_index *ix, int64_t *out, uint64_t cap) {
+    if (!ix || (!out && cap)) return fail(E2FM_ERR_ARG, "bad argument");
+    const uint64_t n = std::min<uint64_t>(cap, ix->img.terminators.size());
+    for (uint64_t i = 0; i < n; i++) out[i] = ix->img.terminators[i];
+    return E2FM_OK;
+}
+
+uint64_t e2fm_index_fasta_headers(const e2fm_index *ix, char *out, uint64_t cap) {
+    if (!ix) return 0;
+    const std::string &h = ix->img.fasta_headers;
+    if (out && cap) memcpy(out, h.data(), (size_t)std::min<uint64_t>(cap, h.size()));
+    return h.size();
+}
+
+void *e2fm_index_stream(const e2fm_index *ix) { return ix ? (void *)ix->stream : nullptr; }
+
+int e2fm_search_batch(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint64_t n, int mode, e2fm_result **out) {
+    if (n && !offsets) return fail(E2FM_ERR_ARG, "offsets missing");
+    return search_common(ix, bytes, offsets, 0, n, n ? offsets[n] : 0, false, mode, out);
+}
+int e2fm_search_batch_fixed(e2fm_index *ix, const uint8_t *bytes, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
+    return search_common(ix, bytes, nullptr, length, n, n * length, false, mode, out);
+}
+int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n, uint64_t total_bytes, int mode,
+                             e2fm_result **out) {
+    if (n && !d_offsets) return fail(E2FM_ERR_ARG, "offsets missing");
+    return search_common(ix, d_bytes, d_offsets, 0, n, total_bytes, true, mode, out);
+}
+int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
+    return search_common(ix, d_bytes, nullptr, length, n, n * length, true, mode, out);
+}
+
+uint64_t e2fm_result_patterns(const e2fm_result *r) { return r ? r->n : 0; }
+uint64_t e2fm_result_total_positions(const e2fm_result *r) { return r ? r->total : 0; }
+
+int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, uint64_t *positions, uint32_t *seq_index,
+                      uint64_t *seq_offset) {
+    if (!r) return fail(E2FM_ERR_ARG, "bad argument");
+    try {
+        CK(cudaSetDevice(r->ix->device));
+        cudaStream_t s = r->ix->stream;
+        if (counts && r->n) CK(cudaMemcpyAsync(counts, r->d_counts, r->n * 8, cudaMemcpyDeviceToHost, s));
+        if (pos_offsets) {
+            if (r->located) CK(cudaMemcpyAsync(pos_offsets, r->d_off, (r->n + 1) * 8, cudaMemcpyDeviceToHost, s));
+            else memset(pos_offsets, 0, (r->n + 1) * 8);
+        }
+        if (r->located && r->total) {
+            if (positions) CK(cudaMemcpyAsync(positions, r->d_pos, r->total * 8, cudaMemcpyDeviceToHost, s));
+            if (seq_index) CK(cudaMemcpyAsync(seq_index, r->d_seq, r->total * 4, cudaMemcpyDeviceToHost, s));
+            if (seq_offset) CK(cudaMemcpyAsync(seq_offset, r->d_seqoff, r->total * 8, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
+int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uint64_t **d_pos_offsets, const uint64_t **d_positions,
+                            const uint32_t **d_seq_index, const uint64_t **d_seq_offset) {
+    if (!r) return fail(E2FM_ERR_ARG, "bad argument");
+    if (d_counts) *d_counts = reinterpret_cast<const uint64_t *>(r->d_counts);
+    if (d_pos_offsets) *d_pos_offsets = r->d_off;
+    if (d_positions) *d_positions = r->d_pos;
+    if (d_seq_index) *d_seq_index = r->d_seq;
+    if (d_seq_offset) *d_seq_offset = r->d_seqoff;
+    return E2FM_OK;
+}
+
+void e2fm_result_free(e2fm_result *r) {
+    if (!r) return;
+    if (r->ix) {
+        cudaSetDevice(r->ix->device);
+        cudaStream_t s = r->ix->stream;
+        if (r->d_counts) cudaFreeAsync(r->d_counts, s);
+        if (r->d_off) cudaFreeAsync(r->d_off, s);
+        if (r->d_pos) cudaFreeAsync(r->d_pos, s);
+        if (r->d_seq) cudaFreeAsync(r->d_seq, s);
+        if (r->d_seqoff) cudaFreeAsync(r->d_seqoff, s);
+    }
+    delete r;
+}
+
+int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]) {
+    if (!ix || !out) return fail(E2FM_ERR_ARG, "bad argument");
+    memcpy(out, ix->batch_ms, sizeof(ix->batch_ms));
+    return E2FM_OK;
+}
+int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]) {
+    if (!ix || !out) return fail(E2FM_ERR_ARG, "bad argument");
+    memcpy(out, ix->batch_ctr, sizeof(ix->batch_ctr));
+    return E2FM_OK;
+}
+int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
+    if (!ix) return fail(E2FM_ERR_ARG, "bad argument");
+    switch (option) {
+        case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (1u << 20); return E2FM_OK;
+        case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
+        default: return fail(E2FM_ERR_ARG, "unknown option");
+    }
+}
+
+// ---------------------------------------------------------------- test hooks
+
+int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, uint32_t max_value, uint64_t start, uint64_t count,
+                         uint32_t *out) {
+    if (!key64 || (!out && count)) return fail(E2FM_ERR_ARG, "bad argument");
+    cudaStream_t s;
+    int rc = with_device(device, &s);
+    if (rc) return rc;
+    if (count == 0) return E2FM_OK;
+    try {
+        uint32_t kw[8];
+        key_words(key64 + 32, kw);
+        const uint32_t bits = int_log2((uint64_t)max_value + 1);   // RandomGenerator.cpp:136
+        DBuf<uint32_t> d(count, s);
+        launch_keystream_debug(kw, nonce, bits, start, count, d.p, s);
+        CK(cudaMemcpyAsync(out, d.p, count * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
+int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block, uint64_t n_blocks, uint8_t *out) {
+    if (!key32 || (!out && n_blocks)) return fail(E2FM_ERR_ARG, "bad argument");
+    cudaStream_t s;
+    int rc = with_device(device, &s);
+    if (rc) return rc;
+    if (n_blocks == 0) return E2FM_OK;
+    try {
+        uint32_t kw[8];
+        key_words(key32, kw);
+        DBuf<uint32_t> d(n_blocks * 16, s);
+        launch_salsa_debug(kw, nonce, first_block, n_blocks, d.p, s);
+        CK(cudaMemcpyAsync(out, d.p, n_blocks * 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
+int e2fm_debug_bwt(const e2fm_index *ix, uint64_t row0, uint64_t count, uint32_t *out) {
+    return debug_call(ix, [&](cudaStream_t s) {
+        DBuf<uint32_t> d(std::max<uint64_t>(count, 1), s);
+        launch_debug_bwt(ix->dix, row0, count, d.p, s);
+        if (count) CK(cudaMemcpyAsync(out, d.p, count * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+int e2fm_debug_marks(const e2fm_index *ix, uint64_t row0, uint64_t count, uint64_t *out) {
+    return debug_call(ix, [&](cudaStream_t s) {
+        DBuf<uint64_t> d(std::max<uint64_t>(count, 1), s);
+        launch_debug_marks(ix->dix, row0, count, d.p, s);
+        if (count) CK(cudaMemcpyAsync(out, d.p, count * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+int e2fm_debug_lf(const e2fm_index *ix, const uint64_t *rows, uint64_t count, uint64_t *out) {
+    return debug_call(ix, [&](cudaStream_t s) {
+        DBuf<uint64_t> d_in(std::max<uint64_t>(count, 1), s), d(std::max<uint64_t>(count, 1), s);
+        if (count) CK(cudaMemcpyAsync(d_in.p, rows, count * 8, cudaMemcpyHostToDevice, s));
+        launch_debug_lf(ix->dix, d_in.p, count, d.p, s);
+        if (count) CK(cudaMemcpyAsync(out, d.p, count * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+int e2fm_debug_rank(const e2fm_index *ix, const uint32_t *codes, const uint64_t *rows, uint64_t count, uint64_t *out) {
+    return debug_call(ix, [&](cudaStream_t s) {
+        DBuf<uint32_t> d_c(std::max<uint64_t>(count, 1), s);
+        DBuf<uint64_t> d_in(std::max<uint64_t>(count, 1), s), d(std::max<uint64_t>(count, 1), s);
+        if (count) {
+            CK(cudaMemcpyAsync(d_c.p, codes, count * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_in.p, rows, count * 8, cudaMemcpyHostToDevice, s));
+        }
+        launch_debug_rank(ix->dix, d_c.p, d_in.p, count, d.p, s);
+        if (count) CK(cudaMemcpyAsync(out, d.p, count * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+
+}  // extern "C"

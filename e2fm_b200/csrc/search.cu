@@ -1,0 +1,751 @@
+// search.cu — batched exact-pattern search over the flattened device index.
+//
+//   K3  backward_search_kernel   EFMIndex::computeSuperPatterns + exactMatch(interval) + backwardStep
+//                                (EFMIndex.cpp:2055-2207, :1901-1963, :1966-2001) for every (pattern, shift):
+//                                one (pattern, shift) per LANE, lanes refilled from a warp-local slice of a global
+//                                work queue, one 32-byte rank sector per occ() instead of the reference's
+//                                super-bucket + bucket + position-list chain (SuperBucket.cpp:82, Bucket.cpp:656-779).
+//   K4  walk_kernel              one BWT row per lane: backwardStepIfMatch (EFMIndex.cpp:2011-2041), getRowPosition
+//                                (:2468-2497) + Bucket::getMarkedTextPosition (Bucket.cpp:823), findWholePatternMatches +
+//                                extractSuperCharacter (:1862-1899, :2216-2269). One dependent 8-byte gather per
+//                                step; results compacted with warp-aggregated atomics.
+//   result pipeline              per-pattern CSR (scan + scatter), segmented sort + adjacent de-duplication
+//                                (EFMIndex::locateOccurrences, :2281-2301), position -> (sequence, offset)
+//                                (EFMCollection::search, EFMCollection.cpp:124-148).
+#include "search.cuh"
+
+#include "../../include/e2fm_b200.h"
+
+namespace e2fm {
+
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------- helpers
+
+__device__ __forceinline__ void pattern_span(const PatternView &pv, uint32_t pl, const uint8_t *&ptr, uint32_t &m) {
+    const uint64_t p = pv.first + pl;
+    if (pv.off) {
+        const uint64_t a = __ldg(pv.off + p), b = __ldg(pv.off + p + 1);
+        ptr = pv.bytes + a;
+        m = (uint32_t)(b - a);
+    } else {
+        ptr = pv.bytes + p * pv.fixed_len;
+        m = pv.fixed_len;
+    }
+}
+
+// natural value (base n_sym, most significant symbol first) of `cnt` pattern bytes; 0xFFFFFFFF if a byte is
+// not one of the index's original symbols (EFMIndex.cpp:1702-1717 rejects such patterns)
+__device__ __forceinline__ uint32_t natural_value(const DevIndex &ix, const uint8_t *p, uint32_t cnt) {
+    uint32_t v = 0;
+    bool bad = false;
+    for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t s = __ldg(ix.sym_index + __ldg(p + j));
+        bad |= (s == 0xFFu);
+        v = v * ix.n_sym + s;
+    }
+    return bad ? 0xFFFFFFFFu : v;
+}
+
+// compact code of a fully specified super-character, 0xFFFF when the pattern holds a foreign symbol or the
+// k-mer never occurs in the text (the reference drops the whole shift, EFMIndex.cpp:2188-2197)
+__device__ __forceinline__ uint32_t fixed_code(const DevIndex &ix, const uint8_t *p) {
+    const uint32_t nat = natural_value(ix, p, ix.k);
+    if (nat == 0xFFFFFFFFu) return 0xFFFFu;
+    return __ldg(ix.compact_of_natural + nat);
+}
+
+__device__ __forceinline__ uint32_t ipow(uint32_t b, uint32_t e) {
+    uint32_t r = 1;
+    for (uint32_t i = 0; i < e; i++) r *= b;
+    return r;
+}
+
+struct Sector { uint4 lo, hi; };
+
+__device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {
+    const uint4 *s = ix.occ + ((size_t)blk * ix.A + c) * 2;
+    Sector r;
+    r.lo = __ldg(s);
+    r.hi = __ldg(s + 1);
+    return r;
+}
+
+// C[c] + #{rows of the sector's block with in-block offset <= x that hold c}
+__device__ __forceinline__ uint32_t sector_rank(const DevIndex &ix, const Sector &s, uint32_t x) {
+    const uint32_t xx = x | (x << 16);
+    const uint32_t first = s.lo.y & 0xFFFFu;
+    if ((first & 0x8000u) == 0 || first == 0xFFFFu) {
+        return s.lo.x + count_le2(s.lo.y, xx) + count_le2(s.lo.z, xx) + count_le2(s.lo.w, xx) + count_le2(s.hi.x, xx) +
+               count_le2(s.hi.y, xx) + count_le2(s.hi.z, xx) + count_le2(s.hi.w, xx);
+    }
+    uint32_t cnt = ((first & 0x7FFFu) <= x) + ((s.lo.y >> 16) <= x);
+    cnt += count_le2(s.lo.z, xx) + count_le2(s.lo.w, xx) + count_le2(s.hi.x, xx) + count_le2(s.hi.y, xx) + count_le2(s.hi.z, xx);
+    if (cnt == SECTOR_INLINE_OVF) {
+        const uint16_t *p = ix.ovf + s.hi.w;
+        while (true) {
+            const uint32_t o = __ldg(p++);
+            if (o > x) break;
+            cnt++;
+        }
+    }
+    return s.lo.x + cnt;
+}
+
+// LF of a row whose record is r (marked rows keep their LF in the marked-row table)
+__device__ __forceinline__ uint32_t lf_from_rec(const DevIndex &ix, uint64_t r) {
+    const uint32_t low = rec_low(r);
+    return rec_marked(r) ? __ldg(&ix.mark_tab[low].y) : low;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// ---------------------------------------------------------------- K3: backward search
+
+static constexpr uint32_t BS_GRAB = 256;   // items a warp takes from the global queue at a time
+
+__global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
+    const DevIndex &ix = a.ix;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t k = ix.k;
+    const uint32_t n_items = a.pv.count * k;
+    const uint32_t blk_mask = (1u << ix.blk_shift) - 1;
+    uint32_t wnext = 0, wend = 0;
+    bool exhausted = false, active = false;
+    uint32_t item = 0, s = 0, e = 0, sa = 0, m = 0;   // SA interval [s, e)
+    int i = 0;
+    const uint8_t *ptr = nullptr;
+    unsigned long long n_rank = 0, n_tasks = 0;
+
+    for (;;) {
+        if (wnext >= wend && !exhausted) {
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(a.stats + ST_QUEUE, (unsigned long long)BS_GRAB);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= n_items) exhausted = true;
+            else { wnext = (uint32_t)b; wend = min((uint32_t)b + BS_GRAB, n_items); }
+        }
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (!active && wnext < wend) {
+            const uint32_t idx = wnext + __popc(need & lt);
+            if (idx < wend) {
+                // ---- EFMIndex::computeSuperPatterns (:2055-2207) + start interval (:1728-1748) for one shift
+                item = idx;
+                const uint32_t pl = idx / k;
+                sa = idx - pl * k;
+                pattern_span(a.pv, pl, ptr, m);
+                if (m > 0) {
+                    const uint32_t L = (m + sa + k - 1) / k;
+                    const bool last_var = (m + sa) % k != 0;
+                    int l = -1;
+                    if (!last_var) { if (!(L == 1 && sa > 0)) l = (int)L; }              // last super-character fixed
+                    else if (L > 1 && (L > 2 || sa == 0)) l = (int)L - 1;                // hat: start from its predecessor
+                    // otherwise the shift yields nothing (variable last character without fixed predecessor, :2132/:1745)
+                    if (l > 0) {
+                        const uint32_t cc = fixed_code(ix, ptr + (size_t)(l - 1) * k - sa);
+                        if (cc != 0xFFFFu) {
+                            s = (uint32_t)__ldg(ix.C + cc);
+                            e = (uint32_t)__ldg(ix.C + cc + 1);
+                            i = l - 2;
+                            active = e > s;
+                        }
+                    }
+                }
+                if (!active) a.iv[item] = make_uint2(0u, 0u);
+            }
+        }
+        wnext = min(wend, wnext + (uint32_t)__popc(need));
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active) {
+            const bool first_var = (i == 0 && sa > 0);
+            if (i < 0 || first_var) {
+                // ---- end of EFMIndex::exactMatch(interval) (:1901-1963): hand the interval on
+                const uint32_t len = e - s;
+                const bool hat = (m + sa) % k != 0;
+                if (a.mode == E2FM_MODE_COUNT && !hat && !first_var) {
+                    atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
+                    a.iv[item] = make_uint2(s, 0u);
+                } else {
+                    a.iv[item] = make_uint2(s, len);
+                    n_tasks += len;
+                }
+                active = false;
+            } else {
+                // ---- EFMIndex::backwardStep (:1966-2001)
+                const uint32_t cc = fixed_code(ix, ptr + (size_t)i * k - sa);
+                if (cc == 0xFFFFu) {
+                    a.iv[item] = make_uint2(0u, 0u);
+                    active = false;
+                } else {
+                    const uint32_t re = e - 1;
+                    const Sector se = load_sector(ix, cc, re >> ix.blk_shift);
+                    uint32_t ns;
+                    if (s == 0) ns = (uint32_t)__ldg(ix.C + cc);
+                    else {
+                        const uint32_t rs = s - 1;
+                        if ((rs >> ix.blk_shift) == (re >> ix.blk_shift)) ns = sector_rank(ix, se, rs & blk_mask);
+                        else {
+                            const Sector ss = load_sector(ix, cc, rs >> ix.blk_shift);
+                            ns = sector_rank(ix, ss, rs & blk_mask);
+                        }
+                    }
+                    const uint32_t ne = sector_rank(ix, se, re & blk_mask);
+                    n_rank += 2;
+                    s = ns;
+                    e = ne;
+                    i--;
+                    if (e <= s) {
+                        a.iv[item] = make_uint2(0u, 0u);
+                        active = false;
+                    }
+                }
+            }
+        }
+    }
+    n_rank = warp_sum(n_rank);
+    n_tasks = warp_sum(n_tasks);
+    if (lane == 0) {
+        if (n_rank) atomicAdd(a.stats + ST_RANK, n_rank);
+        if (n_tasks) atomicAdd(a.stats + ST_TASKS, n_tasks);
+    }
+}
+
+void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s) {
+    const uint64_t n_items = (uint64_t)a.pv.count * a.ix.k;
+    if (n_items == 0) return;
+    uint64_t blocks = (n_items + 255) / 256;
+    const uint64_t cap = (uint64_t)n_sm * 8;   // 8 x 256 threads = 2048 resident threads per SM
+    if (blocks > cap) blocks = cap;
+    backward_search_kernel<<<(uint32_t)blocks, 256, 0, s>>>(a);
+}
+
+// ---------------------------------------------------------------- scans
+
+static constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+
+struct LoadIvLen { const uint2 *p; __device__ unsigned long long operator()(uint64_t i) const { return p[i].y; } };
+struct LoadU64 { const unsigned long long *p; __device__ unsigned long long operator()(uint64_t i) const { return p[i]; } };
+
+template <class Load>
+__global__ void __launch_bounds__(SCAN_T) scan_block_sums_kernel(Load in, uint64_t n, uint64_t *sums) {
+    __shared__ unsigned long long ws[SCAN_T / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_B;
+    unsigned long long v = 0;
+    for (int j = 0; j < SCAN_E; j++) {
+        const uint64_t i = base + (uint64_t)j * SCAN_T + threadIdx.x;
+        if (i < n) v += in(i);
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < SCAN_T / 32; w++) t += ws[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+// single block: in-place exclusive scan of sums[0..nb), total to sums[nb]
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint64_t *sums, uint64_t nb) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < nb ? sums[i] : 0;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(FULL, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        if (lane == 31) ws[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = ws[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(FULL, winc, d);
+                if ((int)lane >= d) winc += t;
+            }
+            ws[lane] = winc - w;
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        if (i < nb) sums[i] = carry + ws[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + ws[warp] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[nb] = carry_s;
+}
+
+template <class Load>
+__global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(Load in, uint64_t n, const uint64_t *sums, uint64_t nb, uint64_t *out) {
+    __shared__ unsigned long long ws[SCAN_T / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_E;
+    unsigned long long v[SCAN_E], tot = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_E; j++) {
+        v[j] = base + j < n ? in(base + j) : 0;
+        tot += v[j];
+    }
+    unsigned long long inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    unsigned long long run = sums[blockIdx.x] + inc - tot;
+    for (uint32_t w = 0; w < warp; w++) run += ws[w];
+#pragma unroll
+    for (int j = 0; j < SCAN_E; j++) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
+}
+
+size_t scan_scratch_elems(uint64_t n) { return (size_t)((n + SCAN_B - 1) / SCAN_B + 2); }
+
+template <class Load>
+static void scan_impl(Load in, uint64_t *off, uint64_t n, uint64_t *scratch, cudaStream_t s) {
+    const uint64_t nb = (n + SCAN_B - 1) / SCAN_B;
+    if (n == 0) {
+        cudaMemsetAsync(off, 0, 8, s);
+        return;
+    }
+    scan_block_sums_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(in, n, scratch);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(scratch, nb);
+    scan_apply_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(in, n, scratch, nb, off);
+}
+
+void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s) {
+    scan_impl(LoadIvLen{iv}, off, n_items, scratch, s);
+}
+void launch_scan_u64(const unsigned long long *in, uint64_t *off, uint64_t n, uint64_t *scratch, cudaStream_t s) {
+    scan_impl(LoadU64{in}, off, n, scratch, s);
+}
+
+// ---------------------------------------------------------------- interval expansion
+
+// one (pattern, shift) interval per lane; rows [sp, sp+len) become row tasks at off[item] - w0 (clipped to the
+// task window [w0, w1)). Long intervals are written by the whole warp.
+__global__ void __launch_bounds__(256) expand_kernel(const uint2 *__restrict__ iv, const uint64_t *__restrict__ off, uint32_t n_items,
+                                                      uint64_t w0, uint64_t w1, uint2 *__restrict__ tasks) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t row0 = 0, len = 0;
+    uint64_t dst = 0;
+    if (item < n_items) {
+        const uint2 v = iv[item];
+        uint64_t a = off[item], b = a + v.y;
+        const uint64_t ca = a < w0 ? w0 : a, cb = b > w1 ? w1 : b;
+        if (cb > ca) {
+            row0 = v.x + (uint32_t)(ca - a);
+            len = (uint32_t)(cb - ca);
+            dst = ca - w0;
+        }
+    }
+    const bool longer = len > 8;
+    if (!longer)
+        for (uint32_t q = 0; q < len; q++) tasks[dst + q] = make_uint2(row0 + q, item);
+    unsigned mask = __ballot_sync(FULL, longer);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t r0 = __shfl_sync(FULL, row0, src), ln = __shfl_sync(FULL, len, src), it = __shfl_sync(FULL, item, src);
+        const uint64_t d = __shfl_sync(FULL, dst, src);
+        for (uint32_t q = lane; q < ln; q += 32) tasks[d + q] = make_uint2(r0 + q, it);
+    }
+}
+
+void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks, cudaStream_t s) {
+    if (n_items == 0 || w1 <= w0) return;
+    expand_kernel<<<(n_items + 255) / 256, 256, 0, s>>>(iv, off, n_items, w0, w1, tasks);
+}
+
+// ---------------------------------------------------------------- K4: row walks
+
+enum : uint32_t { PH_FIRST = 0, PH_WALK = 1, PH_HAT_START = 2, PH_HAT_WALK = 3, PH_HAT_FINAL = 4 };
+static constexpr uint32_t WALK_GRAB = 128;
+
+__global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
+    const DevIndex &ix = a.ix;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t k = ix.k, no = ix.n_sym;
+    const uint64_t *mark_tab64 = reinterpret_cast<const uint64_t *>(ix.mark_tab);
+    uint32_t wnext = 0, wend = 0;
+    bool exhausted = false, active = false;
+    uint32_t phase = 0, row = 0, t = 0, item = 0, tp = 0;
+    unsigned long long n_lf = 0, n_mark = 0;
+
+    for (;;) {
+        if (wnext >= wend && !exhausted) {
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(a.stats + ST_QUEUE, (unsigned long long)WALK_GRAB);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= a.n_tasks) exhausted = true;
+            else { wnext = (uint32_t)b; wend = min((uint32_t)b + WALK_GRAB, a.n_tasks); }
+        }
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (!active && wnext < wend) {
+            const uint32_t idx = wnext + __popc(need & lt);
+            if (idx < wend) {
+                const uint2 tk = __ldg(a.tasks + idx);
+                row = tk.x;
+                item = tk.y;
+                const uint32_t pl = item / k, sa = item - pl * k;
+                const uint8_t *ptr;
+                uint32_t m;
+                pattern_span(a.pv, pl, ptr, m);
+                const bool last_var = (m + sa) % k != 0;
+                const uint32_t L = (m + sa + k - 1) / k;
+                const uint32_t l = last_var ? L - 1 : L;
+                phase = (sa > 0 && l >= 2) ? PH_FIRST : PH_WALK;
+                t = 0;
+                active = true;
+            }
+        }
+        wnext = min(wend, wnext + (uint32_t)__popc(need));
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        bool emit = false;
+        if (active) {
+            // one dependent 8-byte gather per step, whatever the phase
+            const uint64_t x = __ldg(phase == PH_HAT_START ? mark_tab64 + row : ix.rec + row);
+            const uint32_t pl = item / k, sa = item - pl * k;
+            if (phase == PH_WALK) {
+                // ---- EFMIndex::getRowPosition (:2468-2497)
+                n_mark++;
+                if (!rec_marked(x)) {
+                    n_lf++;
+                    row = rec_low(x);
+                    t++;
+                    if (t > ix.rate) active = false;            // a valid index marks every rate-th text position
+                } else {
+                    tp = (uint32_t)(((uint64_t)rec_low(x) * ix.rate + t) % ix.n);
+                    const uint8_t *ptr;
+                    uint32_t m;
+                    pattern_span(a.pv, pl, ptr, m);
+                    if ((m + sa) % k != 0) {
+                        // ---- EFMIndex::extractSuperCharacter (:2216-2269): start from the next marked row
+                        const uint32_t L = (m + sa + k - 1) / k;
+                        const uint64_t p = (uint64_t)tp + L - 1;
+                        const uint64_t nv = p / ix.rate + 1;
+                        uint64_t nxt = nv * ix.rate;
+                        if (nxt > ix.n - 1) nxt = ix.n;
+                        row = (uint32_t)(nv % ix.mrn);          // marked value whose row we need
+                        t = (uint32_t)(nxt - p - 1);            // LF steps to take from it
+                        phase = PH_HAT_START;
+                    } else {
+                        emit = true;
+                        active = false;
+                    }
+                }
+            } else if (phase == PH_FIRST) {
+                // ---- EFMIndex::backwardStepIfMatch (:2011-2041): '?'-prefixed first super-character
+                n_lf++;
+                const uint8_t *ptr;
+                uint32_t m;
+                pattern_span(a.pv, pl, ptr, m);
+                const uint32_t f = k - sa;                      // fixed symbols at the low end of the k-mer
+                const uint32_t want = natural_value(ix, ptr, f);
+                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
+                if (want != 0xFFFFFFFFu && nat % ipow(no, f) == want) {
+                    row = lf_from_rec(ix, x);
+                    if (a.mode == E2FM_MODE_COUNT && (m + sa) % k == 0) {
+                        emit = true;
+                        active = false;
+                    } else {
+                        phase = PH_WALK;
+                        t = 0;
+                    }
+                } else active = false;
+            } else if (phase == PH_HAT_START) {
+                const uint32_t mrow = (uint32_t)x, mlf = (uint32_t)(x >> 32);
+                if (mrow >= ix.n) active = false;               // no such marked value (corrupt index)
+                else if (t == 0) { row = mrow; phase = PH_HAT_FINAL; }
+                else {
+                    n_lf++;
+                    row = mlf;
+                    t--;
+                    phase = t ? PH_HAT_WALK : PH_HAT_FINAL;
+                }
+            } else if (phase == PH_HAT_WALK) {
+                n_lf++;
+                row = lf_from_rec(ix, x);
+                t--;
+                if (t == 0) phase = PH_HAT_FINAL;
+            } else {
+                // ---- EFMIndex::findWholePatternMatches (:1862-1899): compare the '?'-suffixed last super-character
+                n_lf++;
+                const uint8_t *ptr;
+                uint32_t m;
+                pattern_span(a.pv, pl, ptr, m);
+                const uint32_t L = (m + sa + k - 1) / k;
+                const uint32_t from = (L - 1) * k - sa;         // first pattern byte of the last super-character
+                const uint32_t f = m - from;                    // fixed symbols at the high end of the k-mer
+                const uint32_t want = natural_value(ix, ptr + from, f);
+                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
+                emit = want != 0xFFFFFFFFu && nat / ipow(no, k - f) == want;
+                active = false;
+            }
+        }
+        // ---- warp-aggregated result compaction
+        const unsigned em = __ballot_sync(FULL, emit);
+        if (em) {
+            const uint32_t pl = item / k, sa = item - pl * k;
+            if (emit) atomicAdd(a.counts + a.pv.first + pl, 1ull);
+            if (a.mode == E2FM_MODE_LOCATE) {
+                unsigned long long base = 0;
+                const int leader = __ffs(em) - 1;
+                if ((int)lane == leader) base = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)__popc(em));
+                base = __shfl_sync(FULL, base, leader);
+                if (emit) {
+                    const unsigned long long slot = base + __popc(em & lt);
+                    a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
+                    a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;   // EFMIndex.cpp:2312-2319
+                }
+            }
+        }
+    }
+    n_lf = warp_sum(n_lf);
+    n_mark = warp_sum(n_mark);
+    if (lane == 0) {
+        if (n_lf) atomicAdd(a.stats + ST_LF, n_lf);
+        if (n_mark) atomicAdd(a.stats + ST_MARK, n_mark);
+    }
+}
+
+void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
+    if (a.n_tasks == 0) return;
+    uint64_t blocks = ((uint64_t)a.n_tasks + 255) / 256;
+    const uint64_t cap = (uint64_t)n_sm * 8;
+    if (blocks > cap) blocks = cap;
+    walk_kernel<<<(uint32_t)blocks, 256, 0, s>>>(a);
+}
+
+// ---------------------------------------------------------------- result pipeline
+
+__global__ void __launch_bounds__(256) scatter_kernel(const uint32_t *__restrict__ res_pat, const uint64_t *__restrict__ res_pos, uint64_t n_res,
+                                                       const uint64_t *__restrict__ off, uint32_t *__restrict__ cursor,
+                                                       uint64_t *__restrict__ positions) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_res) return;
+    const uint32_t p = res_pat[i];
+    const uint64_t slot = off[p] + atomicAdd(cursor + p, 1u);
+    positions[slot] = res_pos[i];
+}
+
+void launch_scatter(const uint32_t *res_pat, const uint64_t *res_pos, uint64_t n_res, const uint64_t *off, uint32_t *cursor,
+                    uint64_t *positions, cudaStream_t s) {
+    if (n_res == 0) return;
+    scatter_kernel<<<(uint32_t)((n_res + 255) / 256), 256, 0, s>>>(res_pat, res_pos, n_res, off, cursor, positions);
+}
+
+static constexpr uint32_t SORT_SMALL = 24;     // segments up to this length are sorted by one thread
+static constexpr uint32_t SORT_SMEM = 4096;    // ... up to this length by one CTA in shared memory
+
+// adjacent de-duplication of a sorted segment (EFMIndex.cpp:2296-2299); returns the unique length
+__device__ __forceinline__ uint32_t unique_serial(uint64_t *p, uint32_t len) {
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < len; i++)
+        if (i == 0 || p[i] != p[w - 1]) p[w++] = p[i];
+    return w;
+}
+
+__global__ void __launch_bounds__(256) segment_sort_small_kernel(uint64_t *positions, const uint64_t *__restrict__ off, uint64_t n_pat,
+                                                                  uint32_t *big_list, uint32_t *ulen, unsigned long long *stats) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pat) return;
+    const uint64_t a = off[p], b = off[p + 1];
+    const uint64_t len = b - a;
+    if (len <= 1) { ulen[p] = (uint32_t)len; return; }
+    if (len > SORT_SMALL) {
+        const unsigned long long at = atomicAdd(stats + ST_BIGSEG, 1ull);
+        big_list[at] = (uint32_t)p;
+        return;
+    }
+    uint64_t *q = positions + a;
+    for (uint32_t i = 1; i < (uint32_t)len; i++) {          // insertion sort (std::sort, EFMIndex.cpp:2291)
+        const uint64_t v = q[i];
+        uint32_t j = i;
+        while (j > 0 && q[j - 1] > v) { q[j] = q[j - 1]; j--; }
+        q[j] = v;
+    }
+    const uint32_t u = unique_serial(q, (uint32_t)len);
+    ulen[p] = u;
+    if (u != len) atomicAdd(stats + ST_DUPS, (unsigned long long)(len - u));
+}
+
+void launch_segment_sort(uint64_t *positions, const uint64_t *off, uint64_t n_pat, uint32_t *big_list, uint32_t *ulen,
+                         unsigned long long *stats, cudaStream_t s) {
+    if (n_pat == 0) return;
+    segment_sort_small_kernel<<<(uint32_t)((n_pat + 255) / 256), 256, 0, s>>>(positions, off, n_pat, big_list, ulen, stats);
+}
+
+// ascending-only bitonic network (mirror step + half-cleaners): entries at index >= len behave as +infinity, so no
+// padding storage is needed. T indexes either shared or global memory.
+template <class Arr>
+__device__ __forceinline__ void bitonic_sort_block(Arr arr, uint32_t len) {
+    uint32_t N = 1;
+    while (N < len) N <<= 1;
+    for (uint32_t kk = 2; kk <= N; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < N / 2; t += blockDim.x) {
+                uint32_t i, l;
+                if (j == (kk >> 1)) {
+                    const uint32_t blk = t / j, pos = t - blk * j;
+                    i = blk * kk + pos;
+                    l = blk * kk + kk - 1 - pos;
+                } else {
+                    i = 2 * j * (t / j) + (t % j);
+                    l = i + j;
+                }
+                if (l < len) {
+                    const uint64_t x = arr[i], y = arr[l];
+                    if (x > y) { arr[i] = y; arr[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) segment_sort_big_kernel(uint64_t *positions, const uint64_t *__restrict__ off,
+                                                                const uint32_t *__restrict__ big_list, uint32_t *ulen,
+                                                                unsigned long long *stats) {
+    __shared__ uint64_t sm[SORT_SMEM];
+    __shared__ uint32_t u_s;
+    const uint32_t p = big_list[blockIdx.x];
+    const uint64_t a = off[p];
+    const uint64_t len64 = off[p + 1] - a;
+    const uint32_t len = (uint32_t)len64;
+    uint64_t *q = positions + a;
+    if (len <= SORT_SMEM) {
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sm[i] = q[i];
+        __syncthreads();
+        bitonic_sort_block(sm, len);
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) q[i] = sm[i];
+    } else {
+        __syncthreads();
+        bitonic_sort_block(q, len);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u_s = unique_serial(q, len);
+        ulen[p] = u_s;
+        if (u_s != len) atomicAdd(stats + ST_DUPS, (unsigned long long)(len - u_s));
+    }
+}
+
+void launch_segment_sort_big(uint64_t *positions, const uint64_t *off, const uint32_t *big_list, uint32_t n_big, uint32_t *ulen,
+                             unsigned long long *stats, cudaStream_t s) {
+    if (n_big == 0) return;
+    segment_sort_big_kernel<<<n_big, 256, 0, s>>>(positions, off, big_list, ulen, stats);
+}
+
+__global__ void __launch_bounds__(256) ulen_widen_kernel(const uint32_t *__restrict__ ulen, unsigned long long *__restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ulen[i];
+}
+void launch_ulen_widen(const uint32_t *ulen, unsigned long long *out, uint64_t n, cudaStream_t s) {
+    if (n) ulen_widen_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ulen, out, n);
+}
+
+// one warp per pattern: copy the unique head of its old segment to its new place
+__global__ void __launch_bounds__(256) repack_kernel(const uint64_t *__restrict__ old_pos, const uint64_t *__restrict__ old_off,
+                                                      const uint64_t *__restrict__ new_off, uint64_t n_pat, uint64_t *__restrict__ new_pos) {
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (p >= n_pat) return;
+    const uint64_t src = old_off[p], dst = new_off[p], len = new_off[p + 1] - dst;
+    for (uint64_t i = lane; i < len; i += 32) new_pos[dst + i] = old_pos[src + i];
+}
+void launch_repack(const uint64_t *old_pos, const uint64_t *old_off, const uint64_t *new_off, uint64_t n_pat, uint64_t *new_pos,
+                   cudaStream_t s) {
+    if (n_pat) repack_kernel<<<(uint32_t)((n_pat * 32 + 255) / 256), 256, 0, s>>>(old_pos, old_off, new_off, n_pat, new_pos);
+}
+
+// EFMCollection::search (EFMCollection.cpp:124-148): sequence = first terminator beyond the position
+__global__ void __launch_bounds__(256) map_positions_kernel(DevIndex ix, const uint64_t *__restrict__ positions, uint64_t n_pos,
+                                                             uint32_t *__restrict__ seq, uint64_t *__restrict__ off) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pos) return;
+    const uint64_t pos = positions[i];
+    uint32_t lo = 0, hi = ix.n_term;                       // first index with terminators[idx] > pos
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)__ldg(ix.terminators + mid) > pos) hi = mid;
+        else lo = mid + 1;
+    }
+    const bool found = lo < ix.n_term;
+    seq[i] = found ? lo : 0xFFFFFFFFu;                     // the reference leaves sequenceIndex = -1
+    uint64_t start = 0;
+    if (found && lo > 0) start = (uint64_t)__ldg(ix.terminators + lo - 1) + ix.k;
+    off[i] = pos - start;
+}
+void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_t n_pos, uint32_t *seq, uint64_t *off, cudaStream_t s) {
+    if (n_pos) map_positions_kernel<<<(uint32_t)((n_pos + 255) / 256), 256, 0, s>>>(ix, positions, n_pos, seq, off);
+}
+
+// ---------------------------------------------------------------- test hooks
+
+__global__ void debug_lf_kernel(DevIndex ix, const uint64_t *rows, uint64_t n, uint64_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t row = rows[i];
+    out[i] = row < ix.n ? (uint64_t)lf_from_rec(ix, ld_rec(ix, (uint32_t)row)) : ~0ull;
+}
+__global__ void debug_rank_kernel(DevIndex ix, const uint32_t *codes, const uint64_t *rows, uint64_t n, uint64_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = codes[i];
+    const uint64_t row = rows[i];
+    if (c >= ix.A || row >= ix.n) { out[i] = ~0ull; return; }
+    const Sector s = load_sector(ix, c, (uint32_t)row >> ix.blk_shift);
+    out[i] = sector_rank(ix, s, (uint32_t)row & ((1u << ix.blk_shift) - 1));
+}
+__global__ void debug_bwt_kernel(DevIndex ix, uint64_t row0, uint64_t n, uint32_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = row0 + i < ix.n ? rec_code(ix.rec[row0 + i]) : 0xFFFFFFFFu;
+}
+__global__ void debug_marks_kernel(DevIndex ix, uint64_t row0, uint64_t n, uint64_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = ~0ull;
+    if (row0 + i < ix.n) {
+        const uint64_t r = ix.rec[row0 + i];
+        if (rec_marked(r)) v = rec_low(r);
+    }
+    out[i] = v;
+}
+void launch_debug_lf(const DevIndex &ix, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s) {
+    if (n) debug_lf_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ix, rows, n, out);
+}
+void launch_debug_rank(const DevIndex &ix, const uint32_t *codes, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s) {
+    if (n) debug_rank_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ix, codes, rows, n, out);
+}
+void launch_debug_bwt(const DevIndex &ix, uint64_t row0, uint64_t n, uint32_t *out, cudaStream_t s) {
+    if (n) debug_bwt_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ix, row0, n, out);
+}
+void launch_debug_marks(const DevIndex &ix, uint64_t row0, uint64_t n, uint64_t *out, cudaStream_t s) {
+    if (n) debug_marks_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ix, row0, n, out);
+}
+
+}  // namespace e2fm

@@ -1,0 +1,84 @@
+// search.cuh — device side of the batched search: backward search (count), interval expansion,
+// row walks (locate / wildcard / hat verification), and the result pipeline (scan, scatter, segmented
+// sort, de-duplication, sequence mapping).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "device_index.cuh"
+
+namespace e2fm {
+
+// A chunk of the pattern batch as the kernels see it.
+struct PatternView {
+    const uint8_t *bytes;       // device: all pattern bytes of the batch
+    const uint64_t *off;        // device: byte offsets [n+1] of the whole batch, or nullptr for fixed-length patterns
+    uint32_t fixed_len;         // used when off == nullptr
+    uint64_t first;             // batch index of the first pattern of the chunk
+    uint32_t count;             // patterns in the chunk
+};
+
+// device-side statistics of one batch (u64 each)
+enum {
+    ST_RANK = 0,     // getOffsetInformations(CountOnly) equivalents   (Bucket.cpp:656)
+    ST_LF = 1,       // getOffsetInformations(RetrieveCharacter) equivalents
+    ST_MARK = 2,     // getMarkedTextPosition equivalents              (Bucket.cpp:823)
+    ST_TASKS = 3,    // row tasks of the current chunk
+    ST_RESULTS = 4,  // located occurrences appended so far
+    ST_BIGSEG = 5,   // result segments longer than the per-thread sort limit
+    ST_DUPS = 6,     // duplicate positions removed (EFMIndex.cpp:2296-2299)
+    ST_QUEUE = 7,    // work-queue cursor of the running kernel
+    ST_N = 8
+};
+
+struct SearchArgs {
+    DevIndex ix;
+    PatternView pv;
+    int mode;                        // E2FM_MODE_*
+    uint2 *iv;                       // [count*k] {sp, len} of the interval each (pattern, shift) ends with
+    unsigned long long *counts;      // [batch n] matches per pattern
+    unsigned long long *stats;       // [ST_N]
+};
+
+struct WalkArgs {
+    DevIndex ix;
+    PatternView pv;
+    int mode;
+    const uint2 *tasks;              // {row, item} with item = localPattern*k + shift
+    uint32_t n_tasks;
+    unsigned long long *counts;
+    uint32_t *res_pat;               // batch pattern index of each located occurrence
+    uint64_t *res_pos;               // its global text position
+    unsigned long long *stats;
+};
+
+void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
+// exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
+void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);
+void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks, cudaStream_t s);
+void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s);
+
+// exclusive scan of counts[0..n) into off[0..n] (off[n] = total); scratch holds >= scan_scratch_elems(n) u64
+size_t scan_scratch_elems(uint64_t n);
+void launch_scan_u64(const unsigned long long *in, uint64_t *off, uint64_t n, uint64_t *scratch, cudaStream_t s);
+
+// result pipeline
+void launch_scatter(const uint32_t *res_pat, const uint64_t *res_pos, uint64_t n_res, const uint64_t *off, uint32_t *cursor,
+                    uint64_t *positions, cudaStream_t s);
+void launch_segment_sort(uint64_t *positions, const uint64_t *off, uint64_t n_pat, uint32_t *big_list, uint32_t *ulen,
+                         unsigned long long *stats, cudaStream_t s);
+void launch_segment_sort_big(uint64_t *positions, const uint64_t *off, const uint32_t *big_list, uint32_t n_big, uint32_t *ulen,
+                             unsigned long long *stats, cudaStream_t s);
+// after de-duplication changed some segment lengths: ulen[p] unique entries at the head of each old segment
+void launch_repack(const uint64_t *old_pos, const uint64_t *old_off, const uint64_t *new_off, uint64_t n_pat, uint64_t *new_pos,
+                   cudaStream_t s);
+void launch_ulen_widen(const uint32_t *ulen, unsigned long long *out, uint64_t n, cudaStream_t s);
+void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_t n_pos, uint32_t *seq, uint64_t *off, cudaStream_t s);
+
+// test hooks
+void launch_debug_lf(const DevIndex &ix, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);
+void launch_debug_rank(const DevIndex &ix, const uint32_t *codes, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);
+void launch_debug_bwt(const DevIndex &ix, uint64_t row0, uint64_t n, uint32_t *out, cudaStream_t s);
+void launch_debug_marks(const DevIndex &ix, uint64_t row0, uint64_t n, uint64_t *out, cudaStream_t s);
+
+}  // namespace e2fm

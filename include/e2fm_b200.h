@@ -1,0 +1,143 @@
+/* e2fm_b200.h — C ABI of the B200-native E2FM search path (libe2fm_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions.
+ * Every entry point names the reference interface it replaces (file:line into montecuollo/E2FM).
+ * The reference has no FFI of its own; INTEGRATION.md shows the few lines a maintainer adds to
+ * EFMIndex / EFMCollection to call these instead of the CPU path.
+ *
+ * All functions return E2FM_OK (0) or a negative error class; e2fm_last_error() gives the text
+ * (thread-local). There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef E2FM_B200_H_
+#define E2FM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2FM_OK 0
+#define E2FM_ERR_CUDA (-1)      /* CUDA runtime error / no device */
+#define E2FM_ERR_FORMAT (-2)    /* not an E2FM index, corrupt file, or wrong key */
+#define E2FM_ERR_ARG (-3)       /* bad argument */
+#define E2FM_ERR_UNSUPPORTED (-4) /* e.g. locate on an index without marked rows (EFMIndex.cpp:2305) */
+#define E2FM_ERR_OOM (-5)
+
+#define E2FM_MODE_COUNT 0        /* EFMIndex::exactMatch + countOccurrences           (EFMIndex.cpp:1694,2273) */
+#define E2FM_MODE_LOCATE 1       /* ... + locateOccurrences + (sequence, offset) map   (EFMIndex.cpp:2281, EFMCollection.cpp:115) */
+
+typedef struct e2fm_index e2fm_index;     /* device-resident flattened index (one GPU) */
+typedef struct e2fm_result e2fm_result;   /* device-resident result of one batch */
+
+typedef struct e2fm_info {
+    uint64_t text_length;        /* n, super-text length (EFMIndex.h:372) */
+    uint64_t bucket_size;        /* EFMIndex::getBucketSize      */
+    uint64_t superbucket_size;   /* EFMIndex::getSuperBucketSize */
+    uint64_t n_buckets;          /* EFMIndex::getBucketsNumber   */
+    uint64_t n_superbuckets;     /* EFMIndex::getSuperBucketsNumber */
+    uint64_t n_sequences;        /* FMCollection::getSize        */
+    uint64_t initial_n;          /* initialNCharacters           */
+    uint64_t device_bytes;       /* bytes of HBM held by the index */
+    uint32_t k;                  /* EFMIndex::getSuperAlphabetOrder */
+    uint32_t n_symbols;          /* original alphabet size       */
+    uint32_t compact_alphabet;   /* compactAlphabetSize          */
+    uint32_t marked_rows_percentage; /* EFMIndex::getMarkedRowsPercentage */
+    uint32_t marking_rate;
+    uint32_t rank_block;         /* rows per rank block of the device layout */
+    uint32_t quirks;             /* bit0: floor(n/rate) is a power of two (reference locate is corrupt, EFMIndex.cpp:399 vs :1280)
+                                    bit1: n % rate == 0 (reference reads one junk marked-row entry, EFMIndex.cpp:1278) */
+    uint32_t reserved;
+    float load_ms[8];            /* one-time costs: [0] host parse, [1] H2D, [2] superbucket parse, [3] bucket decrypt+decode,
+                                    [4] histogram, [5] scan, [6] rank sectors + LF fill, [7] total device */
+} e2fm_info;
+
+/* Replaces EFMIndex::load / EFMCollection::load (EFMIndex.cpp:1536, EFMCollection.cpp:333) + the lazy
+ * SuperBucket::load / Bucket::readHeader / Bucket::readTextUntilTo (SuperBucket.cpp:37, Bucket.cpp:549,288):
+ * `file` is the whole .efm index image (what MemoryBitReader::loadDataFromFile returns, MemoryBitReader.cpp:93),
+ * `key64` the 64-byte key (EncryptionManager::initSALSA20Keys, EncryptionManager.cpp:47).
+ * Header secrets are derived on the host; every bucket is decrypted + decoded on the device. */
+int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], int device, e2fm_index **out);
+/* EFMIndex::close (EFMIndex.cpp:1602) */
+void e2fm_index_close(e2fm_index *ix);
+int e2fm_index_info(const e2fm_index *ix, e2fm_info *out);
+/* sequence terminators (EFMCollection::readHeader, EFMCollection.cpp:289): copies min(cap, n_sequences) entries */
+int e2fm_index_terminators(const e2fm_index *ix, int64_t *out, uint64_t cap);
+/* FASTA headers blob (EFMCollection::loadFastaHeaders, EFMCollection.cpp:97): returns its size; copies up to cap bytes */
+uint64_t e2fm_index_fasta_headers(const e2fm_index *ix, char *out, uint64_t cap);
+/* the CUDA stream (cudaStream_t) every kernel of this index is launched on */
+void *e2fm_index_stream(const e2fm_index *ix);
+
+/* Batched replacement of the per-pattern loop around EFMCollection::search (Main.cpp:1055-1079,
+ * EFMCollection.cpp:115): patterns are `n` byte strings, pattern i = bytes[offsets[i] .. offsets[i+1]).
+ * HOST buffers; the call copies them to the device, runs the search and leaves the result on the device. */
+int e2fm_search_batch(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint64_t n, int mode,
+                      e2fm_result **out);
+/* Fixed-length batch: pattern i = bytes[i*length .. (i+1)*length) (no offsets array to ship). */
+int e2fm_search_batch_fixed(e2fm_index *ix, const uint8_t *bytes, uint64_t n, uint32_t length, int mode,
+                            e2fm_result **out);
+/* Same two with DEVICE-resident pattern buffers (no host<->device traffic). */
+int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n,
+                             uint64_t total_bytes, int mode, e2fm_result **out);
+int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint64_t n, uint32_t length, int mode,
+                                   e2fm_result **out);
+/* Page-locked host memory for pattern / result buffers (plain malloc'ed buffers work too, only slower). */
+void *e2fm_host_alloc(size_t bytes);
+void e2fm_host_free(void *p);
+/* number of visible CUDA devices (0 when there is none: every compute call then fails with E2FM_ERR_CUDA) */
+int e2fm_device_count(void);
+
+uint64_t e2fm_result_patterns(const e2fm_result *r);
+uint64_t e2fm_result_total_positions(const e2fm_result *r);
+/* D2H copy of whichever arrays are non-NULL:
+ *   counts[n]            EFMIndex::countOccurrences
+ *   pos_offsets[n+1]     CSR offsets into the arrays below
+ *   positions[total]     sorted, de-duplicated global text positions (EFMIndex::locateOccurrences, EFMIndex.cpp:2281-2301)
+ *   seq_index[total], seq_offset[total]   Occurrence{sequenceIndex, patternPosition} (EFMCollection.cpp:124-148) */
+int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, uint64_t *positions,
+                      uint32_t *seq_index, uint64_t *seq_offset);
+/* device pointers of the same arrays (valid until e2fm_result_free) */
+int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uint64_t **d_pos_offsets,
+                            const uint64_t **d_positions, const uint32_t **d_seq_index,
+                            const uint64_t **d_seq_offset);
+void e2fm_result_free(e2fm_result *r);
+
+/* Per-phase device times (ms, CUDA events on the index stream) of the most recent batch:
+ * [0] pattern H2D, [1] backward search kernel, [2] interval scan + expansion, [3] row-walk kernel, [4] reserved,
+ * [5] CSR build + sort + dedupe + sequence map, [6] whole batch (first copy to last kernel), [7] reserved */
+int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
+/* Operation counters of the most recent batch, in the reference's units:
+ * [0] rank (= Bucket::getOffsetInformations(CountOnly) calls, Bucket.cpp:656), [1] lf (= ...(RetrieveCharacter)),
+ * [2] mark (= Bucket::getMarkedTextPosition, Bucket.cpp:823), [3] row tasks, [4] duplicate positions removed,
+ * [5] kernels launched by the batch, [6] located occurrences, [7] reserved */
+int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
+#define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^20) */
+#define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
+int e2fm_set_option(e2fm_index *ix, int option, uint64_t value);
+
+/* ---- test hooks (parity of the individual kernels against the oracle) ---- */
+/* K1: Salsa20 keystream kernel. Replaces RandomGenerator::populateKeyStreamBuffer + nextInt over salsa20.S
+ * (RandomGenerator.cpp:125,60): `count` values of int_log2(max_value+1) bits starting at value `start`
+ * of the stream (key = bytes 32..63 of key64, nonce = `nonce`). */
+int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, uint32_t max_value,
+                         uint64_t start, uint64_t count, uint32_t *out);
+/* raw Salsa20/20 blocks [first_block, first_block + n_blocks) for a 32-byte key */
+int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block,
+                       uint64_t n_blocks, uint8_t *out);
+/* K2 output: decoded BWT (compact codes, logical row order) rows [row0, row0+count) */
+int e2fm_debug_bwt(const e2fm_index *ix, uint64_t row0, uint64_t count, uint32_t *out);
+/* marked value of each row in [row0,row0+count) or UINT64_MAX if the row is not marked */
+int e2fm_debug_marks(const e2fm_index *ix, uint64_t row0, uint64_t count, uint64_t *out);
+/* LF-mapping of rows (device rank structure) */
+int e2fm_debug_lf(const e2fm_index *ix, const uint64_t *rows, uint64_t count, uint64_t *out);
+/* C[c] + occ(c,row) for `count` (code,row) pairs — the rank primitive of EFMIndex::backwardStep (EFMIndex.cpp:1966) */
+int e2fm_debug_rank(const e2fm_index *ix, const uint32_t *codes, const uint64_t *rows, uint64_t count, uint64_t *out);
+
+const char *e2fm_last_error(void);
+const char *e2fm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2FM_B200_H_ */

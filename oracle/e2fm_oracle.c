@@ -683,6 +683,26 @@ int64_t orc_search(orc_index *ix, const uint8_t *pat, uint32_t m, int mode, uint
     return (int64_t)w;
 }
 
+/* ---- per-row views of the decoded index, for the kernel-level parity tests ---- */
+void orc_get_bwt(const orc_index *ix, uint64_t row0, uint64_t count, uint32_t *out) {
+    for (uint64_t i = 0; i < count; i++) out[i] = row0 + i < ix->n ? ix->bwt[row0 + i] : 0xFFFFFFFFu;
+}
+void orc_get_marks(const orc_index *ix, uint64_t row0, uint64_t count, uint64_t *out) {
+    for (uint64_t i = 0; i < count; i++) out[i] = (row0 + i < ix->n && ix->marked[row0 + i]) ? ix->mark_val[row0 + i] : ~0ull;
+}
+void orc_lf_rows(orc_index *ix, const uint64_t *rows, uint64_t count, uint64_t *out) {
+    uint64_t keep = ix->c_lf;
+    for (uint64_t i = 0; i < count; i++) out[i] = rows[i] < ix->n ? lf(ix, rows[i], NULL) : ~0ull;
+    ix->c_lf = keep;
+}
+/* C[c] + occ(c,row): the quantity EFMIndex::backwardStep adds up (EFMIndex.cpp:1966-2001) */
+void orc_rank_rows(orc_index *ix, const uint32_t *codes, const uint64_t *rows, uint64_t count, uint64_t *out) {
+    uint64_t keep = ix->c_rank;
+    for (uint64_t i = 0; i < count; i++)
+        out[i] = (codes[i] < ix->A && rows[i] < ix->n) ? ix->C[codes[i]] + occ_upto(ix, codes[i], rows[i]) : ~0ull;
+    ix->c_rank = keep;
+}
+
 void orc_map_position(const orc_index *ix, uint64_t p, uint32_t *seq, uint64_t *off) {
     int64_t s = -1;
     for (uint64_t i = 0; i < ix->n_term && s == -1; i++) if ((uint64_t)ix->term[i] > p) s = (int64_t)i;

@@ -53,6 +53,13 @@ int64_t orc_search(orc_index *ix, const uint8_t *pattern, uint32_t len, int mode
 /* EFMCollection::search position -> (sequenceIndex, offset)   (EFMCollection.cpp:124-148) */
 void orc_map_position(const orc_index *ix, uint64_t pos, uint32_t *seq, uint64_t *off);
 
+/* per-row views of the decoded index (kernel-level parity tests): compact BWT codes, marked values (~0 = unmarked),
+ * LF(row), and C[c] + occ(c,row) */
+void orc_get_bwt(const orc_index *ix, uint64_t row0, uint64_t count, uint32_t *out);
+void orc_get_marks(const orc_index *ix, uint64_t row0, uint64_t count, uint64_t *out);
+void orc_lf_rows(orc_index *ix, const uint64_t *rows, uint64_t count, uint64_t *out);
+void orc_rank_rows(orc_index *ix, const uint32_t *codes, const uint64_t *rows, uint64_t count, uint64_t *out);
+
 /* op counters since open: rank = getOffsetInformations(CountOnly),
  * lf = getOffsetInformations(RetrieveCharacter), mark = getMarkedTextPosition */
 void orc_get_counters(const orc_index *ix, uint64_t *n_rank, uint64_t *n_lf, uint64_t *n_mark);

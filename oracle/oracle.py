@@ -58,6 +58,10 @@ def lib():
         L.orc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64),
                                  C.c_void_p, C.c_uint64]
         L.orc_map_position.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_get_bwt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_get_marks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_lf_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_rank_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_get_counters.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
         L.orc_reset_counters.argtypes = [C.c_void_p]
         _lib = L
@@ -170,6 +174,29 @@ class OracleIndex:
         s, o = C.c_uint32(0), C.c_uint64(0)
         lib().orc_map_position(self._h, int(pos), C.byref(s), C.byref(o))
         return int(s.value), int(o.value)
+
+    def bwt(self, row0: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint32)
+        lib().orc_get_bwt(self._h, row0, count, out.ctypes.data)
+        return out
+
+    def marks(self, row0: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint64)
+        lib().orc_get_marks(self._h, row0, count, out.ctypes.data)
+        return out
+
+    def lf_rows(self, rows) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(len(rows), dtype=np.uint64)
+        lib().orc_lf_rows(self._h, rows.ctypes.data, len(rows), out.ctypes.data)
+        return out
+
+    def rank_rows(self, codes, rows) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(len(rows), dtype=np.uint64)
+        lib().orc_rank_rows(self._h, codes.ctypes.data, rows.ctypes.data, len(rows), out.ctypes.data)
+        return out
 
     def counters(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -1,0 +1,66 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/e2fm_b200.h declares, and
+fails loudly (no fallback) when there is no CUDA device. No compute calls here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from e2fm_b200 import capi
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "e2fm_b200.h")) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(e2fm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    decl = declared_symbols()
+    assert len(decl) >= 25
+    for name in decl:
+        assert hasattr(L, name), f"{name} is declared in include/e2fm_b200.h but not exported"
+    assert sorted(capi.EXPORTS) == decl
+    assert b"sm_100a" in L.e2fm_version()
+
+
+def test_info_struct_layout_matches_header():
+    # 8 u64 + 8 u32 + 8 float
+    import ctypes
+    assert ctypes.sizeof(capi.Info) == 8 * 8 + 8 * 4 + 8 * 4
+
+
+def test_no_cpu_fallback(golden, key64):
+    """Without a GPU every compute entry point must fail with E2FM_ERR_CUDA, never compute on the host."""
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.E2FMError) as e:
+        capi.DeviceIndex(golden["col3_k4"]["index"], key64)
+    assert e.value.code == -1 and "no CPU search path" in str(e.value)
+    with pytest.raises(capi.E2FMError):
+        capi.debug_keystream(key64, 5, 256, 0, 16)
+    with pytest.raises(capi.E2FMError):
+        capi.debug_salsa20(key64[:32], 0, 0, 1)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under e2fm_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("e2fm_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp.split(os.sep):
+                continue
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                    with open(os.path.join(dp, fn), errors="replace") as f:
+                        txt = f.read()
+                    if re.search(r"liboracle|e2fm_oracle|from oracle|import oracle|oracle/", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_key_must_be_64_bytes(golden):
+    with pytest.raises(ValueError):
+        capi.DeviceIndex(golden["col3_k4"]["index"], b"short")

@@ -1,0 +1,281 @@
+"""GPU parity: every kernel of the CUDA path, through the C ABI, against the oracle (oracle/e2fm_oracle.c)
+and the committed reference results (tests/golden/*.res). Integer work: the bar is bit-exact."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_SEARCH_CASES, pack
+from e2fm_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    assert capi.device_count() > 0, "GPU tests need a CUDA device"
+    return 0
+
+
+# ---------------------------------------------------------------- K1
+
+def test_salsa20_blocks(gpu, oracle_mod):
+    key = bytes([0x80] + [0] * 31)
+    got = capi.debug_salsa20(key, 0, 0, 2)
+    assert got[:64] == oracle_mod.salsa20_block(key, 0, 0)
+    assert got[64:] == oracle_mod.salsa20_block(key, 0, 1)
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        nonce = int(rng.integers(0, 2**62))
+        first = int(rng.integers(0, 2**40))
+        got = capi.debug_salsa20(key, nonce, first, 5)
+        for b in range(5):
+            assert got[64 * b:64 * b + 64] == oracle_mod.salsa20_block(key, nonce, first + b)
+
+
+@pytest.mark.parametrize("max_value", [1, 2, 3, 255, 256, 257, 1023, 70000])
+def test_keystream_integers(gpu, oracle_mod, key64, max_value):
+    for nonce, start, count in [(0, 0, 1), (5, 0, 4200), (77, 100, 333), (2**40 + 3, 12345, 5000)]:
+        got = capi.debug_keystream(key64, nonce, max_value, start, count)
+        want = oracle_mod.keystream_ints(key64[32:], nonce, max_value, start, count)
+        assert np.array_equal(got, want), (max_value, nonce, start)
+
+
+# ---------------------------------------------------------------- K2 + rank structure
+
+@pytest.fixture(scope="module")
+def opened(gpu, golden, key64, oracle_mod):
+    out = {}
+    for name in GOLDEN_SEARCH_CASES:
+        out[name] = (capi.DeviceIndex(golden[name]["index"], key64), oracle_mod.OracleIndex(golden[name]["index"], key64))
+    yield out
+    for d, _ in out.values():
+        d.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+def test_decoded_bwt_and_marks(opened, name):
+    dev, orc = opened[name]
+    n = int(dev.info.text_length)
+    assert n == orc.info.n and dev.info.k == orc.info.k and dev.info.compact_alphabet == orc.info.compact_alphabet
+    assert dev.info.n_buckets == orc.info.n_buckets and dev.info.n_sequences == orc.info.n_sequences
+    assert dev.info.quirks == 0
+    assert np.array_equal(dev.debug_bwt(0, n + 3), orc.bwt(0, n + 3))
+    assert np.array_equal(dev.debug_marks(0, n + 3), orc.marks(0, n + 3))
+
+
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+def test_lf_and_rank(opened, name):
+    dev, orc = opened[name]
+    n = int(dev.info.text_length)
+    rows = np.arange(n, dtype=np.uint64)
+    assert np.array_equal(dev.debug_lf(rows), orc.lf_rows(rows))
+    rng = np.random.default_rng(3)
+    A = int(dev.info.compact_alphabet)
+    codes = rng.integers(0, A, 200000, dtype=np.uint32)
+    rr = rng.integers(0, n, 200000, dtype=np.uint64)
+    # block boundaries and the ends
+    blk = int(dev.info.rank_block)
+    edge = np.array([0, 1, blk - 1, blk, blk + 1, n - 1, n - 2], dtype=np.uint64) % n
+    rr[:len(edge)] = edge
+    assert np.array_equal(dev.debug_rank(codes, rr), orc.rank_rows(codes, rr))
+
+
+# ---------------------------------------------------------------- K3 + K4 + result pipeline
+
+def check_against_res(dev, patterns, res, locate):
+    data, offs = pack(patterns)
+    r = dev.search(data, offs, locate)
+    out = r.fetch()
+    assert np.array_equal(out["counts"], res["counts"])
+    if locate:
+        assert np.array_equal(out["pos_offsets"], res["pos_offsets"])
+        assert np.array_equal(out["positions"], res["positions"])
+        assert np.array_equal(out["seq"], res["seq"])
+        assert np.array_equal(out["off"], res["off"])
+    r.free()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+@pytest.mark.parametrize("locate", [False, True])
+def test_search_matches_reference_goldens(opened, golden, name, locate):
+    dev, _ = opened[name]
+    check_against_res(dev, golden[name]["patterns"], golden[name]["res"], locate)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+def test_search_small_chunks_and_windows(opened, golden, name):
+    """same results when the batch is cut into many chunks and task windows"""
+    dev, _ = opened[name]
+    dev.set_option(capi.OPT_CHUNK, 7)
+    dev.set_option(capi.OPT_WINDOW, 5)
+    try:
+        check_against_res(dev, golden[name]["patterns"], golden[name]["res"], True)
+    finally:
+        dev.set_option(capi.OPT_CHUNK, 0)
+        dev.set_option(capi.OPT_WINDOW, 0)
+
+
+def test_op_counters_match_oracle(opened, golden):
+    """rank / lf / mark operation counts equal the oracle's for the same batch"""
+    dev, orc = opened["col3_k4"]
+    pats = [p for p in golden["col3_k4"]["patterns"] if len(p) >= 8]
+    orc.reset_counters()
+    for p in pats:
+        orc.search(p, True)
+    want = orc.counters()
+    data, offs = pack(pats)
+    r = dev.search(data, offs, True)
+    c = dev.last_batch_counters()
+    r.free()
+    assert (c["rank"], c["lf"], c["mark"]) == want
+
+
+def test_edge_batches(opened, oracle_mod):
+    dev, orc = opened["col3_k4"]
+    # empty batch
+    r = dev.search(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64), True)
+    assert r.n == 0 and r.total == 0
+    r.free()
+    # ragged lengths incl. empty pattern, foreign symbols, lower case (not upper-cased by the library), '&' and '$'
+    pats = [b"", b"A", b"ACG", b"ACGT", b"ACGTA", b"acgtacgt", b"ACGTNNNNACGT", b"&&&&", b"ACGT&&&&", b"$$$$", b"TTTTTTTT" * 40,
+            b"ACGTACGTACGTACGT", b"GATTACA", b"CATCATCAT"]
+    data, offs = pack(pats)
+    for locate in (False, True):
+        r = dev.search(data, offs, locate)
+        out = r.fetch()
+        for i, p in enumerate(pats):
+            cnt, pos = orc.search(p, True)
+            assert int(out["counts"][i]) == cnt, (p, locate)
+            if locate:
+                a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+                assert np.array_equal(out["positions"][a:b], pos), p
+                for j in range(a, b):
+                    assert orc.map_position(int(out["positions"][j])) == (int(out["seq"][j]), int(out["off"][j]))
+        r.free()
+
+
+def test_heavy_hitters_sort_paths(opened):
+    """short patterns with thousands of occurrences exercise the CTA / global-memory segment sorts"""
+    dev, orc = opened["col2_k2"]
+    pats = [b"AC", b"ACG", b"TTT", b"GA", b"CCCC", b"A" * 5]
+    data, offs = pack(pats)
+    r = dev.search(data, offs, True)
+    out = r.fetch()
+    for i, p in enumerate(pats):
+        cnt, pos = orc.search(p, True)
+        a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+        assert int(out["counts"][i]) == cnt
+        assert np.array_equal(out["positions"][a:b], pos), p
+    r.free()
+
+
+def test_fixed_length_entry_point_and_pinned_buffers(opened, golden):
+    dev, orc = opened["col3_k4"]
+    pats = [p for p in golden["col3_k4"]["patterns"] if len(p) == 20]
+    pin = capi.PinnedArray((len(pats), 20), np.uint8)
+    pin.array[:] = np.frombuffer(b"".join(pats), dtype=np.uint8).reshape(len(pats), 20)
+    r = dev.search_fixed(pin.array, True)
+    out = r.fetch()
+    for i, p in enumerate(pats):
+        cnt, pos = orc.search(p, True)
+        a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+        assert int(out["counts"][i]) == cnt and np.array_equal(out["positions"][a:b], pos)
+    r.free()
+    pin.free()
+
+
+def test_error_behaviour(gpu, golden, key64):
+    idx = golden["col3_k4"]["index"]
+    with pytest.raises(capi.E2FMError) as e:       # bad magic: the reference's message (EFMIndex.cpp:1155)
+        capi.DeviceIndex(b"XY" + idx[2:], key64)
+    assert e.value.code == -2 and "not Encrypted and Compressed Genomic Index" in str(e.value)
+    wrong = bytes((b + 1) & 0xFF for b in key64)
+    with pytest.raises(capi.E2FMError) as e:       # wrong key: C[] does not decrypt
+        capi.DeviceIndex(idx, wrong)
+    assert e.value.code == -2
+    with pytest.raises(capi.E2FMError):            # truncated file
+        capi.DeviceIndex(idx[:len(idx) // 2], key64)
+    nm = capi.DeviceIndex(golden["col2_k4_nomarks"]["index"], key64)
+    with pytest.raises(capi.E2FMError) as e:       # EFMIndex.cpp:2305-2306
+        nm.search_list([b"ACGTACGT"], True)
+    assert e.value.code == -4 and "marked rows" in str(e.value)
+    nm.close()
+
+
+# ---------------------------------------------------------------- BASELINE config 1 at full size
+
+@pytest.fixture(scope="module")
+def config1(gpu, key64, oracle_mod, tmp_path_factory):
+    """10 Mbp random ACGT, k=4, bucket 4096, mrp=2, built by the compiled reference (oracle/_ref travels to the box)."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref/e2fm_ref not built")
+    d = tmp_path_factory.mktemp("cfg1")
+    lens = synth.safe_lengths([10_000_000], 4, 50)
+    seqs = synth.random_sequences(lens, 42)
+    fa, efm, keyfile = str(d / "c1.fa"), str(d / "c1.efm"), os.path.join(GOLDEN, "key.bin")
+    synth.write_fasta(fa, seqs)
+    oracle_mod.ref_build(fa, efm, keyfile, k=4, bucket_size=4096, mrp=2, threads=min(16, os.cpu_count() or 2))
+    with open(efm, "rb") as f:
+        raw = f.read()
+    return {"seqs": seqs, "index": raw, "efm": efm, "keyfile": keyfile, "dir": d}
+
+
+def test_config1_count_locate_vs_reference(config1, key64, oracle_mod):
+    """BASELINE.json configs[0]: 10k patterns of length 20, count + locate, against the reference's own CPU search"""
+    pats = synth.sample_patterns(config1["seqs"], 10_000, 20, 43)
+    pfile = str(config1["dir"] / "p.txt")
+    synth.write_patterns(pfile, pats)
+    res, _ = oracle_mod.ref_search(config1["efm"], config1["keyfile"], pfile, str(config1["dir"] / "r.res"), True, 2)
+    dev = capi.DeviceIndex(config1["index"], key64)
+    for locate in (False, True):
+        r = dev.search_fixed(np.ascontiguousarray(pats), locate)
+        out = r.fetch()
+        assert np.array_equal(out["counts"], res["counts"])
+        if locate:
+            assert np.array_equal(out["pos_offsets"], res["pos_offsets"])
+            assert np.array_equal(out["positions"], res["positions"])
+            assert np.array_equal(out["seq"], res["seq"]) and np.array_equal(out["off"], res["off"])
+        r.free()
+    dev.close()
+
+
+def test_config1_whole_index_decode_and_properties(config1, key64, oracle_mod):
+    """every decoded row == the oracle's; LF is a permutation; 1M sampled patterns all found at their sample position"""
+    dev = capi.DeviceIndex(config1["index"], key64)
+    orc = oracle_mod.OracleIndex(config1["index"], key64)
+    n = int(dev.info.text_length)
+    assert np.array_equal(dev.debug_bwt(0, n), orc.bwt(0, n))
+    assert np.array_equal(dev.debug_marks(0, n), orc.marks(0, n))
+    lf = dev.debug_lf(np.arange(n, dtype=np.uint64))
+    assert np.array_equal(np.sort(lf), np.arange(n, dtype=np.uint64))      # LF-mapping is a bijection on rows
+    # size-independent property at a large batch: a pattern cut from the text at position p is located at p
+    seq = config1["seqs"][0]
+    rng = np.random.default_rng(5)
+    npat, L = 1_000_000, 32
+    starts = rng.integers(0, len(seq) - L, npat)
+    pats = seq[starts[:, None] + np.arange(L)[None, :]]
+    r = dev.search_fixed(np.ascontiguousarray(pats), True)
+    out = r.fetch()
+    offs = out["pos_offsets"]
+    assert np.array_equal(out["counts"], np.diff(offs))
+    assert (out["counts"] >= 1).all()
+    first = offs[:-1].astype(np.int64)
+    # every segment sorted ascending and contains the sampling position
+    pos = out["positions"]
+    seg = np.repeat(np.arange(npat), np.diff(offs).astype(np.int64))
+    assert (np.diff(pos.astype(np.int64))[np.diff(seg) == 0] > 0).all()
+    hit = np.zeros(npat, dtype=bool)
+    hit[seg[pos == starts[seg].astype(np.uint64)]] = True
+    assert hit.all()
+    # count-only agrees with locate
+    r2 = dev.search_fixed(np.ascontiguousarray(pats), False)
+    assert np.array_equal(r2.fetch()["counts"], out["counts"])
+    # spot-check 300 of them against the oracle
+    for i in rng.integers(0, npat, 300):
+        cnt, p = orc.search(pats[i].tobytes(), True)
+        assert cnt == int(out["counts"][i]) and np.array_equal(p, pos[int(offs[i]):int(offs[i + 1])])
+    r.free(); r2.free()
+    dev.close()
