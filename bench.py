@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — batched pattern search throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ecoli|collection100|config1] [--impl reference]
+
+A step = one pass of the hot path over one batch of synthetic patterns (count, or count+locate).
+  value      whole-job patterns/s with the pattern batch already resident in HBM (device time, CUDA events on
+             the library's stream, max over ranks)
+  e2e        the same through the C ABI with HOST (pinned) buffers: H2D of the patterns and D2H of the counts
+             (and positions) inside the timed region
+  roofline   dominant kernel: algorithmic bytes (160 B/rank + 224 B/lf + 64 B/mark, operation
+             counts measured by the kernels and pinned to the oracle's by tests) / its CUDA-event time
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/e2fm_ref) on the host cores over a bounded sample
+--impl reference times that CPU reference as the main line.
+The index is always built by the reference's own CPU builder (north star: index construction stays on the CPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from e2fm_b200 import synth  # noqa: E402
+
+CACHE = os.path.join(ROOT, "data", "bench_cache")
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: E. coli-sized 4.6 Mbp synthetic genome, 1M patterns len 32, count only, 1 GPU
+    "ecoli": dict(seq_lens=[4_641_652], seed=43, n_patterns=1_000_000, pat_len=32, locate=False,
+                  name="configs[1]: 4.6 Mbp synthetic genome, 1M patterns len 32, count"),
+    # BASELINE.json configs[0]: 10 Mbp random ACGT, 10k patterns len 20, count+locate
+    "config1": dict(seq_lens=[10_000_000], seed=42, n_patterns=10_000, pat_len=20, locate=True,
+                    name="configs[0]: 10 Mbp random ACGT, 10k patterns len 20, count+locate"),
+    # BASELINE.json configs[2] on ONE GPU (whole collection in one index): larger than L2, HBM-bound
+    "collection100": dict(seq_lens=[4_641_652] * 100, seed=1000, n_patterns=10_000_000, pat_len=24, locate=True,
+                          name="configs[2]: 100 x 4.6 Mbp synthetic genomes, 10M patterns len 24, count+locate"),
+    # a collection100 shard-sized index for quicker HBM-bound runs
+    "collection25": dict(seq_lens=[4_641_652] * 25, seed=1000, n_patterns=4_000_000, pat_len=24, locate=True,
+                         name="25 x 4.6 Mbp synthetic genomes, 4M patterns len 24, count+locate"),
+}
+K, BUCKET, MRP = 4, 4096, 2   # the authors' regime (Main.cpp:469,747)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def ref_bin():
+    p = os.path.join(ROOT, "oracle", "_ref", "e2fm_ref")
+    if not os.path.exists(p):
+        raise SystemExit("oracle/_ref/e2fm_ref is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "in the authoring container (the reference index builder is required)")
+    return p
+
+
+def prepare(workload: str, rank: int = 0):
+    """Synthetic collection + reference-built index (cached on disk) -> dict"""
+    w = WORKLOADS[workload]
+    os.makedirs(CACHE, exist_ok=True)
+    lens = synth.safe_lengths(w["seq_lens"], K, 100 // MRP)
+    seqs = []
+    for i, L in enumerate(lens):
+        seqs += synth.random_sequences([L], w["seed"] + i)
+    base = os.path.join(CACHE, f"{workload}_k{K}_b{BUCKET}_m{MRP}")
+    keyfile = os.path.join(CACHE, "key.bin")
+    efm = base + ".efm"
+    if rank == 0:
+        if not os.path.exists(keyfile):
+            with open(keyfile, "wb") as f:
+                f.write(synth.test_key())
+        if not os.path.exists(efm):
+            t0 = time.time()
+            fa = base + ".fa"
+            synth.write_fasta(fa, seqs)
+            threads = str(min(32, os.cpu_count() or 2))
+            r = subprocess.run([ref_bin(), "build", fa, efm + ".tmp", keyfile, str(K), str(BUCKET), str(MRP), threads],
+                               capture_output=True, text=True)
+            if r.returncode != 0 or not os.path.exists(efm + ".tmp"):
+                raise SystemExit("reference index build failed: " + r.stderr[-400:])
+            os.replace(efm + ".tmp", efm)
+            os.remove(fa)
+            log(f"[bench] reference built {efm} ({os.path.getsize(efm) / 1e6:.1f} MB) in {time.time() - t0:.1f}s")
+    return dict(w=w, seqs=seqs, efm=efm, keyfile=keyfile)
+
+
+def wait_for(path, timeout=3600):
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > timeout:
+            raise SystemExit("timed out waiting for " + path)
+        time.sleep(0.5)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    p = [x.strip() for x in line.split(",")]
+                    if len(p) < 9:
+                        continue
+                    try:
+                        sm.append(float(p[1])); mx.append(float(p[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ CPU reference
+
+def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdir: str):
+    """P independent processes of the unmodified reference, each over a 1/P slice (the reference is serial and not
+    re-entrant per object); 1 matcher thread each; 2 passes: cold (lazy bucket decode) and warm.
+    Returns (patterns/s warm aggregate, patterns/s cold aggregate, wall seconds)."""
+    slices = np.array_split(np.arange(len(pats)), procs)
+    ps = []
+    t0 = time.time()
+    for i, sl in enumerate(slices):
+        pf = os.path.join(tmpdir, f"p{i}.txt")
+        synth.write_patterns(pf, pats[sl])
+        ps.append(subprocess.Popen([ref_bin(), "search", prep["efm"], prep["keyfile"], pf, os.path.join(tmpdir, f"r{i}.res"),
+                                    "1" if locate else "0", "1", "2"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    cold = warm = 0.0
+    for p, sl in zip(ps, slices):
+        out, _ = p.communicate()
+        line = [l for l in out.splitlines() if l.startswith("{")]
+        if p.returncode != 0 or not line:
+            raise SystemExit("reference search failed")
+        j = json.loads(line[-1])
+        cold = max(cold, j["pass_ms"][0])
+        warm = max(warm, j["pass_ms"][1])
+    return len(pats) / (warm / 1e3), len(pats) / (cold / 1e3), time.time() - t0
+
+
+def reference_arm(args, prep):
+    w = prep["w"]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    per_proc = 4000 if w["pat_len"] >= 20 else 400
+    sample = min(w["n_patterns"], procs * per_proc)
+    pats = synth.sample_patterns(prep["seqs"], sample, w["pat_len"], w["seed"] + 1)[:sample]
+    vals, colds = [], []
+    with tempfile.TemporaryDirectory() as td:
+        t_all = time.time()
+        for step in range(args.warmup + args.steps):
+            v, c, wall = run_reference_sample(prep, pats, w["locate"], procs, td)
+            if step >= args.warmup:
+                vals.append(v); colds.append(c)
+        wall_all = time.time() - t_all
+    value = float(np.mean(vals))
+    desc = (f"{sample} of {w['n_patterns']} patterns (len {w['pat_len']}) split over {procs} processes of the unmodified "
+            f"reference, 1 matcher thread each; value = warm pass (2nd pass, buckets already decoded), cold pass = "
+            f"{float(np.mean(colds)):.0f} patterns/s")
+    line = {
+        "impl": "reference", "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": w["name"], "mode": "count+locate" if w["locate"] else "count", "k": K, "bucket_size": BUCKET,
+                   "mrp": MRP, "sample_patterns": sample},
+        "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": procs, "kind": "reference", "sample": desc,
+                         "cold_value": float(np.mean(colds)), "host_cores": cores},
+        "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from e2fm_b200 import capi
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev_t = torch.device("cuda", local_rank)
+
+    prep = prepare(args.workload, rank)
+    if world > 1:
+        dist.barrier()
+    wait_for(prep["efm"])
+    w = prep["w"]
+    locate = w["locate"]
+    with open(prep["efm"], "rb") as f:
+        raw = f.read()
+    t0 = time.time()
+    ix = capi.DeviceIndex(raw, synth.test_key(), local_rank)
+    load_s = time.time() - t0
+    info = ix.info
+    log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
+        f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
+
+    # weak scaling: every rank searches its own batch of the workload's size against its replica of the index
+    # (single-sequence workloads do not shard: replicas only)
+    npat, L = w["n_patterns"], w["pat_len"]
+    pats = synth.sample_patterns(prep["seqs"], npat, L, w["seed"] + 1 + 7919 * rank)[:npat]
+    pin_p = capi.PinnedArray((npat, L), np.uint8)
+    pin_p.array[:] = pats
+    pin_counts = capi.PinnedArray(npat, np.uint64)
+    d_pats = torch.from_numpy(pats).to(dev_t)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def l2_flush():
+        flush.add_(1)
+        torch.cuda.synchronize()
+
+    def step_device():
+        r = ix.search_device_fixed(d_pats.data_ptr(), npat, L, locate)
+        ms = ix.last_batch_ms()
+        ctr = ix.last_batch_counters()
+        tot = r.total
+        r.free()
+        return ms, ctr, tot
+
+    pin_pos = {}
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        r = ix.search_fixed(pin_p.array, locate)
+        if locate:
+            need = max(r.total, 1)
+            if pin_pos.get("n", 0) < need:
+                for k_ in ("pos", "off"):
+                    if k_ in pin_pos:
+                        pin_pos[k_].free()
+                pin_pos["pos"] = capi.PinnedArray(int(need * 1.2) + 16, np.uint64)
+                pin_pos["off"] = capi.PinnedArray(npat + 1, np.uint64)
+                pin_pos["n"] = int(need * 1.2) + 16
+            r.fetch(counts=pin_counts.array, pos_offsets=pin_pos["off"].array, positions=pin_pos["pos"].array[:r.total],
+                    want_seq=False)
+        else:
+            r.fetch(counts=pin_counts.array)
+        dt = time.perf_counter() - t0
+        tot = r.total
+        r.free()
+        return dt, tot
+
+    for _ in range(args.warmup):
+        l2_flush(); step_device()
+        l2_flush(); step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, bs_ms, walk_ms, exp_ms, res_ms = 0.0, 0.0, 0.0, 0.0, 0.0
+    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0}
+    occ_total = 0
+    for _ in range(args.steps):
+        l2_flush()
+        ms, ctr, tot = step_device()
+        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]
+        for k_ in ctr_sum:
+            ctr_sum[k_] += ctr[k_]
+        occ_total += tot
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_dev = time.perf_counter() - wall0
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        l2_flush()
+        dt, _tot = step_e2e()
+        e2e_s += dt
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3, bs_ms, walk_ms], dtype=torch.float64, device=dev_t)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max, bs_ms_max, walk_ms_max = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        steps = args.steps
+        value = world * npat * steps / (dev_ms_max / 1e3)
+        e2e_value = world * npat * steps / (e2e_ms_max / 1e3)
+        # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
+        bytes_bs = 160.0 * ctr_sum["rank"]
+        bytes_walk = 224.0 * ctr_sum["lf"] + 64.0 * ctr_sum["mark"]
+        kern = {
+            "backward_search_kernel": {"ms_per_step": bs_ms / steps, "alg_bytes_per_step": bytes_bs / steps,
+                                       "achieved_gbs": bytes_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0},
+            "walk_kernel": {"ms_per_step": walk_ms / steps, "alg_bytes_per_step": bytes_walk / steps,
+                            "achieved_gbs": bytes_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0},
+        }
+        dom = "backward_search_kernel" if bs_ms >= walk_ms else "walk_kernel"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_kind,
+                    "note": "achieved = reference-algorithm bytes (160 B/rank + 224 B/lf + 64 B/mark, SURVEY.md 8(d)) / kernel time; "
+                            "the flattened layout moves fewer real bytes per operation (1 sector per rank, 8 B per LF step)",
+                    "kernels": kern}
+        line = {
+            "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "mode": "count+locate" if locate else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
+                       "patterns_per_gpu": npat, "pattern_len": L, "parallelism": f"replicas x{world} (pattern batch per GPU)",
+                       "l2": "256 MB flush between timed iterations",
+                       "index_device_MB": round(info.device_bytes / 1e6, 1), "index_load_s": round(load_s, 3)},
+            "occurrences_per_s": (world * occ_total / (dev_ms_max / 1e3)) if locate else None,
+            "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": int(npat * L),
+                    "d2h_bytes_per_step": int(npat * 8 + ((npat + 1) * 8 + (occ_total // max(steps, 1)) * 8 if locate else 0)),
+                    "ms_per_step": e2e_ms_max / steps},
+            "gpu_launches": int(ctr_sum["launches"]),
+            "roofline": roofline,
+            "ops_per_pattern": {"rank": ctr_sum["rank"] / (npat * steps), "lf": ctr_sum["lf"] / (npat * steps),
+                                "mark": ctr_sum["mark"] / (npat * steps)},
+            "phase_ms_per_step": {"backward_search": bs_ms / steps, "expand": exp_ms / steps, "walk": walk_ms / steps,
+                                  "results": res_ms / steps},
+            "clocks": clocks, "wall_s_timed_device_loop": wall_dev,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            procs = max(1, min(cores, 32))
+            per_proc = 4000 if L >= 20 else 400
+            sample = min(npat, procs * per_proc)
+            with tempfile.TemporaryDirectory() as td:
+                v, c, wall = run_reference_sample(prep, pats[:sample], locate, procs, td)
+            line["cpu_baseline"] = {"value": v, "unit": "patterns/s", "cores": procs, "kind": "reference", "host_cores": cores,
+                                    "cold_value": c,
+                                    "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified "
+                                              f"reference (1 matcher thread each), warm pass; cold pass {c:.0f} patterns/s; {wall:.1f}s wall"}
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
+    ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reference_arm(args, prepare(args.workload, 0))
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
