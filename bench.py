@@ -98,49 +98,60 @@ def wait_for(path, timeout=3600):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every ~10 ms DURING the timed region (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints, B200_PROFILING.md)."""
 
     def __init__(self, gpu_index: int):
-        self.path = tempfile.mktemp(suffix=".csv")
         self.gpu = gpu_index
-        self.proc = None
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_sm = None
+        self._stop = False
+        self._thr = None
+
+    def _loop(self):
+        import pynvml as nv
+        try:
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while True:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k_, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k_)
+                if self._stop:
+                    break
+                time.sleep(0.01)
+        except Exception as e:   # noqa: BLE001
+            self.reasons.add("nvml unavailable: " + type(e).__name__)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        import threading
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            with open(self.path) as f:
-                for line in f:
-                    p = [x.strip() for x in line.split(",")]
-                    if len(p) < 9:
-                        continue
-                    try:
-                        sm.append(float(p[1])); mx.append(float(p[2]))
-                    except ValueError:
-                        continue
-                    for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
-            os.remove(self.path)
-        except OSError:
-            pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop = True
+        if self._thr:
+            self._thr.join(timeout=5)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons)}
 
 
 def measured_peak():
@@ -295,7 +306,7 @@ def gpu_arm(args, rank, world, local_rank):
     sampler.start()
     wall0 = time.perf_counter()
     dev_ms, bs_ms, walk_ms, exp_ms, res_ms = 0.0, 0.0, 0.0, 0.0, 0.0
-    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0}
+    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0}
     occ_total = 0
     for _ in range(args.steps):
         l2_flush()
@@ -332,11 +343,18 @@ def gpu_arm(args, rank, world, local_rank):
         # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
         bytes_bs = 160.0 * ctr_sum["rank"]
         bytes_walk = 224.0 * ctr_sum["lf"] + 64.0 * ctr_sum["mark"]
+        # what the flattened layout has to touch at minimum: one 32-byte sector per distinct rank sector / walk gather
+        lay_bs = 32.0 * ctr_sum["rank_sectors"]
+        lay_walk = 32.0 * ctr_sum["walk_gathers"]
         kern = {
             "backward_search_kernel": {"ms_per_step": bs_ms / steps, "alg_bytes_per_step": bytes_bs / steps,
-                                       "achieved_gbs": bytes_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0},
+                                       "achieved_gbs": bytes_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0,
+                                       "layout_sector_bytes_per_step": lay_bs / steps,
+                                       "layout_sector_gbs": lay_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0},
             "walk_kernel": {"ms_per_step": walk_ms / steps, "alg_bytes_per_step": bytes_walk / steps,
-                            "achieved_gbs": bytes_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0},
+                            "achieved_gbs": bytes_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0,
+                            "layout_sector_bytes_per_step": lay_walk / steps,
+                            "layout_sector_gbs": lay_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0},
         }
         dom = "backward_search_kernel" if bs_ms >= walk_ms else "walk_kernel"
         traffic = None
@@ -349,8 +367,10 @@ def gpu_arm(args, rank, world, local_rank):
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_kind,
+                    "layout_sector_gbs": kern[dom]["layout_sector_gbs"], "layout_sector_frac": kern[dom]["layout_sector_gbs"] / peak,
                     "note": "achieved = reference-algorithm bytes (160 B/rank + 224 B/lf + 64 B/mark, SURVEY.md 8(d)) / kernel time; "
-                            "the flattened layout moves fewer real bytes per operation (1 sector per rank, 8 B per LF step)",
+                            "layout_sector_* = 32 B x the sectors this layout really has to gather (1 per rank sector, 1 per LF step), "
+                            "the random-gather figure to hold against the HBM peak",
                     "kernels": kern}
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -393,7 +413,7 @@ def gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
     ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))

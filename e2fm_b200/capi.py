@@ -271,12 +271,12 @@ class DeviceIndex:
     def last_batch_ms(self):
         a = (C.c_float * 8)()
         check(lib().e2fm_last_batch_ms(self._h, C.byref(a)))
-        return dict(zip(["h2d", "backward_search", "expand", "walk", "r4", "results", "total", "r7"], [float(x) for x in a]))
+        return dict(zip(["h2d", "backward_search", "expand", "walk", "encode", "results", "total", "r7"], [float(x) for x in a]))
 
     def last_batch_counters(self):
         a = (C.c_uint64 * 8)()
         check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
-        return dict(zip(["rank", "lf", "mark", "tasks", "dups", "launches", "occurrences", "r7"], [int(x) for x in a]))
+        return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers"], [int(x) for x in a]))
 
     # ---- test hooks
     def debug_bwt(self, row0: int, count: int) -> np.ndarray:

@@ -328,6 +328,7 @@ struct Batch {
     const uint64_t *d_off;
     uint32_t fixed_len;
     uint64_t n;
+    uint64_t total_bytes;
 };
 
 void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, EventTimer &tm) {
@@ -352,13 +353,23 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     DBuf<uint64_t> res_pos;
     uint64_t n_results = 0, total_tasks = 0;
 
+    // ---- pre-pass: k-mer code at every pattern byte
+    DBuf<uint16_t> codes(b.total_bytes + 8, s);
+    {
+        const int h = tm.begin(4);
+        PatternView all{b.d_bytes, b.d_off, b.fixed_len, 0, (uint32_t)b.n};
+        launch_encode_patterns(dix, all, 0, b.total_bytes, codes.p, s);
+        launches++;
+        tm.end(h);
+    }
+
     for (uint64_t first = 0; first < b.n; first += chunk) {
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
         CK(cudaMemsetAsync(ix->d_stats + ST_TASKS, 0, 8, s));
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, iv.p, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, counts.p, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);
@@ -461,10 +472,10 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[1] = ix->h_stats[ST_LF];
     ix->batch_ctr[2] = ix->h_stats[ST_MARK];
     ix->batch_ctr[3] = total_tasks;
-    ix->batch_ctr[4] = dups;
+    ix->batch_ctr[4] = ix->h_stats[ST_SECT_BS];
     ix->batch_ctr[5] = launches;
     ix->batch_ctr[6] = n_results;
-    ix->batch_ctr[7] = 0;
+    ix->batch_ctr[7] = ix->h_stats[ST_GATHER];
 }
 
 int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
@@ -488,7 +499,7 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
         const int whole = tm.begin(6);
         DBuf<uint8_t> d_bytes;
         DBuf<uint64_t> d_off;
-        Batch b{bytes, offsets, fixed_len, n};
+        Batch b{bytes, offsets, fixed_len, n, total_bytes};
         if (!on_device) {
             const int h = tm.begin(0);
             d_bytes.alloc(total_bytes + 16, s);

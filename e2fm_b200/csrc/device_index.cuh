@@ -4,12 +4,13 @@
 // Layout (all in HBM; sizes for n super-characters, compact alphabet A):
 //   rec[n]        u64 per BWT row:  bit 63 marked | bits 32..47 compact code | bits 0..31 LF(row)
 //                 (for a marked row the low word holds the marked value = textPos/markingRate instead)
-//   occ[nBlk][A]  one 32-byte SECTOR per (rank block, symbol):
-//                   u32 base  = C[c] + #{rows < blockStart : bwt[row]==c}
-//                   u16 off[14] ascending in-block offsets of the occurrences of c, 0xFFFF padded
-//                 so that  C[c] + occ(c,row) = base + #{off <= row % BLK}  costs ONE sector gather.
-//                 A block with more than 14 occurrences sets bit 15 of off[0]; off[0..11] hold the
-//                 first 12 offsets and off[12..13] the index (u32) of the rest in the `ovf` pool.
+//   occ[nBlk][A]  one 32-byte SECTOR per (rank block, symbol), 8 words:
+//                   w0     = C[c] + #{rows < blockStart : bwt[row]==c}
+//                   w1..w7 = 14 u16 slots (slot j in word 1+j/2, half j&1): ascending in-block offsets of the
+//                            occurrences of c, padded with 0x7FFF (> any offset: blocks hold <= 16384 rows)
+//                 so that  C[c] + occ(c,row) = w0 + #{slot <= row % BLK}  costs ONE sector gather and a SWAR
+//                 compare. A block with more than 14 occurrences sets bit 31 of w1 (bit 15 of slot 1): slots
+//                 0..11 hold the first 12 offsets and w7 the index of the rest in the `ovf` pool (0xFFFF-terminated).
 //   markTab[mrn]  uint2 {row, LF(row)} of the row whose marked value is v  (reverse of rec's marks;
 //                 replaces markedRowsBuckets + Bucket::getMarkedBwtPosition, Bucket.cpp:794)
 // The reference's two-level counters + per-bucket position lists (SuperBucket.cpp:82, Bucket.cpp:656-779)
@@ -51,35 +52,60 @@ __device__ __forceinline__ uint32_t rec_code(uint64_t r) { return (uint32_t)(r >
 __device__ __forceinline__ uint32_t rec_low(uint64_t r) { return (uint32_t)r; }
 __device__ __forceinline__ bool rec_marked(uint64_t r) { return (r >> 63) != 0; }
 
-// number of 16-bit lanes of w that are <= x (x < 0x8000), both halves
-__device__ __forceinline__ uint32_t count_le2(uint32_t w, uint32_t xx) {
-    return __popc(__vcmpleu2(w, xx)) >> 4;
+constexpr uint32_t SLOT_PAD = 0x7FFFu;
+constexpr uint32_t SWAR_M = 0x80008000u;
+
+struct Sector { uint4 lo, hi; };
+
+__device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {
+    const uint4 *s = ix.occ + ((size_t)blk * ix.A + c) * 2;
+    Sector r;
+    r.lo = __ldg(s);
+    r.hi = __ldg(s + 1);
+    return r;
+}
+
+// bits 15 and 31 of the result are set iff the low / high u16 slot of w is <= x (slots and x below 0x8000):
+// (x | 0x8000) - slot keeps bit 15 exactly when no borrow is needed, and the set top bit stops the borrow
+// from leaving its half.
+__device__ __forceinline__ uint32_t swar_le(uint32_t w, uint32_t xm) { return xm - w; }
+
+// C[c] + #{rows of the sector's block with in-block offset <= x that hold c}
+__device__ __forceinline__ uint32_t sector_rank(const DevIndex &ix, const Sector &s, uint32_t x) {
+    const uint32_t xm = (x | (x << 16)) | SWAR_M;
+    if ((int32_t)s.lo.y >= 0) {
+        uint32_t acc = swar_le(s.lo.y, xm) & SWAR_M;
+        acc |= (swar_le(s.lo.z, xm) & SWAR_M) >> 1;
+        acc |= (swar_le(s.lo.w, xm) & SWAR_M) >> 2;
+        acc |= (swar_le(s.hi.x, xm) & SWAR_M) >> 3;
+        acc |= (swar_le(s.hi.y, xm) & SWAR_M) >> 4;
+        acc |= (swar_le(s.hi.z, xm) & SWAR_M) >> 5;
+        acc |= (swar_le(s.hi.w, xm) & SWAR_M) >> 6;
+        return s.lo.x + __popc(acc);
+    }
+    // overflow sector: 12 inline slots, then the pool
+    uint32_t acc = swar_le(s.lo.y & 0x7FFFFFFFu, xm) & SWAR_M;
+    acc |= (swar_le(s.lo.z, xm) & SWAR_M) >> 1;
+    acc |= (swar_le(s.lo.w, xm) & SWAR_M) >> 2;
+    acc |= (swar_le(s.hi.x, xm) & SWAR_M) >> 3;
+    acc |= (swar_le(s.hi.y, xm) & SWAR_M) >> 4;
+    acc |= (swar_le(s.hi.z, xm) & SWAR_M) >> 5;
+    uint32_t cnt = __popc(acc);
+    if (cnt == SECTOR_INLINE_OVF) {
+        const uint16_t *p = ix.ovf + s.hi.w;
+        while (true) {
+            const uint32_t o = __ldg(p++);
+            if (o > x) break;   // the 0xFFFF terminator compares greater than any offset
+            cnt++;
+        }
+    }
+    return s.lo.x + cnt;
 }
 
 // C[c] + #{rows <= row : bwt[row]==c}  — one 32-byte gather (two 16-byte loads of the same sector).
 __device__ __forceinline__ uint32_t rank_c(const DevIndex &ix, uint32_t c, uint32_t row) {
-    const uint32_t blk = row >> ix.blk_shift;
-    const uint32_t x = row & ((1u << ix.blk_shift) - 1);
-    const uint4 *s = ix.occ + ((size_t)blk * ix.A + c) * 2;
-    const uint4 lo = __ldg(s), hi = __ldg(s + 1);
-    const uint32_t xx = x | (x << 16);
-    const uint32_t first = lo.y & 0xFFFFu;
-    if ((first & 0x8000u) == 0 || first == 0xFFFFu) {
-        return lo.x + count_le2(lo.y, xx) + count_le2(lo.z, xx) + count_le2(lo.w, xx) + count_le2(hi.x, xx) +
-               count_le2(hi.y, xx) + count_le2(hi.z, xx) + count_le2(hi.w, xx);
-    }
-    // overflow sector: off[0] carries the flag, off[12..13] the pool index
-    uint32_t cnt = ((first & 0x7FFFu) <= x) + (((lo.y >> 16)) <= x);
-    cnt += count_le2(lo.z, xx) + count_le2(lo.w, xx) + count_le2(hi.x, xx) + count_le2(hi.y, xx) + count_le2(hi.z, xx);
-    if (cnt == SECTOR_INLINE_OVF) {
-        const uint16_t *p = ix.ovf + hi.w;
-        while (true) {
-            uint32_t o = __ldg(p++);
-            if (o > x) break;   // 0xFFFF terminator compares greater than any offset
-            cnt++;
-        }
-    }
-    return lo.x + cnt;
+    const Sector s = load_sector(ix, c, row >> ix.blk_shift);
+    return sector_rank(ix, s, row & ((1u << ix.blk_shift) - 1));
 }
 
 // LF(row) given the row's record. Unmarked rows carry it; a marked row's low word is its marked value,

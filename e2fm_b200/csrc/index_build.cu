@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) rank_fill_kernel(RankBuildParams p) {
         const uint32_t cc = c | (c << 16);
         uint16_t off[SECTOR_SLOTS];
 #pragma unroll
-        for (int i = 0; i < SECTOR_SLOTS; i++) off[i] = 0xFFFF;
+        for (int i = 0; i < SECTOR_SLOTS; i++) off[i] = (uint16_t)SLOT_PAD;
         uint32_t cnt = 0;
         for (uint32_t v = 0; v < BLK / 8; v++) {
             const uint4 w = cv[v];
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256) rank_fill_kernel(RankBuildParams p) {
             const unsigned long long at = atomicAdd(p.ovf_cursor + 1, (unsigned long long)extra);
 #pragma unroll
             for (int i = 0; i < 6; i++) w[1 + i] = (uint32_t)off[2 * i] | ((uint32_t)off[2 * i + 1] << 16);
-            w[1] |= 0x8000u;
+            w[1] |= 0x80000000u;   // overflow flag: bit 15 of slot 1 (the high half, so a SWAR borrow cannot leak)
             w[7] = (uint32_t)at;
             uint32_t seen = 0, q = 0;
             for (uint32_t i = 0; i < rows; i++) {

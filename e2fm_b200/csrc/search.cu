@@ -61,37 +61,6 @@ __device__ __forceinline__ uint32_t ipow(uint32_t b, uint32_t e) {
     return r;
 }
 
-struct Sector { uint4 lo, hi; };
-
-__device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {
-    const uint4 *s = ix.occ + ((size_t)blk * ix.A + c) * 2;
-    Sector r;
-    r.lo = __ldg(s);
-    r.hi = __ldg(s + 1);
-    return r;
-}
-
-// C[c] + #{rows of the sector's block with in-block offset <= x that hold c}
-__device__ __forceinline__ uint32_t sector_rank(const DevIndex &ix, const Sector &s, uint32_t x) {
-    const uint32_t xx = x | (x << 16);
-    const uint32_t first = s.lo.y & 0xFFFFu;
-    if ((first & 0x8000u) == 0 || first == 0xFFFFu) {
-        return s.lo.x + count_le2(s.lo.y, xx) + count_le2(s.lo.z, xx) + count_le2(s.lo.w, xx) + count_le2(s.hi.x, xx) +
-               count_le2(s.hi.y, xx) + count_le2(s.hi.z, xx) + count_le2(s.hi.w, xx);
-    }
-    uint32_t cnt = ((first & 0x7FFFu) <= x) + ((s.lo.y >> 16) <= x);
-    cnt += count_le2(s.lo.z, xx) + count_le2(s.lo.w, xx) + count_le2(s.hi.x, xx) + count_le2(s.hi.y, xx) + count_le2(s.hi.z, xx);
-    if (cnt == SECTOR_INLINE_OVF) {
-        const uint16_t *p = ix.ovf + s.hi.w;
-        while (true) {
-            const uint32_t o = __ldg(p++);
-            if (o > x) break;
-            cnt++;
-        }
-    }
-    return s.lo.x + cnt;
-}
-
 // LF of a row whose record is r (marked rows keep their LF in the marked-row table)
 __device__ __forceinline__ uint32_t lf_from_rec(const DevIndex &ix, uint64_t r) {
     const uint32_t low = rec_low(r);
@@ -104,22 +73,58 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+// ---------------------------------------------------------------- pattern pre-pass
+
+// codes[j] = compact code of the k-mer that starts at byte j of the batch, 0xFFFF when it would cross the end of
+// its pattern, holds a symbol outside the index's alphabet (EFMIndex.cpp:1702-1717) or never occurs in the text
+// (EFMIndex.cpp:2188-2197). One thread per byte; every backward step then costs one 2-byte load instead of
+// ScrambledSuperAlphabet::getCode + charactersRemappings (EFMIndex.cpp:2186-2191).
+__global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t byte0, uint64_t n_bytes,
+                                                              uint16_t *__restrict__ codes) {
+    const uint64_t j = byte0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= byte0 + n_bytes) return;
+    uint64_t end;
+    if (pv.off) {
+        // binary search of the pattern that owns byte j (only ragged batches pay for it)
+        uint64_t lo = pv.first, hi = pv.first + pv.count;
+        while (lo + 1 < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(pv.off + mid) <= j) lo = mid; else hi = mid;
+        }
+        end = __ldg(pv.off + lo + 1);
+    } else {
+        end = (j / pv.fixed_len + 1) * pv.fixed_len;
+    }
+    uint32_t c = 0xFFFFu;
+    if (j + ix.k <= end) c = fixed_code(ix, pv.bytes + j);
+    codes[j] = (uint16_t)c;
+}
+
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t byte0, uint64_t n_bytes, uint16_t *codes, cudaStream_t s) {
+    if (n_bytes == 0) return;
+    encode_patterns_kernel<<<(uint32_t)((n_bytes + 255) / 256), 256, 0, s>>>(ix, pv, byte0, n_bytes, codes);
+}
+
 // ---------------------------------------------------------------- K3: backward search
 
 static constexpr uint32_t BS_GRAB = 256;   // items a warp takes from the global queue at a time
+static constexpr int BS_BURST = 4;         // backward steps between two refills
 
+// KT = compile-time super-alphabet order (0 = read it from the index)
+template <int KT>
 __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const uint32_t k = ix.k;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k;
     const uint32_t n_items = a.pv.count * k;
-    const uint32_t blk_mask = (1u << ix.blk_shift) - 1;
+    const uint32_t blk_shift = ix.blk_shift, blk_mask = (1u << blk_shift) - 1;
     uint32_t wnext = 0, wend = 0;
     bool exhausted = false, active = false;
-    uint32_t item = 0, s = 0, e = 0, sa = 0, m = 0;   // SA interval [s, e)
-    int i = 0;
-    const uint8_t *ptr = nullptr;
-    unsigned long long n_rank = 0, n_tasks = 0;
+    uint32_t item = 0, s = 0, e = 0, flags = 0;   // SA interval [s, e); flags: bit0 first super-character variable, bit1 hat
+    int i = 0, lo = 0;                           // next super-character to process, and the last fixed one
+    const uint16_t *cptr = nullptr;              // codes of this pattern, shifted so that character c is cptr[c*k]
+    uint32_t n_rank = 0, n_sect = 0;
+    unsigned long long n_tasks = 0;
 
     for (;;) {
         if (wnext >= wend && !exhausted) {
@@ -129,15 +134,22 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             if (b >= n_items) exhausted = true;
             else { wnext = (uint32_t)b; wend = min((uint32_t)b + BS_GRAB, n_items); }
         }
+        // ---- refill idle lanes: EFMIndex::computeSuperPatterns (:2055-2207) + start interval (:1728-1748) of one shift
         const unsigned need = __ballot_sync(FULL, !active);
         if (!active && wnext < wend) {
             const uint32_t idx = wnext + __popc(need & lt);
             if (idx < wend) {
-                // ---- EFMIndex::computeSuperPatterns (:2055-2207) + start interval (:1728-1748) for one shift
                 item = idx;
-                const uint32_t pl = idx / k;
-                sa = idx - pl * k;
-                pattern_span(a.pv, pl, ptr, m);
+                const uint32_t pl = idx / k, sa = idx - pl * k;
+                uint64_t base;
+                uint32_t m;
+                if (a.pv.off) {
+                    base = __ldg(a.pv.off + a.pv.first + pl);
+                    m = (uint32_t)(__ldg(a.pv.off + a.pv.first + pl + 1) - base);
+                } else {
+                    m = a.pv.fixed_len;
+                    base = (a.pv.first + pl) * m;
+                }
                 if (m > 0) {
                     const uint32_t L = (m + sa + k - 1) / k;
                     const bool last_var = (m + sa) % k != 0;
@@ -146,16 +158,18 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
                     else if (L > 1 && (L > 2 || sa == 0)) l = (int)L - 1;                // hat: start from its predecessor
                     // otherwise the shift yields nothing (variable last character without fixed predecessor, :2132/:1745)
                     if (l > 0) {
-                        const uint32_t cc = fixed_code(ix, ptr + (size_t)(l - 1) * k - sa);
+                        cptr = a.codes + base - sa;
+                        const uint32_t cc = __ldg(cptr + (size_t)(l - 1) * k);
                         if (cc != 0xFFFFu) {
                             s = (uint32_t)__ldg(ix.C + cc);
                             e = (uint32_t)__ldg(ix.C + cc + 1);
                             i = l - 2;
+                            lo = sa > 0 ? 1 : 0;
+                            flags = (sa > 0 ? 1u : 0u) | (last_var ? 2u : 0u);
                             active = e > s;
                         }
                     }
                 }
-                if (!active) a.iv[item] = make_uint2(0u, 0u);
             }
         }
         wnext = min(wend, wnext + (uint32_t)__popc(need));
@@ -163,56 +177,54 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             if (exhausted) break;
             continue;
         }
-        if (active) {
-            const bool first_var = (i == 0 && sa > 0);
-            if (i < 0 || first_var) {
-                // ---- end of EFMIndex::exactMatch(interval) (:1901-1963): hand the interval on
-                const uint32_t len = e - s;
-                const bool hat = (m + sa) % k != 0;
-                if (a.mode == E2FM_MODE_COUNT && !hat && !first_var) {
-                    atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
-                    a.iv[item] = make_uint2(s, 0u);
-                } else {
-                    a.iv[item] = make_uint2(s, len);
-                    n_tasks += len;
-                }
-                active = false;
-            } else {
-                // ---- EFMIndex::backwardStep (:1966-2001)
-                const uint32_t cc = fixed_code(ix, ptr + (size_t)i * k - sa);
-                if (cc == 0xFFFFu) {
-                    a.iv[item] = make_uint2(0u, 0u);
-                    active = false;
-                } else {
+        // ---- EFMIndex::backwardStep (:1966-2001), a few steps per refill
+#pragma unroll 1
+        for (int it = 0; it < BS_BURST; it++) {
+            const bool go = active && i >= lo;
+            if (!__any_sync(FULL, go)) break;
+            if (go) {
+                const uint32_t cc = __ldg(cptr + (size_t)i * k);
+                if (cc == 0xFFFFu) active = false;
+                else {
                     const uint32_t re = e - 1;
-                    const Sector se = load_sector(ix, cc, re >> ix.blk_shift);
+                    const Sector se = load_sector(ix, cc, re >> blk_shift);
                     uint32_t ns;
                     if (s == 0) ns = (uint32_t)__ldg(ix.C + cc);
                     else {
                         const uint32_t rs = s - 1;
-                        if ((rs >> ix.blk_shift) == (re >> ix.blk_shift)) ns = sector_rank(ix, se, rs & blk_mask);
+                        if ((rs >> blk_shift) == (re >> blk_shift)) ns = sector_rank(ix, se, rs & blk_mask);
                         else {
-                            const Sector ss = load_sector(ix, cc, rs >> ix.blk_shift);
+                            const Sector ss = load_sector(ix, cc, rs >> blk_shift);
                             ns = sector_rank(ix, ss, rs & blk_mask);
+                            n_sect++;
                         }
                     }
-                    const uint32_t ne = sector_rank(ix, se, re & blk_mask);
-                    n_rank += 2;
+                    e = sector_rank(ix, se, re & blk_mask);
                     s = ns;
-                    e = ne;
+                    n_sect++;
+                    n_rank += 2;
                     i--;
-                    if (e <= s) {
-                        a.iv[item] = make_uint2(0u, 0u);
-                        active = false;
-                    }
+                    active = e > s;
                 }
             }
         }
+        // ---- end of EFMIndex::exactMatch(interval) (:1901-1963): hand the surviving interval on
+        if (active && i < lo) {
+            const uint32_t len = e - s;
+            if (a.mode == E2FM_MODE_COUNT && flags == 0) {
+                atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
+            } else {
+                a.iv[item] = make_uint2(s, len);
+                n_tasks += len;
+            }
+            active = false;
+        }
     }
-    n_rank = warp_sum(n_rank);
+    unsigned long long r = warp_sum((unsigned long long)n_rank), q = warp_sum((unsigned long long)n_sect);
     n_tasks = warp_sum(n_tasks);
     if (lane == 0) {
-        if (n_rank) atomicAdd(a.stats + ST_RANK, n_rank);
+        if (q) atomicAdd(a.stats + ST_SECT_BS, q);
+        if (r) atomicAdd(a.stats + ST_RANK, r);
         if (n_tasks) atomicAdd(a.stats + ST_TASKS, n_tasks);
     }
 }
@@ -220,10 +232,12 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s) {
     const uint64_t n_items = (uint64_t)a.pv.count * a.ix.k;
     if (n_items == 0) return;
+    cudaMemsetAsync(a.iv, 0, n_items * sizeof(uint2), s);   // shifts that die or drop out leave an empty interval
     uint64_t blocks = (n_items + 255) / 256;
-    const uint64_t cap = (uint64_t)n_sm * 8;   // 8 x 256 threads = 2048 resident threads per SM
+    const uint64_t cap = (uint64_t)n_sm * 8;   // persistent: up to 8 x 256 threads per SM
     if (blocks > cap) blocks = cap;
-    backward_search_kernel<<<(uint32_t)blocks, 256, 0, s>>>(a);
+    if (a.ix.k == 4) backward_search_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    else backward_search_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- scans
@@ -379,18 +393,23 @@ void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint6
 
 // ---------------------------------------------------------------- K4: row walks
 
-enum : uint32_t { PH_FIRST = 0, PH_WALK = 1, PH_HAT_START = 2, PH_HAT_WALK = 3, PH_HAT_FINAL = 4 };
+// phases of one row task; WALK and HAT_WALK are the hot ones (one dependent 8-byte gather per step, nothing else)
+enum : uint32_t { PH_FIRST = 0, PH_WALK = 1, PH_ATMARK = 2, PH_HAT_START = 3, PH_HAT_WALK = 4, PH_HAT_FINAL = 5 };
 static constexpr uint32_t WALK_GRAB = 128;
+static constexpr int WALK_BURST = 8;       // LF steps between two passes over the rare phases / refills
 
+template <int KT>
 __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const uint32_t k = ix.k, no = ix.n_sym;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
+    const uint32_t rate = ix.rate;
+    const uint64_t *__restrict__ rec = ix.rec;
     const uint64_t *mark_tab64 = reinterpret_cast<const uint64_t *>(ix.mark_tab);
     uint32_t wnext = 0, wend = 0;
     bool exhausted = false, active = false;
     uint32_t phase = 0, row = 0, t = 0, item = 0, tp = 0;
-    unsigned long long n_lf = 0, n_mark = 0;
+    uint32_t n_lf = 0, n_mark = 0, n_gather = 0;
 
     for (;;) {
         if (wnext >= wend && !exhausted) {
@@ -407,14 +426,7 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
                 const uint2 tk = __ldg(a.tasks + idx);
                 row = tk.x;
                 item = tk.y;
-                const uint32_t pl = item / k, sa = item - pl * k;
-                const uint8_t *ptr;
-                uint32_t m;
-                pattern_span(a.pv, pl, ptr, m);
-                const bool last_var = (m + sa) % k != 0;
-                const uint32_t L = (m + sa + k - 1) / k;
-                const uint32_t l = last_var ? L - 1 : L;
-                phase = (sa > 0 && l >= 2) ? PH_FIRST : PH_WALK;
+                phase = (item % k) ? PH_FIRST : PH_WALK;   // a shifted pattern starts with a '?'-prefixed super-character
                 t = 0;
                 active = true;
             }
@@ -424,86 +436,77 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
             if (exhausted) break;
             continue;
         }
+        // ---- rare phases: at most one gather per lane per pass
         bool emit = false;
-        if (active) {
-            // one dependent 8-byte gather per step, whatever the phase
-            const uint64_t x = __ldg(phase == PH_HAT_START ? mark_tab64 + row : ix.rec + row);
+        if (active && phase != PH_WALK && phase != PH_HAT_WALK) {
             const uint32_t pl = item / k, sa = item - pl * k;
-            if (phase == PH_WALK) {
-                // ---- EFMIndex::getRowPosition (:2468-2497)
-                n_mark++;
-                if (!rec_marked(x)) {
-                    n_lf++;
-                    row = rec_low(x);
-                    t++;
-                    if (t > ix.rate) active = false;            // a valid index marks every rate-th text position
+            const uint8_t *ptr;
+            uint32_t m;
+            pattern_span(a.pv, pl, ptr, m);
+            const bool hat = (m + sa) % k != 0;
+            if (phase == PH_ATMARK) {
+                // ---- EFMIndex::getRowPosition (:2468-2497) reached a marked row: `row` holds its marked value
+                n_mark += t + 1;
+                n_lf += t;
+                n_gather += t + 1;
+                tp = (uint32_t)(((uint64_t)row * rate + t) % ix.n);
+                if (hat) {
+                    // ---- EFMIndex::extractSuperCharacter (:2216-2269): start from the next marked row
+                    const uint32_t L = (m + sa + k - 1) / k;
+                    const uint64_t p = (uint64_t)tp + L - 1;
+                    const uint64_t nv = p / rate + 1;
+                    uint64_t nxt = nv * rate;
+                    if (nxt > ix.n - 1) nxt = ix.n;
+                    row = (uint32_t)(nv % ix.mrn);          // marked value whose row is needed
+                    t = (uint32_t)(nxt - p - 1);            // LF steps to take from it
+                    n_lf += t + 1;
+                    n_gather += t ? t + 1 : 2;
+                    phase = PH_HAT_START;
                 } else {
-                    tp = (uint32_t)(((uint64_t)rec_low(x) * ix.rate + t) % ix.n);
-                    const uint8_t *ptr;
-                    uint32_t m;
-                    pattern_span(a.pv, pl, ptr, m);
-                    if ((m + sa) % k != 0) {
-                        // ---- EFMIndex::extractSuperCharacter (:2216-2269): start from the next marked row
-                        const uint32_t L = (m + sa + k - 1) / k;
-                        const uint64_t p = (uint64_t)tp + L - 1;
-                        const uint64_t nv = p / ix.rate + 1;
-                        uint64_t nxt = nv * ix.rate;
-                        if (nxt > ix.n - 1) nxt = ix.n;
-                        row = (uint32_t)(nv % ix.mrn);          // marked value whose row we need
-                        t = (uint32_t)(nxt - p - 1);            // LF steps to take from it
-                        phase = PH_HAT_START;
-                    } else {
-                        emit = true;
-                        active = false;
-                    }
+                    emit = true;
+                    active = false;
                 }
-            } else if (phase == PH_FIRST) {
-                // ---- EFMIndex::backwardStepIfMatch (:2011-2041): '?'-prefixed first super-character
-                n_lf++;
-                const uint8_t *ptr;
-                uint32_t m;
-                pattern_span(a.pv, pl, ptr, m);
-                const uint32_t f = k - sa;                      // fixed symbols at the low end of the k-mer
-                const uint32_t want = natural_value(ix, ptr, f);
-                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
-                if (want != 0xFFFFFFFFu && nat % ipow(no, f) == want) {
-                    row = lf_from_rec(ix, x);
-                    if (a.mode == E2FM_MODE_COUNT && (m + sa) % k == 0) {
-                        emit = true;
-                        active = false;
-                    } else {
-                        phase = PH_WALK;
-                        t = 0;
-                    }
-                } else active = false;
-            } else if (phase == PH_HAT_START) {
-                const uint32_t mrow = (uint32_t)x, mlf = (uint32_t)(x >> 32);
-                if (mrow >= ix.n) active = false;               // no such marked value (corrupt index)
-                else if (t == 0) { row = mrow; phase = PH_HAT_FINAL; }
-                else {
+            }
+            if (active) {
+                if (phase == PH_FIRST) {
+                    // ---- EFMIndex::backwardStepIfMatch (:2011-2041): '?'-prefixed first super-character
+                    const uint64_t x = __ldg(rec + row);
                     n_lf++;
-                    row = mlf;
-                    t--;
-                    phase = t ? PH_HAT_WALK : PH_HAT_FINAL;
+                    n_gather++;
+                    const uint32_t f = k - sa;                      // fixed symbols at the low end of the k-mer
+                    const uint32_t want = natural_value(ix, ptr, f);
+                    const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
+                    if (want != 0xFFFFFFFFu && nat % ipow(no, f) == want) {
+                        row = lf_from_rec(ix, x);
+                        if (a.mode == E2FM_MODE_COUNT && !hat) {
+                            emit = true;
+                            active = false;
+                        } else {
+                            phase = PH_WALK;
+                            t = 0;
+                        }
+                    } else active = false;
+                } else if (phase == PH_HAT_START) {
+                    const uint64_t x = __ldg(mark_tab64 + row);
+                    const uint32_t mrow = (uint32_t)x, mlf = (uint32_t)(x >> 32);
+                    if (mrow >= ix.n) active = false;               // no such marked value (corrupt index)
+                    else if (t == 0) { row = mrow; phase = PH_HAT_FINAL; }
+                    else {
+                        row = mlf;
+                        t--;
+                        phase = t ? PH_HAT_WALK : PH_HAT_FINAL;
+                    }
+                } else if (phase == PH_HAT_FINAL) {
+                    // ---- EFMIndex::findWholePatternMatches (:1862-1899): compare the '?'-suffixed last super-character
+                    const uint64_t x = __ldg(rec + row);
+                    const uint32_t L = (m + sa + k - 1) / k;
+                    const uint32_t from = (L - 1) * k - sa;         // first pattern byte of the last super-character
+                    const uint32_t f = m - from;                    // fixed symbols at the high end of the k-mer
+                    const uint32_t want = natural_value(ix, ptr + from, f);
+                    const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
+                    emit = want != 0xFFFFFFFFu && nat / ipow(no, k - f) == want;
+                    active = false;
                 }
-            } else if (phase == PH_HAT_WALK) {
-                n_lf++;
-                row = lf_from_rec(ix, x);
-                t--;
-                if (t == 0) phase = PH_HAT_FINAL;
-            } else {
-                // ---- EFMIndex::findWholePatternMatches (:1862-1899): compare the '?'-suffixed last super-character
-                n_lf++;
-                const uint8_t *ptr;
-                uint32_t m;
-                pattern_span(a.pv, pl, ptr, m);
-                const uint32_t L = (m + sa + k - 1) / k;
-                const uint32_t from = (L - 1) * k - sa;         // first pattern byte of the last super-character
-                const uint32_t f = m - from;                    // fixed symbols at the high end of the k-mer
-                const uint32_t want = natural_value(ix, ptr + from, f);
-                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
-                emit = want != 0xFFFFFFFFu && nat / ipow(no, k - f) == want;
-                active = false;
             }
         }
         // ---- warp-aggregated result compaction
@@ -523,12 +526,31 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
                 }
             }
         }
+        // ---- hot phases: a burst of LF steps, one dependent gather each
+#pragma unroll 1
+        for (int it = 0; it < WALK_BURST; it++) {
+            const bool fw = active && phase == PH_WALK, fh = active && phase == PH_HAT_WALK;
+            if (!__any_sync(FULL, fw || fh)) break;
+            if (fw || fh) {
+                const uint64_t x = __ldg(rec + row);
+                const uint32_t low = rec_low(x);
+                if (fw) {
+                    row = low;                                      // LF(row), or the marked value when the walk ends
+                    if (rec_marked(x)) phase = PH_ATMARK;
+                    else if (++t > rate) active = false;            // a valid index marks every rate-th text position
+                } else {
+                    row = rec_marked(x) ? __ldg(&ix.mark_tab[low].y) : low;
+                    if (--t == 0) phase = PH_HAT_FINAL;
+                }
+            }
+        }
     }
-    n_lf = warp_sum(n_lf);
-    n_mark = warp_sum(n_mark);
+    const unsigned long long l = warp_sum((unsigned long long)n_lf), mk = warp_sum((unsigned long long)n_mark),
+                             g = warp_sum((unsigned long long)n_gather);
     if (lane == 0) {
-        if (n_lf) atomicAdd(a.stats + ST_LF, n_lf);
-        if (n_mark) atomicAdd(a.stats + ST_MARK, n_mark);
+        if (g) atomicAdd(a.stats + ST_GATHER, g);
+        if (l) atomicAdd(a.stats + ST_LF, l);
+        if (mk) atomicAdd(a.stats + ST_MARK, mk);
     }
 }
 
@@ -537,7 +559,8 @@ void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
     uint64_t blocks = ((uint64_t)a.n_tasks + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 8;
     if (blocks > cap) blocks = cap;
-    walk_kernel<<<(uint32_t)blocks, 256, 0, s>>>(a);
+    if (a.ix.k == 4) walk_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    else walk_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- result pipeline

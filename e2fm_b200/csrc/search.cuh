@@ -28,13 +28,16 @@ enum {
     ST_BIGSEG = 5,   // result segments longer than the per-thread sort limit
     ST_DUPS = 6,     // duplicate positions removed (EFMIndex.cpp:2296-2299)
     ST_QUEUE = 7,    // work-queue cursor of the running kernel
-    ST_N = 8
+    ST_SECT_BS = 8,  // distinct 32-byte rank sectors gathered by the backward-search kernel
+    ST_GATHER = 9,   // dependent 8-byte gathers issued by the walk kernel
+    ST_N = 10
 };
 
 struct SearchArgs {
     DevIndex ix;
     PatternView pv;
     int mode;                        // E2FM_MODE_*
+    const uint16_t *codes;           // [batch bytes] k-mer code starting at every pattern byte (encode_patterns_kernel)
     uint2 *iv;                       // [count*k] {sp, len} of the interval each (pattern, shift) ends with
     unsigned long long *counts;      // [batch n] matches per pattern
     unsigned long long *stats;       // [ST_N]
@@ -52,6 +55,8 @@ struct WalkArgs {
     unsigned long long *stats;
 };
 
+// codes[j] for the bytes [byte0, byte0 + n_bytes) of the batch (pv describes the patterns they belong to)
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t byte0, uint64_t n_bytes, uint16_t *codes, cudaStream_t s);
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
 // exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);

@@ -104,13 +104,14 @@ int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uin
 void e2fm_result_free(e2fm_result *r);
 
 /* Per-phase device times (ms, CUDA events on the index stream) of the most recent batch:
- * [0] pattern H2D, [1] backward search kernel, [2] interval scan + expansion, [3] row-walk kernel, [4] reserved,
+ * [0] pattern H2D, [1] backward search kernel, [2] interval scan + expansion, [3] row-walk kernel, [4] pattern pre-pass (k-mer codes),
  * [5] CSR build + sort + dedupe + sequence map, [6] whole batch (first copy to last kernel), [7] reserved */
 int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
 /* Operation counters of the most recent batch, in the reference's units:
  * [0] rank (= Bucket::getOffsetInformations(CountOnly) calls, Bucket.cpp:656), [1] lf (= ...(RetrieveCharacter)),
- * [2] mark (= Bucket::getMarkedTextPosition, Bucket.cpp:823), [3] row tasks, [4] duplicate positions removed,
- * [5] kernels launched by the batch, [6] located occurrences, [7] reserved */
+ * [2] mark (= Bucket::getMarkedTextPosition, Bucket.cpp:823), [3] row tasks,
+ * [4] distinct 32-byte rank sectors gathered by the backward-search kernel, [5] kernels launched by the batch,
+ * [6] located occurrences, [7] dependent 8-byte gathers issued by the walk kernel */
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^20) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
