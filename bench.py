@@ -245,6 +245,8 @@ def gpu_arm(args, rank, world, local_rank):
     t0 = time.time()
     ix = capi.DeviceIndex(raw, synth.test_key(), local_rank)
     load_s = time.time() - t0
+    if args.walk:
+        ix.set_option(capi.OPT_DENSE, 0)
     info = ix.info
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
@@ -379,6 +381,7 @@ def gpu_arm(args, rank, world, local_rank):
             "config": {"workload": w["name"], "mode": "count+locate" if locate else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
                        "patterns_per_gpu": npat, "pattern_len": L, "parallelism": f"replicas x{world} (pattern batch per GPU)",
                        "l2": "256 MB flush between timed iterations",
+                       "locate_tables": "per-query walks from marked rows" if args.walk else "dense sa[]/text[] built at load",
                        "index_device_MB": round(info.device_bytes / 1e6, 1), "index_load_s": round(load_s, 3)},
             "occurrences_per_s": (world * occ_total / (dev_ms_max / 1e3)) if locate else None,
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": int(npat * L),
@@ -418,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
     ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -18,6 +18,7 @@ MODE_COUNT = 0
 MODE_LOCATE = 1
 OPT_CHUNK = 2
 OPT_WINDOW = 3
+OPT_DENSE = 4
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
@@ -42,7 +43,7 @@ class Info(C.Structure):
                 ("n_buckets", C.c_uint64), ("n_superbuckets", C.c_uint64), ("n_sequences", C.c_uint64),
                 ("initial_n", C.c_uint64), ("device_bytes", C.c_uint64), ("k", C.c_uint32), ("n_symbols", C.c_uint32),
                 ("compact_alphabet", C.c_uint32), ("marked_rows_percentage", C.c_uint32), ("marking_rate", C.c_uint32),
-                ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("reserved", C.c_uint32), ("load_ms", C.c_float * 8)]
+                ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("dense", C.c_uint32), ("load_ms", C.c_float * 8)]
 
 
 _lib = None

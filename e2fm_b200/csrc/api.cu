@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -118,6 +119,7 @@ struct e2fm_index {
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
     uint64_t batch_ctr[8] = {0};
+    bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
     uint64_t chunk_patterns = 1u << 20;
     uint64_t window_tasks = 64u << 20;
     unsigned long long *d_stats = nullptr;
@@ -293,6 +295,23 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     tm.end(h);
     check_build_status(ix, d_status.p, "rank build");
 
+    // ---- dense locate tables (6 bytes per row) when HBM allows: EFMIndex::getRowPosition walked once for every row
+    uint32_t *sa = nullptr;
+    uint16_t *text = nullptr;
+    if (mrn > 0 && !(getenv("E2FM_DENSE") && atoi(getenv("E2FM_DENSE")) == 0)) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if ((double)img.n * 6.0 < 0.5 * (double)free_b) {
+            h = tm.begin(6);
+            sa = dev_keep<uint32_t>(ix, img.n);
+            text = dev_keep<uint16_t>(ix, img.n);
+            launch_dense_build(rec, mark_tab, mrn, img.rate, img.n, sa, text, d_status.p, s);
+            tm.end(h);
+            check_build_status(ix, d_status.p, "dense table build");
+            ix->use_dense = true;
+        }
+    }
+
     // ---- small tables
     uint8_t sym_index[256];
     memset(sym_index, 0xFF, sizeof(sym_index));
@@ -313,6 +332,8 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     d.occ = occ;
     d.ovf = rp.ovf;
     d.mark_tab = mark_tab;
+    d.sa = sa;
+    d.text = text;
     d.C = d_C;
     d.compact_of_natural = dev_keep_copy<uint16_t>(ix, img.compact_of_natural.data(), img.compact_of_natural.size());
     d.natural_of_compact = dev_keep_copy<uint32_t>(ix, img.natural_of_compact.data(), img.natural_of_compact.size());
@@ -404,7 +425,8 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             h = tm.begin(3);
             WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), counts.p, res_pat.p, res_pos.p, ix->d_stats};
-            launch_walk(wa, ix->n_sm, s);
+            if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
+            else launch_walk(wa, ix->n_sm, s);
             launches++;
             tm.end(h);
             read_stats(ix);
@@ -606,6 +628,14 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ix->n_sm = prop.multiProcessorCount;
+        if (const char *g = getenv("E2FM_L2_FETCH")) {   // experiment knob: L2 fetch granularity in bytes (32/64/128)
+            CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
+        }
+        {
+            size_t gran = 0;
+            cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity);
+            if (getenv("E2FM_VERBOSE")) fprintf(stderr, "[e2fm] L2 fetch granularity %zu B\n", gran);
+        }
         CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -660,6 +690,7 @@ int e2fm_index_info(const e2fm_index *ix, e2fm_info *o) {
     o->marking_rate = g.rate;
     o->rank_block = 1u << ix->dix.blk_shift;
     o->quirks = g.quirks;
+    o->dense = ix->dix.sa ? (ix->use_dense ? 1u : 2u) : 0u;
     memcpy(o->load_ms, ix->load_ms, sizeof(o->load_ms));
     return E2FM_OK;
 }
@@ -762,6 +793,10 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
     switch (option) {
         case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (1u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
+        case E2FM_OPT_DENSE:
+            if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");
+            ix->use_dense = value != 0;
+            return E2FM_OK;
         default: return fail(E2FM_ERR_ARG, "unknown option");
     }
 }

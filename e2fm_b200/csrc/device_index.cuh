@@ -11,6 +11,11 @@
 //                 so that  C[c] + occ(c,row) = w0 + #{slot <= row % BLK}  costs ONE sector gather and a SWAR
 //                 compare. A block with more than 14 occurrences sets bit 31 of w1 (bit 15 of slot 1): slots
 //                 0..11 hold the first 12 offsets and w7 the index of the rest in the `ovf` pool (0xFFFF-terminated).
+//   sa[n], text[n]  (dense locate tables, built once at load by walking LF from every marked row — the marked-SA-sample
+//                 walk of EFMIndex::getRowPosition done in bulk for ALL rows instead of per query): sa[row] = super-text
+//                 position of the row's suffix, text[p] = compact code of super-character p. With them locate is one
+//                 gather per occurrence and hat verification (EFMIndex::extractSuperCharacter) one more. 6 bytes per row;
+//                 skipped when HBM is short (the per-query walk kernel then does the same work on demand).
 //   markTab[mrn]  uint2 {row, LF(row)} of the row whose marked value is v  (reverse of rec's marks;
 //                 replaces markedRowsBuckets + Bucket::getMarkedBwtPosition, Bucket.cpp:794)
 // The reference's two-level counters + per-bucket position lists (SuperBucket.cpp:82, Bucket.cpp:656-779)
@@ -39,6 +44,8 @@ struct DevIndex {
     const uint4 *occ;           // 2 x uint4 per sector
     const uint16_t *ovf;
     const uint2 *mark_tab;
+    const uint32_t *sa;         // [n] or nullptr
+    const uint16_t *text;       // [n] or nullptr
     const uint64_t *C;          // [A+1]
     const uint16_t *compact_of_natural;   // [sigma_k]
     const uint32_t *natural_of_compact;   // [A]

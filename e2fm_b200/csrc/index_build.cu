@@ -502,4 +502,36 @@ cudaError_t configure_rank_fill(size_t smem) {
     return cudaFuncSetAttribute(rank_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// ---------------------------------------------------------------- dense locate tables
+
+__global__ void __launch_bounds__(256) dense_build_kernel(const uint64_t *__restrict__ rec, const uint2 *__restrict__ mark_tab, uint64_t mrn,
+                                                           uint32_t rate, uint64_t n, uint32_t *__restrict__ sa, uint16_t *__restrict__ text,
+                                                           uint32_t *status) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= mrn) return;
+    const uint2 mt = mark_tab[v];
+    if (mt.x >= n) { atomicOr(status, BUILD_ERR_MARKS); return; }   // a marked value without a row
+    uint64_t pos = v * rate;                                        // text position of the marked row's suffix
+    uint32_t row = mt.x;
+    uint64_t r = rec[row];
+    sa[row] = (uint32_t)pos;
+    text[pos == 0 ? n - 1 : pos - 1] = (uint16_t)rec_code(r);       // BWT[row] precedes the suffix in the text
+    row = mt.y;                                                     // LF of the marked row
+    for (uint32_t step = 0; step <= rate; step++) {
+        r = rec[row];
+        if (rec_marked(r)) return;                                  // the previous marked row: its own thread continues
+        pos = pos == 0 ? n - 1 : pos - 1;
+        sa[row] = (uint32_t)pos;
+        text[pos == 0 ? n - 1 : pos - 1] = (uint16_t)rec_code(r);
+        row = rec_low(r);
+    }
+    atomicOr(status, BUILD_ERR_MARKS);                              // no marked row within `rate` steps: corrupt index
+}
+
+void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn, uint32_t rate, uint64_t n, uint32_t *sa,
+                        uint16_t *text, uint32_t *status, cudaStream_t s) {
+    if (mrn == 0) return;
+    dense_build_kernel<<<(uint32_t)((mrn + 255) / 256), 256, 0, s>>>(rec, mark_tab, mrn, rate, n, sa, text, status);
+}
+
 }  // namespace e2fm

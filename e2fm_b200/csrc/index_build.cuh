@@ -58,6 +58,11 @@ void launch_rank_hist(const RankBuildParams &p, cudaStream_t s);
 void launch_rank_scan(const RankBuildParams &p, uint32_t *chunk_totals, uint32_t n_chunks, uint32_t chunk_blocks, cudaStream_t s);
 void launch_rank_fill(const RankBuildParams &p, cudaStream_t s);
 
+// dense locate tables: one thread per marked row walks LF until the next marked row (<= rate steps), writing
+// sa[row] = text position and text[position-1] = BWT[row] on the way (EFMIndex::getRowPosition, EFMIndex.cpp:2468, in bulk)
+void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn, uint32_t rate, uint64_t n, uint32_t *sa,
+                        uint16_t *text, uint32_t *status, cudaStream_t s);
+
 // standalone K1 test hook
 void launch_keystream_debug(const uint32_t key[8], uint64_t nonce, uint32_t bits, uint64_t start, uint64_t count,
                             uint32_t *d_out, cudaStream_t s);

@@ -563,6 +563,98 @@ void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
     else walk_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
 }
 
+// ---------------------------------------------------------------- K4 (dense tables): resolve row tasks without walking
+
+// Same row tasks as walk_kernel, answered from the dense tables built at load (device_index.cuh): the position of a
+// row is sa[row] (what EFMIndex::getRowPosition walks to), the super-character at a text position is text[p] (what
+// EFMIndex::extractSuperCharacter walks to). 1-3 independent gathers per task, one task per thread.
+template <int KT>
+__global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
+    const DevIndex &ix = a.ix;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
+    uint32_t n_sa = 0, n_text = 0, n_rec = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps iterate together so that the result compaction below stays warp-uniform
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < a.n_tasks; base += stride) {
+        const uint32_t idx = base + lane;
+        bool emit = false;
+        uint32_t item = 0, tp = 0;
+        if (idx < a.n_tasks) {
+            const uint2 tk = __ldg(a.tasks + idx);
+            uint32_t row = tk.x;
+            item = tk.y;
+            const uint32_t pl = item / k, sa = item - pl * k;
+            const uint8_t *ptr;
+            uint32_t m;
+            pattern_span(a.pv, pl, ptr, m);
+            const bool hat = (m + sa) % k != 0;
+            bool ok = true, have_tp = false;
+            if (sa > 0) {
+                // EFMIndex::backwardStepIfMatch (:2011-2041): the row's BWT character against the '?'-prefixed first one;
+                // a match stands for the suffix one super-character earlier
+                const uint64_t x = __ldg(ix.rec + row);
+                n_rec++;
+                const uint32_t f = k - sa;
+                const uint32_t want = natural_value(ix, ptr, f);
+                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
+                ok = want != 0xFFFFFFFFu && nat % ipow(no, f) == want;
+                if (ok && (hat || a.mode == E2FM_MODE_LOCATE)) {
+                    const uint32_t p = __ldg(ix.sa + row);
+                    n_sa++;
+                    tp = p == 0 ? (uint32_t)(ix.n - 1) : p - 1;
+                    have_tp = true;
+                }
+            }
+            if (ok && !have_tp && (hat || a.mode == E2FM_MODE_LOCATE)) {
+                tp = __ldg(ix.sa + row);                            // EFMIndex::getRowPosition (:2468-2497)
+                n_sa++;
+            }
+            if (ok && hat) {
+                // EFMIndex::findWholePatternMatches (:1862-1899) / extractSuperCharacter (:2216-2269)
+                const uint32_t L = (m + sa + k - 1) / k;
+                const uint64_t p = (uint64_t)tp + L - 1;
+                const uint32_t from = (L - 1) * k - sa, f = m - from;
+                const uint32_t want = natural_value(ix, ptr + from, f);
+                ok = false;
+                if (p < ix.n && want != 0xFFFFFFFFu) {
+                    const uint32_t nat = __ldg(ix.natural_of_compact + __ldg(ix.text + p));
+                    n_text++;
+                    ok = nat / ipow(no, k - f) == want;
+                }
+            }
+            emit = ok;
+        }
+        const unsigned em = __ballot_sync(FULL, emit);
+        if (em) {
+            const uint32_t pl = item / k, sa = item - pl * k;
+            if (emit) atomicAdd(a.counts + a.pv.first + pl, 1ull);
+            if (a.mode == E2FM_MODE_LOCATE) {
+                unsigned long long b = 0;
+                const int leader = __ffs(em) - 1;
+                if ((int)lane == leader) b = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)__popc(em));
+                b = __shfl_sync(FULL, b, leader);
+                if (emit) {
+                    const unsigned long long slot = b + __popc(em & lt);
+                    a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
+                    a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;
+                }
+            }
+        }
+    }
+    const unsigned long long g = warp_sum((unsigned long long)(n_sa + n_text + n_rec));
+    if (lane == 0 && g) atomicAdd(a.stats + ST_GATHER, g);
+}
+
+void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s) {
+    if (a.n_tasks == 0) return;
+    uint64_t blocks = ((uint64_t)a.n_tasks + 255) / 256;
+    const uint64_t cap = (uint64_t)n_sm * 32;
+    if (blocks > cap) blocks = cap;
+    if (a.ix.k == 4) resolve_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    else resolve_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
+}
+
 // ---------------------------------------------------------------- result pipeline
 
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t *__restrict__ res_pat, const uint64_t *__restrict__ res_pos, uint64_t n_res,

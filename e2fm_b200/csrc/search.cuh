@@ -62,6 +62,8 @@ void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);
 void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks, cudaStream_t s);
 void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s);
+// the same row tasks answered from the dense sa[] / text[] tables (requires a.ix.sa != nullptr)
+void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s);
 
 // exclusive scan of counts[0..n) into off[0..n] (off[n] = total); scratch holds >= scan_scratch_elems(n) u64
 size_t scan_scratch_elems(uint64_t n);

@@ -48,7 +48,7 @@ typedef struct e2fm_info {
     uint32_t rank_block;         /* rows per rank block of the device layout */
     uint32_t quirks;             /* bit0: floor(n/rate) is a power of two (reference locate is corrupt, EFMIndex.cpp:399 vs :1280)
                                     bit1: n % rate == 0 (reference reads one junk marked-row entry, EFMIndex.cpp:1278) */
-    uint32_t reserved;
+    uint32_t dense;              /* 0: no dense locate tables (HBM short); 1: built and in use; 2: built, switched off (E2FM_OPT_DENSE) */
     float load_ms[8];            /* one-time costs: [0] host parse, [1] H2D, [2] superbucket parse, [3] bucket decrypt+decode,
                                     [4] histogram, [5] scan, [6] rank sectors + LF fill, [7] total device */
 } e2fm_info;
@@ -115,6 +115,10 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^20) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
+#define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
+                                    tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
+                                    of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).
+                                    Same results either way. */
 int e2fm_set_option(e2fm_index *ix, int option, uint64_t value);
 
 /* ---- test hooks (parity of the individual kernels against the oracle) ---- */

@@ -100,9 +100,16 @@ def check_against_res(dev, patterns, res, locate):
 
 @pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
 @pytest.mark.parametrize("locate", [False, True])
-def test_search_matches_reference_goldens(opened, golden, name, locate):
+@pytest.mark.parametrize("dense", [0, 1])
+def test_search_matches_reference_goldens(opened, golden, name, locate, dense):
+    """dense=1: positions from the sa[]/text[] tables built at load; dense=0: per-query walks from the marked rows"""
     dev, _ = opened[name]
-    check_against_res(dev, golden[name]["patterns"], golden[name]["res"], locate)
+    assert dev.info.dense == 1
+    dev.set_option(capi.OPT_DENSE, dense)
+    try:
+        check_against_res(dev, golden[name]["patterns"], golden[name]["res"], locate)
+    finally:
+        dev.set_option(capi.OPT_DENSE, 1)
 
 
 @pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
@@ -112,10 +119,13 @@ def test_search_small_chunks_and_windows(opened, golden, name):
     dev.set_option(capi.OPT_CHUNK, 7)
     dev.set_option(capi.OPT_WINDOW, 5)
     try:
-        check_against_res(dev, golden[name]["patterns"], golden[name]["res"], True)
+        for dense in (0, 1):
+            dev.set_option(capi.OPT_DENSE, dense)
+            check_against_res(dev, golden[name]["patterns"], golden[name]["res"], True)
     finally:
         dev.set_option(capi.OPT_CHUNK, 0)
         dev.set_option(capi.OPT_WINDOW, 0)
+        dev.set_option(capi.OPT_DENSE, 1)
 
 
 def test_op_counters_match_oracle(opened, golden):
@@ -127,9 +137,13 @@ def test_op_counters_match_oracle(opened, golden):
         orc.search(p, True)
     want = orc.counters()
     data, offs = pack(pats)
-    r = dev.search(data, offs, True)
-    c = dev.last_batch_counters()
-    r.free()
+    dev.set_option(capi.OPT_DENSE, 0)      # the per-query walks execute the reference's operations one for one
+    try:
+        r = dev.search(data, offs, True)
+        c = dev.last_batch_counters()
+        r.free()
+    finally:
+        dev.set_option(capi.OPT_DENSE, 1)
     assert (c["rank"], c["lf"], c["mark"]) == want
 
 
@@ -230,15 +244,17 @@ def test_config1_count_locate_vs_reference(config1, key64, oracle_mod):
     synth.write_patterns(pfile, pats)
     res, _ = oracle_mod.ref_search(config1["efm"], config1["keyfile"], pfile, str(config1["dir"] / "r.res"), True, 2)
     dev = capi.DeviceIndex(config1["index"], key64)
-    for locate in (False, True):
-        r = dev.search_fixed(np.ascontiguousarray(pats), locate)
-        out = r.fetch()
-        assert np.array_equal(out["counts"], res["counts"])
-        if locate:
-            assert np.array_equal(out["pos_offsets"], res["pos_offsets"])
-            assert np.array_equal(out["positions"], res["positions"])
-            assert np.array_equal(out["seq"], res["seq"]) and np.array_equal(out["off"], res["off"])
-        r.free()
+    for dense in (1, 0):
+        dev.set_option(capi.OPT_DENSE, dense)
+        for locate in (False, True):
+            r = dev.search_fixed(np.ascontiguousarray(pats), locate)
+            out = r.fetch()
+            assert np.array_equal(out["counts"], res["counts"])
+            if locate:
+                assert np.array_equal(out["pos_offsets"], res["pos_offsets"])
+                assert np.array_equal(out["positions"], res["positions"])
+                assert np.array_equal(out["seq"], res["seq"]) and np.array_equal(out["off"], res["off"])
+            r.free()
     dev.close()
 
 
@@ -270,9 +286,15 @@ def test_config1_whole_index_decode_and_properties(config1, key64, oracle_mod):
     hit = np.zeros(npat, dtype=bool)
     hit[seg[pos == starts[seg].astype(np.uint64)]] = True
     assert hit.all()
-    # count-only agrees with locate
+    # count-only agrees with locate, and the per-query walks agree with the dense tables
     r2 = dev.search_fixed(np.ascontiguousarray(pats), False)
     assert np.array_equal(r2.fetch()["counts"], out["counts"])
+    dev.set_option(capi.OPT_DENSE, 0)
+    r3 = dev.search_fixed(np.ascontiguousarray(pats), True)
+    out3 = r3.fetch()
+    assert np.array_equal(out3["positions"], pos) and np.array_equal(out3["pos_offsets"], offs)
+    r3.free()
+    dev.set_option(capi.OPT_DENSE, 1)
     # spot-check 300 of them against the oracle
     for i in rng.integers(0, npat, 300):
         cnt, p = orc.search(pats[i].tobytes(), True)
