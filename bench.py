@@ -247,6 +247,8 @@ def gpu_arm(args, rank, world, local_rank):
     load_s = time.time() - t0
     if args.walk:
         ix.set_option(capi.OPT_DENSE, 0)
+    if args.chunk:
+        ix.set_option(capi.OPT_CHUNK, args.chunk)
     info = ix.info
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
@@ -307,13 +309,13 @@ def gpu_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     sampler.start()
     wall0 = time.perf_counter()
-    dev_ms, bs_ms, walk_ms, exp_ms, res_ms = 0.0, 0.0, 0.0, 0.0, 0.0
+    dev_ms, bs_ms, walk_ms, exp_ms, res_ms, enc_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
     ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0}
     occ_total = 0
     for _ in range(args.steps):
         l2_flush()
         ms, ctr, tot = step_device()
-        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]
+        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]; enc_ms += ms["encode"]
         for k_ in ctr_sum:
             ctr_sum[k_] += ctr[k_]
         occ_total += tot
@@ -391,7 +393,7 @@ def gpu_arm(args, rank, world, local_rank):
             "roofline": roofline,
             "ops_per_pattern": {"rank": ctr_sum["rank"] / (npat * steps), "lf": ctr_sum["lf"] / (npat * steps),
                                 "mark": ctr_sum["mark"] / (npat * steps)},
-            "phase_ms_per_step": {"backward_search": bs_ms / steps, "expand": exp_ms / steps, "walk": walk_ms / steps,
+            "phase_ms_per_step": {"encode": enc_ms / steps, "backward_search": bs_ms / steps, "expand": exp_ms / steps, "walk": walk_ms / steps,
                                   "results": res_ms / steps},
             "clocks": clocks, "wall_s_timed_device_loop": wall_dev,
         }
@@ -421,6 +423,7 @@ def main():
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
     ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)

@@ -120,7 +120,7 @@ struct e2fm_index {
     float batch_ms[8] = {0};
     uint64_t batch_ctr[8] = {0};
     bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
-    uint64_t chunk_patterns = 1u << 20;
+    uint64_t chunk_patterns = 4u << 20;
     uint64_t window_tasks = 64u << 20;
     unsigned long long *d_stats = nullptr;
     unsigned long long *h_stats = nullptr;   // pinned
@@ -379,7 +379,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     {
         const int h = tm.begin(4);
         PatternView all{b.d_bytes, b.d_off, b.fixed_len, 0, (uint32_t)b.n};
-        launch_encode_patterns(dix, all, 0, b.total_bytes, codes.p, s);
+        launch_encode_patterns(dix, all, b.total_bytes, codes.p, ix->n_sm, s);
         launches++;
         tm.end(h);
     }
@@ -791,7 +791,7 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]) {
 int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
     if (!ix) return fail(E2FM_ERR_ARG, "bad argument");
     switch (option) {
-        case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (1u << 20); return E2FM_OK;
+        case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (4u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");

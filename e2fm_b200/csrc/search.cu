@@ -14,6 +14,8 @@
 //                                (EFMCollection::search, EFMCollection.cpp:124-148).
 #include "search.cuh"
 
+#include <algorithm>
+
 #include "../../include/e2fm_b200.h"
 
 namespace e2fm {
@@ -77,32 +79,99 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 
 // codes[j] = compact code of the k-mer that starts at byte j of the batch, 0xFFFF when it would cross the end of
 // its pattern, holds a symbol outside the index's alphabet (EFMIndex.cpp:1702-1717) or never occurs in the text
-// (EFMIndex.cpp:2188-2197). One thread per byte; every backward step then costs one 2-byte load instead of
+// (EFMIndex.cpp:2188-2197). Every backward step then costs one 2-byte load instead of
 // ScrambledSuperAlphabet::getCode + charactersRemappings (EFMIndex.cpp:2186-2191).
-__global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t byte0, uint64_t n_bytes,
-                                                              uint16_t *__restrict__ codes) {
-    const uint64_t j = byte0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= byte0 + n_bytes) return;
-    uint64_t end;
+// One thread per 8 consecutive bytes: two 8-byte loads, symbol and k-mer tables in shared memory, one 16-byte store.
+static constexpr int ENC_PER = 8;
+static constexpr uint32_t ENC_SMEM_KMERS = 20480;   // k-mer table entries kept in shared memory (else read through L1)
+
+__global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t n_bytes, uint16_t *__restrict__ codes) {
+    extern __shared__ uint16_t enc_smem[];
+    uint8_t *sym_s = reinterpret_cast<uint8_t *>(enc_smem);            // [256]
+    uint16_t *kmer_s = enc_smem + 128;                                  // [sigma_k] when it fits
+    const bool kmers_in_smem = ix.sigma_k <= ENC_SMEM_KMERS;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) sym_s[i] = ix.sym_index[i];
+    if (kmers_in_smem)
+        for (uint32_t i = threadIdx.x; i < ix.sigma_k; i += blockDim.x) kmer_s[i] = ix.compact_of_natural[i];
+    __syncthreads();
+    const uint32_t k = ix.k, no = ix.n_sym;
+    // persistent blocks: the tables above are filled once per CTA, not once per 2 KB of patterns
+    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ENC_PER; j0 < n_bytes;
+         j0 += (uint64_t)gridDim.x * blockDim.x * ENC_PER) {
+    // bytes j0 .. j0+15 (enough for k <= 9; longer k-mers fall back to byte loads below)
+    uint8_t b[ENC_PER + 8];
+    const bool aligned = (reinterpret_cast<uintptr_t>(pv.bytes) & 7) == 0;
+    if (aligned && j0 + 16 <= n_bytes) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(pv.bytes + j0);
+        const uint2 lo = __ldg(q), hi = __ldg(q + 1);
+        const uint32_t w[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = j0 + i < n_bytes ? __ldg(pv.bytes + j0 + i) : (uint8_t)0;
+    }
+    // end of the pattern that owns byte j0
+    uint64_t pat = 0, end;
     if (pv.off) {
-        // binary search of the pattern that owns byte j (only ragged batches pay for it)
         uint64_t lo = pv.first, hi = pv.first + pv.count;
         while (lo + 1 < hi) {
             const uint64_t mid = (lo + hi) >> 1;
-            if (__ldg(pv.off + mid) <= j) lo = mid; else hi = mid;
+            if (__ldg(pv.off + mid) <= j0) lo = mid; else hi = mid;
         }
-        end = __ldg(pv.off + lo + 1);
+        pat = lo;
+        end = __ldg(pv.off + pat + 1);
     } else {
-        end = (j / pv.fixed_len + 1) * pv.fixed_len;
+        const uint32_t len = pv.fixed_len;
+        end = (n_bytes >> 32) ? (j0 / len + 1) * len : (uint64_t)((uint32_t)j0 / len + 1) * len;
     }
-    uint32_t c = 0xFFFFu;
-    if (j + ix.k <= end) c = fixed_code(ix, pv.bytes + j);
-    codes[j] = (uint16_t)c;
+    uint32_t out[ENC_PER];
+#pragma unroll
+    for (int q = 0; q < ENC_PER; q++) {
+        const uint64_t j = j0 + q;
+        while (j >= end && j < n_bytes) {                               // step into the next pattern
+            if (pv.off) { pat++; end = __ldg(pv.off + pat + 1); }
+            else end += pv.fixed_len;
+        }
+        uint32_t c = 0xFFFFu;
+        if (j + k <= end) {
+            uint32_t nat = 0;
+            bool bad = false;
+            if (k <= 9) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    if (i < (int)k) {
+                        const uint32_t sy = sym_s[b[q + i]];
+                        bad |= sy == 0xFFu;
+                        nat = nat * no + sy;
+                    }
+                }
+            } else {
+                for (uint32_t i = 0; i < k; i++) {
+                    const uint32_t sy = sym_s[__ldg(pv.bytes + j + i)];
+                    bad |= sy == 0xFFu;
+                    nat = nat * no + sy;
+                }
+            }
+            if (!bad) c = kmers_in_smem ? kmer_s[nat] : __ldg(ix.compact_of_natural + nat);
+        }
+        out[q] = c;
+    }
+    if (j0 + ENC_PER <= n_bytes) {
+        uint4 v = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
+        *reinterpret_cast<uint4 *>(codes + j0) = v;
+    } else {
+        for (int q = 0; q < ENC_PER && j0 + q < n_bytes; q++) codes[j0 + q] = (uint16_t)out[q];
+    }
+    }
 }
 
-void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t byte0, uint64_t n_bytes, uint16_t *codes, cudaStream_t s) {
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t n_bytes, uint16_t *codes, int n_sm, cudaStream_t s) {
     if (n_bytes == 0) return;
-    encode_patterns_kernel<<<(uint32_t)((n_bytes + 255) / 256), 256, 0, s>>>(ix, pv, byte0, n_bytes, codes);
+    const uint64_t threads = (n_bytes + ENC_PER - 1) / ENC_PER;
+    const size_t smem = 256 + (ix.sigma_k <= ENC_SMEM_KMERS ? (size_t)ix.sigma_k * 2 : 0);
+    const uint64_t blocks = std::min<uint64_t>((threads + 255) / 256, (uint64_t)n_sm * 8);
+    encode_patterns_kernel<<<(uint32_t)blocks, 256, smem, s>>>(ix, pv, n_bytes, codes);
 }
 
 // ---------------------------------------------------------------- K3: backward search

@@ -55,8 +55,8 @@ struct WalkArgs {
     unsigned long long *stats;
 };
 
-// codes[j] for the bytes [byte0, byte0 + n_bytes) of the batch (pv describes the patterns they belong to)
-void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t byte0, uint64_t n_bytes, uint16_t *codes, cudaStream_t s);
+// codes[j] for the n_bytes pattern bytes of the batch (pv describes all its patterns)
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t n_bytes, uint16_t *codes, int n_sm, cudaStream_t s);
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
 // exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);

@@ -1,0 +1,199 @@
+"""Collections sharded by sequence across the GPUs of one box.
+
+One process per GPU (torch.distributed; NCCL on the GPUs, gloo in the CPU tests). The collection is cut into
+`world` contiguous groups of sequences balanced by length; rank r holds the E2FM index the reference built
+for group r. A batch is answered in one exchange step:
+
+    broadcast(patterns from rank 0)  ->  local search on every shard (CUDA, e2fm_b200.capi)
+    all_reduce(SUM, counts)          ->  EFMIndex::countOccurrences over the whole collection
+    all_gather(per-pattern occurrence counts) + all_gather(padded occurrence arrays)
+                                     ->  per-pattern concatenation in shard order
+
+Exact patterns never span a terminator and every sequence starts k-aligned (EFMCollection.cpp:218-225), so an
+occurrence has the same (sequence, offset) whether its sequence is indexed alone, in a shard or in the whole
+collection; adding the shard's text base gives the very position the unsharded reference index reports, and
+because shards are contiguous sequence ranges the concatenation is already sorted (EFMIndex.cpp:2291).
+
+The merge below is device-agnostic tensor code: the CPU tests drive it with world_size-2 gloo groups.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def padded_length(seq_len: int, k: int) -> int:
+    """bytes a sequence occupies in the indexed text: padded to a multiple of k plus a k-long terminator
+    (EFMCollection.cpp:187-233)"""
+    return (seq_len + k - 1) // k * k + k
+
+
+def plan_shards(seq_lens, world: int, k: int):
+    """Contiguous groups balanced by length -> list of (first_seq, n_seqs, text_base) per rank."""
+    lens = [int(x) for x in seq_lens]
+    total = sum(lens)
+    bounds = [0]
+    acc = 0
+    for i, L in enumerate(lens):
+        acc += L
+        # close a group once it reaches its share (keep at least one sequence per remaining rank when possible)
+        while len(bounds) < world and acc >= total * len(bounds) / world and i + 1 <= len(lens) - (world - len(bounds)):
+            bounds.append(i + 1)
+    while len(bounds) < world:
+        bounds.append(len(lens))
+    bounds.append(len(lens))
+    out = []
+    base = 0
+    for r in range(world):
+        a, b = bounds[r], bounds[r + 1]
+        out.append((a, b - a, base))
+        base += sum(padded_length(L, k) for L in lens[a:b])
+    return out
+
+
+@dataclass
+class LocalResult:
+    """what one shard found, as tensors on the rank's device"""
+    counts: torch.Tensor        # int64 [n]
+    pos_offsets: torch.Tensor   # int64 [n+1]
+    positions: torch.Tensor     # int64 [total]  text positions inside the shard's index
+    seq: torch.Tensor           # int64 [total]  sequence index inside the shard
+    off: torch.Tensor           # int64 [total]  offset inside the sequence
+
+
+@dataclass
+class MergedResult:
+    counts: torch.Tensor        # int64 [n]   whole-collection counts (on every rank)
+    pos_offsets: torch.Tensor   # int64 [n+1]
+    positions: torch.Tensor     # int64 [total] positions in the unsharded collection text, ascending per pattern
+    seq: torch.Tensor           # int64 [total] collection-wide sequence index
+    off: torch.Tensor           # int64 [total]
+
+
+def broadcast_patterns(pats: torch.Tensor | None, shape, device, group=None) -> torch.Tensor:
+    """rank 0 holds the (n, L) uint8 batch; every rank returns it on `device`"""
+    rank = dist.get_rank(group)
+    t = pats.to(device) if rank == 0 else torch.empty(shape, dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0, group=group)
+    return t
+
+
+def merge_counts(counts: torch.Tensor, group=None) -> torch.Tensor:
+    out = counts.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def merge_results(local: LocalResult, first_seq: int, text_base: int, group=None, locate: bool = True) -> MergedResult:
+    """The exchange step. Every rank ends up with the whole merged result."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = local.counts.device
+    n = local.counts.numel()
+    counts = merge_counts(local.counts, group)
+    if not locate:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return MergedResult(counts, torch.zeros(n + 1, dtype=torch.int64, device=dev), z, z, z)
+    # per-pattern occurrence counts of every rank
+    mine = (local.pos_offsets[1:] - local.pos_offsets[:-1]).contiguous()
+    per_rank = torch.empty(world * n, dtype=torch.int64, device=dev)     # flat: gloo only takes 1-D outputs
+    dist.all_gather_into_tensor(per_rank, mine, group=group)
+    per_rank = per_rank.view(world, n)
+    totals = per_rank.sum(dim=1)                                   # occurrences per rank
+    max_total = int(totals.max().item()) if n else 0
+    # all-gather-v as a padded all-gather of one packed [3, max_total] tensor per rank
+    packed = torch.zeros((3, max(max_total, 1)), dtype=torch.int64, device=dev)
+    t = local.positions.numel()
+    if t:
+        packed[0, :t] = local.positions + text_base
+        packed[1, :t] = local.seq + first_seq
+        packed[2, :t] = local.off
+        # sequence index -1 (no terminator beyond the position, EFMCollection.cpp:124-133) stays -1
+        packed[1, :t] = torch.where(local.seq < 0, local.seq, packed[1, :t])
+    gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, packed.view(-1), group=group)
+    gathered = gathered.view(world, 3, max(max_total, 1))
+    # global CSR: pattern p holds rank 0's occurrences, then rank 1's, ...
+    per_pattern = per_rank.sum(dim=0)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(per_pattern, dim=0, out=offsets[1:])
+    total = int(offsets[-1].item()) if n else 0
+    positions = torch.empty(total, dtype=torch.int64, device=dev)
+    seq = torch.empty(total, dtype=torch.int64, device=dev)
+    off = torch.empty(total, dtype=torch.int64, device=dev)
+    before = torch.cumsum(per_rank, dim=0) - per_rank              # occurrences of earlier ranks, per pattern
+    for r in range(world):
+        tr = int(totals[r].item())
+        if tr == 0:
+            continue
+        cnt = per_rank[r]
+        local_off = torch.cumsum(cnt, dim=0) - cnt                 # rank r's own CSR starts
+        pat = torch.repeat_interleave(torch.arange(n, device=dev), cnt)
+        within = torch.arange(tr, device=dev) - local_off[pat]
+        dest = offsets[:-1][pat] + before[r][pat] + within
+        positions[dest] = gathered[r, 0, :tr]
+        seq[dest] = gathered[r, 1, :tr]
+        off[dest] = gathered[r, 2, :tr]
+    _ = rank
+    return MergedResult(counts, offsets, positions, seq, off)
+
+
+# ------------------------------------------------------------------ GPU side
+
+
+class _DevArray:
+    """zero-copy view of a device pointer for torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def local_result_from_device(res, device) -> LocalResult:
+    """Wrap an e2fm_b200.capi.Result (device-resident) as int64 tensors without leaving the GPU."""
+    p = res.device_ptrs()
+    n, t = res.n, res.total
+
+    def view(ptr, count, typestr, dtype):
+        if count == 0 or not ptr:
+            return torch.zeros(0, dtype=dtype, device=device)
+        return torch.as_tensor(_DevArray(ptr, count, typestr), device=device)
+
+    counts = view(p["counts"], n, "<i8", torch.int64).clone()
+    if not res.locate:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return LocalResult(counts, torch.zeros(n + 1, dtype=torch.int64, device=device), z, z, z)
+    offs = view(p["pos_offsets"], n + 1, "<i8", torch.int64).clone()
+    pos = view(p["positions"], t, "<i8", torch.int64).clone()
+    seq = view(p["seq"], t, "<i4", torch.int32).to(torch.int64)      # 0xFFFFFFFF (no sequence) becomes -1
+    off = view(p["off"], t, "<i8", torch.int64).clone()
+    return LocalResult(counts, offs, pos, seq, off)
+
+
+class ShardedCollection:
+    """rank-local handle: this rank's shard index on its GPU + the collective merge"""
+
+    def __init__(self, index_bytes: bytes, key64: bytes, device_index: int, first_seq: int, text_base: int, group=None):
+        from . import capi
+        self.capi = capi
+        self.ix = capi.DeviceIndex(index_bytes, key64, device_index)
+        self.device = torch.device("cuda", device_index)
+        self.first_seq = first_seq
+        self.text_base = text_base
+        self.group = group
+
+    def search_batch(self, pats_rank0, shape, locate: bool) -> MergedResult:
+        """pats_rank0: (n, L) uint8 tensor on rank 0 (ignored elsewhere); shape = (n, L) known to every rank."""
+        d_pats = broadcast_patterns(pats_rank0, shape, self.device, self.group)
+        torch.cuda.synchronize(self.device)   # the library searches on its own stream
+        n, L = shape
+        res = self.ix.search_device_fixed(d_pats.data_ptr(), n, L, locate)
+        local = local_result_from_device(res, self.device)
+        torch.cuda.synchronize(self.device)
+        res.free()
+        return merge_results(local, self.first_seq, self.text_base, self.group, locate)
+
+    def close(self):
+        self.ix.close()

@@ -113,7 +113,7 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
  * [4] distinct 32-byte rank sectors gathered by the backward-search kernel, [5] kernels launched by the batch,
  * [6] located occurrences, [7] dependent 8-byte gathers issued by the walk kernel */
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
-#define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^20) */
+#define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row

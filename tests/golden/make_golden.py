@@ -83,6 +83,20 @@ def main():
                     bad += 1
         print(f"{name}: n_patterns={len(pats)} occurrences={len(res['positions'])} index={os.path.getsize(base + '.efm')} B "
               f"reference-vs-naive mismatches={bad}")
+        if name == "col3_k4":
+            # the same collection cut into 2 shards by sequence (e2fm_b200/sharded.py): one reference index per shard;
+            # the merged shard results must equal the unsharded col3_k4.res
+            from e2fm_b200.sharded import plan_shards
+            for r, (first, cnt, tbase) in enumerate(plan_shards(lens, 2, k)):
+                sl = lens[first:first + cnt]
+                n_sh = synth.supertext_length(sl, k)
+                q = n_sh // rate
+                assert n_sh % rate != 0 and (q & (q - 1)) != 0, "shard hits a reference load-time quirk: change the lengths"
+                sb = os.path.join(OUT, f"{name}_shard{r}of2")
+                synth.write_fasta(sb + ".fa", seqs[first:first + cnt])
+                oracle.ref_build(sb + ".fa", sb + ".efm", keyfile, k=k, bucket_size=bs, mrp=mrp, threads=2)
+                os.remove(sb + ".fa")
+                print(f"  shard {r}: sequences {first}..{first + cnt - 1}, text base {tbase}, n={n_sh}, index={os.path.getsize(sb + '.efm')} B")
 
 
 if __name__ == "__main__":

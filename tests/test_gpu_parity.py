@@ -301,3 +301,19 @@ def test_config1_whole_index_decode_and_properties(config1, key64, oracle_mod):
         assert cnt == int(out["counts"][i]) and np.array_equal(p, pos[int(offs[i]):int(offs[i + 1])])
     r.free(); r2.free()
     dev.close()
+
+
+# ---------------------------------------------------------------- 2 GPUs: shard by sequence, merge over NCCL
+
+def test_sharded_two_gpus(gpu):
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import sys
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded_gpu_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), worker], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
