@@ -362,19 +362,32 @@ def gpu_arm(args, rank, world, local_rank):
         }
         dom = "backward_search_kernel" if bs_ms >= walk_ms else "walk_kernel"
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                with open(tpath) as f:
-                    traffic = json.load(f).get(args.workload, {}).get(dom)
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_kind,
-                    "layout_sector_gbs": kern[dom]["layout_sector_gbs"], "layout_sector_frac": kern[dom]["layout_sector_gbs"] / peak,
-                    "note": "achieved = reference-algorithm bytes (160 B/rank + 224 B/lf + 64 B/mark, SURVEY.md 8(d)) / kernel time; "
-                            "layout_sector_* = 32 B x the sectors this layout really has to gather (1 per rank sector, 1 per LF step), "
-                            "the random-gather figure to hold against the HBM peak",
+        short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}[args.workload]
+        try:
+            import glob
+            tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
+            if tfiles:
+                with open(tfiles[-1]) as f:
+                    tj = json.load(f)
+                want = ("walk_kernel" if args.walk else "resolve_kernel") if dom == "walk_kernel" else dom
+                for name, d in tj.items():
+                    if name.startswith(f"prof_{short}_") and want in d:
+                        traffic = d[want]
+        except Exception:
+            traffic = None
+        # roofline.achieved = 32 B x the sectors THIS layout has to gather / the kernel's CUDA-event time;
+        # reference_model = SURVEY.md 8(d)'s per-operation bytes of the REFERENCE's structure x the operations counted
+        roofline = {"bound": "hbm", "kernel": dom + (" (resolve_kernel: dense tables)" if dom == "walk_kernel" and not args.walk else ""),
+                    "achieved": kern[dom]["layout_sector_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["layout_sector_gbs"] / peak, "traffic": traffic, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": kern[dom]["layout_sector_bytes_per_step"],
+                    "reference_model": {"bytes_per_launch": kern[dom]["alg_bytes_per_step"], "gbs": kern[dom]["achieved_gbs"],
+                                        "frac": kern[dom]["achieved_gbs"] / peak,
+                                        "note": "160 B/rank + 224 B/lf + 64 B/mark (SURVEY.md 8(d)) x operations the kernels executed; "
+                                                "above the peak by construction: one sector per rank instead of five, and with the dense "
+                                                "tables the walks are not executed at all"},
+                    "note": "achieved = 32 B x sectors this layout must gather (distinct rank sectors / row-task gathers), per launch, "
+                            "over the kernel's average CUDA-event duration; traffic = ncu dram read+write of one launch (profiles/)",
                     "kernels": kern}
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -415,6 +428,113 @@ def gpu_arm(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def sharded_arm(args, rank, world, local_rank):
+    """Collection sharded by sequence over the ranks: rank r indexes sequence group r with the reference
+    builder, every rank searches the whole (broadcast) batch against its shard, counts and positions are merged over NCCL.
+    Total work is fixed as N grows -> strong scaling."""
+    import torch
+    import torch.distributed as dist
+
+    from e2fm_b200 import capi, sharded
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    dev_t = torch.device("cuda", local_rank)
+    w = WORKLOADS[args.workload]
+    locate = w["locate"]
+    lens = synth.safe_lengths(w["seq_lens"], K, 100 // MRP)
+    plan = sharded.plan_shards(lens, world, K)
+    first, cnt, text_base = plan[rank]
+    os.makedirs(CACHE, exist_ok=True)
+    keyfile = os.path.join(CACHE, f"key_r{rank}.bin")
+    with open(keyfile, "wb") as f:
+        f.write(synth.test_key())
+    seqs = []
+    for i in range(first, first + cnt):
+        seqs += synth.random_sequences([lens[i]], w["seed"] + i)
+    efm = os.path.join(CACHE, f"{args.workload}_shard{rank}of{world}_k{K}_b{BUCKET}_m{MRP}.efm")
+    if not os.path.exists(efm):
+        t0 = time.time()
+        fa = efm[:-4] + ".fa"
+        # every shard must dodge the reference's load-time quirks on its own (SURVEY.md 8 quirks 2, 3)
+        sl = synth.safe_lengths([len(x) for x in seqs], K, 100 // MRP)
+        assert sl == [len(x) for x in seqs], "shard length hits a reference quirk; change the workload lengths"
+        synth.write_fasta(fa, seqs)
+        threads = str(max(2, min(32, (os.cpu_count() or 2) // world)))
+        r = subprocess.run([ref_bin(), "build", fa, efm + ".tmp", keyfile, str(K), str(BUCKET), str(MRP), threads], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SystemExit("reference shard build failed: " + r.stderr[-400:])
+        os.replace(efm + ".tmp", efm)
+        os.remove(fa)
+        log(f"[bench r{rank}] reference built shard {efm} in {time.time() - t0:.1f}s")
+    with open(efm, "rb") as f:
+        raw = f.read()
+    col = sharded.ShardedCollection(raw, synth.test_key(), local_rank, first, text_base)
+    if args.walk:
+        col.ix.set_option(capi.OPT_DENSE, 0)
+    npat, L = w["n_patterns"], w["pat_len"]
+    pats0 = None
+    if rank == 0:
+        # patterns are sampled from the WHOLE collection: rank 0 regenerates the sequences it does not index
+        all_seqs = []
+        for i in range(len(lens)):
+            all_seqs += synth.random_sequences([lens[i]], w["seed"] + i)
+        pats0 = torch.from_numpy(synth.sample_patterns(all_seqs, npat, L, w["seed"] + 1)[:npat]).pin_memory()
+        del all_seqs
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
+    dist.barrier()
+
+    def step():
+        flush.add_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        m = col.search_batch(pats0, (npat, L), locate)
+        e1.record()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, int(m.positions.numel()), int(m.counts.sum().item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    tot_s, occ, cnt_sum = 0.0, 0, 0
+    for _ in range(args.steps):
+        dt, o, c = step()
+        tot_s += dt
+        occ, cnt_sum = o, c
+    dist.barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([tot_s], dtype=torch.float64, device=dev_t)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item()) * 1e3 / args.steps
+        line = {
+            "metric": "patterns/sec", "value": npat / (ms / 1e3), "unit": "patterns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": w["name"], "mode": "count+locate" if locate else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
+                       "patterns": npat, "pattern_len": L, "parallelism": f"collection sharded by sequence over {world} GPUs; "
+                       "patterns broadcast, counts all-reduced, positions all-gathered (NCCL)", "shards": plan,
+                       "l2": "256 MB flush between timed iterations", "timing": "wall clock around broadcast + search + merge, device synchronised, max over ranks"},
+            "occurrences_per_s": occ / (ms / 1e3) if locate else None, "total_count": cnt_sum,
+            "e2e": {"value": npat / (ms / 1e3), "unit": "patterns/s", "h2d_bytes_per_step": npat * L, "d2h_bytes_per_step": 0,
+                    "note": "patterns start in pinned host memory on rank 0; the merged result stays on the GPUs"},
+            "gpu_launches": None, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    col.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -423,6 +543,7 @@ def main():
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
     ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
@@ -435,7 +556,10 @@ def main():
             return
         reference_arm(args, prepare(args.workload, 0))
         return
-    gpu_arm(args, rank, world, local_rank)
+    if args.sharded:
+        sharded_arm(args, rank, world, local_rank)
+    else:
+        gpu_arm(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

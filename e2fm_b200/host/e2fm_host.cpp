@@ -1,0 +1,193 @@
+// e2fm_host.cpp — see e2fm_host.h. Thin: file I/O, key handling, marshalling to / from the C ABI.
+#include "e2fm_host.h"
+
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+#include "../../include/e2fm_b200.h"
+
+namespace e2fm {
+
+namespace {
+[[noreturn]] void raise_last(const char *what) { throw std::runtime_error(std::string(what) + ": " + e2fm_last_error()); }
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+EFMIndex::EFMIndex()
+    : handle_(nullptr), device_(0), numberOfThreads_(1), haveKey_(false), infoBucketSize_(0), infoSuperBucketSize_(0), infoBuckets_(0),
+      infoSuperBuckets_(0), infoN_(0), infoK_(0), infoMrp_(0) {
+    memset(key_, 0, sizeof(key_));
+}
+
+EFMIndex::~EFMIndex() { close(); }
+
+void EFMIndex::setEncryptionKey(u8 *encryptionKey) {
+    memcpy(key_, encryptionKey, 64);
+    haveKey_ = true;
+}
+
+// EncryptionManager::EncryptionManager(string&) (EncryptionManager.cpp:15-36): same checks, same messages
+void EFMIndex::setEncryptionKeyFilePath(std::string encryptionKeyFilePath) {
+    keyFilePath_ = encryptionKeyFilePath;
+    std::ifstream is(encryptionKeyFilePath, std::ifstream::binary);
+    if (!is) throw std::runtime_error("Error opening key file " + encryptionKeyFilePath);
+    is.seekg(0, is.end);
+    uint64_t length = (uint64_t)is.tellg();
+    is.seekg(0, is.beg);
+    if (length != 64) throw std::runtime_error("File " + encryptionKeyFilePath + "is not a valid key file");
+    is.read((char *)key_, 64);
+    haveKey_ = true;
+}
+std::string EFMIndex::getEncryptionKeyFilePath() { return keyFilePath_; }
+void EFMIndex::setNumberOfThreads(uint32_t n) { numberOfThreads_ = n; }
+uint32_t EFMIndex::getNumberOfThreads() { return numberOfThreads_; }
+void EFMIndex::setDevice(int device) { device_ = device; }
+
+void EFMIndex::load(std::string fileName) {
+    close();
+    if (!haveKey_) throw std::runtime_error("Encryption key not set");
+    std::ifstream is(fileName, std::ifstream::binary);
+    if (!is) throw std::runtime_error("Error opening index file " + fileName);
+    is.seekg(0, is.end);
+    size_t size = (size_t)is.tellg();
+    is.seekg(0, is.beg);
+    std::vector<uint8_t> file(size);   // MemoryBitReader::loadDataFromFile (MemoryBitReader.cpp:93): the whole file in RAM
+    is.read((char *)file.data(), (std::streamsize)size);
+    if (e2fm_index_open(file.data(), size, key_, device_, &handle_) != E2FM_OK) {
+        handle_ = nullptr;
+        throw std::runtime_error(e2fm_last_error());   // e.g. "File type is not Encrypted and Compressed Genomic Index"
+    }
+    e2fm_info info;
+    e2fm_index_info(handle_, &info);
+    infoBucketSize_ = info.bucket_size;
+    infoSuperBucketSize_ = info.superbucket_size;
+    infoBuckets_ = info.n_buckets;
+    infoSuperBuckets_ = info.n_superbuckets;
+    infoN_ = info.text_length;
+    infoK_ = info.k;
+    infoMrp_ = info.marked_rows_percentage;
+    terminators_.resize(info.n_sequences);
+    e2fm_index_terminators(handle_, terminators_.data(), terminators_.size());
+    uint64_t hs = e2fm_index_fasta_headers(handle_, nullptr, 0);
+    headersBuffer_.resize(hs);
+    if (hs) e2fm_index_fasta_headers(handle_, &headersBuffer_[0], hs);
+}
+
+void EFMIndex::clearMatches() {
+    for (Match *m : allSuperPatternMatches) delete m;
+    allSuperPatternMatches.clear();
+}
+
+void EFMIndex::close() {
+    clearMatches();
+    if (handle_) e2fm_index_close(handle_);
+    handle_ = nullptr;
+}
+
+void EFMIndex::requireLoaded() const {
+    if (!handle_) throw std::runtime_error("Index not loaded");
+}
+
+BatchResult EFMIndex::searchBatch(const std::vector<std::string> &patterns, Mode mode) {
+    requireLoaded();
+    const double t0 = now_ms();
+    BatchResult out;
+    const uint64_t n = patterns.size();
+    std::vector<uint64_t> offs(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) offs[i + 1] = offs[i] + patterns[i].size();
+    std::vector<uint8_t> bytes(offs[n] + 1);
+    for (uint64_t i = 0; i < n; i++) memcpy(bytes.data() + offs[i], patterns[i].data(), patterns[i].size());
+    e2fm_result *r = nullptr;
+    if (e2fm_search_batch(handle_, bytes.data(), offs.data(), n, (int)mode, &r) != E2FM_OK) throw std::runtime_error(e2fm_last_error());
+    const uint64_t total = e2fm_result_total_positions(r);
+    out.counts.resize(n);
+    out.offsets.assign(n + 1, 0);
+    out.positions.resize(total);
+    out.sequenceIndex.resize(total);
+    out.sequenceOffset.resize(total);
+    int rc = e2fm_result_fetch(r, out.counts.data(), out.offsets.data(), out.positions.data(), out.sequenceIndex.data(),
+                               out.sequenceOffset.data());
+    e2fm_result_free(r);
+    if (rc != E2FM_OK) raise_last("e2fm_result_fetch");
+    e2fm_last_batch_ms(handle_, out.deviceMs);
+    out.elapsedMs = now_ms() - t0;
+    return out;
+}
+
+// EFMIndex::exactMatch (EFMIndex.cpp:1694): one pattern; the outcome is parked in allSuperPatternMatches
+void EFMIndex::exactMatch(std::string pattern) {
+    clearMatches();
+    BatchResult b = searchBatch(std::vector<std::string>(1, pattern), Mode::Locate);
+    Match *m = new Match();
+    m->count = b.counts[0];
+    m->occurrences = std::move(b.positions);
+    m->sequenceIndex = std::move(b.sequenceIndex);
+    m->sequenceOffset = std::move(b.sequenceOffset);
+    allSuperPatternMatches.push_back(m);
+}
+
+uint64_t EFMIndex::countOccurrences(std::vector<Match *> *matches) {
+    uint64_t c = 0;
+    for (Match *m : *matches) c += m->count;
+    return c;
+}
+
+std::vector<uint64_t> *EFMIndex::locateOccurrences(std::vector<Match *> *matches) {
+    std::vector<uint64_t> *occs = new std::vector<uint64_t>();
+    for (Match *m : *matches) occs->insert(occs->end(), m->occurrences.begin(), m->occurrences.end());
+    return occs;
+}
+
+uint64_t EFMIndex::getBucketSize() const { return infoBucketSize_; }
+uint64_t EFMIndex::getSuperBucketSize() { return infoSuperBucketSize_; }
+uint64_t EFMIndex::getBucketsNumber() { return infoBuckets_; }
+uint64_t EFMIndex::getSuperBucketsNumber() { return infoSuperBuckets_; }
+uint64_t EFMIndex::getNumberOfLoadedBuckets() { return handle_ ? infoBuckets_ : 0; }
+uint64_t EFMIndex::getNumberOfLoadedSuperBuckets() { return handle_ ? infoSuperBuckets_ : 0; }
+uint8_t EFMIndex::getMarkedRowsPercentage() { return (uint8_t)infoMrp_; }
+uint8_t EFMIndex::getSuperAlphabetOrder() const { return (uint8_t)infoK_; }
+uint64_t EFMIndex::getTextLength() const { return infoN_; }
+
+// ------------------------------------------------------------------ EFMCollection
+
+uint32_t EFMCollection::getSize() { return (uint32_t)terminators_.size(); }
+
+std::string EFMCollection::getDescription(uint32_t sequenceIndex) {
+    if (!headersSplit_) {   // boost::split(headersBuffer, "\n") (FMCollection.cpp:72)
+        fastaHeaders_.clear();
+        size_t a = 0;
+        while (true) {
+            size_t b = headersBuffer_.find('\n', a);
+            fastaHeaders_.push_back(headersBuffer_.substr(a, b == std::string::npos ? std::string::npos : b - a));
+            if (b == std::string::npos) break;
+            a = b + 1;
+        }
+        headersSplit_ = true;
+    }
+    return fastaHeaders_.at(sequenceIndex);   // throws std::out_of_range like vector::at in the reference
+}
+
+std::vector<SearchResult> EFMCollection::searchBatch(const std::vector<std::string> &patterns, Mode mode, bool retrieveSequenceDescriptions) {
+    BatchResult b = EFMIndex::searchBatch(patterns, mode);
+    std::vector<SearchResult> out(patterns.size());
+    const double per = patterns.empty() ? 0 : b.elapsedMs / (double)patterns.size();
+    for (size_t i = 0; i < patterns.size(); i++) {
+        out[i].pattern = patterns[i];
+        out[i].elapsedTime = per;
+        for (uint64_t j = b.offsets[i]; j < b.offsets[i + 1]; j++) {
+            const uint32_t s = b.sequenceIndex[j];
+            out[i].occurrences.emplace_back(s, (retrieveSequenceDescriptions && s != 0xFFFFFFFFu) ? getDescription(s) : std::string(),
+                                            b.sequenceOffset[j]);
+        }
+    }
+    return out;
+}
+
+SearchResult *EFMCollection::search(std::string pattern, bool retrieveSequenceDescriptions) {
+    std::vector<SearchResult> v = searchBatch(std::vector<std::string>(1, pattern), Mode::Locate, retrieveSequenceDescriptions);
+    return new SearchResult(std::move(v[0]));
+}
+
+}  // namespace e2fm

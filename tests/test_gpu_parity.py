@@ -317,3 +317,62 @@ def test_sharded_two_gpus(gpu):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), worker], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+# ---------------------------------------------------------------- C++ host classes and the locate CLI
+
+HOST_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "e2fm_b200")
+
+
+def test_cpp_host_classes_match_reference(gpu, golden):
+    """EFMIndex::exactMatch / countOccurrences / locateOccurrences, EFMCollection::search, SFMCollection::search,
+    driven from C++ exactly as the reference's drivers call them, against the reference's results"""
+    exe = os.path.join(HOST_DIR, "e2fm_host_selftest")
+    assert os.path.exists(exe), "build e2fm_b200/host (python -c 'import __graft_entry__ as g; g.build()')"
+    g = golden["col3_k4"]
+    r = subprocess.run([exe, g["base"] + ".efm", os.path.join(GOLDEN, "key.bin"), g["base"] + ".pat"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    info = [l for l in lines if l.startswith("INFO")][0].split()
+    assert info[1:4] == ["3", "4", "256"] and info[7] == "2"
+    descs = [l.split(" ", 2)[2] for l in lines if l.startswith("DESC")]
+    assert descs == ["seq0", "seq1", "seq2"]
+    res = g["res"]
+    plines = [l for l in lines if l.startswith("P ")]
+    assert len(plines) == len(g["patterns"])
+    for i, l in enumerate(plines):
+        head, efm_part, sfm_part = l.split("|")
+        f = head.split()
+        a, b = int(res["pos_offsets"][i]), int(res["pos_offsets"][i + 1])
+        assert int(f[2]) == int(res["counts"][i]) and int(f[3]) == b - a
+        assert [int(x) for x in f[4:]] == [int(x) for x in res["positions"][a:b]]
+        want = [f"{int(res['seq'][j])}:{int(res['off'][j])}" for j in range(a, b)]
+        assert [":".join(x.split(":")[:2]) for x in efm_part.split()] == want
+        assert all(x.split(":")[2] == f"seq{x.split(':')[0]}" for x in efm_part.split())
+        assert sfm_part.split() == want
+    errs = [l for l in lines if l.startswith("ERR")]
+    assert "is not a valid key file" in errs[0]                                    # EncryptionManager.cpp:25
+    assert "File type is not Encrypted and Compressed Genomic Index" in errs[1]    # EFMIndex.cpp:1155
+
+
+def test_locate_cli_formats(gpu, golden, tmp_path):
+    """e2fm_locate writes the reference CLI's results TSV (Main.cpp:1052,1074) and statistics CSV (Main.cpp:1138-1146)"""
+    exe = os.path.join(HOST_DIR, "e2fm_locate")
+    g = golden["col3_k4"]
+    pat = tmp_path / "p.txt"
+    pat.write_bytes(b"\n".join(p.lower() for p in g["patterns"]) + b"\n")    # the CLI upper-cases (Main.cpp:1056-1059)
+    out, st = tmp_path / "r.tsv", tmp_path / "s.csv"
+    r = subprocess.run([exe, g["base"] + ".efm", os.path.join(GOLDEN, "key.bin"), str(pat), str(out), str(st), "1"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = out.read_text().splitlines()
+    assert rows[0] == "Pattern\tsequenceIndex\tsequenceDescription\tpatternPosition"
+    res = g["res"]
+    want = []
+    for i, p in enumerate(g["patterns"]):
+        for j in range(int(res["pos_offsets"][i]), int(res["pos_offsets"][i + 1])):
+            want.append(f"{p.decode()}\t{int(res['seq'][j])}\tseq{int(res['seq'][j])}\t{int(res['off'][j])}")
+    assert rows[1:] == want
+    s = st.read_text().splitlines()
+    assert s[0].startswith("indexFileName,k,bucketSize,markedRowsPercentage,numberOfPatterns,patternsLength,median")
+    assert s[1].split(",")[1:5] == ["4", "256", "2", str(len(g["patterns"]))]
