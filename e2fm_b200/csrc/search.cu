@@ -85,6 +85,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 static constexpr int ENC_PER = 8;
 static constexpr uint32_t ENC_SMEM_KMERS = 20480;   // k-mer table entries kept in shared memory (else read through L1)
 
+// KT = compile-time super-alphabet order, 1..8 (0 = generic, any k, slower)
+template <int KT>
 __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t n_bytes, uint16_t *__restrict__ codes) {
     extern __shared__ uint16_t enc_smem[];
     uint8_t *sym_s = reinterpret_cast<uint8_t *>(enc_smem);            // [256]
@@ -94,75 +96,74 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
     if (kmers_in_smem)
         for (uint32_t i = threadIdx.x; i < ix.sigma_k; i += blockDim.x) kmer_s[i] = ix.compact_of_natural[i];
     __syncthreads();
-    const uint32_t k = ix.k, no = ix.n_sym;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
+    const bool aligned = (reinterpret_cast<uintptr_t>(pv.bytes) & 7) == 0;
     // persistent blocks: the tables above are filled once per CTA, not once per 2 KB of patterns
     for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ENC_PER; j0 < n_bytes;
          j0 += (uint64_t)gridDim.x * blockDim.x * ENC_PER) {
-    // bytes j0 .. j0+15 (enough for k <= 9; longer k-mers fall back to byte loads below)
-    uint8_t b[ENC_PER + 8];
-    const bool aligned = (reinterpret_cast<uintptr_t>(pv.bytes) & 7) == 0;
-    if (aligned && j0 + 16 <= n_bytes) {
-        const uint2 *q = reinterpret_cast<const uint2 *>(pv.bytes + j0);
-        const uint2 lo = __ldg(q), hi = __ldg(q + 1);
-        const uint32_t w[4] = {lo.x, lo.y, hi.x, hi.y};
+        // symbols of bytes j0 .. j0+15 (0xFF = not in the index's alphabet)
+        uint32_t sy[16];
+        if (aligned && j0 + 16 <= n_bytes) {
+            const uint2 *q = reinterpret_cast<const uint2 *>(pv.bytes + j0);
+            const uint2 lo = __ldg(q), hi = __ldg(q + 1);
+            const uint32_t w[4] = {lo.x, lo.y, hi.x, hi.y};
 #pragma unroll
-        for (int i = 0; i < 16; i++) b[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-    } else {
+            for (int i = 0; i < 16; i++) sy[i] = sym_s[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu];
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; i++) b[i] = j0 + i < n_bytes ? __ldg(pv.bytes + j0 + i) : (uint8_t)0;
-    }
-    // end of the pattern that owns byte j0
-    uint64_t pat = 0, end;
-    if (pv.off) {
-        uint64_t lo = pv.first, hi = pv.first + pv.count;
-        while (lo + 1 < hi) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if (__ldg(pv.off + mid) <= j0) lo = mid; else hi = mid;
+            for (int i = 0; i < 16; i++) sy[i] = j0 + i < n_bytes ? sym_s[__ldg(pv.bytes + j0 + i)] : 0xFFu;
         }
-        pat = lo;
-        end = __ldg(pv.off + pat + 1);
-    } else {
-        const uint32_t len = pv.fixed_len;
-        end = (n_bytes >> 32) ? (j0 / len + 1) * len : (uint64_t)((uint32_t)j0 / len + 1) * len;
-    }
-    uint32_t out[ENC_PER];
+        uint32_t badmask = 0;
 #pragma unroll
-    for (int q = 0; q < ENC_PER; q++) {
-        const uint64_t j = j0 + q;
-        while (j >= end && j < n_bytes) {                               // step into the next pattern
-            if (pv.off) { pat++; end = __ldg(pv.off + pat + 1); }
-            else end += pv.fixed_len;
+        for (int i = 0; i < 16; i++) badmask |= (sy[i] == 0xFFu ? 1u : 0u) << i;
+        // bytes left in the pattern that owns byte j0 (room), and the length of the next patterns
+        uint64_t pat = 0, room;
+        if (pv.off) {
+            uint64_t lo = pv.first, hi = pv.first + pv.count;
+            while (lo + 1 < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(pv.off + mid) <= j0) lo = mid; else hi = mid;
+            }
+            pat = lo;
+            room = __ldg(pv.off + pat + 1) - j0;
+        } else {
+            const uint32_t len = pv.fixed_len;
+            room = len - ((n_bytes >> 32) ? (uint32_t)(j0 % len) : (uint32_t)j0 % len);
         }
-        uint32_t c = 0xFFFFu;
-        if (j + k <= end) {
-            uint32_t nat = 0;
-            bool bad = false;
-            if (k <= 9) {
+        uint32_t out[ENC_PER];
 #pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    if (i < (int)k) {
-                        const uint32_t sy = sym_s[b[q + i]];
-                        bad |= sy == 0xFFu;
-                        nat = nat * no + sy;
+        for (int q = 0; q < ENC_PER; q++) {
+            while (room == 0 && j0 + q < n_bytes) {                      // step into the next pattern
+                if (pv.off) { pat++; room = __ldg(pv.off + pat + 1) - __ldg(pv.off + pat); }
+                else room = pv.fixed_len;
+            }
+            uint32_t c = 0xFFFFu;
+            if (k <= room) {
+                uint32_t nat = 0;
+                bool bad;
+                if (KT) {
+#pragma unroll
+                    for (int i = 0; i < (KT ? KT : 1); i++) nat = nat * no + sy[q + i];
+                    bad = ((badmask >> q) & ((1u << KT) - 1)) != 0;
+                } else {
+                    bad = false;
+                    for (uint32_t i = 0; i < k; i++) {
+                        const uint32_t v = sym_s[__ldg(pv.bytes + j0 + q + i)];
+                        bad |= v == 0xFFu;
+                        nat = nat * no + v;
                     }
                 }
-            } else {
-                for (uint32_t i = 0; i < k; i++) {
-                    const uint32_t sy = sym_s[__ldg(pv.bytes + j + i)];
-                    bad |= sy == 0xFFu;
-                    nat = nat * no + sy;
-                }
+                if (!bad) c = kmers_in_smem ? kmer_s[nat] : __ldg(ix.compact_of_natural + nat);
             }
-            if (!bad) c = kmers_in_smem ? kmer_s[nat] : __ldg(ix.compact_of_natural + nat);
+            out[q] = c;
+            room--;
         }
-        out[q] = c;
-    }
-    if (j0 + ENC_PER <= n_bytes) {
-        uint4 v = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
-        *reinterpret_cast<uint4 *>(codes + j0) = v;
-    } else {
-        for (int q = 0; q < ENC_PER && j0 + q < n_bytes; q++) codes[j0 + q] = (uint16_t)out[q];
-    }
+        if (j0 + ENC_PER <= n_bytes) {
+            uint4 v = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
+            *reinterpret_cast<uint4 *>(codes + j0) = v;
+        } else {
+            for (int q = 0; q < ENC_PER && j0 + q < n_bytes; q++) codes[j0 + q] = (uint16_t)out[q];
+        }
     }
 }
 
@@ -170,8 +171,14 @@ void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t 
     if (n_bytes == 0) return;
     const uint64_t threads = (n_bytes + ENC_PER - 1) / ENC_PER;
     const size_t smem = 256 + (ix.sigma_k <= ENC_SMEM_KMERS ? (size_t)ix.sigma_k * 2 : 0);
-    const uint64_t blocks = std::min<uint64_t>((threads + 255) / 256, (uint64_t)n_sm * 8);
-    encode_patterns_kernel<<<(uint32_t)blocks, 256, smem, s>>>(ix, pv, n_bytes, codes);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((threads + 255) / 256, (uint64_t)n_sm * 8);
+    switch (ix.k) {
+        case 2: encode_patterns_kernel<2><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+        case 3: encode_patterns_kernel<3><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+        case 4: encode_patterns_kernel<4><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+        case 5: encode_patterns_kernel<5><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+        default: encode_patterns_kernel<0><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+    }
 }
 
 // ---------------------------------------------------------------- K3: backward search
