@@ -40,6 +40,15 @@ WORKLOADS = {
     # BASELINE.json configs[2] on ONE GPU (whole collection in one index): larger than L2, HBM-bound
     "collection100": dict(seq_lens=[4_641_652] * 100, seed=1000, n_patterns=10_000_000, pat_len=24, locate=True,
                           name="configs[2]: 100 x 4.6 Mbp synthetic genomes, 10M patterns len 24, count+locate"),
+    # BASELINE.json configs[4]: chr1-sized 248 Mbp single sequence, locate-heavy short patterns (len 12)
+    "chr1": dict(seq_lens=[248_956_422], seed=45, n_patterns=1_000_000, pat_len=12, locate=True,
+                 name="configs[4]: 248 Mbp chr1-sized synthetic sequence, 1M patterns len 12, count+locate"),
+    # BASELINE.json configs[3]: human-genome-sized 3.1 Gbp collection (24 sequences, hg38-like proportions), 10M patterns len 50
+    "human": dict(seq_lens=[248_956_422, 242_193_529, 198_295_559, 190_214_555, 181_538_259, 170_805_979, 159_345_973, 145_138_636,
+                            138_394_717, 133_797_422, 135_086_622, 133_275_309, 114_364_328, 107_043_718, 101_991_189, 90_338_345,
+                            83_257_441, 80_373_285, 58_617_616, 64_444_167, 46_709_983, 50_818_468, 156_040_895, 57_227_415],
+                  seed=44, n_patterns=10_000_000, pat_len=50, locate=True,
+                  name="configs[3]: 3.1 Gbp human-genome-sized synthetic collection (24 sequences), 10M patterns len 50, count+locate"),
     # a collection100 shard-sized index for quicker HBM-bound runs
     "collection25": dict(seq_lens=[4_641_652] * 25, seed=1000, n_patterns=4_000_000, pat_len=24, locate=True,
                          name="25 x 4.6 Mbp synthetic genomes, 4M patterns len 24, count+locate"),
@@ -249,6 +258,8 @@ def gpu_arm(args, rank, world, local_rank):
         ix.set_option(capi.OPT_DENSE, 0)
     if args.chunk:
         ix.set_option(capi.OPT_CHUNK, args.chunk)
+    if args.pipe:
+        ix.set_option(capi.OPT_PIPE, args.pipe)
     info = ix.info
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
@@ -277,10 +288,11 @@ def gpu_arm(args, rank, world, local_rank):
         return ms, ctr, tot
 
     pin_pos = {}
+    e2e_dev_ms = []
 
     def step_e2e():
         t0 = time.perf_counter()
-        r = ix.search_fixed(pin_p.array, locate)
+        r = ix.search_stream(pin_p.array, locate, pin_counts.array)
         if locate:
             need = max(r.total, 1)
             if pin_pos.get("n", 0) < need:
@@ -290,13 +302,13 @@ def gpu_arm(args, rank, world, local_rank):
                 pin_pos["pos"] = capi.PinnedArray(int(need * 1.2) + 16, np.uint64)
                 pin_pos["off"] = capi.PinnedArray(npat + 1, np.uint64)
                 pin_pos["n"] = int(need * 1.2) + 16
-            r.fetch(counts=pin_counts.array, pos_offsets=pin_pos["off"].array, positions=pin_pos["pos"].array[:r.total],
-                    want_seq=False)
+            r.fetch_positions(pos_offsets=pin_pos["off"].array, positions=pin_pos["pos"].array[:r.total])
         else:
-            r.fetch(counts=pin_counts.array)
+            pass   # count mode: the counts were streamed into pin_counts chunk by chunk (e2fm_search_batch_stream)
         dt = time.perf_counter() - t0
         tot = r.total
         r.free()
+        e2e_dev_ms.append(ix.last_batch_ms()["total"])
         return dt, tot
 
     for _ in range(args.warmup):
@@ -362,7 +374,7 @@ def gpu_arm(args, rank, world, local_rank):
         }
         dom = "backward_search_kernel" if bs_ms >= walk_ms else "walk_kernel"
         traffic = None
-        short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}[args.workload]
+        short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}.get(args.workload, args.workload)
         try:
             import glob
             tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
@@ -401,7 +413,8 @@ def gpu_arm(args, rank, world, local_rank):
             "occurrences_per_s": (world * occ_total / (dev_ms_max / 1e3)) if locate else None,
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": int(npat * L),
                     "d2h_bytes_per_step": int(npat * 8 + ((npat + 1) * 8 + (occ_total // max(steps, 1)) * 8 if locate else 0)),
-                    "ms_per_step": e2e_ms_max / steps},
+                    "ms_per_step": e2e_ms_max / steps,
+                    "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None},
             "gpu_launches": int(ctr_sum["launches"]),
             "roofline": roofline,
             "ops_per_pattern": {"rank": ctr_sum["rank"] / (npat * steps), "lf": ctr_sum["lf"] / (npat * steps),
@@ -545,6 +558,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
+    ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)

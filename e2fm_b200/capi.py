@@ -19,12 +19,13 @@ MODE_LOCATE = 1
 OPT_CHUNK = 2
 OPT_WINDOW = 3
 OPT_DENSE = 4
+OPT_PIPE = 5
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
     "e2fm_index_open", "e2fm_index_close", "e2fm_index_info", "e2fm_index_terminators", "e2fm_index_fasta_headers",
     "e2fm_index_stream", "e2fm_search_batch", "e2fm_search_batch_fixed", "e2fm_search_batch_device",
-    "e2fm_search_batch_device_fixed", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
+    "e2fm_search_batch_device_fixed", "e2fm_search_batch_stream", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
     "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
     "e2fm_result_free", "e2fm_last_batch_ms", "e2fm_last_batch_counters", "e2fm_set_option",
     "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
@@ -76,6 +77,7 @@ def lib():
     L.e2fm_index_stream.argtypes = [vp]
     L.e2fm_search_batch.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp)]
     L.e2fm_search_batch_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_search_batch_stream.argtypes = [vp, vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
     L.e2fm_search_batch_device.argtypes = [vp, vp, vp, u64, u64, i32, C.POINTER(vp)]
     L.e2fm_search_batch_device_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
     L.e2fm_result_patterns.restype = u64
@@ -163,6 +165,10 @@ class Result:
         check(lib().e2fm_result_fetch(self._h, p(counts), pos_offsets.ctypes.data if pos_offsets is not None else None,
                                       p(positions), p(seq_index), p(seq_offset)))
         return out
+
+    def fetch_positions(self, pos_offsets, positions):
+        """D2H of the CSR offsets and positions only (counts already streamed back)"""
+        check(lib().e2fm_result_fetch(self._h, None, pos_offsets.ctypes.data, positions.ctypes.data if positions.size else None, None, None))
 
     def device_ptrs(self):
         ptrs = [C.c_void_p() for _ in range(5)]
@@ -263,6 +269,16 @@ class DeviceIndex:
             offs[1:] = np.cumsum([len(p) for p in patterns])
         data = np.frombuffer(b"".join(patterns), dtype=np.uint8)
         return self.search(data, offs, locate)
+
+    def search_stream(self, pats: np.ndarray, locate: bool, counts_out: np.ndarray) -> Result:
+        """fixed-length host batch, pipelined; counts arrive in counts_out (uint64[n], pinned for full overlap)"""
+        assert pats.dtype == np.uint8 and pats.ndim == 2 and pats.flags.c_contiguous
+        assert counts_out.dtype == np.uint64 and counts_out.size >= pats.shape[0]
+        h = C.c_void_p()
+        n, L = pats.shape
+        check(lib().e2fm_search_batch_stream(self._h, pats.ctypes.data if pats.size else None, None, n, L,
+                                             MODE_LOCATE if locate else MODE_COUNT, counts_out.ctypes.data, C.byref(h)))
+        return Result(h, locate)
 
     def search_device_fixed(self, d_ptr: int, n: int, length: int, locate: bool) -> Result:
         h = C.c_void_p()

@@ -78,16 +78,16 @@ struct EventTimer {
     std::vector<Span> spans;
     cudaStream_t s;
     explicit EventTimer(cudaStream_t st) : s(st) {}
-    int begin(int slot) {
+    int begin(int slot, cudaStream_t on = nullptr) {
         Span sp;
         sp.slot = slot;
         CK(cudaEventCreate(&sp.a));
         CK(cudaEventCreate(&sp.b));
-        CK(cudaEventRecord(sp.a, s));
+        CK(cudaEventRecord(sp.a, on ? on : s));
         spans.push_back(sp);
         return (int)spans.size() - 1;
     }
-    void end(int h) { CK(cudaEventRecord(spans[h].b, s)); }
+    void end(int h, cudaStream_t on = nullptr) { CK(cudaEventRecord(spans[h].b, on ? on : s)); }
     // after the stream has been synchronised
     void collect(float *out, int n_slots) {
         for (auto &sp : spans) {
@@ -112,6 +112,8 @@ struct e2fm_index {
     int device = 0;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-buffer pipeline
+    uint64_t pipe_patterns = 1u << 18;                          // patterns per pipeline stage when the batch comes from the host
     HostImage img;              // header fields (the per-row vectors stay small: terminators, C, tables)
     DevIndex dix{};
     std::vector<void *> owned;  // device allocations that live as long as the index
@@ -119,6 +121,8 @@ struct e2fm_index {
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
     uint64_t batch_ctr[8] = {0};
+    double results_per_pattern = 2.0; // learned occurrence density: sizes the fast path's result store
+    double tasks_per_pattern = 2.0;   // learned row-task density: sizes the fast path's task buffer
     bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
     uint64_t chunk_patterns = 4u << 20;
     uint64_t window_tasks = 64u << 20;
@@ -350,6 +354,10 @@ struct Batch {
     uint32_t fixed_len;
     uint64_t n;
     uint64_t total_bytes;
+    // host-buffer pipeline (all null for device-resident batches)
+    const uint8_t *h_bytes = nullptr;     // patterns on the host: copied chunk by chunk on the H2D stream while earlier chunks search
+    const uint64_t *h_off = nullptr;      // their offsets (ragged batches)
+    uint64_t *h_counts = nullptr;         // optional: counts are copied back chunk by chunk on the D2H stream
 };
 
 void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, EventTimer &tm) {
@@ -364,7 +372,32 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
 
     uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ix->chunk_patterns, (1ull << 31) / k));
+    if (b.h_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, ix->pipe_patterns));
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1024, (uint64_t)((double)ix->window_tasks / ix->tasks_per_pattern)));
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
+    auto byte_at = [&](uint64_t i) -> uint64_t { return b.h_off ? b.h_off[i] : i * (uint64_t)b.fixed_len; };
+
+    // ---- host batches: every chunk's H2D copy is queued up front on the copy stream; the search of chunk c waits for its
+    // own event only, so copies of later chunks overlap the kernels of earlier ones
+    struct Ev { std::vector<cudaEvent_t> v; ~Ev() { for (auto e : v) cudaEventDestroy(e); } } h2d_ev, d2h_ev;
+    if (b.h_bytes) {
+        cudaEvent_t ready;
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        d2h_ev.v.push_back(ready);
+        CK(cudaEventRecord(ready, s));                       // the device buffers were allocated in order on s
+        CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
+        const int h = tm.begin(0, ix->h2d_stream);
+        for (uint64_t first = 0; first < b.n; first += chunk) {
+            const uint64_t last = std::min<uint64_t>(b.n, first + chunk);
+            const uint64_t lo = byte_at(first), hi = byte_at(last);
+            if (hi > lo) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b.d_bytes) + lo, b.h_bytes + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h2d_ev.v.push_back(e);
+            CK(cudaEventRecord(e, ix->h2d_stream));
+        }
+        tm.end(h, ix->h2d_stream);
+    }
     const uint64_t items_cap = chunk * k;
     DBuf<uint2> iv(items_cap, s);
     DBuf<uint64_t> task_off(items_cap + 1, s);
@@ -373,20 +406,111 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     DBuf<uint32_t> res_pat;
     DBuf<uint64_t> res_pos;
     uint64_t n_results = 0, total_tasks = 0;
+    unsigned long long redo_rank = 0, redo_sect = 0;
 
-    // ---- pre-pass: k-mer code at every pattern byte
+    // ---- pre-pass: k-mer code at every pattern byte (device batches: all at once; host batches: per chunk, as it arrives)
     DBuf<uint16_t> codes(b.total_bytes + 8, s);
-    {
+    const PatternView all{b.d_bytes, b.d_off, b.fixed_len, 0, (uint32_t)b.n};
+    if (!b.h_bytes) {
         const int h = tm.begin(4);
-        PatternView all{b.d_bytes, b.d_off, b.fixed_len, 0, (uint32_t)b.n};
-        launch_encode_patterns(dix, all, b.total_bytes, codes.p, ix->n_sm, s);
+        launch_encode_patterns(dix, all, 0, b.total_bytes, b.total_bytes, codes.p, ix->n_sm, s);
         launches++;
         tm.end(h);
     }
 
-    for (uint64_t first = 0; first < b.n; first += chunk) {
+    // counts of a finished chunk go back to the host on the D2H stream while the next chunk searches
+    auto stream_counts_back = [&](uint64_t first, uint32_t cnt) {
+        if (!b.h_counts) return;
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d2h_ev.v.push_back(e);
+        CK(cudaEventRecord(e, s));
+        CK(cudaStreamWaitEvent(ix->d2h_stream, e, 0));
+        CK(cudaMemcpyAsync(b.h_counts + first, counts.p + first, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h_stream));
+    };
+    auto grow_results = [&](uint64_t need) {
+        if (res_pos.n >= need) return;
+        const uint64_t cap = std::max<uint64_t>(need, res_pos.n + res_pos.n / 2);
+        DBuf<uint32_t> np(cap, s);
+        DBuf<uint64_t> nq(cap, s);
+        if (n_results) {
+            CK(cudaMemcpyAsync(np.p, res_pat.p, n_results * 4, cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpyAsync(nq.p, res_pos.p, n_results * 8, cudaMemcpyDeviceToDevice, s));
+        }
+        std::swap(res_pat.p, np.p); std::swap(res_pat.n, np.n); res_pat.s = s;
+        std::swap(res_pos.p, nq.p); std::swap(res_pos.n, nq.n); res_pos.s = s;
+    };
+
+    // ---- FAST PATH: every chunk is queued without a host round trip. Row tasks go into a buffer of `cap` entries
+    // (tasks-per-pattern learned from earlier batches); the task count stays on the device (expand_kernel -> walk/resolve).
+    // A chunk whose tasks do not fit writes nothing and is redone below through the windowed path.
+    const uint64_t n_chunks = b.n ? (b.n + chunk - 1) / chunk : 0;
+    const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(ix->window_tasks, (uint64_t)(ix->tasks_per_pattern * (double)chunk) + 1024));
+    DBuf<unsigned long long> chunk_tasks(std::max<uint64_t>(n_chunks, 1), s);
+    chunk_tasks.zero();
+    tasks.alloc(cap, s);
+    // result store: every row task yields at most one occurrence, but far fewer in practice (wildcard rows that do not
+    // match): size it from the learned density; the kernels flag an overflow instead of writing past the end
+    if (mode == E2FM_MODE_LOCATE)
+        grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
+    uint64_t chunk_no = 0;
+    for (uint64_t first = 0; first < b.n; first += chunk, chunk_no++) {
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
+        if (b.h_bytes) {
+            CK(cudaStreamWaitEvent(s, h2d_ev.v[chunk_no], 0));
+            const int h = tm.begin(4);
+            launch_encode_patterns(dix, all, byte_at(first), byte_at(first + cnt), b.total_bytes, codes.p, ix->n_sm, s);
+            launches++;
+            tm.end(h);
+        }
+        CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
+        int h = tm.begin(1);
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, counts.p, ix->d_stats};
+        launch_backward_search(sa, ix->n_sm, s);
+        launches++;
+        tm.end(h);
+        h = tm.begin(2);
+        launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
+        launch_expand(iv.p, task_off.p, cnt * k, 0, cap, tasks.p, chunk_tasks.p + chunk_no, s);
+        launches += 4;
+        tm.end(h);
+        CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
+        h = tm.begin(3);
+        WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)cap, chunk_tasks.p + chunk_no, counts.p, res_pat.p, res_pos.p, res_pos.n, ix->d_stats};
+        if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
+        else launch_walk(wa, ix->n_sm, s);
+        launches++;
+        tm.end(h);
+        stream_counts_back(first, cnt);
+    }
+    std::vector<unsigned long long> h_chunk_tasks(n_chunks, 0);
+    if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_tasks.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
+    read_stats(ix);
+    n_results = ix->h_stats[ST_RESULTS];
+    for (uint64_t c = 0; c < n_chunks; c++) total_tasks += h_chunk_tasks[c];
+    std::vector<char> redo(n_chunks, 0);
+    bool full_redo = false;
+    for (uint64_t c = 0; c < n_chunks; c++) redo[c] = h_chunk_tasks[c] > cap;
+    if (ix->h_stats[ST_RES_OVF]) {
+        // the result store was too small: start the whole batch over through the exact-size path
+        CK(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(b.n, 1) * 8, s));
+        CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
+        n_results = 0;
+        full_redo = true;
+        std::fill(redo.begin(), redo.end(), 1);
+    }
+
+    // ---- SLOW PATH for the chunks that overflowed: same kernels, task windows sized from the host
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        if (!redo[c]) continue;
+        const uint64_t first = c * chunk;
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
+        PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
+        // the fast path already added this chunk's directly counted intervals: start its counts over
+        CK(cudaMemsetAsync(counts.p + first, 0, (size_t)cnt * 8, s));
+        read_stats(ix);
+        const unsigned long long rank0 = ix->h_stats[ST_RANK], sect0 = ix->h_stats[ST_SECT_BS];
         CK(cudaMemsetAsync(ix->d_stats + ST_TASKS, 0, 8, s));
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
@@ -395,9 +519,12 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         launches++;
         tm.end(h);
         read_stats(ix);
-        const uint64_t n_tasks = ix->h_stats[ST_TASKS];
-        if (n_tasks == 0) continue;
-        total_tasks += n_tasks;
+        // the backward search ran twice for this chunk: keep its operations counted once
+        if (!full_redo) {
+            redo_rank += ix->h_stats[ST_RANK] - rank0;
+            redo_sect += ix->h_stats[ST_SECT_BS] - sect0;
+        }
+        const uint64_t n_tasks = h_chunk_tasks[c];
         h = tm.begin(2);
         launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
         launches += 3;
@@ -407,24 +534,13 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         for (uint64_t w0 = 0; w0 < n_tasks; w0 += win) {
             const uint64_t w1 = std::min(n_tasks, w0 + win);
             h = tm.begin(2);
-            launch_expand(iv.p, task_off.p, cnt * k, w0, w1, tasks.p, s);
+            launch_expand(iv.p, task_off.p, cnt * k, w0, w1, tasks.p, nullptr, s);
             launches++;
             tm.end(h);
-            if (mode == E2FM_MODE_LOCATE && res_pos.n < n_results + (w1 - w0)) {
-                // grow the result store: every row task yields at most one occurrence
-                const uint64_t cap = std::max<uint64_t>(n_results + (w1 - w0), res_pos.n + res_pos.n / 2);
-                DBuf<uint32_t> np(cap, s);
-                DBuf<uint64_t> nq(cap, s);
-                if (n_results) {
-                    CK(cudaMemcpyAsync(np.p, res_pat.p, n_results * 4, cudaMemcpyDeviceToDevice, s));
-                    CK(cudaMemcpyAsync(nq.p, res_pos.p, n_results * 8, cudaMemcpyDeviceToDevice, s));
-                }
-                std::swap(res_pat.p, np.p); std::swap(res_pat.n, np.n); res_pat.s = s;
-                std::swap(res_pos.p, nq.p); std::swap(res_pos.n, nq.n); res_pos.s = s;
-            }
+            if (mode == E2FM_MODE_LOCATE) grow_results(n_results + (w1 - w0));   // every row task yields at most one occurrence
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), counts.p, res_pat.p, res_pos.p, ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, res_pos.n, ix->d_stats};
             if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
             else launch_walk(wa, ix->n_sm, s);
             launches++;
@@ -432,6 +548,13 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             read_stats(ix);
             n_results = ix->h_stats[ST_RESULTS];
         }
+        stream_counts_back(first, cnt);
+    }
+    if (b.h_counts) CK(cudaStreamSynchronize(ix->d2h_stream));
+    // learn the task density for the next batch's capacity (x1.5 head room)
+    if (b.n) {
+        ix->tasks_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)total_tasks / (double)b.n));
+        if (mode == E2FM_MODE_LOCATE) ix->results_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)n_results / (double)b.n));
     }
 
     // ---- result pipeline (locate): CSR offsets, scatter, segmented sort + de-duplication, sequence mapping
@@ -490,18 +613,18 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     read_stats(ix);
-    ix->batch_ctr[0] = ix->h_stats[ST_RANK];
+    ix->batch_ctr[0] = ix->h_stats[ST_RANK] - redo_rank;
     ix->batch_ctr[1] = ix->h_stats[ST_LF];
     ix->batch_ctr[2] = ix->h_stats[ST_MARK];
     ix->batch_ctr[3] = total_tasks;
-    ix->batch_ctr[4] = ix->h_stats[ST_SECT_BS];
+    ix->batch_ctr[4] = ix->h_stats[ST_SECT_BS] - redo_sect;
     ix->batch_ctr[5] = launches;
     ix->batch_ctr[6] = n_results;
     ix->batch_ctr[7] = ix->h_stats[ST_GATHER];
 }
 
 int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
-                  bool on_device, int mode, e2fm_result **out) {
+                  bool on_device, int mode, e2fm_result **out, uint64_t *counts_out = nullptr) {
     if (!ix || !out || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
     if (n && !bytes && total_bytes) return fail(E2FM_ERR_ARG, "pattern bytes missing");
     if (n >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 patterns in one batch");
@@ -523,18 +646,21 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
         DBuf<uint64_t> d_off;
         Batch b{bytes, offsets, fixed_len, n, total_bytes};
         if (!on_device) {
-            const int h = tm.begin(0);
+            // the pattern bytes travel chunk by chunk inside run_batch (H2D stream); only the offsets go ahead of them
             d_bytes.alloc(total_bytes + 16, s);
-            if (total_bytes) CK(cudaMemcpyAsync(d_bytes.p, bytes, total_bytes, cudaMemcpyHostToDevice, s));
             b.d_bytes = d_bytes.p;
+            b.h_bytes = bytes;
+            b.h_off = offsets;
+            b.h_counts = counts_out;
             if (offsets) {
                 d_off.alloc(n + 1, s);
                 CK(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
                 b.d_off = d_off.p;
             }
-            tm.end(h);
+            if (n == 0 || total_bytes == 0) b.h_bytes = nullptr;
         }
         run_batch(ix, b, mode, res, tm);
+        if (on_device && counts_out && n) CK(cudaMemcpyAsync(counts_out, res->d_counts, n * 8, cudaMemcpyDeviceToHost, s));
         tm.end(whole);
         CK(cudaStreamSynchronize(s));
         tm.collect(ix->batch_ms, 8);
@@ -637,6 +763,8 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
             if (getenv("E2FM_VERBOSE")) fprintf(stderr, "[e2fm] L2 fetch granularity %zu B\n", gran);
         }
         CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ix->h2d_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ix->d2h_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = ~0ull;   // keep freed blocks in the pool: batches reuse their work buffers
@@ -666,6 +794,8 @@ void e2fm_index_close(e2fm_index *ix) {
     for (void *p : ix->owned) cudaFree(p);
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->h_stats) cudaFreeHost(ix->h_stats);
+    if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);
+    if (ix->d2h_stream) cudaStreamDestroy(ix->d2h_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     cudaGetLastError();
     delete ix;
@@ -717,6 +847,11 @@ int e2fm_search_batch(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offs
 }
 int e2fm_search_batch_fixed(e2fm_index *ix, const uint8_t *bytes, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
     return search_common(ix, bytes, nullptr, length, n, n * length, false, mode, out);
+}
+int e2fm_search_batch_stream(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint64_t n, uint32_t length, int mode,
+                             uint64_t *counts_out, e2fm_result **out) {
+    if (offsets) return search_common(ix, bytes, offsets, 0, n, n ? offsets[n] : 0, false, mode, out, counts_out);
+    return search_common(ix, bytes, nullptr, length, n, n * length, false, mode, out, counts_out);
 }
 int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n, uint64_t total_bytes, int mode,
                              e2fm_result **out) {
@@ -793,6 +928,7 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
     switch (option) {
         case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (4u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
+        case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");
             ix->use_dense = value != 0;

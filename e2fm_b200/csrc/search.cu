@@ -87,7 +87,7 @@ static constexpr uint32_t ENC_SMEM_KMERS = 20480;   // k-mer table entries kept 
 
 // KT = compile-time super-alphabet order, 1..8 (0 = generic, any k, slower)
 template <int KT>
-__global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t n_bytes, uint16_t *__restrict__ codes) {
+__global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t j_begin, uint64_t n_bytes, uint16_t *__restrict__ codes) {
     extern __shared__ uint16_t enc_smem[];
     uint8_t *sym_s = reinterpret_cast<uint8_t *>(enc_smem);            // [256]
     uint16_t *kmer_s = enc_smem + 128;                                  // [sigma_k] when it fits
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
     const bool aligned = (reinterpret_cast<uintptr_t>(pv.bytes) & 7) == 0;
     // persistent blocks: the tables above are filled once per CTA, not once per 2 KB of patterns
-    for (uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ENC_PER; j0 < n_bytes;
+    for (uint64_t j0 = j_begin + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * ENC_PER; j0 < n_bytes;
          j0 += (uint64_t)gridDim.x * blockDim.x * ENC_PER) {
         // symbols of bytes j0 .. j0+15 (0xFF = not in the index's alphabet)
         uint32_t sy[16];
@@ -167,17 +167,21 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
     }
 }
 
-void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t n_bytes, uint16_t *codes, int n_sm, cudaStream_t s) {
-    if (n_bytes == 0) return;
-    const uint64_t threads = (n_bytes + ENC_PER - 1) / ENC_PER;
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t j_begin, uint64_t j_end, uint64_t n_bytes, uint16_t *codes,
+                            int n_sm, cudaStream_t s) {
+    j_begin &= ~(uint64_t)(ENC_PER - 1);    // threads own aligned groups of 8 bytes; re-encoding a few earlier bytes is harmless
+    if (j_end > n_bytes) j_end = n_bytes;
+    if (j_end <= j_begin) return;
+    const uint64_t threads = (j_end - j_begin + ENC_PER - 1) / ENC_PER;
+    n_bytes = j_end;   // a chunk ends at a pattern end: nothing beyond it is read (later chunks may not be resident yet)
     const size_t smem = 256 + (ix.sigma_k <= ENC_SMEM_KMERS ? (size_t)ix.sigma_k * 2 : 0);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((threads + 255) / 256, (uint64_t)n_sm * 8);
     switch (ix.k) {
-        case 2: encode_patterns_kernel<2><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
-        case 3: encode_patterns_kernel<3><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
-        case 4: encode_patterns_kernel<4><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
-        case 5: encode_patterns_kernel<5><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
-        default: encode_patterns_kernel<0><<<blocks, 256, smem, s>>>(ix, pv, n_bytes, codes); break;
+        case 2: encode_patterns_kernel<2><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
+        case 3: encode_patterns_kernel<3><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
+        case 4: encode_patterns_kernel<4><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
+        case 5: encode_patterns_kernel<5><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
+        default: encode_patterns_kernel<0><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
     }
 }
 
@@ -434,9 +438,16 @@ void launch_scan_u64(const unsigned long long *in, uint64_t *off, uint64_t n, ui
 // one (pattern, shift) interval per lane; rows [sp, sp+len) become row tasks at off[item] - w0 (clipped to the
 // task window [w0, w1)). Long intervals are written by the whole warp.
 __global__ void __launch_bounds__(256) expand_kernel(const uint2 *__restrict__ iv, const uint64_t *__restrict__ off, uint32_t n_items,
-                                                      uint64_t w0, uint64_t w1, uint2 *__restrict__ tasks) {
+                                                      uint64_t w0, uint64_t w1, uint2 *__restrict__ tasks, unsigned long long *n_tasks_out) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_tasks_out) {
+        // fast path (no host round trip): the window is [0, capacity); publish the chunk's task count and write nothing
+        // when it does not fit — the host then redoes the chunk through the windowed path
+        const uint64_t total = off[n_items];
+        if (item == 0) *n_tasks_out = total;
+        if (total > w1) return;
+    }
     uint32_t row0 = 0, len = 0;
     uint64_t dst = 0;
     if (item < n_items) {
@@ -462,9 +473,10 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint2 *__restrict__ i
     }
 }
 
-void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks, cudaStream_t s) {
+void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks,
+                   unsigned long long *n_tasks_out, cudaStream_t s) {
     if (n_items == 0 || w1 <= w0) return;
-    expand_kernel<<<(n_items + 255) / 256, 256, 0, s>>>(iv, off, n_items, w0, w1, tasks);
+    expand_kernel<<<(n_items + 255) / 256, 256, 0, s>>>(iv, off, n_items, w0, w1, tasks, n_tasks_out);
 }
 
 // ---------------------------------------------------------------- K4: row walks
@@ -486,6 +498,10 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
     bool exhausted = false, active = false;
     uint32_t phase = 0, row = 0, t = 0, item = 0, tp = 0;
     uint32_t n_lf = 0, n_mark = 0, n_gather = 0;
+    if (a.n_tasks_dev) {                                   // fast path: the count lives on the device (expand_kernel)
+        const unsigned long long nt = *a.n_tasks_dev;
+        a.n_tasks = nt > a.n_tasks ? 0u : (uint32_t)nt;   // a.n_tasks holds the capacity; an overflowing chunk is redone by the host
+    }
 
     for (;;) {
         if (wnext >= wend && !exhausted) {
@@ -597,8 +613,10 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
                 base = __shfl_sync(FULL, base, leader);
                 if (emit) {
                     const unsigned long long slot = base + __popc(em & lt);
-                    a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
-                    a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;   // EFMIndex.cpp:2312-2319
+                    if (slot < a.res_cap) {
+                        a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
+                        a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;   // EFMIndex.cpp:2312-2319
+                    } else atomicAdd(a.stats + ST_RES_OVF, 1ull);
                 }
             }
         }
@@ -632,7 +650,7 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkArgs a) {
 
 void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
     if (a.n_tasks == 0) return;
-    uint64_t blocks = ((uint64_t)a.n_tasks + 255) / 256;
+    uint64_t blocks = a.n_tasks_dev ? ~0ull : ((uint64_t)a.n_tasks + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 8;
     if (blocks > cap) blocks = cap;
     if (a.ix.k == 4) walk_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
@@ -651,6 +669,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
     uint32_t n_sa = 0, n_text = 0, n_rec = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
+    if (a.n_tasks_dev) {
+        const unsigned long long nt = *a.n_tasks_dev;
+        a.n_tasks = nt > a.n_tasks ? 0u : (uint32_t)nt;
+    }
     // whole warps iterate together so that the result compaction below stays warp-uniform
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < a.n_tasks; base += stride) {
         const uint32_t idx = base + lane;
@@ -712,8 +734,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
                 b = __shfl_sync(FULL, b, leader);
                 if (emit) {
                     const unsigned long long slot = b + __popc(em & lt);
-                    a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
-                    a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;
+                    if (slot < a.res_cap) {
+                        a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
+                        a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;
+                    } else atomicAdd(a.stats + ST_RES_OVF, 1ull);
                 }
             }
         }
@@ -724,7 +748,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
 
 void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s) {
     if (a.n_tasks == 0) return;
-    uint64_t blocks = ((uint64_t)a.n_tasks + 255) / 256;
+    uint64_t blocks = a.n_tasks_dev ? ~0ull : ((uint64_t)a.n_tasks + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 32;
     if (blocks > cap) blocks = cap;
     if (a.ix.k == 4) resolve_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);

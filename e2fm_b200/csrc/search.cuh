@@ -30,7 +30,8 @@ enum {
     ST_QUEUE = 7,    // work-queue cursor of the running kernel
     ST_SECT_BS = 8,  // distinct 32-byte rank sectors gathered by the backward-search kernel
     ST_GATHER = 9,   // dependent 8-byte gathers issued by the walk kernel
-    ST_N = 10
+    ST_RES_OVF = 10, // occurrences that did not fit the result store (the host then redoes the batch with exact sizes)
+    ST_N = 11
 };
 
 struct SearchArgs {
@@ -48,19 +49,25 @@ struct WalkArgs {
     PatternView pv;
     int mode;
     const uint2 *tasks;              // {row, item} with item = localPattern*k + shift
-    uint32_t n_tasks;
+    uint32_t n_tasks;                // number of tasks, or the capacity of `tasks` when n_tasks_dev is set
+    const unsigned long long *n_tasks_dev;   // fast path: device-resident task count written by expand_kernel (nullptr: use n_tasks)
     unsigned long long *counts;
     uint32_t *res_pat;               // batch pattern index of each located occurrence
     uint64_t *res_pos;               // its global text position
+    unsigned long long res_cap;      // capacity of the two arrays above
     unsigned long long *stats;
 };
 
-// codes[j] for the n_bytes pattern bytes of the batch (pv describes all its patterns)
-void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t n_bytes, uint16_t *codes, int n_sm, cudaStream_t s);
+// codes[j] for the pattern bytes [j_begin, j_end) of a batch of n_bytes bytes (pv describes all its patterns; j_end is a pattern end)
+void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t j_begin, uint64_t j_end, uint64_t n_bytes, uint16_t *codes,
+                            int n_sm, cudaStream_t s);
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
 // exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);
-void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks, cudaStream_t s);
+// n_tasks_out != nullptr: fast path — window [0, w1) is the capacity, *n_tasks_out receives the chunk's task count, nothing is
+// written when it exceeds the capacity
+void launch_expand(const uint2 *iv, const uint64_t *off, uint32_t n_items, uint64_t w0, uint64_t w1, uint2 *tasks,
+                   unsigned long long *n_tasks_out, cudaStream_t s);
 void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s);
 // the same row tasks answered from the dense sa[] / text[] tables (requires a.ix.sa != nullptr)
 void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s);

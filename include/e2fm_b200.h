@@ -77,6 +77,11 @@ int e2fm_search_batch(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offs
 /* Fixed-length batch: pattern i = bytes[i*length .. (i+1)*length) (no offsets array to ship). */
 int e2fm_search_batch_fixed(e2fm_index *ix, const uint8_t *bytes, uint64_t n, uint32_t length, int mode,
                             e2fm_result **out);
+/* The pipelined form of the two calls above: offsets == NULL means fixed-length patterns of `length` bytes. When
+ * counts_out (host, n entries, ideally from e2fm_host_alloc) is given, the counts of every finished chunk are copied
+ * back while later chunks are still being copied in and searched, so that H2D, kernels and D2H overlap. */
+int e2fm_search_batch_stream(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint64_t n, uint32_t length,
+                             int mode, uint64_t *counts_out, e2fm_result **out);
 /* Same two with DEVICE-resident pattern buffers (no host<->device traffic). */
 int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n,
                              uint64_t total_bytes, int mode, e2fm_result **out);
@@ -115,6 +120,7 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
+#define E2FM_OPT_PIPE 5          /* patterns per pipeline stage of a host-buffer batch (0 = default 2^18) */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).

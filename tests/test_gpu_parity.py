@@ -201,6 +201,35 @@ def test_fixed_length_entry_point_and_pinned_buffers(opened, golden):
     pin.free()
 
 
+@pytest.mark.parametrize("pipe", [3, 64, 0])
+def test_pipelined_host_batches(opened, golden, pipe):
+    """host batches are copied in and searched chunk by chunk (H2D / kernels / D2H of counts overlap): same answers
+    for any pipeline stage size, ragged or fixed-length"""
+    dev, orc = opened["col3_k4"]
+    g = golden["col3_k4"]
+    dev.set_option(capi.OPT_PIPE, pipe)
+    try:
+        check_against_res(dev, g["patterns"], g["res"], True)          # ragged, through e2fm_search_batch
+        pats = [p for p in g["patterns"] if len(p) == 13]
+        arr = np.frombuffer(b"".join(pats), dtype=np.uint8).reshape(len(pats), 13).copy()
+        for locate in (False, True):
+            pin = capi.PinnedArray(len(pats), np.uint64)
+            pin.array[:] = 12345
+            r = dev.search_stream(arr, locate, pin.array)
+            out = r.fetch()
+            assert np.array_equal(pin.array, out["counts"])
+            for i, p in enumerate(pats):
+                cnt, pos = orc.search(p, True)
+                assert int(pin.array[i]) == cnt
+                if locate:
+                    a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+                    assert np.array_equal(out["positions"][a:b], pos)
+            r.free()
+            pin.free()
+    finally:
+        dev.set_option(capi.OPT_PIPE, 0)
+
+
 def test_error_behaviour(gpu, golden, key64):
     idx = golden["col3_k4"]["index"]
     with pytest.raises(capi.E2FMError) as e:       # bad magic: the reference's message (EFMIndex.cpp:1155)
