@@ -276,6 +276,8 @@ def gpu_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     def l2_flush():
+        if os.environ.get("E2FM_BENCH_NOFLUSH"):
+            return
         flush.add_(1)
         torch.cuda.synchronize()
 
@@ -319,7 +321,8 @@ def gpu_arm(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if not os.environ.get("E2FM_BENCH_NOSAMPLER"):
+        sampler.start()
     wall0 = time.perf_counter()
     dev_ms, bs_ms, walk_ms, exp_ms, res_ms, enc_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
     ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0}

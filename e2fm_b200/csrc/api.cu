@@ -73,30 +73,51 @@ struct DBuf {
     ~DBuf() { release(); }
 };
 
+// Events are expensive to create on the launch path: the index owns a pool that grows on demand and is reused by every batch.
+struct EventPool {
+    std::vector<cudaEvent_t> timed, untimed;
+    size_t used_timed = 0, used_untimed = 0;
+    cudaEvent_t get(bool timing) {
+        std::vector<cudaEvent_t> &v = timing ? timed : untimed;
+        size_t &u = timing ? used_timed : used_untimed;
+        if (u == v.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+            v.push_back(e);
+        }
+        return v[u++];
+    }
+    void reset() { used_timed = used_untimed = 0; }
+    void destroy() {
+        for (auto e : timed) cudaEventDestroy(e);
+        for (auto e : untimed) cudaEventDestroy(e);
+        timed.clear();
+        untimed.clear();
+    }
+};
+
 struct EventTimer {
     struct Span { cudaEvent_t a, b; int slot; };
     std::vector<Span> spans;
     cudaStream_t s;
-    explicit EventTimer(cudaStream_t st) : s(st) {}
+    EventPool *pool;
+    EventTimer(cudaStream_t st, EventPool *p) : s(st), pool(p) { spans.reserve(64); }
     int begin(int slot, cudaStream_t on = nullptr) {
         Span sp;
         sp.slot = slot;
-        CK(cudaEventCreate(&sp.a));
-        CK(cudaEventCreate(&sp.b));
+        sp.a = pool->get(true);
+        sp.b = pool->get(true);
         CK(cudaEventRecord(sp.a, on ? on : s));
         spans.push_back(sp);
         return (int)spans.size() - 1;
     }
     void end(int h, cudaStream_t on = nullptr) { CK(cudaEventRecord(spans[h].b, on ? on : s)); }
-    // after the stream has been synchronised
+    // after the streams have been synchronised
     void collect(float *out, int n_slots) {
         for (auto &sp : spans) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.slot < n_slots) out[sp.slot] += ms;
         }
-    }
-    ~EventTimer() {
-        for (auto &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     }
 };
 
@@ -128,6 +149,10 @@ struct e2fm_index {
     uint64_t window_tasks = 64u << 20;
     unsigned long long *d_stats = nullptr;
     unsigned long long *h_stats = nullptr;   // pinned
+    EventPool events;
+    // work buffers of the search path: grow-only, reused by every batch (allocation calls cost more than the kernels of a
+    // 1M-pattern batch)
+    struct Slot { void *p = nullptr; size_t bytes = 0; } ws[16];
 };
 
 struct e2fm_result {
@@ -158,6 +183,41 @@ T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
     return p;
 }
 
+// view of a workspace slot with the DBuf interface; contents are preserved across a growth only when asked
+enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SURV, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_IVL, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
+       WS_CURSOR, WS_BIG_LIST };
+template <class T>
+struct WsBuf {
+    e2fm_index *ix;
+    int slot;
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s;
+    WsBuf(e2fm_index *ix_, int slot_, cudaStream_t st) : ix(ix_), slot(slot_), s(st) {
+        p = (T *)ix->ws[slot].p;
+        n = ix->ws[slot].bytes / sizeof(T);
+    }
+    WsBuf(e2fm_index *ix_, int slot_, size_t count, cudaStream_t st) : WsBuf(ix_, slot_, st) { alloc(count); }
+    void alloc(size_t count, size_t keep_elems = 0) {
+        auto &sl = ix->ws[slot];
+        if (count * sizeof(T) > sl.bytes) {
+            const size_t want = count * sizeof(T) + count * sizeof(T) / 4 + 256;
+            void *q = nullptr;
+            CK(cudaMalloc(&q, want));
+            if (keep_elems && sl.p) CK(cudaMemcpyAsync(q, sl.p, keep_elems * sizeof(T), cudaMemcpyDeviceToDevice, s));
+            if (sl.p) {
+                CK(cudaStreamSynchronize(s));
+                CK(cudaFree(sl.p));          // waits for the device: nothing in flight still uses the old block
+            }
+            sl.p = q;
+            sl.bytes = want;
+        }
+        p = (T *)sl.p;
+        n = sl.bytes / sizeof(T);
+    }
+    void zero(size_t count) { if (count) CK(cudaMemsetAsync(p, 0, count * sizeof(T), s)); }
+};
+
 void read_stats(e2fm_index *ix) {
     CK(cudaMemcpyAsync(ix->h_stats, ix->d_stats, ST_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
@@ -181,7 +241,8 @@ void check_build_status(e2fm_index *ix, const uint32_t *d_status, const char *st
 void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     HostImage &img = ix->img;
     cudaStream_t s = ix->stream;
-    EventTimer tm(s);
+    ix->events.reset();
+    EventTimer tm(s, &ix->events);
 
     // ---- raw image + start tables to the device (temporary: freed once every bucket is decoded)
     int h = tm.begin(1);
@@ -301,7 +362,7 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
 
     // ---- dense locate tables (6 bytes per row) when HBM allows: EFMIndex::getRowPosition walked once for every row
     uint32_t *sa = nullptr;
-    uint16_t *text = nullptr;
+    uint16_t *text = nullptr, *bwt16 = nullptr;
     if (mrn > 0 && !(getenv("E2FM_DENSE") && atoi(getenv("E2FM_DENSE")) == 0)) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
@@ -310,6 +371,8 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
             sa = dev_keep<uint32_t>(ix, img.n);
             text = dev_keep<uint16_t>(ix, img.n);
             launch_dense_build(rec, mark_tab, mrn, img.rate, img.n, sa, text, d_status.p, s);
+            bwt16 = dev_keep<uint16_t>(ix, img.n + 16);   // firstcheck_kernel reads aligned 16-byte groups
+            launch_bwt16_build(rec, img.n, bwt16, s);
             tm.end(h);
             check_build_status(ix, d_status.p, "dense table build");
             ix->use_dense = true;
@@ -338,12 +401,21 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     d.mark_tab = mark_tab;
     d.sa = sa;
     d.text = text;
+    d.bwt16 = bwt16;
+    d.pair_tab = nullptr;
     d.C = d_C;
     d.compact_of_natural = dev_keep_copy<uint16_t>(ix, img.compact_of_natural.data(), img.compact_of_natural.size());
     d.natural_of_compact = dev_keep_copy<uint32_t>(ix, img.natural_of_compact.data(), img.natural_of_compact.size());
     d.sym_index = dev_keep_copy<uint8_t>(ix, sym_index, 256);
     d.terminators = dev_keep_copy<int64_t>(ix, img.terminators.data(), img.terminators.size());
+    // start-interval table over pairs of super-characters (needs the finished DevIndex: it ranks through the sectors)
+    if ((uint64_t)img.A * img.A <= (4u << 20)) {
+        uint2 *pt = dev_keep<uint2>(ix, (size_t)img.A * img.A);
+        launch_pair_build(d, pt, s);
+        d.pair_tab = pt;
+    }
     CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
     tm.collect(ix->load_ms, 7);
     for (int i = 1; i < 7; i++) ix->load_ms[7] += ix->load_ms[i];
 }
@@ -379,11 +451,9 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
 
     // ---- host batches: every chunk's H2D copy is queued up front on the copy stream; the search of chunk c waits for its
     // own event only, so copies of later chunks overlap the kernels of earlier ones
-    struct Ev { std::vector<cudaEvent_t> v; ~Ev() { for (auto e : v) cudaEventDestroy(e); } } h2d_ev, d2h_ev;
+    std::vector<cudaEvent_t> h2d_ev;
     if (b.h_bytes) {
-        cudaEvent_t ready;
-        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        d2h_ev.v.push_back(ready);
+        cudaEvent_t ready = ix->events.get(false);
         CK(cudaEventRecord(ready, s));                       // the device buffers were allocated in order on s
         CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
         const int h = tm.begin(0, ix->h2d_stream);
@@ -391,25 +461,25 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             const uint64_t last = std::min<uint64_t>(b.n, first + chunk);
             const uint64_t lo = byte_at(first), hi = byte_at(last);
             if (hi > lo) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b.d_bytes) + lo, b.h_bytes + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            h2d_ev.v.push_back(e);
+            cudaEvent_t e = ix->events.get(false);
+            h2d_ev.push_back(e);
             CK(cudaEventRecord(e, ix->h2d_stream));
         }
         tm.end(h, ix->h2d_stream);
     }
     const uint64_t items_cap = chunk * k;
-    DBuf<uint2> iv(items_cap, s);
-    DBuf<uint64_t> task_off(items_cap + 1, s);
-    DBuf<uint64_t> scratch(scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
-    DBuf<uint2> tasks;
-    DBuf<uint32_t> res_pat;
-    DBuf<uint64_t> res_pos;
+    WsBuf<uint2> iv(ix, WS_IV, items_cap, s);
+    WsBuf<uint2> ivw(ix, WS_SURV, s);
+    WsBuf<uint64_t> task_off(ix, WS_TASK_OFF, items_cap + 1, s);
+    WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
+    WsBuf<uint2> tasks(ix, WS_TASKS, s);
+    WsBuf<uint32_t> res_pat(ix, WS_RES_PAT, s);
+    WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s);
     uint64_t n_results = 0, total_tasks = 0;
     unsigned long long redo_rank = 0, redo_sect = 0;
 
     // ---- pre-pass: k-mer code at every pattern byte (device batches: all at once; host batches: per chunk, as it arrives)
-    DBuf<uint16_t> codes(b.total_bytes + 8, s);
+    WsBuf<uint16_t> codes(ix, WS_CODES, b.total_bytes + 8, s);
     const PatternView all{b.d_bytes, b.d_off, b.fixed_len, 0, (uint32_t)b.n};
     if (!b.h_bytes) {
         const int h = tm.begin(4);
@@ -421,118 +491,124 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // counts of a finished chunk go back to the host on the D2H stream while the next chunk searches
     auto stream_counts_back = [&](uint64_t first, uint32_t cnt) {
         if (!b.h_counts) return;
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        d2h_ev.v.push_back(e);
+        cudaEvent_t e = ix->events.get(false);
         CK(cudaEventRecord(e, s));
         CK(cudaStreamWaitEvent(ix->d2h_stream, e, 0));
         CK(cudaMemcpyAsync(b.h_counts + first, counts.p + first, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h_stream));
     };
     auto grow_results = [&](uint64_t need) {
-        if (res_pos.n >= need) return;
+        if (res_pos.n >= need && res_pat.n >= need) return;
         const uint64_t cap = std::max<uint64_t>(need, res_pos.n + res_pos.n / 2);
-        DBuf<uint32_t> np(cap, s);
-        DBuf<uint64_t> nq(cap, s);
-        if (n_results) {
-            CK(cudaMemcpyAsync(np.p, res_pat.p, n_results * 4, cudaMemcpyDeviceToDevice, s));
-            CK(cudaMemcpyAsync(nq.p, res_pos.p, n_results * 8, cudaMemcpyDeviceToDevice, s));
-        }
-        std::swap(res_pat.p, np.p); std::swap(res_pat.n, np.n); res_pat.s = s;
-        std::swap(res_pos.p, nq.p); std::swap(res_pos.n, nq.n); res_pos.s = s;
+        res_pat.alloc(cap, n_results);
+        res_pos.alloc(cap, n_results);
     };
 
-    // ---- FAST PATH: every chunk is queued without a host round trip. Row tasks go into a buffer of `cap` entries
-    // (tasks-per-pattern learned from earlier batches); the task count stays on the device (expand_kernel -> walk/resolve).
-    // A chunk whose tasks do not fit writes nothing and is redone below through the windowed path.
+    // ---- FAST PATH (dense tables): every chunk is queued without a host round trip. The backward search hands its
+    // intervals straight on as row tasks / wildcard intervals, the task count stays on the device. Row tasks go into a
+    // buffer of `cap` entries (density learned from earlier batches); a chunk whose tasks do not fit is redone below.
+    const bool fast = ix->use_dense && dix.sa && dix.bwt16;
     const uint64_t n_chunks = b.n ? (b.n + chunk - 1) / chunk : 0;
     const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(ix->window_tasks, (uint64_t)(ix->tasks_per_pattern * (double)chunk) + 1024));
-    DBuf<unsigned long long> chunk_tasks(std::max<uint64_t>(n_chunks, 1), s);
-    chunk_tasks.zero();
-    tasks.alloc(cap, s);
-    // result store: every row task yields at most one occurrence, but far fewer in practice (wildcard rows that do not
-    // match): size it from the learned density; the kernels flag an overflow instead of writing past the end
-    if (mode == E2FM_MODE_LOCATE)
-        grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
-    uint64_t chunk_no = 0;
-    for (uint64_t first = 0; first < b.n; first += chunk, chunk_no++) {
-        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
-        PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
-        if (b.h_bytes) {
-            CK(cudaStreamWaitEvent(s, h2d_ev.v[chunk_no], 0));
-            const int h = tm.begin(4);
-            launch_encode_patterns(dix, all, byte_at(first), byte_at(first + cnt), b.total_bytes, codes.p, ix->n_sm, s);
+    WsBuf<unsigned long long> chunk_ctr(ix, WS_CHUNK_CTR, std::max<uint64_t>(n_chunks, 1), s);   // row tasks of every chunk
+    chunk_ctr.zero(std::max<uint64_t>(n_chunks, 1));
+
+    std::vector<unsigned long long> h_chunk_tasks(n_chunks, 0);
+    std::vector<char> redo(n_chunks, fast ? 0 : 1);
+    bool full_redo = false;
+    auto encode_chunk = [&](uint64_t first, uint32_t cnt, uint64_t chunk_no) {
+        if (!b.h_bytes) return;
+        CK(cudaStreamWaitEvent(s, h2d_ev[chunk_no], 0));
+        const int h = tm.begin(4);
+        launch_encode_patterns(dix, all, byte_at(first), byte_at(first + cnt), b.total_bytes, codes.p, ix->n_sm, s);
+        launches++;
+        tm.end(h);
+    };
+    if (fast) {
+        tasks.alloc(cap);
+        ivw.alloc(items_cap);
+        // result store: every row task yields at most one occurrence; sized from the learned density, the kernels flag an
+        // overflow instead of writing past the end
+        if (mode == E2FM_MODE_LOCATE)
+            grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
+        uint64_t chunk_no = 0;
+        for (uint64_t first = 0; first < b.n; first += chunk, chunk_no++) {
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
+            PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
+            encode_chunk(first, cnt, chunk_no);
+            CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
+            CK(cudaMemsetAsync(ix->d_stats + ST_ANY_LONG, 0, 8, s));
+            int h = tm.begin(1);
+            SearchArgs sa{dix, pv, mode, codes.p, iv.p, ivw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
+            launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
+            h = tm.begin(2);
+            launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
+            launch_expand(iv.p, task_off.p, cnt * k, 0, cap, tasks.p, chunk_ctr.p + chunk_no, s);   // sets the chunk's task count
+            launch_firstcheck(sa, ix->n_sm, s);                                                      // appends the wildcard survivors
+            launches += 5;
+            tm.end(h);
+            h = tm.begin(3);
+            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
+            launch_resolve(wa, ix->n_sm, s);
+            launches++;
+            tm.end(h);
+            stream_counts_back(first, cnt);
         }
-        CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
-        int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, counts.p, ix->d_stats};
-        launch_backward_search(sa, ix->n_sm, s);
-        launches++;
-        tm.end(h);
-        h = tm.begin(2);
-        launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
-        launch_expand(iv.p, task_off.p, cnt * k, 0, cap, tasks.p, chunk_tasks.p + chunk_no, s);
-        launches += 4;
-        tm.end(h);
-        CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
-        h = tm.begin(3);
-        WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)cap, chunk_tasks.p + chunk_no, counts.p, res_pat.p, res_pos.p, res_pos.n, ix->d_stats};
-        if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
-        else launch_walk(wa, ix->n_sm, s);
-        launches++;
-        tm.end(h);
-        stream_counts_back(first, cnt);
-    }
-    std::vector<unsigned long long> h_chunk_tasks(n_chunks, 0);
-    if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_tasks.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
-    read_stats(ix);
-    n_results = ix->h_stats[ST_RESULTS];
-    for (uint64_t c = 0; c < n_chunks; c++) total_tasks += h_chunk_tasks[c];
-    std::vector<char> redo(n_chunks, 0);
-    bool full_redo = false;
-    for (uint64_t c = 0; c < n_chunks; c++) redo[c] = h_chunk_tasks[c] > cap;
-    if (ix->h_stats[ST_RES_OVF]) {
-        // the result store was too small: start the whole batch over through the exact-size path
-        CK(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(b.n, 1) * 8, s));
-        CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
-        n_results = 0;
-        full_redo = true;
-        std::fill(redo.begin(), redo.end(), 1);
+        if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_ctr.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
+        read_stats(ix);
+        n_results = ix->h_stats[ST_RESULTS];
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            total_tasks += h_chunk_tasks[c];
+            redo[c] = h_chunk_tasks[c] > cap;
+        }
+        if (ix->h_stats[ST_RES_OVF]) {
+            // the result store was too small: start the whole batch over through the exact-size path
+            CK(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(b.n, 1) * 8, s));
+            CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
+            n_results = 0;
+            full_redo = true;
+            std::fill(redo.begin(), redo.end(), 1);
+        }
     }
 
-    // ---- SLOW PATH for the chunks that overflowed: same kernels, task windows sized from the host
+    // ---- WINDOWED PATH: per-query walks (dense tables off), and the chunks of the fast path that overflowed. One interval
+    // per (pattern, shift), scanned and expanded into row-task windows sized from the host.
     for (uint64_t c = 0; c < n_chunks; c++) {
         if (!redo[c]) continue;
         const uint64_t first = c * chunk;
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
-        // the fast path already added this chunk's directly counted intervals: start its counts over
-        CK(cudaMemsetAsync(counts.p + first, 0, (size_t)cnt * 8, s));
-        read_stats(ix);
-        const unsigned long long rank0 = ix->h_stats[ST_RANK], sect0 = ix->h_stats[ST_SECT_BS];
-        CK(cudaMemsetAsync(ix->d_stats + ST_TASKS, 0, 8, s));
+        unsigned long long rank0 = 0, sect0 = 0;
+        if (fast) {
+            // the fast path already added this chunk's directly counted intervals: start its counts over
+            CK(cudaMemsetAsync(counts.p + first, 0, (size_t)cnt * 8, s));
+            read_stats(ix);
+            rank0 = ix->h_stats[ST_RANK];
+            sect0 = ix->h_stats[ST_SECT_BS];
+        } else encode_chunk(first, cnt, c);
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, nullptr, nullptr, nullptr, 0, counts.p, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);
-        read_stats(ix);
-        // the backward search ran twice for this chunk: keep its operations counted once
-        if (!full_redo) {
-            redo_rank += ix->h_stats[ST_RANK] - rank0;
-            redo_sect += ix->h_stats[ST_SECT_BS] - sect0;
-        }
-        const uint64_t n_tasks = h_chunk_tasks[c];
         h = tm.begin(2);
         launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
         launches += 3;
         tm.end(h);
+        unsigned long long n_tasks = 0;
+        CK(cudaMemcpyAsync(&n_tasks, task_off.p + (size_t)cnt * k, 8, cudaMemcpyDeviceToHost, s));
+        read_stats(ix);
+        if (fast && !full_redo) {   // the backward search ran twice for this chunk: keep its operations counted once
+            redo_rank += ix->h_stats[ST_RANK] - rank0;
+            redo_sect += ix->h_stats[ST_SECT_BS] - sect0;
+        }
+        if (!fast) total_tasks += n_tasks;
         const uint64_t win = std::min<uint64_t>(n_tasks, ix->window_tasks);
-        if (tasks.n < win) tasks.alloc(win, s);
+        if (tasks.n < win) tasks.alloc(win);
         for (uint64_t w0 = 0; w0 < n_tasks; w0 += win) {
-            const uint64_t w1 = std::min(n_tasks, w0 + win);
+            const uint64_t w1 = std::min<uint64_t>(n_tasks, w0 + win);
             h = tm.begin(2);
             launch_expand(iv.p, task_off.p, cnt * k, w0, w1, tasks.p, nullptr, s);
             launches++;
@@ -540,7 +616,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             if (mode == E2FM_MODE_LOCATE) grow_results(n_results + (w1 - w0));   // every row task yields at most one occurrence
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, res_pos.n, ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
             if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
             else launch_walk(wa, ix->n_sm, s);
             launches++;
@@ -553,7 +629,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     if (b.h_counts) CK(cudaStreamSynchronize(ix->d2h_stream));
     // learn the task density for the next batch's capacity (x1.5 head room)
     if (b.n) {
-        ix->tasks_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)total_tasks / (double)b.n));
+        if (fast) ix->tasks_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)total_tasks / (double)b.n));
         if (mode == E2FM_MODE_LOCATE) ix->results_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)n_results / (double)b.n));
     }
 
@@ -565,11 +641,11 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         launch_scan_u64(counts.p, off.p, b.n, scratch.p, s);
         launches += 3;
         DBuf<uint64_t> pos(std::max<uint64_t>(n_results, 1), s);
-        DBuf<uint32_t> cursor(std::max<uint64_t>(b.n, 1), s);
-        cursor.zero();
+        WsBuf<uint32_t> cursor(ix, WS_CURSOR, std::max<uint64_t>(b.n, 1), s);
+        cursor.zero(std::max<uint64_t>(b.n, 1));
         launch_scatter(res_pat.p, res_pos.p, n_results, off.p, cursor.p, pos.p, s);
         launches++;
-        DBuf<uint32_t> big_list(n_results / 24 + 1, s);
+        WsBuf<uint32_t> big_list(ix, WS_BIG_LIST, n_results / 24 + 1, s);
         uint32_t *ulen = cursor.p;   // the cursors are dead after the scatter
         launch_segment_sort(pos.p, off.p, b.n, big_list.p, ulen, ix->d_stats, s);
         launches++;
@@ -640,20 +716,21 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
         CK(cudaSetDevice(ix->device));
         cudaStream_t s = ix->stream;
         memset(ix->batch_ms, 0, sizeof(ix->batch_ms));
-        EventTimer tm(s);
+        ix->events.reset();
+        EventTimer tm(s, &ix->events);
         const int whole = tm.begin(6);
-        DBuf<uint8_t> d_bytes;
-        DBuf<uint64_t> d_off;
+        WsBuf<uint8_t> d_bytes(ix, WS_BYTES, s);
+        WsBuf<uint64_t> d_off(ix, WS_OFF, s);
         Batch b{bytes, offsets, fixed_len, n, total_bytes};
         if (!on_device) {
             // the pattern bytes travel chunk by chunk inside run_batch (H2D stream); only the offsets go ahead of them
-            d_bytes.alloc(total_bytes + 16, s);
+            d_bytes.alloc(total_bytes + 16);
             b.d_bytes = d_bytes.p;
             b.h_bytes = bytes;
             b.h_off = offsets;
             b.h_counts = counts_out;
             if (offsets) {
-                d_off.alloc(n + 1, s);
+                d_off.alloc(n + 1);
                 CK(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
                 b.d_off = d_off.p;
             }
@@ -792,6 +869,8 @@ void e2fm_index_close(e2fm_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (void *p : ix->owned) cudaFree(p);
+    for (auto &sl : ix->ws) if (sl.p) cudaFree(sl.p);
+    ix->events.destroy();
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->h_stats) cudaFreeHost(ix->h_stats);
     if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);

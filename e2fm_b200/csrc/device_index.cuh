@@ -16,6 +16,11 @@
 //                 position of the row's suffix, text[p] = compact code of super-character p. With them locate is one
 //                 gather per occurrence and hat verification (EFMIndex::extractSuperCharacter) one more. 6 bytes per row;
 //                 skipped when HBM is short (the per-query walk kernel then does the same work on demand).
+//   bwt16[n]      compact BWT code per row, 2 bytes (built with the dense tables): the '?'-prefixed first super-character
+//                 makes the search test EVERY row of an interval (EFMIndex::backwardStepIfMatch); rows of an interval are
+//                 consecutive, so that test streams 2 bytes per row instead of gathering 8-byte records.
+//   pair_tab[A*A] uint2 {s,e}: the SA interval after the last two super-characters of a shift (start interval from C[] +
+//                 one backwardStep, EFMIndex.cpp:1728-1748, :1966) in one gather; built at load with A*A rank pairs.
 //   markTab[mrn]  uint2 {row, LF(row)} of the row whose marked value is v  (reverse of rec's marks;
 //                 replaces markedRowsBuckets + Bucket::getMarkedBwtPosition, Bucket.cpp:794)
 // The reference's two-level counters + per-bucket position lists (SuperBucket.cpp:82, Bucket.cpp:656-779)
@@ -46,6 +51,8 @@ struct DevIndex {
     const uint2 *mark_tab;
     const uint32_t *sa;         // [n] or nullptr
     const uint16_t *text;       // [n] or nullptr
+    const uint16_t *bwt16;      // [n] or nullptr: compact BWT code of every row (2 bytes: wildcard rows are scanned in row order)
+    const uint2 *pair_tab;      // [A*A] or nullptr: SA interval [s,e) after the last two super-characters (a = last, b = previous)
     const uint64_t *C;          // [A+1]
     const uint16_t *compact_of_natural;   // [sigma_k]
     const uint32_t *natural_of_compact;   // [A]

@@ -534,4 +534,30 @@ void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn
     dense_build_kernel<<<(uint32_t)((mrn + 255) / 256), 256, 0, s>>>(rec, mark_tab, mrn, rate, n, sa, text, status);
 }
 
+__global__ void __launch_bounds__(256) bwt16_build_kernel(const uint64_t *__restrict__ rec, uint64_t n, uint16_t *__restrict__ bwt16) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bwt16[i] = (uint16_t)rec_code(rec[i]);
+}
+void launch_bwt16_build(const uint64_t *rec, uint64_t n, uint16_t *bwt16, cudaStream_t s) {
+    if (n) bwt16_build_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rec, n, bwt16);
+}
+
+__global__ void __launch_bounds__(256) pair_build_kernel(DevIndex ix, uint2 *__restrict__ pair_tab) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ix.A * ix.A) return;
+    const uint32_t a = t / ix.A, b = t - a * ix.A;
+    const uint32_t s = (uint32_t)ix.C[a], e = (uint32_t)ix.C[a + 1];
+    uint2 out = make_uint2(0u, 0u);
+    if (e > s) {
+        const uint32_t ns = s == 0 ? (uint32_t)ix.C[b] : rank_c(ix, b, s - 1);
+        const uint32_t ne = rank_c(ix, b, e - 1);
+        out = make_uint2(ns, ne > ns ? ne : ns);
+    }
+    pair_tab[t] = out;
+}
+void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s) {
+    const uint32_t n = ix.A * ix.A;
+    if (n) pair_build_kernel<<<(n + 255) / 256, 256, 0, s>>>(ix, pair_tab);
+}
+
 }  // namespace e2fm

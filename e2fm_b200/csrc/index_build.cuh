@@ -63,6 +63,11 @@ void launch_rank_fill(const RankBuildParams &p, cudaStream_t s);
 void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn, uint32_t rate, uint64_t n, uint32_t *sa,
                         uint16_t *text, uint32_t *status, cudaStream_t s);
 
+// bwt16[row] = compact code of the row (from rec)
+void launch_bwt16_build(const uint64_t *rec, uint64_t n, uint16_t *bwt16, cudaStream_t s);
+// pair_tab[a*A + b] = {s,e}: [C[a], C[a+1]) after one backward step with b
+void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s);
+
 // standalone K1 test hook
 void launch_keystream_debug(const uint32_t key[8], uint64_t nonce, uint32_t bits, uint64_t start, uint64_t count,
                             uint32_t *d_out, cudaStream_t s);

@@ -15,6 +15,7 @@
 #include "search.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/e2fm_b200.h"
 
@@ -187,6 +188,7 @@ void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t 
 
 // ---------------------------------------------------------------- K3: backward search
 
+static constexpr uint32_t FC_MIN_LEN = 32;  // wildcard intervals shorter than this are expanded into row tasks like any other interval
 static constexpr uint32_t BS_GRAB = 256;   // items a warp takes from the global queue at a time
 static constexpr int BS_BURST = 4;         // backward steps between two refills
 
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
     int i = 0, lo = 0;                           // next super-character to process, and the last fixed one
     const uint16_t *cptr = nullptr;              // codes of this pattern, shifted so that character c is cptr[c*k]
     uint32_t n_rank = 0, n_sect = 0;
-    unsigned long long n_tasks = 0;
+    
 
     for (;;) {
         if (wnext >= wend && !exhausted) {
@@ -239,13 +241,25 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
                     // otherwise the shift yields nothing (variable last character without fixed predecessor, :2132/:1745)
                     if (l > 0) {
                         cptr = a.codes + base - sa;
+                        lo = sa > 0 ? 1 : 0;
+                        flags = (sa > 0 ? 1u : 0u) | (last_var ? 2u : 0u);
                         const uint32_t cc = __ldg(cptr + (size_t)(l - 1) * k);
-                        if (cc != 0xFFFFu) {
-                            s = (uint32_t)__ldg(ix.C + cc);
-                            e = (uint32_t)__ldg(ix.C + cc + 1);
-                            i = l - 2;
-                            lo = sa > 0 ? 1 : 0;
-                            flags = (sa > 0 ? 1u : 0u) | (last_var ? 2u : 0u);
+                        // the code of the next super-character is independent of the first: both loads are in flight together
+                        const uint32_t c1 = (l - 2 >= lo) ? (uint32_t)__ldg(cptr + (size_t)(l - 2) * k) : 0xFFFEu;
+                        if (cc != 0xFFFFu && c1 != 0xFFFFu) {
+                            if (ix.pair_tab && c1 != 0xFFFEu) {
+                                // start interval (:1728-1748) + first backwardStep (:1966) in one gather of the pair table
+                                const uint2 p = __ldg(ix.pair_tab + (size_t)cc * ix.A + c1);
+                                s = p.x;
+                                e = p.y;
+                                i = l - 3;
+                                n_rank += 2;
+                                n_sect++;
+                            } else {
+                                s = (uint32_t)__ldg(ix.C + cc);
+                                e = (uint32_t)__ldg(ix.C + cc + 1);
+                                i = l - 2;
+                            }
                             active = e > s;
                         }
                     }
@@ -265,7 +279,16 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             if (go) {
                 const uint32_t cc = __ldg(cptr + (size_t)i * k);
                 if (cc == 0xFFFFu) active = false;
-                else {
+                else if (e - s == 1) {
+                    // one row left: occ(c,s) - occ(c,s-1) is 1 iff the row's BWT symbol is c, and then the new row is LF(s):
+                    // one 8-byte gather and a compare instead of a rank sector and two SWAR counts
+                    const uint64_t x = __ldg(ix.rec + s);
+                    n_sect++;
+                    n_rank += 2;
+                    i--;
+                    if (rec_code(x) == cc) { s = lf_from_rec(ix, x); e = s + 1; }
+                    else active = false;
+                } else {
                     const uint32_t re = e - 1;
                     const Sector se = load_sector(ix, cc, re >> blk_shift);
                     uint32_t ns;
@@ -293,19 +316,20 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             const uint32_t len = e - s;
             if (a.mode == E2FM_MODE_COUNT && flags == 0) {
                 atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
+            } else if (a.ivw && (flags & 1u) && len >= FC_MIN_LEN) {
+                // '?'-prefixed first super-character and many rows: tested row by row, in row order, by firstcheck_kernel
+                a.ivw[item] = make_uint2(s, len);
+                a.stats[ST_ANY_LONG] = 1;
             } else {
                 a.iv[item] = make_uint2(s, len);
-                n_tasks += len;
             }
             active = false;
         }
     }
     unsigned long long r = warp_sum((unsigned long long)n_rank), q = warp_sum((unsigned long long)n_sect);
-    n_tasks = warp_sum(n_tasks);
     if (lane == 0) {
         if (q) atomicAdd(a.stats + ST_SECT_BS, q);
         if (r) atomicAdd(a.stats + ST_RANK, r);
-        if (n_tasks) atomicAdd(a.stats + ST_TASKS, n_tasks);
     }
 }
 
@@ -313,11 +337,180 @@ void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s) {
     const uint64_t n_items = (uint64_t)a.pv.count * a.ix.k;
     if (n_items == 0) return;
     cudaMemsetAsync(a.iv, 0, n_items * sizeof(uint2), s);   // shifts that die or drop out leave an empty interval
+    if (a.ivw) cudaMemsetAsync(a.ivw, 0, n_items * sizeof(uint2), s);
     uint64_t blocks = (n_items + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 8;   // persistent: up to 8 x 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (a.ix.k == 4) backward_search_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
     else backward_search_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
+}
+
+// ---------------------------------------------------------------- wildcard first super-character
+
+// EFMIndex::backwardStepIfMatch (:2011-2041) for whole intervals: when a shifted pattern starts with a '?'-prefixed
+// super-character, EVERY row of the interval reached so far has to be tested against the fixed symbols of that k-mer.
+// The rows are consecutive, so the test streams bwt16[] (2 bytes per row, coalesced) instead of expanding the interval
+// into row tasks that each gather an 8-byte record. Rows that pass become row tasks (flagged: their position is
+// sa[row] - 1), or are counted on the spot when nothing else has to be verified.
+static constexpr uint32_t TASK_FIRST_DONE = 0x80000000u;
+
+static constexpr int FC_GROUP = 8;        // warp batches (of 32 items) per task-slot reservation: same-address atomics are the
+                                          // scarce resource (about one per nanosecond device-wide), so they are amortised over 256 items
+
+// low[(f-1)*A + code] = the f low-order symbols of the k-mer of compact code `code` (its natural value mod n_sym^f): what a
+// '?'-prefixed first super-character with f fixed symbols has to equal. In shared memory when it fits, else recomputed.
+struct FcTable {
+    const uint32_t *low;   // shared-memory table or nullptr
+    const DevIndex *ix;
+    uint32_t A;
+    __device__ __forceinline__ bool match(uint32_t code, uint32_t f, uint32_t pw, uint32_t want) const {
+        if (low) return low[(f - 1) * A + code] == want;
+        return __ldg(ix->natural_of_compact + code) % pw == want;
+    }
+};
+
+// 8-bit mask of the matching rows among the 8 consecutive rows [c, c+8) (c a multiple of 8) that fall in [s0, s0+ln)
+__device__ __forceinline__ uint32_t fc_chunk(const FcTable &tab, const uint16_t *bwt16, uint32_t c, uint32_t s0, uint32_t ln, uint32_t f,
+                                             uint32_t pw, uint32_t want) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bwt16 + c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t r = c + t;
+        const uint32_t code = (w[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;
+        if (r >= s0 && r - s0 < ln && tab.match(code, f, pw, want)) m |= 1u << t;
+    }
+    return m;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t use_smem) {
+    extern __shared__ uint32_t fc_low[];
+    if (a.stats[ST_ANY_LONG] == 0) return;              // no long wildcard interval in this chunk (the usual case for long patterns)
+    const DevIndex &ix = a.ix;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
+    const uint32_t n_items = a.pv.count * k;
+    FcTable tab{nullptr, &ix, ix.A};
+    if (use_smem) {
+        for (uint32_t t = threadIdx.x; t < (k - 1) * ix.A; t += blockDim.x) {
+            const uint32_t f = t / ix.A + 1, code = t - (f - 1) * ix.A;
+            fc_low[t] = ix.natural_of_compact[code] % ipow(no, f);
+        }
+        __syncthreads();
+        tab.low = fc_low;
+    }
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_rows = 0;
+    for (uint32_t g0 = warp_global * (32u * FC_GROUP); g0 < n_items; g0 += n_warps * (32u * FC_GROUP)) {
+        // this lane's interval in each batch of the group: rows [s, s+len), f fixed symbols that must equal `want`
+        uint32_t S[FC_GROUP], LEN[FC_GROUP], WANT[FC_GROUP], CNT[FC_GROUP];
+        uint32_t total_mine = 0;
+#pragma unroll
+        for (int b = 0; b < FC_GROUP; b++) {
+            const uint32_t item = g0 + b * 32 + lane;
+            const uint2 v = item < n_items ? a.ivw[item] : make_uint2(0u, 0u);
+            S[b] = v.x;
+            LEN[b] = v.y;
+        }
+        // ---- pass 1: count the matching rows of every interval; the whole warp scans one interval, 256 rows per step
+#pragma unroll
+        for (int b = 0; b < FC_GROUP; b++) {
+            const uint32_t item = g0 + b * 32 + lane;
+            const uint32_t sa = item % k, f = k - sa, pw = ipow(no, f);
+            uint32_t want = 0xFFFFFFFFu, len = LEN[b];
+            bool count_only = false;
+            if (len) {
+                const uint8_t *ptr;
+                uint32_t m;
+                pattern_span(a.pv, item / k, ptr, m);
+                want = natural_value(ix, ptr, f);
+                count_only = a.mode == E2FM_MODE_COUNT && (m + sa) % k == 0;
+                if (want == 0xFFFFFFFFu) len = 0;                   // foreign symbol: no row can match
+                n_rows += len;
+            }
+            uint32_t hits = 0;
+            for (unsigned todo = __ballot_sync(FULL, len > 0); todo;) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t s0 = __shfl_sync(FULL, S[b], src), ln = __shfl_sync(FULL, len, src);
+                const uint32_t w = __shfl_sync(FULL, want, src), ff = __shfl_sync(FULL, f, src), p = __shfl_sync(FULL, pw, src);
+                uint32_t h = 0;
+                for (uint32_t c = (s0 & ~7u) + 8 * lane; c < s0 + ln; c += 256) h += __popc(fc_chunk(tab, ix.bwt16, c, s0, ln, ff, p, w));
+                h = (uint32_t)warp_sum((unsigned long long)h);
+                if ((int)lane == src) hits = h;
+            }
+            if (count_only) {
+                if (hits) atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)hits);
+                hits = 0;
+            }
+            LEN[b] = len;
+            WANT[b] = want;
+            CNT[b] = hits;
+            total_mine += hits;
+        }
+        // ---- one reservation for the whole group
+        uint32_t incl = total_mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.task_cursor, (unsigned long long)total);
+        base = __shfl_sync(FULL, base, 0);
+        unsigned long long dst = base + incl - total_mine;          // this lane's slots, its batches in order
+        // ---- pass 2: write the matching rows as flagged row tasks
+#pragma unroll
+        for (int b = 0; b < FC_GROUP; b++) {
+            const uint32_t item = g0 + b * 32 + lane;
+            const uint32_t sa = item % k, f = k - sa, pw = ipow(no, f);
+            for (unsigned todo = __ballot_sync(FULL, CNT[b] > 0); todo;) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t it = __shfl_sync(FULL, item, src), s0 = __shfl_sync(FULL, S[b], src), ln = __shfl_sync(FULL, LEN[b], src);
+                const uint32_t w = __shfl_sync(FULL, WANT[b], src), ff = __shfl_sync(FULL, f, src), p = __shfl_sync(FULL, pw, src);
+                unsigned long long d = __shfl_sync(FULL, dst, src);
+                for (uint32_t c0 = (s0 & ~7u); c0 < s0 + ln; c0 += 256) {
+                    const uint32_t c = c0 + 8 * lane;
+                    uint32_t m = c < s0 + ln ? fc_chunk(tab, ix.bwt16, c, s0, ln, ff, p, w) : 0u;
+                    const uint32_t mine = __popc(m);
+                    uint32_t inc = mine;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, inc, dd);
+                        if ((int)lane >= dd) inc += t;
+                    }
+                    unsigned long long slot = d + inc - mine;
+                    while (m) {
+                        const uint32_t t = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (slot < a.task_cap) a.tasks[slot] = make_uint2(c + t, it | TASK_FIRST_DONE);
+                        slot++;
+                    }
+                    d += __shfl_sync(FULL, inc, 31);
+                }
+            }
+            dst += CNT[b];
+        }
+    }
+    (void)lt;
+    n_rows = warp_sum(n_rows);
+    if (lane == 0 && n_rows) atomicAdd(a.stats + ST_SCAN_ROWS, n_rows);
+}
+
+void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s) {
+    const uint64_t n_items = (uint64_t)a.pv.count * a.ix.k;
+    if (n_items == 0 || a.ix.k < 2) return;
+    const uint64_t groups = (n_items + 32 * FC_GROUP - 1) / (32 * FC_GROUP);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((groups + 7) / 8, (uint64_t)n_sm * 8);
+    const size_t tab_bytes = (size_t)(a.ix.k - 1) * a.ix.A * 4;
+    const uint32_t use_smem = tab_bytes <= 40 * 1024;
+    if (a.ix.k == 4) firstcheck_kernel<4><<<blocks, 256, use_smem ? tab_bytes : 0, s>>>(a, use_smem);
+    else firstcheck_kernel<0><<<blocks, 256, use_smem ? tab_bytes : 0, s>>>(a, use_smem);
 }
 
 // ---------------------------------------------------------------- scans
@@ -681,14 +874,20 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
         if (idx < a.n_tasks) {
             const uint2 tk = __ldg(a.tasks + idx);
             uint32_t row = tk.x;
-            item = tk.y;
+            const bool first_done = (tk.y & 0x80000000u) != 0;   // firstcheck_kernel already matched the row's BWT symbol
+            item = tk.y & 0x7FFFFFFFu;
             const uint32_t pl = item / k, sa = item - pl * k;
             const uint8_t *ptr;
             uint32_t m;
             pattern_span(a.pv, pl, ptr, m);
             const bool hat = (m + sa) % k != 0;
             bool ok = true, have_tp = false;
-            if (sa > 0) {
+            if (first_done) {
+                const uint32_t p = __ldg(ix.sa + row);              // the match stands for the suffix one super-character earlier
+                n_sa++;
+                tp = p == 0 ? (uint32_t)(ix.n - 1) : p - 1;
+                have_tp = true;
+            } else if (sa > 0) {
                 // EFMIndex::backwardStepIfMatch (:2011-2041): the row's BWT character against the '?'-prefixed first one;
                 // a match stands for the suffix one super-character earlier
                 const uint64_t x = __ldg(ix.rec + row);

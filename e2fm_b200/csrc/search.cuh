@@ -31,7 +31,9 @@ enum {
     ST_SECT_BS = 8,  // distinct 32-byte rank sectors gathered by the backward-search kernel
     ST_GATHER = 9,   // dependent 8-byte gathers issued by the walk kernel
     ST_RES_OVF = 10, // occurrences that did not fit the result store (the host then redoes the batch with exact sizes)
-    ST_N = 11
+    ST_SCAN_ROWS = 11, // rows streamed by firstcheck_kernel (2 bytes each)
+    ST_ANY_LONG = 12,  // set by the backward search when the chunk has a long wildcard interval (firstcheck_kernel has work)
+    ST_N = 13
 };
 
 struct SearchArgs {
@@ -39,7 +41,13 @@ struct SearchArgs {
     PatternView pv;
     int mode;                        // E2FM_MODE_*
     const uint16_t *codes;           // [batch bytes] k-mer code starting at every pattern byte (encode_patterns_kernel)
-    uint2 *iv;                       // [count*k] {sp, len} of the interval each (pattern, shift) ends with
+    uint2 *iv;                       // [count*k] {sp, len} of the interval each (pattern, shift) ends with (windowed path)
+    // fast path (dense tables): intervals whose first super-character is '?'-prefixed are kept apart (ivw) and tested row by row
+    // by firstcheck_kernel, which appends the matching rows to `tasks` after the expanded ones; nullptr = everything goes to iv
+    uint2 *ivw;                      // [count*k]
+    uint2 *tasks;
+    unsigned long long *task_cursor; // device-resident number of row tasks of the chunk (expand_kernel sets it, firstcheck adds)
+    unsigned long long task_cap;
     unsigned long long *counts;      // [batch n] matches per pattern
     unsigned long long *stats;       // [ST_N]
 };
@@ -62,6 +70,8 @@ struct WalkArgs {
 void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t j_begin, uint64_t j_end, uint64_t n_bytes, uint16_t *codes,
                             int n_sm, cudaStream_t s);
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
+// fast path: test every row of the wildcard intervals K3 listed (streams bwt16[]), survivors become flagged row tasks
+void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s);
 // exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);
 // n_tasks_out != nullptr: fast path — window [0, w1) is the capacity, *n_tasks_out receives the chunk's task count, nothing is
