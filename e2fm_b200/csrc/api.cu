@@ -185,7 +185,7 @@ T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
 
 // view of a workspace slot with the DBuf interface; contents are preserved across a growth only when asked
 enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SURV, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_IVL, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
-       WS_CURSOR, WS_BIG_LIST };
+       WS_CURSOR, WS_BIG_LIST, WS_HATW };
 template <class T>
 struct WsBuf {
     e2fm_index *ix;
@@ -470,6 +470,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     const uint64_t items_cap = chunk * k;
     WsBuf<uint2> iv(ix, WS_IV, items_cap, s);
     WsBuf<uint2> ivw(ix, WS_SURV, s);
+    WsBuf<uint32_t> firstw(ix, WS_IVL, items_cap, s), hatw(ix, WS_HATW, items_cap, s);
     WsBuf<uint64_t> task_off(ix, WS_TASK_OFF, items_cap + 1, s);
     WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
     WsBuf<uint2> tasks(ix, WS_TASKS, s);
@@ -538,7 +539,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             CK(cudaMemsetAsync(ix->d_stats + ST_ANY_LONG, 0, 8, s));
             int h = tm.begin(1);
-            SearchArgs sa{dix, pv, mode, codes.p, iv.p, ivw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
+            SearchArgs sa{dix, pv, mode, codes.p, iv.p, ivw.p, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
             launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -549,7 +550,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             launches += 5;
             tm.end(h);
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
             launch_resolve(wa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -589,7 +590,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         } else encode_chunk(first, cnt, c);
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, nullptr, nullptr, nullptr, 0, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, nullptr, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);
@@ -616,7 +617,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             if (mode == E2FM_MODE_LOCATE) grow_results(n_results + (w1 - w0));   // every row task yields at most one occurrence
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
             if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
             else launch_walk(wa, ix->n_sm, s);
             launches++;

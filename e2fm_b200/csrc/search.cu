@@ -317,9 +317,23 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             if (a.mode == E2FM_MODE_COUNT && flags == 0) {
                 atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
             } else if (a.ivw && (flags & 1u) && len >= FC_MIN_LEN) {
-                // '?'-prefixed first super-character and many rows: tested row by row, in row order, by firstcheck_kernel
+                // '?'-prefixed first super-character and many rows: tested row by row, in row order, by firstcheck_kernel.
+                // What those rows are checked against is computed here, once per (pattern, shift) instead of once per row: the
+                // fixed symbols of the '?'-prefixed first and of the '?'-suffixed last super-character.
                 a.ivw[item] = make_uint2(s, len);
                 a.stats[ST_ANY_LONG] = 1;
+                const uint32_t pl = item / k, sa = item - pl * k;
+                const uint8_t *pp;
+                uint32_t pm;
+                pattern_span(a.pv, pl, pp, pm);
+                a.firstw[item] = natural_value(ix, pp, k - sa);
+                uint32_t hw = 0xFFFFFFFFu;
+                if (flags & 2u) {
+                    const uint32_t L = (pm + sa + k - 1) / k, from = (L - 1) * k - sa, f = pm - from;
+                    const uint32_t want = natural_value(ix, pp + from, f);
+                    hw = want == 0xFFFFFFFFu ? 0xFFFFFFFEu : ((f << 28) | want);     // 0xFFFFFFFE: foreign symbol, nothing matches
+                }
+                a.hatw[item] = hw;
             } else {
                 a.iv[item] = make_uint2(s, len);
             }
@@ -354,52 +368,56 @@ void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s) {
 // sa[row] - 1), or are counted on the spot when nothing else has to be verified.
 static constexpr uint32_t TASK_FIRST_DONE = 0x80000000u;
 
-static constexpr int FC_GROUP = 8;        // warp batches (of 32 items) per task-slot reservation: same-address atomics are the
+static constexpr int FC_GROUP = 2;        // warp batches (of 32 items) per task-slot reservation: same-address atomics are the
                                           // scarce resource (about one per nanosecond device-wide), so they are amortised over 256 items
 
 // low[(f-1)*A + code] = the f low-order symbols of the k-mer of compact code `code` (its natural value mod n_sym^f): what a
 // '?'-prefixed first super-character with f fixed symbols has to equal. In shared memory when it fits, else recomputed.
+template <bool SMEM>
 struct FcTable {
-    const uint32_t *low;   // shared-memory table or nullptr
+    const uint32_t *low;   // shared-memory table (SMEM) or unused
     const DevIndex *ix;
     uint32_t A;
-    __device__ __forceinline__ bool match(uint32_t code, uint32_t f, uint32_t pw, uint32_t want) const {
-        if (low) return low[(f - 1) * A + code] == want;
+    // `row` = low + (f-1)*A for the interval at hand
+    __device__ __forceinline__ bool match(const uint32_t *row, uint32_t code, uint32_t pw, uint32_t want) const {
+        if (SMEM) return row[code] == want;
         return __ldg(ix->natural_of_compact + code) % pw == want;
     }
 };
 
-// 8-bit mask of the matching rows among the 8 consecutive rows [c, c+8) (c a multiple of 8) that fall in [s0, s0+ln)
-__device__ __forceinline__ uint32_t fc_chunk(const FcTable &tab, const uint16_t *bwt16, uint32_t c, uint32_t s0, uint32_t ln, uint32_t f,
-                                             uint32_t pw, uint32_t want) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bwt16 + c));
+// 8-bit mask of the matching rows among the 8 consecutive rows [c, c+8) (c a multiple of 8, loaded as v) that fall in [s0, s0+ln)
+template <bool SMEM>
+__device__ __forceinline__ uint32_t fc_eval(const FcTable<SMEM> &tab, const uint4 v, uint32_t c, uint32_t s0, uint32_t ln, uint32_t f,
+                                            uint32_t pw, uint32_t want) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t *row = tab.low + (f - 1) * tab.A;
     uint32_t m = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        const uint32_t r = c + t;
         const uint32_t code = (w[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;
-        if (r >= s0 && r - s0 < ln && tab.match(code, f, pw, want)) m |= 1u << t;
+        m |= (tab.match(row, code, pw, want) ? 1u : 0u) << t;
     }
-    return m;
+    // rows of the group that belong to the interval: [max(s0,c), min(s0+ln, c+8))
+    const uint32_t lo = s0 > c ? s0 - c : 0u, hi = min(s0 + ln - c, 8u);
+    return m & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
+static constexpr int FC_UNROLL = 4;   // 16-byte loads in flight per lane: an interval of up to 1024 rows costs one DRAM round trip
 
-template <int KT>
-__global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t use_smem) {
+template <int KT, bool SMEM>
+__global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a) {
     extern __shared__ uint32_t fc_low[];
     if (a.stats[ST_ANY_LONG] == 0) return;              // no long wildcard interval in this chunk (the usual case for long patterns)
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
     const uint32_t n_items = a.pv.count * k;
-    FcTable tab{nullptr, &ix, ix.A};
-    if (use_smem) {
+    FcTable<SMEM> tab{fc_low, &ix, ix.A};
+    if (SMEM) {
         for (uint32_t t = threadIdx.x; t < (k - 1) * ix.A; t += blockDim.x) {
             const uint32_t f = t / ix.A + 1, code = t - (f - 1) * ix.A;
             fc_low[t] = ix.natural_of_compact[code] % ipow(no, f);
         }
         __syncthreads();
-        tab.low = fc_low;
     }
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long n_rows = 0;
@@ -422,11 +440,8 @@ __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t 
             uint32_t want = 0xFFFFFFFFu, len = LEN[b];
             bool count_only = false;
             if (len) {
-                const uint8_t *ptr;
-                uint32_t m;
-                pattern_span(a.pv, item / k, ptr, m);
-                want = natural_value(ix, ptr, f);
-                count_only = a.mode == E2FM_MODE_COUNT && (m + sa) % k == 0;
+                want = a.firstw[item];
+                count_only = a.mode == E2FM_MODE_COUNT && a.hatw[item] == 0xFFFFFFFFu;
                 if (want == 0xFFFFFFFFu) len = 0;                   // foreign symbol: no row can match
                 n_rows += len;
             }
@@ -437,7 +452,15 @@ __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t 
                 const uint32_t s0 = __shfl_sync(FULL, S[b], src), ln = __shfl_sync(FULL, len, src);
                 const uint32_t w = __shfl_sync(FULL, want, src), ff = __shfl_sync(FULL, f, src), p = __shfl_sync(FULL, pw, src);
                 uint32_t h = 0;
-                for (uint32_t c = (s0 & ~7u) + 8 * lane; c < s0 + ln; c += 256) h += __popc(fc_chunk(tab, ix.bwt16, c, s0, ln, ff, p, w));
+                for (uint32_t c0 = (s0 & ~7u) + 8 * lane; c0 < s0 + ln; c0 += 256 * FC_UNROLL) {
+                    uint4 v[FC_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < FC_UNROLL; u++)
+                        v[u] = c0 + 256 * u < s0 + ln ? __ldg(reinterpret_cast<const uint4 *>(ix.bwt16 + c0 + 256 * u)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < FC_UNROLL; u++)
+                        if (c0 + 256 * u < s0 + ln) h += __popc(fc_eval(tab, v[u], c0 + 256 * u, s0, ln, ff, p, w));
+                }
                 h = (uint32_t)warp_sum((unsigned long long)h);
                 if ((int)lane == src) hits = h;
             }
@@ -474,10 +497,18 @@ __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t 
                 const uint32_t it = __shfl_sync(FULL, item, src), s0 = __shfl_sync(FULL, S[b], src), ln = __shfl_sync(FULL, LEN[b], src);
                 const uint32_t w = __shfl_sync(FULL, WANT[b], src), ff = __shfl_sync(FULL, f, src), p = __shfl_sync(FULL, pw, src);
                 unsigned long long d = __shfl_sync(FULL, dst, src);
-                for (uint32_t c0 = (s0 & ~7u); c0 < s0 + ln; c0 += 256) {
-                    const uint32_t c = c0 + 8 * lane;
-                    uint32_t m = c < s0 + ln ? fc_chunk(tab, ix.bwt16, c, s0, ln, ff, p, w) : 0u;
-                    const uint32_t mine = __popc(m);
+                for (uint32_t c0 = (s0 & ~7u) + 8 * lane; c0 - 8 * lane < s0 + ln; c0 += 256 * FC_UNROLL) {
+                    uint4 v[FC_UNROLL];
+                    uint32_t m[FC_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < FC_UNROLL; u++)
+                        v[u] = c0 + 256 * u < s0 + ln ? __ldg(reinterpret_cast<const uint4 *>(ix.bwt16 + c0 + 256 * u)) : make_uint4(0, 0, 0, 0);
+                    uint32_t mine = 0;
+#pragma unroll
+                    for (int u = 0; u < FC_UNROLL; u++) {
+                        m[u] = c0 + 256 * u < s0 + ln ? fc_eval(tab, v[u], c0 + 256 * u, s0, ln, ff, p, w) : 0u;
+                        mine += __popc(m[u]);
+                    }
                     uint32_t inc = mine;
 #pragma unroll
                     for (int dd = 1; dd < 32; dd <<= 1) {
@@ -485,11 +516,15 @@ __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a, uint32_t 
                         if ((int)lane >= dd) inc += t;
                     }
                     unsigned long long slot = d + inc - mine;
-                    while (m) {
-                        const uint32_t t = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (slot < a.task_cap) a.tasks[slot] = make_uint2(c + t, it | TASK_FIRST_DONE);
-                        slot++;
+#pragma unroll
+                    for (int u = 0; u < FC_UNROLL; u++) {
+                        uint32_t mm = m[u];
+                        while (mm) {
+                            const uint32_t t = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            if (slot < a.task_cap) a.tasks[slot] = make_uint2(c0 + 256 * u + t, it | TASK_FIRST_DONE);
+                            slot++;
+                        }
                     }
                     d += __shfl_sync(FULL, inc, 31);
                 }
@@ -508,9 +543,10 @@ void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s) {
     const uint64_t groups = (n_items + 32 * FC_GROUP - 1) / (32 * FC_GROUP);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((groups + 7) / 8, (uint64_t)n_sm * 8);
     const size_t tab_bytes = (size_t)(a.ix.k - 1) * a.ix.A * 4;
-    const uint32_t use_smem = tab_bytes <= 40 * 1024;
-    if (a.ix.k == 4) firstcheck_kernel<4><<<blocks, 256, use_smem ? tab_bytes : 0, s>>>(a, use_smem);
-    else firstcheck_kernel<0><<<blocks, 256, use_smem ? tab_bytes : 0, s>>>(a, use_smem);
+    const bool use_smem = tab_bytes <= 40 * 1024;
+    if (a.ix.k == 4 && use_smem) firstcheck_kernel<4, true><<<blocks, 256, tab_bytes, s>>>(a);
+    else if (use_smem) firstcheck_kernel<0, true><<<blocks, 256, tab_bytes, s>>>(a);
+    else firstcheck_kernel<0, false><<<blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- scans
@@ -854,18 +890,33 @@ void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
 
 // Same row tasks as walk_kernel, answered from the dense tables built at load (device_index.cuh): the position of a
 // row is sa[row] (what EFMIndex::getRowPosition walks to), the super-character at a text position is text[p] (what
-// EFMIndex::extractSuperCharacter walks to). 1-3 independent gathers per task, one task per thread.
-template <int KT>
+// EFMIndex::extractSuperCharacter walks to). 1-3 independent gathers per task, one task per thread. What a row has to
+// match was computed once per (pattern, shift) by the backward search (firstw / hatw); the per-symbol parts of every
+// k-mer come from two small shared-memory tables, so a task touches no pattern bytes.
+template <int KT, bool SMEM>
 __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
+    extern __shared__ uint32_t rs_tab[];
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
-    uint32_t n_sa = 0, n_text = 0, n_rec = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym, A = ix.A;
+    // low[(f-1)*A + c]  = natural(c) mod no^f      (f low-order symbols:  '?'-prefixed first super-character)
+    // high[(f-1)*A + c] = natural(c) div no^(k-f)  (f high-order symbols: '?'-suffixed last super-character)
+    uint32_t *low = rs_tab, *high = rs_tab + (k - 1) * A;
+    if (SMEM) {
+        for (uint32_t t = threadIdx.x; t < (k - 1) * A; t += blockDim.x) {
+            const uint32_t f = t / A + 1, code = t - (f - 1) * A;
+            const uint32_t nat = ix.natural_of_compact[code];
+            low[t] = nat % ipow(no, f);
+            high[t] = nat / ipow(no, k - f);
+        }
+        __syncthreads();
+    }
     if (a.n_tasks_dev) {
         const unsigned long long nt = *a.n_tasks_dev;
         a.n_tasks = nt > a.n_tasks ? 0u : (uint32_t)nt;
     }
+    uint32_t n_g = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
     // whole warps iterate together so that the result compaction below stays warp-uniform
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < a.n_tasks; base += stride) {
         const uint32_t idx = base + lane;
@@ -873,7 +924,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
         uint32_t item = 0, tp = 0;
         if (idx < a.n_tasks) {
             const uint2 tk = __ldg(a.tasks + idx);
-            uint32_t row = tk.x;
+            const uint32_t row = tk.x;
             const bool first_done = (tk.y & 0x80000000u) != 0;   // firstcheck_kernel already matched the row's BWT symbol
             item = tk.y & 0x7FFFFFFFu;
             const uint32_t pl = item / k, sa = item - pl * k;
@@ -881,43 +932,46 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
             uint32_t m;
             pattern_span(a.pv, pl, ptr, m);
             const bool hat = (m + sa) % k != 0;
-            bool ok = true, have_tp = false;
+            const bool need_tp = hat || a.mode == E2FM_MODE_LOCATE;
+            const uint32_t L = (m + sa + k - 1) / k;
+            bool ok = true;
+            uint32_t hat_f = 0, hat_want = 0;
             if (first_done) {
-                const uint32_t p = __ldg(ix.sa + row);              // the match stands for the suffix one super-character earlier
-                n_sa++;
-                tp = p == 0 ? (uint32_t)(ix.n - 1) : p - 1;
-                have_tp = true;
-            } else if (sa > 0) {
-                // EFMIndex::backwardStepIfMatch (:2011-2041): the row's BWT character against the '?'-prefixed first one;
-                // a match stands for the suffix one super-character earlier
-                const uint64_t x = __ldg(ix.rec + row);
-                n_rec++;
-                const uint32_t f = k - sa;
-                const uint32_t want = natural_value(ix, ptr, f);
-                const uint32_t nat = __ldg(ix.natural_of_compact + rec_code(x));
-                ok = want != 0xFFFFFFFFu && nat % ipow(no, f) == want;
-                if (ok && (hat || a.mode == E2FM_MODE_LOCATE)) {
-                    const uint32_t p = __ldg(ix.sa + row);
-                    n_sa++;
-                    tp = p == 0 ? (uint32_t)(ix.n - 1) : p - 1;
-                    have_tp = true;
+                // rows of a long wildcard interval: their checks were prepared per (pattern, shift) by the backward search
+                const uint32_t hw = __ldg(a.hatw + item);
+                hat_f = hw >> 28;
+                hat_want = hw & 0x0FFFFFFFu;
+                if (hw == 0xFFFFFFFEu) ok = false;
+            } else {
+                if (sa > 0) {
+                    // EFMIndex::backwardStepIfMatch (:2011-2041): the row's BWT character against the '?'-prefixed first one
+                    const uint32_t code = rec_code(__ldg(ix.rec + row));
+                    n_g++;
+                    const uint32_t f = k - sa, want = natural_value(ix, ptr, f);
+                    ok = want != 0xFFFFFFFFu &&
+                         (SMEM ? low[(f - 1) * A + code] : __ldg(ix.natural_of_compact + code) % ipow(no, f)) == want;
+                }
+                if (ok && hat) {
+                    const uint32_t from = (L - 1) * k - sa;
+                    hat_f = m - from;
+                    hat_want = natural_value(ix, ptr + from, hat_f);
+                    if (hat_want == 0xFFFFFFFFu) ok = false;
                 }
             }
-            if (ok && !have_tp && (hat || a.mode == E2FM_MODE_LOCATE)) {
+            if (ok && need_tp) {
                 tp = __ldg(ix.sa + row);                            // EFMIndex::getRowPosition (:2468-2497)
-                n_sa++;
+                n_g++;
+                // a first-character match stands for the suffix one super-character earlier
+                if (sa > 0) tp = tp == 0 ? (uint32_t)(ix.n - 1) : tp - 1;
             }
             if (ok && hat) {
                 // EFMIndex::findWholePatternMatches (:1862-1899) / extractSuperCharacter (:2216-2269)
-                const uint32_t L = (m + sa + k - 1) / k;
                 const uint64_t p = (uint64_t)tp + L - 1;
-                const uint32_t from = (L - 1) * k - sa, f = m - from;
-                const uint32_t want = natural_value(ix, ptr + from, f);
                 ok = false;
-                if (p < ix.n && want != 0xFFFFFFFFu) {
-                    const uint32_t nat = __ldg(ix.natural_of_compact + __ldg(ix.text + p));
-                    n_text++;
-                    ok = nat / ipow(no, k - f) == want;
+                if (p < ix.n) {
+                    const uint32_t code = __ldg(ix.text + p);
+                    n_g++;
+                    ok = (SMEM ? high[(hat_f - 1) * A + code] : __ldg(ix.natural_of_compact + code) / ipow(no, k - hat_f)) == hat_want;
                 }
             }
             emit = ok;
@@ -941,17 +995,20 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
             }
         }
     }
-    const unsigned long long g = warp_sum((unsigned long long)(n_sa + n_text + n_rec));
+    const unsigned long long g = warp_sum((unsigned long long)n_g);
     if (lane == 0 && g) atomicAdd(a.stats + ST_GATHER, g);
 }
 
 void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s) {
     if (a.n_tasks == 0) return;
     uint64_t blocks = a.n_tasks_dev ? ~0ull : ((uint64_t)a.n_tasks + 255) / 256;
-    const uint64_t cap = (uint64_t)n_sm * 32;
+    const uint64_t cap = (uint64_t)n_sm * 16;
     if (blocks > cap) blocks = cap;
-    if (a.ix.k == 4) resolve_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
-    else resolve_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    const size_t tab_bytes = (size_t)2 * (a.ix.k > 1 ? a.ix.k - 1 : 0) * a.ix.A * 4;
+    const bool use_smem = tab_bytes <= 48 * 1024;
+    if (a.ix.k == 4 && use_smem) resolve_kernel<4, true><<<(uint32_t)blocks, 256, tab_bytes, s>>>(a);
+    else if (use_smem) resolve_kernel<0, true><<<(uint32_t)blocks, 256, tab_bytes, s>>>(a);
+    else resolve_kernel<0, false><<<(uint32_t)blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- result pipeline

@@ -45,6 +45,8 @@ struct SearchArgs {
     // fast path (dense tables): intervals whose first super-character is '?'-prefixed are kept apart (ivw) and tested row by row
     // by firstcheck_kernel, which appends the matching rows to `tasks` after the expanded ones; nullptr = everything goes to iv
     uint2 *ivw;                      // [count*k]
+    uint32_t *firstw;                // [count*k] fixed low-order symbols a row's BWT k-mer must equal ('?'-prefixed first character)
+    uint32_t *hatw;                  // [count*k] (f << 28 | fixed high-order symbols) of the '?'-suffixed last character; ~0 = none
     uint2 *tasks;
     unsigned long long *task_cursor; // device-resident number of row tasks of the chunk (expand_kernel sets it, firstcheck adds)
     unsigned long long task_cap;
@@ -57,6 +59,7 @@ struct WalkArgs {
     PatternView pv;
     int mode;
     const uint2 *tasks;              // {row, item} with item = localPattern*k + shift
+    const uint32_t *firstw, *hatw;   // per-item checks written by the backward search (resolve_kernel only)
     uint32_t n_tasks;                // number of tasks, or the capacity of `tasks` when n_tasks_dev is set
     const unsigned long long *n_tasks_dev;   // fast path: device-resident task count written by expand_kernel (nullptr: use n_tasks)
     unsigned long long *counts;
