@@ -325,12 +325,14 @@ def gpu_arm(args, rank, world, local_rank):
         sampler.start()
     wall0 = time.perf_counter()
     dev_ms, bs_ms, walk_ms, exp_ms, res_ms, enc_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
-    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0}
+    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0, "scan_rows": 0,
+               "chunks_redone": 0}
+    fc_ms = 0.0
     occ_total = 0
     for _ in range(args.steps):
         l2_flush()
         ms, ctr, tot = step_device()
-        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]; enc_ms += ms["encode"]
+        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]; enc_ms += ms["encode"]; fc_ms += ms["firstcheck"]
         for k_ in ctr_sum:
             ctr_sum[k_] += ctr[k_]
         occ_total += tot
@@ -360,22 +362,24 @@ def gpu_arm(args, rank, world, local_rank):
         value = world * npat * steps / (dev_ms_max / 1e3)
         e2e_value = world * npat * steps / (e2e_ms_max / 1e3)
         # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
+        # SURVEY.md 8(d) reference-model bytes: only meaningful where the reference's operations are executed one for one
         bytes_bs = 160.0 * ctr_sum["rank"]
         bytes_walk = 224.0 * ctr_sum["lf"] + 64.0 * ctr_sum["mark"]
-        # what the flattened layout has to touch at minimum: one 32-byte sector per distinct rank sector / walk gather
-        lay_bs = 32.0 * ctr_sum["rank_sectors"]
-        lay_walk = 32.0 * ctr_sum["walk_gathers"]
-        kern = {
-            "backward_search_kernel": {"ms_per_step": bs_ms / steps, "alg_bytes_per_step": bytes_bs / steps,
-                                       "achieved_gbs": bytes_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0,
-                                       "layout_sector_bytes_per_step": lay_bs / steps,
-                                       "layout_sector_gbs": lay_bs / (bs_ms / 1e3) / 1e9 if bs_ms else 0.0},
-            "walk_kernel": {"ms_per_step": walk_ms / steps, "alg_bytes_per_step": bytes_walk / steps,
-                            "achieved_gbs": bytes_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0,
-                            "layout_sector_bytes_per_step": lay_walk / steps,
-                            "layout_sector_gbs": lay_walk / (walk_ms / 1e3) / 1e9 if walk_ms else 0.0},
-        }
-        dom = "backward_search_kernel" if bs_ms >= walk_ms else "walk_kernel"
+        # what THIS layout has to touch at minimum: 32 B per distinct sector gathered by the backward search,
+        # 32 B per gather of the walk / resolve kernel, 2 B per row streamed (twice) by the wildcard scan
+        lay = {"backward_search_kernel": 32.0 * ctr_sum["rank_sectors"],
+               "walk_kernel": 32.0 * ctr_sum["walk_gathers"],
+               "firstcheck_kernel": 4.0 * ctr_sum["scan_rows"]}
+        tms = {"backward_search_kernel": bs_ms, "walk_kernel": walk_ms, "firstcheck_kernel": fc_ms}
+        ref = {"backward_search_kernel": bytes_bs, "walk_kernel": bytes_walk, "firstcheck_kernel": 0.0}
+        kern = {}
+        for name in lay:
+            t = tms[name]
+            kern[name] = {"ms_per_step": t / steps, "alg_bytes_per_step": ref[name] / steps,
+                          "achieved_gbs": ref[name] / (t / 1e3) / 1e9 if t else 0.0,
+                          "layout_sector_bytes_per_step": lay[name] / steps,
+                          "layout_sector_gbs": lay[name] / (t / 1e3) / 1e9 if t else 0.0}
+        dom = max(tms, key=lambda n: tms[n])
         traffic = None
         short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}.get(args.workload, args.workload)
         try:
@@ -422,8 +426,8 @@ def gpu_arm(args, rank, world, local_rank):
             "roofline": roofline,
             "ops_per_pattern": {"rank": ctr_sum["rank"] / (npat * steps), "lf": ctr_sum["lf"] / (npat * steps),
                                 "mark": ctr_sum["mark"] / (npat * steps)},
-            "phase_ms_per_step": {"encode": enc_ms / steps, "backward_search": bs_ms / steps, "expand": exp_ms / steps, "walk": walk_ms / steps,
-                                  "results": res_ms / steps},
+            "phase_ms_per_step": {"encode": enc_ms / steps, "backward_search": bs_ms / steps, "scan_expand": exp_ms / steps,
+                                  "firstcheck": fc_ms / steps, "walk_or_resolve": walk_ms / steps, "results": res_ms / steps},
             "clocks": clocks, "wall_s_timed_device_loop": wall_dev,
         }
         if world == 1 and not args.no_cpu_baseline:

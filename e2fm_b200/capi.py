@@ -89,7 +89,7 @@ def lib():
     L.e2fm_result_free.argtypes = [vp]
     L.e2fm_result_free.restype = None
     L.e2fm_last_batch_ms.argtypes = [vp, C.POINTER(C.c_float * 8)]
-    L.e2fm_last_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
+    L.e2fm_last_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64 * 16)]
     L.e2fm_set_option.argtypes = [vp, i32, u64]
     L.e2fm_debug_keystream.argtypes = [i32, C.c_char_p, u64, u32, u64, u64, vp]
     L.e2fm_debug_salsa20.argtypes = [i32, C.c_char_p, u64, u64, u64, vp]
@@ -288,12 +288,13 @@ class DeviceIndex:
     def last_batch_ms(self):
         a = (C.c_float * 8)()
         check(lib().e2fm_last_batch_ms(self._h, C.byref(a)))
-        return dict(zip(["h2d", "backward_search", "expand", "walk", "encode", "results", "total", "r7"], [float(x) for x in a]))
+        return dict(zip(["h2d", "backward_search", "expand", "walk", "encode", "results", "total", "firstcheck"], [float(x) for x in a]))
 
     def last_batch_counters(self):
-        a = (C.c_uint64 * 8)()
+        a = (C.c_uint64 * 16)()
         check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
-        return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers"], [int(x) for x in a]))
+        return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers", "scan_rows",
+                         "chunks_redone"], [int(x) for x in a]))
 
     # ---- test hooks
     def debug_bwt(self, row0: int, count: int) -> np.ndarray:

@@ -141,7 +141,7 @@ struct e2fm_index {
     uint64_t device_bytes = 0;
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
-    uint64_t batch_ctr[8] = {0};
+    uint64_t batch_ctr[16] = {0};
     double results_per_pattern = 2.0; // learned occurrence density: sizes the fast path's result store
     double tasks_per_pattern = 2.0;   // learned row-task density: sizes the fast path's task buffer
     bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
@@ -478,6 +478,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s);
     uint64_t n_results = 0, total_tasks = 0;
     unsigned long long redo_rank = 0, redo_sect = 0;
+    uint64_t n_redone = 0;
 
     // ---- pre-pass: k-mer code at every pattern byte (device batches: all at once; host batches: per chunk, as it arrives)
     WsBuf<uint16_t> codes(ix, WS_CODES, b.total_bytes + 8, s);
@@ -546,8 +547,11 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             h = tm.begin(2);
             launch_task_scan(iv.p, task_off.p, cnt * k, scratch.p, s);
             launch_expand(iv.p, task_off.p, cnt * k, 0, cap, tasks.p, chunk_ctr.p + chunk_no, s);   // sets the chunk's task count
+            launches += 4;
+            tm.end(h);
+            h = tm.begin(7);
             launch_firstcheck(sa, ix->n_sm, s);                                                      // appends the wildcard survivors
-            launches += 5;
+            launches++;
             tm.end(h);
             h = tm.begin(3);
             WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
@@ -577,6 +581,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // per (pattern, shift), scanned and expanded into row-task windows sized from the host.
     for (uint64_t c = 0; c < n_chunks; c++) {
         if (!redo[c]) continue;
+        if (fast) n_redone++;
         const uint64_t first = c * chunk;
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
@@ -698,6 +703,8 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[5] = launches;
     ix->batch_ctr[6] = n_results;
     ix->batch_ctr[7] = ix->h_stats[ST_GATHER];
+    ix->batch_ctr[8] = ix->h_stats[ST_SCAN_ROWS];
+    ix->batch_ctr[9] = n_redone;
 }
 
 int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
@@ -998,7 +1005,7 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]) {
     memcpy(out, ix->batch_ms, sizeof(ix->batch_ms));
     return E2FM_OK;
 }
-int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]) {
+int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]) {
     if (!ix || !out) return fail(E2FM_ERR_ARG, "bad argument");
     memcpy(out, ix->batch_ctr, sizeof(ix->batch_ctr));
     return E2FM_OK;

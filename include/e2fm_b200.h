@@ -110,14 +110,17 @@ void e2fm_result_free(e2fm_result *r);
 
 /* Per-phase device times (ms, CUDA events on the index stream) of the most recent batch:
  * [0] pattern H2D, [1] backward search kernel, [2] interval scan + expansion, [3] row-walk kernel, [4] pattern pre-pass (k-mer codes),
- * [5] CSR build + sort + dedupe + sequence map, [6] whole batch (first copy to last kernel), [7] reserved */
+ * [5] CSR build + sort + dedupe + sequence map, [6] whole batch (first copy to last kernel), [7] firstcheck kernel (row scans of long wildcard intervals) */
 int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
-/* Operation counters of the most recent batch, in the reference's units:
- * [0] rank (= Bucket::getOffsetInformations(CountOnly) calls, Bucket.cpp:656), [1] lf (= ...(RetrieveCharacter)),
- * [2] mark (= Bucket::getMarkedTextPosition, Bucket.cpp:823), [3] row tasks,
- * [4] distinct 32-byte rank sectors gathered by the backward-search kernel, [5] kernels launched by the batch,
- * [6] located occurrences, [7] dependent 8-byte gathers issued by the walk kernel */
-int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[8]);
+/* Operation counters of the most recent batch:
+ * [0] rank (= Bucket::getOffsetInformations(CountOnly) calls the reference would make, Bucket.cpp:656),
+ * [1] lf (= ...(RetrieveCharacter)) and [2] mark (= Bucket::getMarkedTextPosition, Bucket.cpp:823): only the per-query walks
+ *     (E2FM_OPT_DENSE 0) execute these one for one; with the dense tables they stay 0,
+ * [3] row tasks, [4] distinct 32-byte sectors gathered by the backward-search kernel (rank sectors, pair-table entries, records),
+ * [5] kernels launched by the batch, [6] located occurrences, [7] gathers issued by the walk / resolve kernel,
+ * [8] rows streamed by firstcheck_kernel (2 bytes each, read twice), [9] chunks redone through the windowed path,
+ * [10..15] reserved */
+int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
 #define E2FM_OPT_PIPE 5          /* patterns per pipeline stage of a host-buffer batch (0 = default 2^18) */

@@ -405,3 +405,36 @@ def test_locate_cli_formats(gpu, golden, tmp_path):
     s = st.read_text().splitlines()
     assert s[0].startswith("indexFileName,k,bucketSize,markedRowsPercentage,numberOfPatterns,patternsLength,median")
     assert s[1].split(",")[1:5] == ["4", "256", "2", str(len(g["patterns"]))]
+
+
+def test_config1_short_patterns_take_the_wildcard_scan(config1, key64, oracle_mod):
+    """len 9-13 patterns on the 10 Mbp index: the shifted super-patterns reach their '?'-prefixed first character with
+    tens to hundreds of rows left, so the long intervals go through firstcheck_kernel (row-order scan of bwt16) and the
+    short ones through the expanded row tasks; dense tables and per-query walks must both equal the oracle"""
+    dev = capi.DeviceIndex(config1["index"], key64)
+    orc = oracle_mod.OracleIndex(config1["index"], key64)
+    rng = np.random.default_rng(11)
+    seq = config1["seqs"][0]
+    pats = []
+    for L in (9, 10, 11, 12, 13):
+        st = rng.integers(0, len(seq) - L, 120)
+        pats += [seq[s:s + L].tobytes() for s in st]
+    pats += [b"ACGTACGTACGT", b"AAAAAAAAAAAA", b"ACGTNACGTACG"]
+    data, offs = pack(pats)
+    want = [orc.search(p, True) for p in pats]
+    scanned = 0
+    for dense in (1, 0):
+        dev.set_option(capi.OPT_DENSE, dense)
+        for locate in (True, False):
+            r = dev.search(data, offs, locate)
+            out = r.fetch()
+            if dense:
+                scanned += dev.last_batch_counters()["scan_rows"]
+            for i, (cnt, pos) in enumerate(want):
+                assert int(out["counts"][i]) == cnt, (pats[i], dense, locate)
+                if locate:
+                    a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+                    assert np.array_equal(out["positions"][a:b], pos), (pats[i], dense)
+            r.free()
+    assert scanned > 1000          # the row-order scan really ran
+    dev.close()
