@@ -184,13 +184,16 @@ def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdi
         pf = os.path.join(tmpdir, f"p{i}.txt")
         synth.write_patterns(pf, pats[sl])
         ps.append(subprocess.Popen([ref_bin(), "search", prep["efm"], prep["keyfile"], pf, os.path.join(tmpdir, f"r{i}.res"),
-                                    "1" if locate else "0", "1", "2"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+                                    "1" if locate else "0", "1", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     cold = warm = 0.0
     for p, sl in zip(ps, slices):
-        out, _ = p.communicate()
+        out, err = p.communicate()
         line = [l for l in out.splitlines() if l.startswith("{")]
         if p.returncode != 0 or not line:
-            raise SystemExit("reference search failed")
+            for q in ps:
+                if q.poll() is None:
+                    q.kill()
+            raise RuntimeError(f"reference search failed (exit code {p.returncode}): {(err or out)[-300:].strip()}")
         j = json.loads(line[-1])
         cold = max(cold, j["pass_ms"][0])
         warm = max(warm, j["pass_ms"][1])
@@ -435,12 +438,17 @@ def gpu_arm(args, rank, world, local_rank):
             procs = max(1, min(cores, 32))
             per_proc = 4000 if L >= 20 else 400
             sample = min(npat, procs * per_proc)
-            with tempfile.TemporaryDirectory() as td:
-                v, c, wall = run_reference_sample(prep, pats[:sample], locate, procs, td)
+            try:
+                with tempfile.TemporaryDirectory() as td:
+                    v, c, wall = run_reference_sample(prep, pats[:sample], locate, procs, td)
+            except RuntimeError as e:
+                v = c = None
+                wall = 0.0
+                line["cpu_baseline_error"] = str(e)
             line["cpu_baseline"] = {"value": v, "unit": "patterns/s", "cores": procs, "kind": "reference", "host_cores": cores,
                                     "cold_value": c,
                                     "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified "
-                                              f"reference (1 matcher thread each), warm pass; cold pass {c:.0f} patterns/s; {wall:.1f}s wall"}
+                                              f"reference (1 matcher thread each), warm pass; cold pass {c} patterns/s; {wall:.1f}s wall"}
         print(json.dumps(line), flush=True)
     ix.close()
     if world > 1:
