@@ -4,6 +4,7 @@
 //   e2fm_ref build  <fasta> <index> <keyfile> <k> <bucketSize> <mrp> [threads]
 //   e2fm_ref search <index> <keyfile> <patterns.txt> <out.bin> <mode:0=count,1=count+locate> [threads] [passes]
 //   e2fm_ref dump   <index> <keyfile> <out.bin>          (decoded internals after readText())
+//   e2fm_ref extract <index> <keyfile> <queries.txt> <out.txt>   (EFMCollection::extract / getSequence, EFMIndex::extractSnippet)
 //   e2fm_ref kat                                          (known-answer vectors, text)
 //
 // TEST INFRASTRUCTURE ONLY. Nothing in the product path (e2fm_b200/, include/) links or runs this.
@@ -197,6 +198,34 @@ static int cmdDump(int argc, char **argv) {
     _Exit(0);
 }
 
+// extract <index> <keyfile> <queries.txt> <out.txt>: one query per line, "S <seq> <from> <to>" = EFMCollection::extract,
+// "G <seq>" = EFMCollection::getSequence, "X <from> <to>" = EFMIndex::extractSnippet; one result line each ("!" + what() on throw)
+static int cmdExtract(int argc, char **argv) {
+    if (argc < 6) die("extract <index> <keyfile> <queries.txt> <out.txt>");
+    EFMCollection *efm = new EFMCollection();
+    efm->setEncryptionKeyFilePath(argv[3]);
+    efm->setNumberOfThreads(2);
+    efm->load(argv[2]);
+    ifstream in(argv[4]);
+    FILE *f = fopen(argv[5], "w");
+    if (!in || !f) die("cannot open query / output file");
+    string line;
+    while (getline(in, line)) {
+        if (line.empty()) continue;
+        istringstream is(line);
+        char kind; is >> kind;
+        string r;
+        try {
+            if (kind == 'S') { uint32_t q; uint64_t a, b; is >> q >> a >> b; r = efm->extract(q, a, b); }
+            else if (kind == 'G') { uint32_t q; is >> q; r = efm->getSequence(q); }
+            else { uint64_t a, b; is >> a >> b; r = efm->extractSnippet(a, b); }
+        } catch (std::exception &e) { r = string("!") + e.what(); }
+        fprintf(f, "%s\n", r.c_str());
+    }
+    fclose(f);
+    _Exit(0);
+}
+
 static int cmdKat(int, char **) {
     // Salsa20/20 ECRYPT vector: key = 80 00.., iv = 0 (drives the reference's salsa20.S through its C ABI)
     u8 key[32]; memset(key, 0, 32); key[0] = 0x80;
@@ -258,6 +287,7 @@ int main(int argc, char **argv) {
         if (cmd == "build") return cmdBuild(argc, argv);
         if (cmd == "search") return cmdSearch(argc, argv);
         if (cmd == "dump") return cmdDump(argc, argv);
+        if (cmd == "extract") return cmdExtract(argc, argv);
         if (cmd == "kat") return cmdKat(argc, argv);
     } catch (const exception &e) {
         die(string("exception: ") + e.what());
