@@ -173,6 +173,19 @@ def measured_peak():
 
 # ------------------------------------------------------------------ CPU reference
 
+def reference_procs(prep) -> int:
+    """processes the host can run side by side: one per core, but each holds the whole index plus what it decodes lazily
+    (about 12x the index file: bucketText u32 + charactersPositions u64 per super-character)"""
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    per_proc = 12 * os.path.getsize(prep["efm"]) + (256 << 20)
+    return int(max(1, min(cores, 32, (avail // 2) // per_proc)))
+
+
 def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdir: str):
     """P independent processes of the unmodified reference, each over a 1/P slice (the reference is serial and not
     re-entrant per object); 1 matcher thread each; 2 passes: cold (lazy bucket decode) and warm.
@@ -203,8 +216,9 @@ def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdi
 def reference_arm(args, prep):
     w = prep["w"]
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
-    per_proc = 4000 if w["pat_len"] >= 20 else 400
+    procs = reference_procs(prep)
+    big = os.path.getsize(prep["efm"]) > (200 << 20)
+    per_proc = (500 if big else 4000) if w["pat_len"] >= 20 else 400
     sample = min(w["n_patterns"], procs * per_proc)
     pats = synth.sample_patterns(prep["seqs"], sample, w["pat_len"], w["seed"] + 1)[:sample]
     vals, colds = [], []
@@ -435,8 +449,9 @@ def gpu_arm(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            procs = max(1, min(cores, 32))
-            per_proc = 4000 if L >= 20 else 400
+            procs = reference_procs(prep)
+            big = os.path.getsize(prep["efm"]) > (200 << 20)
+            per_proc = (500 if big else 4000) if L >= 20 else 400
             sample = min(npat, procs * per_proc)
             try:
                 with tempfile.TemporaryDirectory() as td:
