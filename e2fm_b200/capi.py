@@ -26,7 +26,7 @@ EXPORTS = [
     "e2fm_index_open", "e2fm_index_close", "e2fm_index_info", "e2fm_index_terminators", "e2fm_index_fasta_headers",
     "e2fm_index_stream", "e2fm_search_batch", "e2fm_search_batch_fixed", "e2fm_search_batch_device",
     "e2fm_search_batch_device_fixed", "e2fm_search_batch_stream", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
-    "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
+    "e2fm_extract", "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
     "e2fm_result_free", "e2fm_last_batch_ms", "e2fm_last_batch_counters", "e2fm_set_option",
     "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
     "e2fm_debug_rank", "e2fm_last_error", "e2fm_version",
@@ -80,6 +80,7 @@ def lib():
     L.e2fm_search_batch_stream.argtypes = [vp, vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
     L.e2fm_search_batch_device.argtypes = [vp, vp, vp, u64, u64, i32, C.POINTER(vp)]
     L.e2fm_search_batch_device_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_extract.argtypes = [vp, u64, u64, vp, u64, C.POINTER(u64)]
     L.e2fm_result_patterns.restype = u64
     L.e2fm_result_patterns.argtypes = [vp]
     L.e2fm_result_total_positions.restype = u64
@@ -284,6 +285,14 @@ class DeviceIndex:
         h = C.c_void_p()
         check(lib().e2fm_search_batch_device_fixed(self._h, d_ptr, n, length, MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
         return Result(h, locate)
+
+    def extract_snippet(self, frm: int, to: int) -> bytes:
+        """EFMIndex::extractSnippet(from, to)"""
+        cap = max(0, to - frm + 1) + 64
+        buf = C.create_string_buffer(cap)
+        n = C.c_uint64(0)
+        check(lib().e2fm_extract(self._h, frm & (2**64 - 1), to & (2**64 - 1), buf, cap, C.byref(n)))
+        return buf.raw[:n.value]
 
     def last_batch_ms(self):
         a = (C.c_float * 8)()

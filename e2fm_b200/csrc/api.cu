@@ -407,6 +407,7 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     d.compact_of_natural = dev_keep_copy<uint16_t>(ix, img.compact_of_natural.data(), img.compact_of_natural.size());
     d.natural_of_compact = dev_keep_copy<uint32_t>(ix, img.natural_of_compact.data(), img.natural_of_compact.size());
     d.sym_index = dev_keep_copy<uint8_t>(ix, sym_index, 256);
+    d.symbols = dev_keep_copy<uint8_t>(ix, img.syms, img.n_sym);
     d.terminators = dev_keep_copy<int64_t>(ix, img.terminators.data(), img.terminators.size());
     // start-interval table over pairs of super-characters (needs the finished DevIndex: it ranks through the sectors)
     if ((uint64_t)img.A * img.A <= (4u << 20)) {
@@ -947,6 +948,47 @@ int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint6
 }
 int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
     return search_common(ix, d_bytes, nullptr, length, n, n * length, true, mode, out);
+}
+
+int e2fm_extract(e2fm_index *ix, uint64_t from, uint64_t to, char *out, uint64_t cap, uint64_t *out_len) {
+    if (!ix || !out_len || (!out && cap)) return fail(E2FM_ERR_ARG, "bad argument");
+    *out_len = 0;
+    if (ix->img.mrp == 0)   // EFMIndex.cpp:2326-2327
+        return fail(E2FM_ERR_UNSUPPORTED, "The index doesn't contain marked rows: the extraction operation is not supported");
+    if (!ix->dix.text) return fail(E2FM_ERR_UNSUPPORTED, "extract needs the dense text table, which was not built for this index");
+    const HostImage &g = ix->img;
+    // EFMIndex::extractSnippet(from, to) (EFMIndex.cpp:2325-2356), unsigned arithmetic and all
+    from -= g.initial_n;
+    to -= g.initial_n;
+    if (from > to) return E2FM_OK;
+    const uint64_t k = g.k;
+    uint64_t st_from = from / k, st_to = to / k;
+    const uint64_t off_from = from % k, off_to = to % k;
+    if (st_to > g.n - 2) st_to = g.n - 2;
+    if (st_from > st_to || (st_from == st_to && off_from > off_to)) return E2FM_OK;
+    const uint64_t count = st_to - st_from + 1;
+    try {
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t s = ix->stream;
+        DBuf<uint8_t> d(count * k, s);
+        launch_extract(ix->dix, st_from, count, d.p, s);
+        std::vector<char> h(count * k);
+        CK(cudaMemcpyAsync(h.data(), d.p, count * k, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        // EFMIndex.cpp:2441-2452. One super-character: substr(stFromOffset, stToOffset + 1) — the second argument is a LENGTH
+        // there, so the reference returns up to stToOffset+1 symbols starting at stFromOffset; mirrored.
+        uint64_t a, b;   // [a, b) of the decoded symbols
+        if (count == 1) { a = off_from; b = std::min<uint64_t>(k, off_from + off_to + 1); }
+        else { a = off_from; b = (count - 1) * k + off_to + 1; }
+        const uint64_t len = b > a ? b - a : 0;
+        *out_len = len;
+        if (len > cap) return fail(E2FM_ERR_ARG, "output buffer too small");
+        memcpy(out, h.data() + a, len);
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
 }
 
 uint64_t e2fm_result_patterns(const e2fm_result *r) { return r ? r->n : 0; }

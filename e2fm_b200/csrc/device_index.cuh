@@ -57,6 +57,7 @@ struct DevIndex {
     const uint16_t *compact_of_natural;   // [sigma_k]
     const uint32_t *natural_of_compact;   // [A]
     const uint8_t *sym_index;   // [256] ASCII -> index in the original alphabet, 0xFF if absent
+    const uint8_t *symbols;     // [n_sym] index -> ASCII
     const int64_t *terminators; // [n_term]
 };
 

@@ -1175,6 +1175,23 @@ void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_
     if (n_pos) map_positions_kernel<<<(uint32_t)((n_pos + 255) / 256), 256, 0, s>>>(ix, positions, n_pos, seq, off);
 }
 
+// ---------------------------------------------------------------- extract
+
+// One thread per super-character: text[p] -> natural value -> k symbols (ScrambledSuperAlphabet::getSymbol,
+// ScrambledSuperAlphabet.cpp:90-112). The reference walks LF from the next marked row for every snippet (EFMIndex.cpp:2367-2440).
+__global__ void __launch_bounds__(256) extract_kernel(DevIndex ix, uint64_t st_from, uint64_t count, uint8_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t nat = __ldg(ix.natural_of_compact + __ldg(ix.text + st_from + i));
+    for (int j = (int)ix.k - 1; j >= 0; j--) {
+        out[i * ix.k + j] = __ldg(ix.symbols + nat % ix.n_sym);
+        nat /= ix.n_sym;
+    }
+}
+void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_t *out, cudaStream_t s) {
+    if (count) extract_kernel<<<(uint32_t)((count + 255) / 256), 256, 0, s>>>(ix, st_from, count, out);
+}
+
 // ---------------------------------------------------------------- test hooks
 
 __global__ void debug_lf_kernel(DevIndex ix, const uint64_t *rows, uint64_t n, uint64_t *out) {

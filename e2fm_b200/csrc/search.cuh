@@ -102,6 +102,9 @@ void launch_repack(const uint64_t *old_pos, const uint64_t *old_off, const uint6
 void launch_ulen_widen(const uint32_t *ulen, unsigned long long *out, uint64_t n, cudaStream_t s);
 void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_t n_pos, uint32_t *seq, uint64_t *off, cudaStream_t s);
 
+// EFMIndex::extractSnippet (EFMIndex.cpp:2367): the k symbols of super-characters [st_from, st_from + count) from the dense text[] table
+void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_t *out, cudaStream_t s);
+
 // test hooks
 void launch_debug_lf(const DevIndex &ix, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);
 void launch_debug_rank(const DevIndex &ix, const uint32_t *codes, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);

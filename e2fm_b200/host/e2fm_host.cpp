@@ -140,6 +140,16 @@ std::vector<uint64_t> *EFMIndex::locateOccurrences(std::vector<Match *> *matches
     return occs;
 }
 
+std::string EFMIndex::extractSnippet(uint64_t from, uint64_t to) {
+    requireLoaded();
+    std::string out;
+    out.resize(to >= from ? (size_t)(to - from + 1) + 64 : 64);
+    uint64_t len = 0;
+    if (e2fm_extract(handle_, from, to, &out[0], out.size(), &len) != E2FM_OK) throw std::runtime_error(e2fm_last_error());
+    out.resize((size_t)len);
+    return out;
+}
+
 uint64_t EFMIndex::getBucketSize() const { return infoBucketSize_; }
 uint64_t EFMIndex::getSuperBucketSize() { return infoSuperBucketSize_; }
 uint64_t EFMIndex::getBucketsNumber() { return infoBuckets_; }
@@ -183,6 +193,27 @@ std::vector<SearchResult> EFMCollection::searchBatch(const std::vector<std::stri
         }
     }
     return out;
+}
+
+// EFMCollection::getSequence (EFMCollection.cpp:43-56)
+std::string EFMCollection::getSequence(uint32_t sequenceIndex) {
+    uint64_t from = sequenceIndex > 0 ? (uint64_t)terminators_.at(sequenceIndex - 1) + getSuperAlphabetOrder() : 0;
+    uint64_t to = (uint64_t)terminators_.at(sequenceIndex);
+    // the reference keeps find('&') in a uint64_t and tests `p > -1` (EFMCollection.cpp:51-55): never true, so the padding and
+    // the first terminator symbol stay in the returned string; mirrored
+    return extractSnippet(from, to);
+}
+
+// EFMCollection::extract (EFMCollection.cpp:67-95): same range checks, same messages
+std::string EFMCollection::extract(uint32_t sequenceIndex, uint64_t from, uint64_t to) {
+    int64_t wholeFrom = sequenceIndex > 0 ? terminators_.at(sequenceIndex - 1) + (int64_t)getSuperAlphabetOrder() : 0;
+    int64_t wholeTo = terminators_.at(sequenceIndex);
+    int64_t maxLen = wholeTo - wholeFrom + 1;   // can exceed the real length by at most k-1 characters
+    if (from > (uint64_t)(maxLen - 1)) throw std::runtime_error("start index out of range");
+    if (to > (uint64_t)(maxLen - 1)) throw std::runtime_error("end index out of range");
+    std::string snippet = extractSnippet((uint64_t)(wholeFrom + (int64_t)from), (uint64_t)(wholeFrom + (int64_t)to));
+    size_t p = snippet.find('&');
+    return p != std::string::npos ? snippet.substr(0, p) : snippet;
 }
 
 SearchResult *EFMCollection::search(std::string pattern, bool retrieveSequenceDescriptions) {

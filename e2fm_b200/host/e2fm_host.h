@@ -73,6 +73,7 @@ public:
     void exactMatch(std::string pattern);
     std::vector<uint64_t> *locateOccurrences(std::vector<Match *> *matches);   // caller owns the result
     uint64_t countOccurrences(std::vector<Match *> *matches);
+    std::string extractSnippet(uint64_t from, uint64_t to);         // EFMIndex.cpp:2325
     // --- getters (EFMIndex.h:245-262)
     uint64_t getBucketSize() const;
     uint64_t getSuperBucketSize();
@@ -121,6 +122,8 @@ public:
     virtual uint32_t getSize();
     virtual std::string getDescription(uint32_t sequenceIndex);   // FMCollection.cpp:68-74
     virtual SearchResult *search(std::string pattern, bool retrieveSequenceDescriptions);   // EFMCollection.cpp:115-153
+    virtual std::string getSequence(uint32_t sequenceIndex);                                // EFMCollection.cpp:43-56
+    virtual std::string extract(uint32_t sequenceIndex, uint64_t from, uint64_t to);        // EFMCollection.cpp:67-95
     // batched: one device call for all patterns (results owned by the caller's vector)
     std::vector<SearchResult> searchBatch(const std::vector<std::string> &patterns, Mode mode, bool retrieveSequenceDescriptions);
 private:

@@ -1,9 +1,12 @@
 // host_selftest — drives the C++ host classes the way the reference's own drivers do (Main.cpp:1022 locate,
 // Test.cpp:113 executePatternSearchInCollection) and prints what they return, for tests/test_gpu_parity.py:
 //   host_selftest <index> <keyfile> <patterns>
+//   host_selftest <index> <keyfile> <patterns> [extract-queries]
 // per pattern one line:  P <i> <count> <n> <pos...> | <seq:off ...> | <sfm seq:off ...>
+// per extract query ("S seq from to" | "G seq" | "X from to", as e2fm_ref extract takes them) one line:  E <result or !what()>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 
 #include "e2fm_host.h"
 
@@ -43,6 +46,23 @@ int main(int argc, char **argv) {
             delete r;
             std::cout << "\n";
             i++;
+        }
+        if (argc > 4) {
+            std::ifstream qf(argv[4]);
+            std::string line;
+            while (std::getline(qf, line)) {
+                if (line.empty()) continue;
+                std::istringstream is(line);
+                char kind;
+                is >> kind;
+                std::string r;
+                try {
+                    if (kind == 'S') { uint32_t q; uint64_t a, b; is >> q >> a >> b; r = efm.extract(q, a, b); }        // EFMCollection.cpp:67
+                    else if (kind == 'G') { uint32_t q; is >> q; r = efm.getSequence(q); }                               // EFMCollection.cpp:43
+                    else { uint64_t a, b; is >> a >> b; r = efm.extractSnippet(a, b); }                                 // EFMIndex.cpp:2325
+                } catch (std::exception &e) { r = std::string("!") + e.what(); }
+                std::cout << "E " << r << "\n";
+            }
         }
         // error behaviour: bad key file, bad magic
         try { EFMCollection bad; bad.setEncryptionKeyFilePath(argv[1]); std::cout << "ERR none\n"; }

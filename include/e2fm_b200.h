@@ -93,6 +93,11 @@ void e2fm_host_free(void *p);
 /* number of visible CUDA devices (0 when there is none: every compute call then fails with E2FM_ERR_CUDA) */
 int e2fm_device_count(void);
 
+/* EFMIndex::extractSnippet(from, to) (EFMIndex.cpp:2325): the original-alphabet text in [from, to] (positions as search reports
+ * them), '&' padding and terminators included. *out_len receives the length; E2FM_ERR_ARG if it exceeds cap. An empty range,
+ * or one past the end, gives length 0 as in the reference. */
+int e2fm_extract(e2fm_index *ix, uint64_t from, uint64_t to, char *out, uint64_t cap, uint64_t *out_len);
+
 uint64_t e2fm_result_patterns(const e2fm_result *r);
 uint64_t e2fm_result_total_positions(const e2fm_result *r);
 /* D2H copy of whichever arrays are non-NULL:

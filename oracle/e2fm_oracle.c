@@ -683,6 +683,29 @@ int64_t orc_search(orc_index *ix, const uint8_t *pat, uint32_t m, int mode, uint
     return (int64_t)w;
 }
 
+/* EFMIndex::extractSnippet(from, to) (EFMIndex.cpp:2325-2452), character by character through super_char_at (the reference walks LF
+ * once from the marked row after stTo; the k-mers read are the same). Returns the length (may exceed cap), -1 without marked rows. */
+int64_t orc_extract(orc_index *ix, uint64_t from, uint64_t to, uint8_t *out, uint64_t cap) {
+    if (ix->mrp == 0) return -1;
+    from -= ix->initial_n; to -= ix->initial_n;
+    if (from > to) return 0;
+    uint64_t k = ix->k, st_from = from / k, off_from = from % k, st_to = to / k, off_to = to % k;
+    if (st_to > ix->n - 2) st_to = ix->n - 2;
+    if (st_from > st_to || (st_from == st_to && off_from > off_to)) return 0;
+    uint64_t count = st_to - st_from + 1, keep_lf = ix->c_lf, w = 0;
+    for (uint64_t c = 0; c < count; c++) {
+        uint8_t km[16];
+        super_char_at(ix, st_from + c, km);
+        uint64_t a = 0, b = k;                                   /* [a,b) of this k-mer */
+        if (count == 1) { a = off_from; b = off_from + off_to + 1; if (b > k) b = k; }   /* substr(pos, LENGTH) quirk, :2441 */
+        else if (c == 0) a = off_from;
+        else if (c == count - 1) b = off_to + 1;
+        for (uint64_t j = a; j < b; j++) { if (w < cap) out[w] = km[j]; w++; }
+    }
+    ix->c_lf = keep_lf;
+    return (int64_t)w;
+}
+
 /* ---- per-row views of the decoded index, for the kernel-level parity tests ---- */
 void orc_get_bwt(const orc_index *ix, uint64_t row0, uint64_t count, uint32_t *out) {
     for (uint64_t i = 0; i < count; i++) out[i] = row0 + i < ix->n ? ix->bwt[row0 + i] : 0xFFFFFFFFu;

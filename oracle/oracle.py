@@ -58,6 +58,8 @@ def lib():
         L.orc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64),
                                  C.c_void_p, C.c_uint64]
         L.orc_map_position.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_extract.restype = C.c_int64
+        L.orc_extract.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_get_bwt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_get_marks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_lf_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -175,6 +177,15 @@ class OracleIndex:
         lib().orc_map_position(self._h, int(pos), C.byref(s), C.byref(o))
         return int(s.value), int(o.value)
 
+    def extract_snippet(self, frm: int, to: int) -> bytes:
+        """EFMIndex::extractSnippet(from, to)"""
+        cap = max(0, to - frm + 1) + 64
+        buf = C.create_string_buffer(cap)
+        n = lib().orc_extract(self._h, frm & (2**64 - 1), to & (2**64 - 1), buf, cap)
+        if n < 0:
+            raise RuntimeError("The index doesn't contain marked rows: the extraction operation is not supported")
+        return buf.raw[:n]
+
     def bwt(self, row0: int, count: int) -> np.ndarray:
         out = np.zeros(count, dtype=np.uint32)
         lib().orc_get_bwt(self._h, row0, count, out.ctypes.data)
@@ -252,6 +263,14 @@ def ref_dump(index: str, keyfile: str, out_file: str) -> None:
     r = subprocess.run([REF_BIN, "dump", index, keyfile, out_file], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference dump failed: " + r.stderr[-500:])
+
+
+def ref_extract(index: str, keyfile: str, queries_file: str, out_file: str):
+    r = subprocess.run([REF_BIN, "extract", index, keyfile, queries_file, out_file], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference extract failed: " + r.stderr[-500:])
+    with open(out_file, "rb") as f:
+        return f.read().split(b"\n")[:-1]
 
 
 def ref_kat() -> dict:

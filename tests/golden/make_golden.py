@@ -83,6 +83,26 @@ def main():
                     bad += 1
         print(f"{name}: n_patterns={len(pats)} occurrences={len(res['positions'])} index={os.path.getsize(base + '.efm')} B "
               f"reference-vs-naive mismatches={bad}")
+        if name in ("col3_k4", "one_k3"):
+            # extract / getSequence / extractSnippet (EFMCollection.cpp:43,67; EFMIndex.cpp:2325) from the reference
+            rng = np.random.default_rng(seed + 77)
+            qs = []
+            for si, L_ in enumerate(lens):
+                qs.append(f"G {si}")
+                for _ in range(12):
+                    a = int(rng.integers(0, L_))
+                    b = int(min(L_ + k, a + rng.integers(0, 80)))
+                    qs.append(f"S {si} {a} {b}")
+                qs += [f"S {si} 0 {L_ - 1}", f"S {si} {L_ - 1} {L_ + 2}", f"S {si} 5 5", f"S {si} 1 2", f"S {si} 9 3", f"S {si} {L_ + 3 * k} {L_ + 4 * k}"]
+            total = sum((L_ + k - 1) // k * k + k for L_ in lens)
+            for _ in range(20):
+                a = int(rng.integers(0, total))
+                qs.append(f"X {a} {a + int(rng.integers(0, 60))}")
+            qs += ["X 0 0", "X 3 3", f"X {total - 3} {total + 5}", f"X {total + 10} {total + 20}", "X 7 2"]
+            with open(base + ".extract.q", "w") as f:
+                f.write("\n".join(qs) + "\n")
+            outs = oracle.ref_extract(base + ".efm", keyfile, base + ".extract.q", base + ".extract.out")
+            print(f"  extract goldens: {len(outs)} queries, {sum(o.startswith(b'!') for o in outs)} that throw")
         if name == "col3_k4":
             # the same collection cut into 2 shards by sequence (e2fm_b200/sharded.py): one reference index per shard;
             # the merged shard results must equal the unsharded col3_k4.res

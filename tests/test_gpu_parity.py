@@ -438,3 +438,50 @@ def test_config1_short_patterns_take_the_wildcard_scan(config1, key64, oracle_mo
             r.free()
     assert scanned > 1000          # the row-order scan really ran
     dev.close()
+
+
+# ---------------------------------------------------------------- extract
+
+@pytest.mark.parametrize("name", ["col3_k4", "one_k3"])
+def test_extract_snippet_matches_reference_and_oracle(opened, golden, name):
+    """e2fm_extract = EFMIndex::extractSnippet (EFMIndex.cpp:2325), including its one-k-mer substr quirk"""
+    dev, orc = opened[name]
+    base = golden[name]["base"]
+    with open(base + ".extract.q", "rb") as f:
+        qs = f.read().split(b"\n")[:-1]
+    with open(base + ".extract.out", "rb") as f:
+        want = f.read().split(b"\n")[:-1]
+    n_x = 0
+    for q, w in zip(qs, want):
+        f_ = q.split()
+        if f_[0] != b"X":
+            continue
+        a, b = int(f_[1]), int(f_[2])
+        assert dev.extract_snippet(a, b) == w, q
+        assert orc.extract_snippet(a, b) == w, q
+        n_x += 1
+    assert n_x >= 20
+    rng = np.random.default_rng(5)
+    total = int(dev.info.text_length) * int(dev.info.k)
+    for _ in range(300):
+        a = int(rng.integers(0, total))
+        b = a + int(rng.integers(0, 200))
+        assert dev.extract_snippet(a, b) == orc.extract_snippet(a, b), (a, b)
+
+
+def test_cpp_host_extract_matches_reference(gpu, golden):
+    """EFMCollection::extract / getSequence / EFMIndex::extractSnippet through the C++ host classes, reference goldens"""
+    exe = os.path.join(HOST_DIR, "e2fm_host_selftest")
+    g = golden["col3_k4"]
+    empty = os.path.join(GOLDEN, "empty.pat")
+    open(empty, "wb").close()
+    try:
+        r = subprocess.run([exe, g["base"] + ".efm", os.path.join(GOLDEN, "key.bin"), empty, g["base"] + ".extract.q"], capture_output=True,
+                           text=True, timeout=600)
+    finally:
+        os.remove(empty)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [l[2:] for l in r.stdout.splitlines() if l.startswith("E ") or l == "E"]
+    with open(g["base"] + ".extract.out") as f:
+        want = f.read().split("\n")[:-1]
+    assert got == want

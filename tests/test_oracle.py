@@ -122,3 +122,44 @@ def test_reference_still_agrees_with_committed_goldens(oracle_mod, golden, key64
     res, _ = oracle_mod.ref_search(g["base"] + ".efm", keyfile, g["base"] + ".pat", str(tmp_path / "r.res"), True, 2)
     assert np.array_equal(res["counts"], g["res"]["counts"])
     assert np.array_equal(res["positions"], g["res"]["positions"])
+
+
+def _collection_extract(ix, terms, k, line):
+    """EFMCollection::extract / getSequence (EFMCollection.cpp:43-95) on top of extractSnippet, as the host classes do it"""
+    f = line.split()
+    def cut(b):
+        p = b.find(b"&")
+        return b[:p] if p >= 0 else b
+    if f[0] == b"X":
+        return ix.extract_snippet(int(f[1]), int(f[2]))
+    q = int(f[1])
+    whole_from = terms[q - 1] + k if q > 0 else 0
+    whole_to = terms[q]
+    if f[0] == b"G":
+        # getSequence holds find()'s result in a uint64_t and tests `p > -1`, which is never true: the '&' padding stays
+        return ix.extract_snippet(whole_from, whole_to)
+    a, b = int(f[2]), int(f[3])
+    max_len = whole_to - whole_from + 1
+    if a > max_len - 1:
+        return b"!start index out of range"
+    if b > max_len - 1:
+        return b"!end index out of range"
+    return cut(ix.extract_snippet(whole_from + a, whole_from + b))
+
+
+@pytest.mark.parametrize("name,k,terms", [("col3_k4", 4, [30012, 50020, 59028]), ("one_k3", 3, None)])
+def test_extract_matches_reference(oracle_mod, golden, key64, name, k, terms):
+    """EFMIndex::extractSnippet / EFMCollection::extract / getSequence against the reference's own output"""
+    ix = oracle_mod.OracleIndex(golden[name]["index"], key64)
+    base = golden[name]["base"]
+    with open(base + ".extract.q", "rb") as f:
+        qs = f.read().split(b"\n")[:-1]
+    with open(base + ".extract.out", "rb") as f:
+        want = f.read().split(b"\n")[:-1]
+    if terms is None:   # single sequence: its terminator is the padded length
+        with open(base + ".fa", "rb") as f:
+            L = len(f.read().split(b"\n")[1])
+        terms = [(L + k - 1) // k * k]
+    assert len(qs) == len(want) > 40
+    for q, w in zip(qs, want):
+        assert _collection_extract(ix, terms, k, q) == w, q
