@@ -134,7 +134,7 @@ struct e2fm_index {
     int n_sm = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-buffer pipeline
-    uint64_t pipe_patterns = 1u << 18;                          // patterns per pipeline stage when the batch comes from the host
+    uint64_t pipe_patterns = 1u << 19;                          // patterns per pipeline stage when the batch comes from the host
     HostImage img;              // header fields (the per-row vectors stay small: terminators, C, tables)
     DevIndex dix{};
     std::vector<void *> owned;  // device allocations that live as long as the index
@@ -470,7 +470,6 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     }
     const uint64_t items_cap = chunk * k;
     WsBuf<uint2> iv(ix, WS_IV, items_cap, s);
-    WsBuf<uint2> ivw(ix, WS_SURV, s);
     WsBuf<uint32_t> firstw(ix, WS_IVL, items_cap, s), hatw(ix, WS_HATW, items_cap, s);
     WsBuf<uint64_t> task_off(ix, WS_TASK_OFF, items_cap + 1, s);
     WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
@@ -528,7 +527,6 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     };
     if (fast) {
         tasks.alloc(cap);
-        ivw.alloc(items_cap);
         // result store: every row task yields at most one occurrence; sized from the learned density, the kernels flag an
         // overflow instead of writing past the end
         if (mode == E2FM_MODE_LOCATE)
@@ -541,7 +539,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             CK(cudaMemsetAsync(ix->d_stats + ST_ANY_LONG, 0, 8, s));
             int h = tm.begin(1);
-            SearchArgs sa{dix, pv, mode, codes.p, iv.p, ivw.p, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
+            SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
             launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -596,7 +594,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         } else encode_chunk(first, cnt, c);
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, nullptr, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, 0u, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);
@@ -1057,7 +1055,7 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
     switch (option) {
         case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (4u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
-        case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
+        case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 19); return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");
             ix->use_dense = value != 0;

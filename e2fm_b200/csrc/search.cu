@@ -87,14 +87,13 @@ static constexpr int ENC_PER = 8;
 static constexpr uint32_t ENC_SMEM_KMERS = 20480;   // k-mer table entries kept in shared memory (else read through L1)
 
 // KT = compile-time super-alphabet order, 1..8 (0 = generic, any k, slower)
-template <int KT>
+template <int KT, bool RAGGED, bool KSMEM>
 __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, PatternView pv, uint64_t j_begin, uint64_t n_bytes, uint16_t *__restrict__ codes) {
     extern __shared__ uint16_t enc_smem[];
     uint8_t *sym_s = reinterpret_cast<uint8_t *>(enc_smem);            // [256]
     uint16_t *kmer_s = enc_smem + 128;                                  // [sigma_k] when it fits
-    const bool kmers_in_smem = ix.sigma_k <= ENC_SMEM_KMERS;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) sym_s[i] = ix.sym_index[i];
-    if (kmers_in_smem)
+    if (KSMEM)
         for (uint32_t i = threadIdx.x; i < ix.sigma_k; i += blockDim.x) kmer_s[i] = ix.compact_of_natural[i];
     __syncthreads();
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
@@ -117,16 +116,17 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
         uint32_t badmask = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) badmask |= (sy[i] == 0xFFu ? 1u : 0u) << i;
-        // bytes left in the pattern that owns byte j0 (room), and the length of the next patterns
-        uint64_t pat = 0, room;
-        if (pv.off) {
+        // bytes left in the pattern that owns byte j0 (room); patterns are shorter than 4 GB
+        uint64_t pat = 0;
+        uint32_t room;
+        if (RAGGED) {
             uint64_t lo = pv.first, hi = pv.first + pv.count;
             while (lo + 1 < hi) {
                 const uint64_t mid = (lo + hi) >> 1;
                 if (__ldg(pv.off + mid) <= j0) lo = mid; else hi = mid;
             }
             pat = lo;
-            room = __ldg(pv.off + pat + 1) - j0;
+            room = (uint32_t)(__ldg(pv.off + pat + 1) - j0);
         } else {
             const uint32_t len = pv.fixed_len;
             room = len - ((n_bytes >> 32) ? (uint32_t)(j0 % len) : (uint32_t)j0 % len);
@@ -134,10 +134,12 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
         uint32_t out[ENC_PER];
 #pragma unroll
         for (int q = 0; q < ENC_PER; q++) {
-            while (room == 0 && j0 + q < n_bytes) {                      // step into the next pattern
-                if (pv.off) { pat++; room = __ldg(pv.off + pat + 1) - __ldg(pv.off + pat); }
-                else room = pv.fixed_len;
-            }
+            if (RAGGED) {
+                while (room == 0 && j0 + q < n_bytes) {                  // step into the next pattern (empty ones included)
+                    pat++;
+                    room = (uint32_t)(__ldg(pv.off + pat + 1) - __ldg(pv.off + pat));
+                }
+            } else if (room == 0) room = pv.fixed_len;
             uint32_t c = 0xFFFFu;
             if (k <= room) {
                 uint32_t nat = 0;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) encode_patterns_kernel(DevIndex ix, Patte
                         nat = nat * no + v;
                     }
                 }
-                if (!bad) c = kmers_in_smem ? kmer_s[nat] : __ldg(ix.compact_of_natural + nat);
+                if (!bad) c = KSMEM ? kmer_s[nat] : __ldg(ix.compact_of_natural + nat);
             }
             out[q] = c;
             room--;
@@ -177,31 +179,39 @@ void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t 
     n_bytes = j_end;   // a chunk ends at a pattern end: nothing beyond it is read (later chunks may not be resident yet)
     const size_t smem = 256 + (ix.sigma_k <= ENC_SMEM_KMERS ? (size_t)ix.sigma_k * 2 : 0);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((threads + 255) / 256, (uint64_t)n_sm * 8);
+    const bool ksmem = ix.sigma_k <= ENC_SMEM_KMERS, ragged = pv.off != nullptr;
+#define E2FM_ENC(KT, RG, KS) encode_patterns_kernel<KT, RG, KS><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes)
+    if (!ksmem) { if (ragged) E2FM_ENC(0, true, false); else E2FM_ENC(0, false, false); return; }
     switch (ix.k) {
-        case 2: encode_patterns_kernel<2><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
-        case 3: encode_patterns_kernel<3><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
-        case 4: encode_patterns_kernel<4><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
-        case 5: encode_patterns_kernel<5><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
-        default: encode_patterns_kernel<0><<<blocks, 256, smem, s>>>(ix, pv, j_begin, n_bytes, codes); break;
+        case 2: if (ragged) E2FM_ENC(2, true, true); else E2FM_ENC(2, false, true); break;
+        case 3: if (ragged) E2FM_ENC(3, true, true); else E2FM_ENC(3, false, true); break;
+        case 4: if (ragged) E2FM_ENC(4, true, true); else E2FM_ENC(4, false, true); break;
+        case 5: if (ragged) E2FM_ENC(5, true, true); else E2FM_ENC(5, false, true); break;
+        default: if (ragged) E2FM_ENC(0, true, true); else E2FM_ENC(0, false, true); break;
     }
+#undef E2FM_ENC
 }
 
 // ---------------------------------------------------------------- K3: backward search
 
+static constexpr uint32_t IV_LONG = 0x80000000u;   // iv[item].y flag: long wildcard interval, scanned by firstcheck_kernel, not expanded
 static constexpr uint32_t FC_MIN_LEN = 32;  // wildcard intervals shorter than this are expanded into row tasks like any other interval
+#ifndef BS_MIN_BLOCKS
+#define BS_MIN_BLOCKS 8
+#endif
 static constexpr uint32_t BS_GRAB = 256;   // items a warp takes from the global queue at a time
 static constexpr int BS_BURST = 4;         // backward steps between two refills
 
 // KT = compile-time super-alphabet order (0 = read it from the index)
 template <int KT>
-__global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
+__global__ void __launch_bounds__(256, BS_MIN_BLOCKS) backward_search_kernel(SearchArgs a) {
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const uint32_t k = KT ? (uint32_t)KT : ix.k;
     const uint32_t n_items = a.pv.count * k;
     const uint32_t blk_shift = ix.blk_shift, blk_mask = (1u << blk_shift) - 1;
     uint32_t wnext = 0, wend = 0;
-    bool exhausted = false, active = false;
+    bool exhausted = false, active = false, owe_iv = false;
     uint32_t item = 0, s = 0, e = 0, flags = 0;   // SA interval [s, e); flags: bit0 first super-character variable, bit1 hat
     int i = 0, lo = 0;                           // next super-character to process, and the last fixed one
     const uint16_t *cptr = nullptr;              // codes of this pattern, shifted so that character c is cptr[c*k]
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             const uint32_t idx = wnext + __popc(need & lt);
             if (idx < wend) {
                 item = idx;
+                owe_iv = true;                       // every item writes iv[item] exactly once (no memset of the array)
                 const uint32_t pl = idx / k, sa = idx - pl * k;
                 uint64_t base;
                 uint32_t m;
@@ -265,6 +276,10 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
                     }
                 }
             }
+        }
+        if (owe_iv && !active) {                     // nothing to search for this shift: an empty interval
+            a.iv[item] = make_uint2(0u, 0u);
+            owe_iv = false;
         }
         wnext = min(wend, wnext + (uint32_t)__popc(need));
         if (!__any_sync(FULL, active)) {
@@ -316,11 +331,12 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
             const uint32_t len = e - s;
             if (a.mode == E2FM_MODE_COUNT && flags == 0) {
                 atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
-            } else if (a.ivw && (flags & 1u) && len >= FC_MIN_LEN) {
+            } else if (a.split_long && (flags & 1u) && len >= FC_MIN_LEN && len < IV_LONG) {
                 // '?'-prefixed first super-character and many rows: tested row by row, in row order, by firstcheck_kernel.
                 // What those rows are checked against is computed here, once per (pattern, shift) instead of once per row: the
                 // fixed symbols of the '?'-prefixed first and of the '?'-suffixed last super-character.
-                a.ivw[item] = make_uint2(s, len);
+                a.iv[item] = make_uint2(s, len | IV_LONG);
+                owe_iv = false;
                 a.stats[ST_ANY_LONG] = 1;
                 const uint32_t pl = item / k, sa = item - pl * k;
                 const uint8_t *pp;
@@ -336,8 +352,13 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
                 a.hatw[item] = hw;
             } else {
                 a.iv[item] = make_uint2(s, len);
+                owe_iv = false;
             }
             active = false;
+        }
+        if (owe_iv && !active) {                     // died, dropped out, or counted directly: an empty interval
+            a.iv[item] = make_uint2(0u, 0u);
+            owe_iv = false;
         }
     }
     unsigned long long r = warp_sum((unsigned long long)n_rank), q = warp_sum((unsigned long long)n_sect);
@@ -350,8 +371,6 @@ __global__ void __launch_bounds__(256) backward_search_kernel(SearchArgs a) {
 void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s) {
     const uint64_t n_items = (uint64_t)a.pv.count * a.ix.k;
     if (n_items == 0) return;
-    cudaMemsetAsync(a.iv, 0, n_items * sizeof(uint2), s);   // shifts that die or drop out leave an empty interval
-    if (a.ivw) cudaMemsetAsync(a.ivw, 0, n_items * sizeof(uint2), s);
     uint64_t blocks = (n_items + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 8;   // persistent: up to 8 x 256 threads per SM
     if (blocks > cap) blocks = cap;
@@ -428,9 +447,9 @@ __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a) {
 #pragma unroll
         for (int b = 0; b < FC_GROUP; b++) {
             const uint32_t item = g0 + b * 32 + lane;
-            const uint2 v = item < n_items ? a.ivw[item] : make_uint2(0u, 0u);
+            const uint2 v = item < n_items ? a.iv[item] : make_uint2(0u, 0u);
             S[b] = v.x;
-            LEN[b] = v.y;
+            LEN[b] = (v.y & IV_LONG) ? (v.y & ~IV_LONG) : 0u;
         }
         // ---- pass 1: count the matching rows of every interval; the whole warp scans one interval, 256 rows per step
 #pragma unroll
@@ -553,7 +572,7 @@ void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s) {
 
 static constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
 
-struct LoadIvLen { const uint2 *p; __device__ unsigned long long operator()(uint64_t i) const { return p[i].y; } };
+struct LoadIvLen { const uint2 *p; __device__ unsigned long long operator()(uint64_t i) const { const uint32_t y = p[i].y; return (y & IV_LONG) ? 0u : y; } };
 struct LoadU64 { const unsigned long long *p; __device__ unsigned long long operator()(uint64_t i) const { return p[i]; } };
 
 template <class Load>
@@ -680,7 +699,8 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint2 *__restrict__ i
     uint32_t row0 = 0, len = 0;
     uint64_t dst = 0;
     if (item < n_items) {
-        const uint2 v = iv[item];
+        uint2 v = iv[item];
+        if (v.y & IV_LONG) v.y = 0;                 // long wildcard intervals are scanned by firstcheck_kernel
         uint64_t a = off[item], b = a + v.y;
         const uint64_t ca = a < w0 ? w0 : a, cb = b > w1 ? w1 : b;
         if (cb > ca) {

@@ -42,9 +42,9 @@ struct SearchArgs {
     int mode;                        // E2FM_MODE_*
     const uint16_t *codes;           // [batch bytes] k-mer code starting at every pattern byte (encode_patterns_kernel)
     uint2 *iv;                       // [count*k] {sp, len} of the interval each (pattern, shift) ends with (windowed path)
-    // fast path (dense tables): intervals whose first super-character is '?'-prefixed are kept apart (ivw) and tested row by row
-    // by firstcheck_kernel, which appends the matching rows to `tasks` after the expanded ones; nullptr = everything goes to iv
-    uint2 *ivw;                      // [count*k]
+    // fast path (dense tables): long intervals whose first super-character is '?'-prefixed are flagged in iv (bit 31 of the length)
+    // and tested row by row by firstcheck_kernel, which appends the matching rows to `tasks` after the expanded ones
+    uint32_t split_long;
     uint32_t *firstw;                // [count*k] fixed low-order symbols a row's BWT k-mer must equal ('?'-prefixed first character)
     uint32_t *hatw;                  // [count*k] (f << 28 | fixed high-order symbols) of the '?'-suffixed last character; ~0 = none
     uint2 *tasks;
