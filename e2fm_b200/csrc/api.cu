@@ -1055,6 +1055,9 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
     switch (option) {
         case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (4u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
+        case E2FM_OPT_DENSITY:   // test hook: forget the learned densities (value = per-mille of one task / result per pattern)
+            ix->tasks_per_pattern = ix->results_per_pattern = (double)value / 1000.0;
+            return E2FM_OK;
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 19); return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");

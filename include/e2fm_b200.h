@@ -129,6 +129,8 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
 #define E2FM_OPT_PIPE 5          /* patterns per pipeline stage of a host-buffer batch (0 = default 2^19) */
+#define E2FM_OPT_DENSITY 6       /* test hook: preset the learned row-task / occurrence densities (per-mille per pattern) that size the
+                                    fast path's buffers; too small a value forces the overflow -> windowed-path redo */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).

@@ -128,6 +128,31 @@ def test_search_small_chunks_and_windows(opened, golden, name):
         dev.set_option(capi.OPT_DENSE, 1)
 
 
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+def test_fast_path_overflow_is_redone_exactly(opened, golden, name):
+    """the fast path sizes its task and result buffers from learned densities; when they are too small the kernels write
+    nothing past the end and the host redoes the chunk (tasks) or the batch (results) through the windowed path"""
+    dev, _ = opened[name]
+    g = golden[name]
+    worst = 0
+    for density in (0, 1, 100):          # per-mille: 0 -> only the fixed slack (1024 tasks per chunk, 4096 results per batch)
+        for chunk in (0, 64, 16):        # 16: every chunk's tasks fit, the whole batch's results may not -> whole-batch redo
+            dev.set_option(capi.OPT_DENSITY, density)
+            dev.set_option(capi.OPT_CHUNK, chunk)
+            try:
+                check_against_res(dev, g["patterns"], g["res"], True)
+                worst = max(worst, dev.last_batch_counters()["chunks_redone"])
+                dev.set_option(capi.OPT_DENSITY, density)
+                check_against_res(dev, g["patterns"], g["res"], False)
+            finally:
+                dev.set_option(capi.OPT_CHUNK, 0)
+    assert worst >= 1                    # the redo path really ran
+    # and once the densities have been learned the same batch goes through without a redo
+    check_against_res(dev, g["patterns"], g["res"], True)
+    check_against_res(dev, g["patterns"], g["res"], True)
+    assert dev.last_batch_counters()["chunks_redone"] == 0
+
+
 def test_op_counters_match_oracle(opened, golden):
     """rank / lf / mark operation counts equal the oracle's for the same batch"""
     dev, orc = opened["col3_k4"]
