@@ -376,6 +376,16 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_kind = measured_peak()
         steps = args.steps
+        # the random-gather roofline of THIS box for a working set of this index's size: independent 8-byte gathers over a
+        # buffer as large as the device image (power of two, at least 256 MB), one 32-byte sector each
+        gbuf = 256 << 20
+        while gbuf < info.device_bytes and gbuf < (64 << 30):
+            gbuf *= 2
+        try:
+            gg = capi.gather_bench(gbuf, 1 << 29, local_rank)
+        except Exception as e:   # noqa: BLE001
+            gg = None
+            log(f"[bench] gather microbenchmark failed: {e}")
         value = world * npat * steps / (dev_ms_max / 1e3)
         e2e_value = world * npat * steps / (e2e_ms_max / 1e3)
         # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
@@ -422,6 +432,12 @@ def gpu_arm(args, rank, world, local_rank):
                                         "note": "160 B/rank + 224 B/lf + 64 B/mark (SURVEY.md 8(d)) x operations the kernels executed; "
                                                 "above the peak by construction: one sector per rank instead of five, and with the dense "
                                                 "tables the walks are not executed at all"},
+                    "random_gather": None if not gg else {
+                        "giga_gathers_per_s": gg, "sector_gbs": gg * 32.0, "frac_of_hbm_peak": gg * 32.0 / peak,
+                        "achieved_frac_of_random_gather": kern[dom]["layout_sector_gbs"] / (gg * 32.0),
+                        "buffer_MB": gbuf >> 20,
+                        "how": "independent 8-byte loads at hashed addresses of a buffer the size of the device image (power of two, "
+                               ">= 256 MB), 2^29 gathers, best of 3 (e2fm_debug_gather_bench); one 32-byte sector per gather"},
                     "note": "achieved = 32 B x sectors this layout must gather (distinct rank sectors / row-task gathers), per launch, "
                             "over the kernel's average CUDA-event duration; traffic = ncu dram read+write of one launch (profiles/)",
                     "kernels": kern}

@@ -29,7 +29,7 @@ EXPORTS = [
     "e2fm_search_batch_device_fixed", "e2fm_search_batch_stream", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
     "e2fm_extract", "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
     "e2fm_result_free", "e2fm_last_batch_ms", "e2fm_last_batch_counters", "e2fm_set_option",
-    "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
+    "e2fm_debug_gather_bench", "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
     "e2fm_debug_rank", "e2fm_last_error", "e2fm_version",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.e2fm_last_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64 * 16)]
     L.e2fm_set_option.argtypes = [vp, i32, u64]
     L.e2fm_debug_keystream.argtypes = [i32, C.c_char_p, u64, u32, u64, u64, vp]
+    L.e2fm_debug_gather_bench.argtypes = [i32, u64, u64, C.POINTER(C.c_double)]
     L.e2fm_debug_salsa20.argtypes = [i32, C.c_char_p, u64, u64, u64, vp]
     L.e2fm_debug_bwt.argtypes = [vp, u64, u64, vp]
     L.e2fm_debug_marks.argtypes = [vp, u64, u64, vp]
@@ -335,6 +336,13 @@ def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count:
     out = np.zeros(count, dtype=np.uint32)
     check(lib().e2fm_debug_keystream(device, key64, nonce, max_value, start, count, out.ctypes.data))
     return out
+
+
+def gather_bench(buffer_bytes: int = 8 << 30, n_gathers: int = 1 << 30, device: int = 0) -> float:
+    """HBM random-gather roofline in 10^9 gathers/s (one 32-byte sector each)"""
+    out = C.c_double(0)
+    check(lib().e2fm_debug_gather_bench(device, buffer_bytes, n_gathers, C.byref(out)))
+    return float(out.value)
 
 
 def debug_salsa20(key32: bytes, nonce: int, first_block: int, n_blocks: int, device: int = 0) -> bytes:

@@ -1091,6 +1091,47 @@ int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, ui
     return E2FM_OK;
 }
 
+int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s) {
+    if (!giga_gathers_per_s || buffer_bytes < 4096 || n_gathers == 0) return fail(E2FM_ERR_ARG, "bad argument");
+    cudaStream_t s;
+    int rc = with_device(device, &s);
+    if (rc) return rc;
+    try {
+        uint64_t n_words = 512;
+        while (n_words * 2 * 8 <= buffer_bytes) n_words *= 2;      // largest power of two that fits
+        uint64_t *buf = nullptr;
+        unsigned long long *sink = nullptr;
+        CK(cudaMalloc((void **)&buf, n_words * 8));
+        CK(cudaMalloc((void **)&sink, 8));
+        CK(cudaMemset(buf, 1, n_words * 8));
+        const uint32_t per_thread = 32;
+        const uint64_t n_threads = (n_gathers + per_thread - 1) / per_thread;
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        launch_gather_bench(buf, n_words, n_threads, per_thread, sink, s);   // warm-up
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            CK(cudaEventRecord(a, s));
+            launch_gather_bench(buf, n_words, n_threads, per_thread, sink, s);
+            CK(cudaEventRecord(b, s));
+            CK(cudaEventSynchronize(b));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            best = std::min(best, ms);
+        }
+        CK(cudaGetLastError());
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        cudaFree(buf);
+        cudaFree(sink);
+        *giga_gathers_per_s = (double)(n_threads * per_thread) / (best * 1e-3) / 1e9;
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
 int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block, uint64_t n_blocks, uint8_t *out) {
     if (!key32 || (!out && n_blocks)) return fail(E2FM_ERR_ARG, "bad argument");
     cudaStream_t s;

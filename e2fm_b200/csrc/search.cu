@@ -1212,6 +1212,29 @@ void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_
     if (count) extract_kernel<<<(uint32_t)((count + 255) / 256), 256, 0, s>>>(ix, st_from, count, out);
 }
 
+// ---------------------------------------------------------------- random-gather microbenchmark
+
+// The roofline this path lives under is not the streaming copy bandwidth but what HBM delivers for independent random
+// sector gathers. Every thread issues `per_thread` independent 8-byte loads at hashed addresses of a large buffer
+// (the access pattern of the LF / sa / text gathers, minus the dependency between steps).
+__global__ void __launch_bounds__(256) gather_bench_kernel(const uint64_t *__restrict__ buf, uint64_t n_words, uint32_t per_thread,
+                                                            unsigned long long *sink) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long acc = 0;
+    uint64_t x = t * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    const uint64_t mask = n_words - 1;                             // n_words is a power of two
+#pragma unroll 8
+    for (uint32_t i = 0; i < per_thread; i++) {
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;    // splitmix-style scramble
+        acc += __ldg(buf + (x & mask));
+    }
+    if (acc == 0x123456789ull) *sink = acc;                        // keep the loads alive
+}
+void launch_gather_bench(const uint64_t *buf, uint64_t n_words, uint64_t n_threads, uint32_t per_thread, unsigned long long *sink,
+                         cudaStream_t s) {
+    gather_bench_kernel<<<(uint32_t)((n_threads + 255) / 256), 256, 0, s>>>(buf, n_words, per_thread, sink);
+}
+
 // ---------------------------------------------------------------- test hooks
 
 __global__ void debug_lf_kernel(DevIndex ix, const uint64_t *rows, uint64_t n, uint64_t *out) {

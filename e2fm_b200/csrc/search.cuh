@@ -105,6 +105,10 @@ void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_
 // EFMIndex::extractSnippet (EFMIndex.cpp:2367): the k symbols of super-characters [st_from, st_from + count) from the dense text[] table
 void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_t *out, cudaStream_t s);
 
+// random 8-byte gathers over a buffer of n_words u64: the HBM random-gather roofline measurement
+void launch_gather_bench(const uint64_t *buf, uint64_t n_words, uint64_t n_threads, uint32_t per_thread, unsigned long long *sink,
+                         cudaStream_t s);
+
 // test hooks
 void launch_debug_lf(const DevIndex &ix, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);
 void launch_debug_rank(const DevIndex &ix, const uint32_t *codes, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);

@@ -143,6 +143,9 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value);
  * of the stream (key = bytes 32..63 of key64, nonce = `nonce`). */
 int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, uint32_t max_value,
                          uint64_t start, uint64_t count, uint32_t *out);
+/* HBM random-gather roofline: independent 8-byte loads at hashed addresses of a buffer_bytes buffer (make it much larger than
+ * L2); returns 10^9 gathers per second (best of 3). Every gather moves one 32-byte sector over the memory system. */
+int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s);
 /* raw Salsa20/20 blocks [first_block, first_block + n_blocks) for a 32-byte key */
 int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block,
                        uint64_t n_blocks, uint8_t *out);
