@@ -478,6 +478,12 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s);
     uint64_t n_results = 0, total_tasks = 0;
     unsigned long long redo_rank = 0, redo_sect = 0;
+    // The single-row step of the backward search (one 8-byte record instead of a rank sector once the interval is one row)
+    // saves instructions while everything is L2-resident, but on an HBM-resident index it adds a second large array to the
+    // gather working set and loses (measured: 4.6 Mbp 0.164 vs 0.170 ms; 116 Mbp 0.65 vs 0.56 ms; 3.1 Gbp 5.6 vs 4.9 ms per
+    // batch): it is used only while rec[] + occ[] fit the L2. E2FM_K3_OPTS (2 = off, 4 = no pair-table start) overrides.
+    uint32_t k3_opts = (uint64_t)dix.n * 12 > (96ull << 20) ? 2u : 0u;
+    if (const char *ov = getenv("E2FM_K3_OPTS")) k3_opts = (uint32_t)atoi(ov) & 6u;
     uint64_t n_redone = 0;
 
     // ---- pre-pass: k-mer code at every pattern byte (device batches: all at once; host batches: per chunk, as it arrives)
@@ -539,7 +545,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             CK(cudaMemsetAsync(ix->d_stats + ST_ANY_LONG, 0, 8, s));
             int h = tm.begin(1);
-            SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
+            SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u | k3_opts, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
             launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -594,7 +600,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         } else encode_chunk(first, cnt, c);
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, 0u, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, k3_opts, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256, BS_MIN_BLOCKS) backward_search_kernel(Sea
                         // the code of the next super-character is independent of the first: both loads are in flight together
                         const uint32_t c1 = (l - 2 >= lo) ? (uint32_t)__ldg(cptr + (size_t)(l - 2) * k) : 0xFFFEu;
                         if (cc != 0xFFFFu && c1 != 0xFFFFu) {
-                            if (ix.pair_tab && c1 != 0xFFFEu) {
+                            if (ix.pair_tab && c1 != 0xFFFEu && !(a.split_long & 4u)) {
                                 // start interval (:1728-1748) + first backwardStep (:1966) in one gather of the pair table
                                 const uint2 p = __ldg(ix.pair_tab + (size_t)cc * ix.A + c1);
                                 s = p.x;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, BS_MIN_BLOCKS) backward_search_kernel(Sea
             if (go) {
                 const uint32_t cc = __ldg(cptr + (size_t)i * k);
                 if (cc == 0xFFFFu) active = false;
-                else if (e - s == 1) {
+                else if (e - s == 1 && !(a.split_long & 2u)) {
                     // one row left: occ(c,s) - occ(c,s-1) is 1 iff the row's BWT symbol is c, and then the new row is LF(s):
                     // one 8-byte gather and a compare instead of a rank sector and two SWAR counts
                     const uint64_t x = __ldg(ix.rec + s);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256, BS_MIN_BLOCKS) backward_search_kernel(Sea
             const uint32_t len = e - s;
             if (a.mode == E2FM_MODE_COUNT && flags == 0) {
                 atomicAdd(a.counts + a.pv.first + item / k, (unsigned long long)len);   // countOccurrences (:2273)
-            } else if (a.split_long && (flags & 1u) && len >= FC_MIN_LEN && len < IV_LONG) {
+            } else if ((a.split_long & 1u) && (flags & 1u) && len >= FC_MIN_LEN && len < IV_LONG) {
                 // '?'-prefixed first super-character and many rows: tested row by row, in row order, by firstcheck_kernel.
                 // What those rows are checked against is computed here, once per (pattern, shift) instead of once per row: the
                 // fixed symbols of the '?'-prefixed first and of the '?'-suffixed last super-character.
