@@ -183,17 +183,28 @@ class ShardedCollection:
         self.first_seq = first_seq
         self.text_base = text_base
         self.group = group
+        self.last_phase_ms = {}
 
     def search_batch(self, pats_rank0, shape, locate: bool) -> MergedResult:
         """pats_rank0: (n, L) uint8 tensor on rank 0 (ignored elsewhere); shape = (n, L) known to every rank."""
+        import time
+        t0 = time.perf_counter()
         d_pats = broadcast_patterns(pats_rank0, shape, self.device, self.group)
         torch.cuda.synchronize(self.device)   # the library searches on its own stream
+        t1 = time.perf_counter()
         n, L = shape
         res = self.ix.search_device_fixed(d_pats.data_ptr(), n, L, locate)
+        search_ms = self.ix.last_batch_ms()["total"]
         local = local_result_from_device(res, self.device)
         torch.cuda.synchronize(self.device)
         res.free()
-        return merge_results(local, self.first_seq, self.text_base, self.group, locate)
+        t2 = time.perf_counter()
+        out = merge_results(local, self.first_seq, self.text_base, self.group, locate)
+        torch.cuda.synchronize(self.device)
+        t3 = time.perf_counter()
+        self.last_phase_ms = {"broadcast": (t1 - t0) * 1e3, "search_device": search_ms, "search_wall": (t2 - t1) * 1e3,
+                              "merge": (t3 - t2) * 1e3}
+        return out
 
     def close(self):
         self.ix.close()
