@@ -97,48 +97,43 @@ def merge_results(local: LocalResult, first_seq: int, text_base: int, group=None
     if not locate:
         z = torch.zeros(0, dtype=torch.int64, device=dev)
         return MergedResult(counts, torch.zeros(n + 1, dtype=torch.int64, device=dev), z, z, z)
-    # per-pattern occurrence counts of every rank
-    mine = (local.pos_offsets[1:] - local.pos_offsets[:-1]).contiguous()
-    per_rank = torch.empty(world * n, dtype=torch.int64, device=dev)     # flat: gloo only takes 1-D outputs
+    # per-pattern occurrence counts of every rank (int32 on the wire: a pattern has < 2^31 occurrences in one shard)
+    mine = (local.pos_offsets[1:] - local.pos_offsets[:-1]).to(torch.int32).contiguous()
+    per_rank = torch.empty(world * n, dtype=torch.int32, device=dev)     # flat: gloo only takes 1-D outputs
     dist.all_gather_into_tensor(per_rank, mine, group=group)
     per_rank = per_rank.view(world, n)
-    totals = per_rank.sum(dim=1)                                   # occurrences per rank
-    max_total = int(totals.max().item()) if n else 0
+    totals = per_rank.sum(dim=1, dtype=torch.int64)                      # occurrences per rank
+    totals_h = totals.tolist()
+    max_total = max(totals_h) if n else 0
     # all-gather-v as a padded all-gather of one packed [3, max_total] tensor per rank
     packed = torch.zeros((3, max(max_total, 1)), dtype=torch.int64, device=dev)
     t = local.positions.numel()
     if t:
         packed[0, :t] = local.positions + text_base
-        packed[1, :t] = local.seq + first_seq
-        packed[2, :t] = local.off
         # sequence index -1 (no terminator beyond the position, EFMCollection.cpp:124-133) stays -1
-        packed[1, :t] = torch.where(local.seq < 0, local.seq, packed[1, :t])
+        packed[1, :t] = torch.where(local.seq < 0, local.seq, local.seq + first_seq)
+        packed[2, :t] = local.off
     gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(gathered, packed.view(-1), group=group)
     gathered = gathered.view(world, 3, max(max_total, 1))
     # global CSR: pattern p holds rank 0's occurrences, then rank 1's, ...
-    per_pattern = per_rank.sum(dim=0)
+    per_pattern = per_rank.sum(dim=0, dtype=torch.int64)
     offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     torch.cumsum(per_pattern, dim=0, out=offsets[1:])
-    total = int(offsets[-1].item()) if n else 0
-    positions = torch.empty(total, dtype=torch.int64, device=dev)
-    seq = torch.empty(total, dtype=torch.int64, device=dev)
-    off = torch.empty(total, dtype=torch.int64, device=dev)
-    before = torch.cumsum(per_rank, dim=0) - per_rank              # occurrences of earlier ranks, per pattern
-    for r in range(world):
-        tr = int(totals[r].item())
-        if tr == 0:
-            continue
-        cnt = per_rank[r]
-        local_off = torch.cumsum(cnt, dim=0) - cnt                 # rank r's own CSR starts
-        pat = torch.repeat_interleave(torch.arange(n, device=dev), cnt)
-        within = torch.arange(tr, device=dev) - local_off[pat]
-        dest = offsets[:-1][pat] + before[r][pat] + within
-        positions[dest] = gathered[r, 0, :tr]
-        seq[dest] = gathered[r, 1, :tr]
-        off[dest] = gathered[r, 2, :tr]
+    total = int(sum(totals_h))
+    out = torch.empty((3, total), dtype=torch.int64, device=dev)
+    if total:
+        # every (rank, pattern) block keeps its order; its destination starts after the blocks of earlier ranks
+        before = torch.cumsum(per_rank, dim=0, dtype=torch.int64) - per_rank          # [world, n]
+        start = (offsets[:-1].unsqueeze(0) + before).view(-1)                          # destination of each block
+        cnt = per_rank.view(-1).to(torch.int64)                                        # blocks in (rank, pattern) order
+        src_start = torch.cumsum(cnt, dim=0) - cnt                                     # = position in the rank-major concatenation
+        block = torch.repeat_interleave(torch.arange(world * n, device=dev), cnt, output_size=total)
+        dest = start[block] + (torch.arange(total, device=dev) - src_start[block])
+        src = torch.cat([gathered[r, :, :totals_h[r]] for r in range(world)], dim=1)   # rank-major, like `block`
+        out[:, dest] = src
     _ = rank
-    return MergedResult(counts, offsets, positions, seq, off)
+    return MergedResult(counts, offsets, out[0], out[1], out[2])
 
 
 # ------------------------------------------------------------------ GPU side
