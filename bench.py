@@ -60,6 +60,24 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to stdout; the driver wants ONE JSON line there. Keep the real stdout
+    for that line and send everything else to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def ref_bin():
     p = os.path.join(ROOT, "oracle", "_ref", "e2fm_ref")
     if not os.path.exists(p):
@@ -480,7 +498,7 @@ def gpu_arm(args, rank, world, local_rank):
                                     "cold_value": c,
                                     "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified "
                                               f"reference (1 matcher thread each), warm pass; cold pass {c} patterns/s; {wall:.1f}s wall"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ix.close()
     if world > 1:
         dist.barrier()
@@ -604,7 +622,7 @@ def sharded_arm(args, rank, world, local_rank):
                     "note": "patterns start in pinned host memory on rank 0; the merged result stays on the GPUs"},
             "gpu_launches": None, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     col.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -632,6 +650,7 @@ def main():
             return
         reference_arm(args, prepare(args.workload, 0))
         return
+    claim_stdout()
     if args.sharded:
         sharded_arm(args, rank, world, local_rank)
     else:
