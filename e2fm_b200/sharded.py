@@ -6,8 +6,10 @@ for group r. A batch is answered in one exchange step:
 
     broadcast(patterns from rank 0)  ->  local search on every shard (CUDA, e2fm_b200.capi)
     all_reduce(SUM, counts)          ->  EFMIndex::countOccurrences over the whole collection
-    all_gather(per-pattern occurrence counts) + all_gather(padded occurrence arrays)
-                                     ->  per-pattern concatenation in shard order
+    all_reduce(SUM, occurrences per pattern) + all_gather(int32 occurrences per pattern per shard)
+                                     ->  merged CSR offsets, and where each shard's occurrences go inside every pattern
+    all_reduce(SUM, zero-filled merged arrays written at disjoint places)
+                                     ->  per-pattern concatenation in shard order, on every rank
 
 Exact patterns never span a terminator and every sequence starts k-aligned (EFMCollection.cpp:218-225), so an
 occurrence has the same (sequence, offset) whether its sequence is indexed alone, in a shard or in the whole
@@ -97,42 +99,30 @@ def merge_results(local: LocalResult, first_seq: int, text_base: int, group=None
     if not locate:
         z = torch.zeros(0, dtype=torch.int64, device=dev)
         return MergedResult(counts, torch.zeros(n + 1, dtype=torch.int64, device=dev), z, z, z)
-    # per-pattern occurrence counts of every rank (int32 on the wire: a pattern has < 2^31 occurrences in one shard)
-    mine = (local.pos_offsets[1:] - local.pos_offsets[:-1]).to(torch.int32).contiguous()
-    per_rank = torch.empty(world * n, dtype=torch.int32, device=dev)     # flat: gloo only takes 1-D outputs
-    dist.all_gather_into_tensor(per_rank, mine, group=group)
-    per_rank = per_rank.view(world, n)
-    totals = per_rank.sum(dim=1, dtype=torch.int64)                      # occurrences per rank
-    totals_h = totals.tolist()
-    max_total = max(totals_h) if n else 0
-    # all-gather-v as a padded all-gather of one packed [3, max_total] tensor per rank
-    packed = torch.zeros((3, max(max_total, 1)), dtype=torch.int64, device=dev)
-    t = local.positions.numel()
-    if t:
-        packed[0, :t] = local.positions + text_base
-        # sequence index -1 (no terminator beyond the position, EFMCollection.cpp:124-133) stays -1
-        packed[1, :t] = torch.where(local.seq < 0, local.seq, local.seq + first_seq)
-        packed[2, :t] = local.off
-    gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, packed.view(-1), group=group)
-    gathered = gathered.view(world, 3, max(max_total, 1))
-    # global CSR: pattern p holds rank 0's occurrences, then rank 1's, ...
-    per_pattern = per_rank.sum(dim=0, dtype=torch.int64)
+    # Per pattern, the merged list is rank 0's occurrences, then rank 1's, ...: every rank computes where ITS occurrences go and
+    # writes them into a zero-filled array of the merged size; destinations are disjoint, so one all-reduce(SUM) assembles the
+    # whole result on every rank (an all-gather-v without padding or a receive-side scatter).
+    mine = (local.pos_offsets[1:] - local.pos_offsets[:-1]).contiguous()            # my occurrences per pattern
+    per_pattern = mine.clone()
+    dist.all_reduce(per_pattern, op=dist.ReduceOp.SUM, group=group)
     offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     torch.cumsum(per_pattern, dim=0, out=offsets[1:])
-    total = int(sum(totals_h))
-    out = torch.empty((3, total), dtype=torch.int64, device=dev)
+    # occurrences of the ranks before me, per pattern (int32 on the wire: a pattern has < 2^31 occurrences in one shard)
+    per_rank = torch.empty(world * n, dtype=torch.int32, device=dev)                # flat: gloo only takes 1-D outputs
+    dist.all_gather_into_tensor(per_rank, mine.to(torch.int32), group=group)
+    before = per_rank.view(world, n)[:rank].sum(dim=0, dtype=torch.int64) if rank > 0 else torch.zeros(n, dtype=torch.int64, device=dev)
+    total = int(offsets[-1].item()) if n else 0
+    out = torch.zeros((3, total), dtype=torch.int64, device=dev)
+    t = local.positions.numel()
+    if t:
+        pat = torch.repeat_interleave(torch.arange(n, device=dev), mine, output_size=t)
+        dest = offsets[:-1][pat] + before[pat] + (torch.arange(t, device=dev) - local.pos_offsets[:-1][pat])
+        out[0, dest] = local.positions + text_base
+        # sequence index -1 (no terminator beyond the position, EFMCollection.cpp:124-133) stays -1
+        out[1, dest] = torch.where(local.seq < 0, local.seq, local.seq + first_seq)
+        out[2, dest] = local.off
     if total:
-        # every (rank, pattern) block keeps its order; its destination starts after the blocks of earlier ranks
-        before = torch.cumsum(per_rank, dim=0, dtype=torch.int64) - per_rank          # [world, n]
-        start = (offsets[:-1].unsqueeze(0) + before).view(-1)                          # destination of each block
-        cnt = per_rank.view(-1).to(torch.int64)                                        # blocks in (rank, pattern) order
-        src_start = torch.cumsum(cnt, dim=0) - cnt                                     # = position in the rank-major concatenation
-        block = torch.repeat_interleave(torch.arange(world * n, device=dev), cnt, output_size=total)
-        dest = start[block] + (torch.arange(total, device=dev) - src_start[block])
-        src = torch.cat([gathered[r, :, :totals_h[r]] for r in range(world)], dim=1)   # rank-major, like `block`
-        out[:, dest] = src
-    _ = rank
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return MergedResult(counts, offsets, out[0], out[1], out[2])
 
 
