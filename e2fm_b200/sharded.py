@@ -170,26 +170,70 @@ class ShardedCollection:
         self.group = group
         self.last_phase_ms = {}
 
-    def search_batch(self, pats_rank0, shape, locate: bool) -> MergedResult:
-        """pats_rank0: (n, L) uint8 tensor on rank 0 (ignored elsewhere); shape = (n, L) known to every rank."""
+    def search_batch(self, pats_rank0, shape, locate: bool, pieces: int | None = None) -> MergedResult:
+        """pats_rank0: (n, L) uint8 tensor on rank 0, ideally pinned (ignored elsewhere); shape = (n, L) known to every rank.
+
+        The batch is cut into pieces: rank 0 queues every piece's host->device copy up front on a side stream, and each piece is
+        broadcast, searched and merged as soon as it has arrived, so the PCIe transfer of the later pieces overlaps the NCCL,
+        kernel and merge time of the earlier ones."""
         import time
-        t0 = time.perf_counter()
-        d_pats = broadcast_patterns(pats_rank0, shape, self.device, self.group)
-        torch.cuda.synchronize(self.device)   # the library searches on its own stream
-        t1 = time.perf_counter()
         n, L = shape
-        res = self.ix.search_device_fixed(d_pats.data_ptr(), n, L, locate)
-        search_ms = self.ix.last_batch_ms()["total"]
-        local = local_result_from_device(res, self.device)
-        torch.cuda.synchronize(self.device)
-        res.free()
-        t2 = time.perf_counter()
-        out = merge_results(local, self.first_seq, self.text_base, self.group, locate)
-        torch.cuda.synchronize(self.device)
-        t3 = time.perf_counter()
-        self.last_phase_ms = {"broadcast": (t1 - t0) * 1e3, "search_device": search_ms, "search_wall": (t2 - t1) * 1e3,
-                              "merge": (t3 - t2) * 1e3}
-        return out
+        rank = dist.get_rank(self.group)
+        if pieces is None:
+            pieces = 4 if n >= (1 << 20) else 1
+        bounds = [n * i // pieces for i in range(pieces + 1)]
+        t0 = time.perf_counter()
+        d_pats = torch.empty((n, L), dtype=torch.uint8, device=self.device)
+        events = []
+        if rank == 0:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for i in range(pieces):
+                    a, b = bounds[i], bounds[i + 1]
+                    d_pats[a:b].copy_(pats_rank0[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+        ph = {"broadcast": 0.0, "search_device": 0.0, "search_wall": 0.0, "merge": 0.0}
+        parts = []
+        for i in range(pieces):
+            a, b = bounds[i], bounds[i + 1]
+            if b == a:
+                continue
+            t1 = time.perf_counter()
+            if rank == 0:
+                torch.cuda.current_stream(self.device).wait_event(events[i])
+            dist.broadcast(d_pats[a:b], src=0, group=self.group)
+            torch.cuda.synchronize(self.device)   # the library searches on its own stream
+            t2 = time.perf_counter()
+            res = self.ix.search_device_fixed(d_pats.data_ptr() + a * L, b - a, L, locate)
+            ph["search_device"] += self.ix.last_batch_ms()["total"]
+            local = local_result_from_device(res, self.device)
+            torch.cuda.synchronize(self.device)
+            res.free()
+            t3 = time.perf_counter()
+            parts.append(merge_results(local, self.first_seq, self.text_base, self.group, locate))
+            torch.cuda.synchronize(self.device)
+            t4 = time.perf_counter()
+            ph["broadcast"] += (t2 - t1) * 1e3
+            ph["search_wall"] += (t3 - t2) * 1e3
+            ph["merge"] += (t4 - t3) * 1e3
+        ph["wall"] = (time.perf_counter() - t0) * 1e3
+        self.last_phase_ms = ph
+        if len(parts) == 1:
+            return parts[0]
+        if not parts:
+            z = torch.zeros(0, dtype=torch.int64, device=self.device)
+            return MergedResult(z, torch.zeros(1, dtype=torch.int64, device=self.device), z, z, z)
+        # pieces are contiguous pattern ranges: concatenate, shifting the CSR offsets
+        offs = [parts[0].pos_offsets]
+        shift = int(parts[0].positions.numel())
+        for p in parts[1:]:
+            offs.append(p.pos_offsets[1:] + shift)
+            shift += int(p.positions.numel())
+        return MergedResult(torch.cat([p.counts for p in parts]), torch.cat(offs), torch.cat([p.positions for p in parts]),
+                            torch.cat([p.seq for p in parts]), torch.cat([p.off for p in parts]))
 
     def close(self):
         self.ix.close()

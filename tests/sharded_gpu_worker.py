@@ -35,8 +35,8 @@ def main():
         pats0 = None
         if rank == 0:
             pats0 = torch.from_numpy(np.frombuffer(b"".join(all_pats[i] for i in keep), dtype=np.uint8).reshape(shape).copy())
-        for locate in (True, False):
-            m = col.search_batch(pats0, shape, locate)
+        for locate, pieces in ((True, None), (False, None), (True, 3)):
+            m = col.search_batch(pats0, shape, locate, pieces)
             assert np.array_equal(m.counts.cpu().numpy(), res["counts"][keep].astype(np.int64)), (rank, L)
             if locate:
                 want_pos, want_seq, want_off = [], [], []
