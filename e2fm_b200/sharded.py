@@ -206,16 +206,17 @@ class ShardedCollection:
             if rank == 0:
                 torch.cuda.current_stream(self.device).wait_event(events[i])
             dist.broadcast(d_pats[a:b], src=0, group=self.group)
-            torch.cuda.synchronize(self.device)   # the library searches on its own stream
+            # (stream-level syncs only: a device-wide one would also wait for the copies of the later pieces)
+            torch.cuda.current_stream(self.device).synchronize()   # the library searches on its own stream
             t2 = time.perf_counter()
             res = self.ix.search_device_fixed(d_pats.data_ptr() + a * L, b - a, L, locate)
             ph["search_device"] += self.ix.last_batch_ms()["total"]
             local = local_result_from_device(res, self.device)
-            torch.cuda.synchronize(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
             res.free()
             t3 = time.perf_counter()
             parts.append(merge_results(local, self.first_seq, self.text_base, self.group, locate))
-            torch.cuda.synchronize(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
             t4 = time.perf_counter()
             ph["broadcast"] += (t2 - t1) * 1e3
             ph["search_wall"] += (t3 - t2) * 1e3
