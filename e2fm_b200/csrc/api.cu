@@ -184,7 +184,7 @@ T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
 }
 
 // view of a workspace slot with the DBuf interface; contents are preserved across a growth only when asked
-enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SURV, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_IVL, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
+enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SPARE, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_FIRSTW, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
        WS_CURSOR, WS_BIG_LIST, WS_HATW };
 template <class T>
 struct WsBuf {
@@ -470,7 +470,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     }
     const uint64_t items_cap = chunk * k;
     WsBuf<uint2> iv(ix, WS_IV, items_cap, s);
-    WsBuf<uint32_t> firstw(ix, WS_IVL, items_cap, s), hatw(ix, WS_HATW, items_cap, s);
+    WsBuf<uint32_t> firstw(ix, WS_FIRSTW, items_cap, s), hatw(ix, WS_HATW, items_cap, s);
     WsBuf<uint64_t> task_off(ix, WS_TASK_OFF, items_cap + 1, s);
     WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
     WsBuf<uint2> tasks(ix, WS_TASKS, s);
@@ -844,14 +844,6 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ix->n_sm = prop.multiProcessorCount;
-        if (const char *g = getenv("E2FM_L2_FETCH")) {   // experiment knob: L2 fetch granularity in bytes (32/64/128)
-            CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
-        }
-        {
-            size_t gran = 0;
-            cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity);
-            if (getenv("E2FM_VERBOSE")) fprintf(stderr, "[e2fm] L2 fetch granularity %zu B\n", gran);
-        }
         CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ix->h2d_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ix->d2h_stream, cudaStreamNonBlocking));

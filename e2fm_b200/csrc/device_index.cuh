@@ -123,13 +123,6 @@ __device__ __forceinline__ uint32_t rank_c(const DevIndex &ix, uint32_t c, uint3
     return sector_rank(ix, s, row & ((1u << ix.blk_shift) - 1));
 }
 
-// LF(row) given the row's record. Unmarked rows carry it; a marked row's low word is its marked value,
-// so its LF is recomputed from the rank sector (2% of rows at the default marking rate).
-__device__ __forceinline__ uint32_t lf_of(const DevIndex &ix, uint64_t r, uint32_t row) {
-    if (!rec_marked(r)) return rec_low(r);
-    return rank_c(ix, rec_code(r), row) - 1;
-}
-
 __device__ __forceinline__ uint64_t ld_rec(const DevIndex &ix, uint32_t row) { return __ldg(ix.rec + row); }
 
 }  // namespace e2fm

@@ -50,14 +50,6 @@ __device__ __forceinline__ uint32_t natural_value(const DevIndex &ix, const uint
     return bad ? 0xFFFFFFFFu : v;
 }
 
-// compact code of a fully specified super-character, 0xFFFF when the pattern holds a foreign symbol or the
-// k-mer never occurs in the text (the reference drops the whole shift, EFMIndex.cpp:2188-2197)
-__device__ __forceinline__ uint32_t fixed_code(const DevIndex &ix, const uint8_t *p) {
-    const uint32_t nat = natural_value(ix, p, ix.k);
-    if (nat == 0xFFFFFFFFu) return 0xFFFFu;
-    return __ldg(ix.compact_of_natural + nat);
-}
-
 __device__ __forceinline__ uint32_t ipow(uint32_t b, uint32_t e) {
     uint32_t r = 1;
     for (uint32_t i = 0; i < e; i++) r *= b;

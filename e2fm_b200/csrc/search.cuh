@@ -23,7 +23,7 @@ enum {
     ST_RANK = 0,     // getOffsetInformations(CountOnly) equivalents   (Bucket.cpp:656)
     ST_LF = 1,       // getOffsetInformations(RetrieveCharacter) equivalents
     ST_MARK = 2,     // getMarkedTextPosition equivalents              (Bucket.cpp:823)
-    ST_TASKS = 3,    // row tasks of the current chunk
+    ST_TASKS = 3,    // (unused: the row-task count of a chunk lives in its own device word, see SearchArgs::task_cursor)
     ST_RESULTS = 4,  // located occurrences appended so far
     ST_BIGSEG = 5,   // result segments longer than the per-thread sort limit
     ST_DUPS = 6,     // duplicate positions removed (EFMIndex.cpp:2296-2299)
