@@ -24,7 +24,7 @@ OPT_DENSITY = 6
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
-    "e2fm_index_open", "e2fm_index_close", "e2fm_index_info", "e2fm_index_terminators", "e2fm_index_fasta_headers",
+    "e2fm_index_open", "e2fm_parse_header", "e2fm_index_close", "e2fm_index_info", "e2fm_index_terminators", "e2fm_index_fasta_headers",
     "e2fm_index_stream", "e2fm_search_batch", "e2fm_search_batch_fixed", "e2fm_search_batch_device",
     "e2fm_search_batch_device_fixed", "e2fm_search_batch_stream", "e2fm_host_alloc", "e2fm_host_free", "e2fm_device_count",
     "e2fm_extract", "e2fm_result_patterns", "e2fm_result_total_positions", "e2fm_result_fetch", "e2fm_result_device_ptrs",
@@ -68,6 +68,7 @@ def lib():
     L.e2fm_host_alloc.argtypes = [C.c_size_t]
     L.e2fm_host_free.argtypes = [vp]
     L.e2fm_index_open.argtypes = [vp, C.c_size_t, C.c_char_p, i32, C.POINTER(vp)]
+    L.e2fm_parse_header.argtypes = [vp, C.c_size_t, C.c_char_p, C.POINTER(Info), vp, u64, vp, u64]
     L.e2fm_index_close.argtypes = [vp]
     L.e2fm_index_close.restype = None
     L.e2fm_index_info.argtypes = [vp, C.POINTER(Info)]
@@ -107,6 +108,16 @@ def lib():
 def check(rc: int) -> None:
     if rc != E2FM_OK:
         raise E2FMError(rc, lib().e2fm_last_error().decode(errors="replace"))
+
+
+def parse_header(index_bytes: bytes, key64: bytes):
+    """host-only header parse (no GPU): -> (Info, C[] as uint64 array, terminators as int64 array)"""
+    info = Info()
+    buf = np.frombuffer(index_bytes, dtype=np.uint8)
+    c = np.zeros(1 << 16, dtype=np.uint64)
+    t = np.zeros(1 << 16, dtype=np.int64)
+    check(lib().e2fm_parse_header(buf.ctypes.data, len(buf), key64, C.byref(info), c.ctypes.data, len(c), t.ctypes.data, len(t)))
+    return info, c[:info.compact_alphabet + 1].copy(), t[:min(int(info.n_sequences), len(t))].copy()
 
 
 def device_count() -> int:

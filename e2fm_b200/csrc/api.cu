@@ -823,6 +823,37 @@ void *e2fm_host_alloc(size_t bytes) {
 }
 void e2fm_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// host-only: what e2fm_index_open does before it touches the device (no CUDA call in here)
+int e2fm_parse_header(const uint8_t *file, size_t size, const uint8_t key64[64], e2fm_info *info, uint64_t *c_out, uint64_t c_cap,
+                      int64_t *term_out, uint64_t term_cap) {
+    if (!file || !key64 || !info) return fail(E2FM_ERR_ARG, "bad argument");
+    try {
+        HostImage g;
+        parse_index_header(file, size, key64, g);
+        memset(info, 0, sizeof(*info));
+        info->text_length = g.n;
+        info->bucket_size = g.b_size;
+        info->superbucket_size = g.sb_size;
+        info->n_buckets = g.B;
+        info->n_superbuckets = g.S;
+        info->n_sequences = g.terminators.size();
+        info->initial_n = g.initial_n;
+        info->k = g.k;
+        info->n_symbols = g.n_sym;
+        info->compact_alphabet = g.A;
+        info->marked_rows_percentage = g.mrp;
+        info->marking_rate = g.rate;
+        info->quirks = g.quirks;
+        for (uint64_t i = 0; i < g.C.size() && i < c_cap && c_out; i++) c_out[i] = g.C[i];
+        for (uint64_t i = 0; i < g.terminators.size() && i < term_cap && term_out; i++) term_out[i] = g.terminators[i];
+    } catch (const std::bad_alloc &) {
+        return fail(E2FM_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_FORMAT, e.what());
+    }
+    return E2FM_OK;
+}
+
 int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], int device, e2fm_index **out) {
     if (!file || !key64 || !out) return fail(E2FM_ERR_ARG, "bad argument");
     *out = nullptr;

@@ -59,6 +59,11 @@ typedef struct e2fm_info {
  * `key64` the 64-byte key (EncryptionManager::initSALSA20Keys, EncryptionManager.cpp:47).
  * Header secrets are derived on the host; every bucket is decrypted + decoded on the device. */
 int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], int device, e2fm_index **out);
+/* The host half of e2fm_index_open alone (no GPU needed): EFMIndex::readHeader + EFMCollection::readHeader (EFMIndex.cpp:1150,
+ * EFMCollection.cpp:289) incl. the key-dependent secrets — scrambling permutation, decrypted C[] (compact_alphabet + 1 entries,
+ * up to c_cap copied), terminators (up to term_cap copied). Same error classes and messages as e2fm_index_open. */
+int e2fm_parse_header(const uint8_t *file, size_t size, const uint8_t key64[64], e2fm_info *info, uint64_t *c_out, uint64_t c_cap,
+                      int64_t *term_out, uint64_t term_cap);
 /* EFMIndex::close (EFMIndex.cpp:1602) */
 void e2fm_index_close(e2fm_index *ix);
 int e2fm_index_info(const e2fm_index *ix, e2fm_info *out);

@@ -683,6 +683,10 @@ int64_t orc_search(orc_index *ix, const uint8_t *pat, uint32_t m, int mode, uint
     return (int64_t)w;
 }
 
+/* header views for the host-parse tests: C[0..A] and the terminators */
+void orc_get_C(const orc_index *ix, uint64_t *out) { for (uint32_t i = 0; i <= ix->A; i++) out[i] = ix->C[i]; }
+void orc_get_terminators(const orc_index *ix, int64_t *out) { for (uint64_t i = 0; i < ix->n_term; i++) out[i] = ix->term[i]; }
+
 /* EFMIndex::extractSnippet(from, to) (EFMIndex.cpp:2325-2452), character by character through super_char_at (the reference walks LF
  * once from the marked row after stTo; the k-mers read are the same). Returns the length (may exceed cap), -1 without marked rows. */
 int64_t orc_extract(orc_index *ix, uint64_t from, uint64_t to, uint8_t *out, uint64_t cap) {

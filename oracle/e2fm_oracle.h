@@ -53,6 +53,8 @@ int64_t orc_search(orc_index *ix, const uint8_t *pattern, uint32_t len, int mode
 /* EFMCollection::search position -> (sequenceIndex, offset)   (EFMCollection.cpp:124-148) */
 void orc_map_position(const orc_index *ix, uint64_t pos, uint32_t *seq, uint64_t *off);
 
+void orc_get_C(const orc_index *ix, uint64_t *out);                 /* compact_alphabet + 1 entries */
+void orc_get_terminators(const orc_index *ix, int64_t *out);        /* n_sequences entries */
 /* EFMIndex::extractSnippet(from,to) (EFMIndex.cpp:2325): returns the length written (may exceed cap), -1 without marked rows */
 int64_t orc_extract(orc_index *ix, uint64_t from, uint64_t to, uint8_t *out, uint64_t cap);
 

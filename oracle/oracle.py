@@ -58,6 +58,8 @@ def lib():
         L.orc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64),
                                  C.c_void_p, C.c_uint64]
         L.orc_map_position.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_get_C.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_get_terminators.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_extract.restype = C.c_int64
         L.orc_extract.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_get_bwt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -176,6 +178,16 @@ class OracleIndex:
         s, o = C.c_uint32(0), C.c_uint64(0)
         lib().orc_map_position(self._h, int(pos), C.byref(s), C.byref(o))
         return int(s.value), int(o.value)
+
+    def header_C(self) -> np.ndarray:
+        out = np.zeros(int(self.info.compact_alphabet) + 1, dtype=np.uint64)
+        lib().orc_get_C(self._h, out.ctypes.data)
+        return out
+
+    def header_terminators(self) -> np.ndarray:
+        out = np.zeros(int(self.info.n_sequences), dtype=np.int64)
+        lib().orc_get_terminators(self._h, out.ctypes.data)
+        return out
 
     def extract_snippet(self, frm: int, to: int) -> bytes:
         """EFMIndex::extractSnippet(from, to)"""

@@ -64,3 +64,32 @@ def test_product_never_imports_the_oracle():
 def test_key_must_be_64_bytes(golden):
     with pytest.raises(ValueError):
         capi.DeviceIndex(golden["col3_k4"]["index"], b"short")
+
+
+@pytest.mark.parametrize("name", ["col3_k4", "one_k3", "col2_k2", "col2_k4_nomarks"])
+def test_host_header_parse_matches_oracle(golden, key64, oracle_mod, name):
+    """the host half of e2fm_index_open (magic, geometry, scrambling permutation, C[] decryption, terminators) runs without a
+    GPU and must agree with the oracle, which is pinned to the reference's dump"""
+    info, Cc, term = capi.parse_header(golden[name]["index"], key64)
+    orc = oracle_mod.OracleIndex(golden[name]["index"], key64)
+    o = orc.info
+    assert (info.text_length, info.k, info.n_symbols, info.marked_rows_percentage) == (o.n, o.k, o.n_sym, o.mrp)
+    assert (info.bucket_size, info.superbucket_size, info.n_buckets, info.n_superbuckets) == (
+        o.bucket_size, o.superbucket_size, o.n_buckets, o.n_superbuckets)
+    assert info.compact_alphabet == o.compact_alphabet and info.n_sequences == o.n_sequences and info.initial_n == o.initial_n
+    assert info.quirks == 0
+    assert np.array_equal(Cc, orc.header_C())
+    assert np.array_equal(term, orc.header_terminators())
+
+
+def test_host_header_parse_errors(golden, key64):
+    idx = golden["col3_k4"]["index"]
+    with pytest.raises(capi.E2FMError) as e:
+        capi.parse_header(b"XY" + idx[2:], key64)
+    assert e.value.code == -2 and "File type is not Encrypted and Compressed Genomic Index" in str(e.value)   # EFMIndex.cpp:1155
+    with pytest.raises(capi.E2FMError) as e:
+        capi.parse_header(idx, bytes((b + 1) & 0xFF for b in key64))
+    assert e.value.code == -2 and "wrong encryption key" in str(e.value)
+    for cut in (10, 60, 200, len(idx) // 3):
+        with pytest.raises(capi.E2FMError):
+            capi.parse_header(idx[:cut], key64)
