@@ -652,6 +652,61 @@ __global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(Load in, uint64_t n,
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
 }
 
+// Fast path: the apply pass of the interval scan writes the row tasks directly (no offset array, no separate expansion
+// kernel). Thread t owns SCAN_E consecutive (pattern, shift) items; its first task slot is the scanned prefix. The chunk's task
+// count goes to *n_tasks_out; when it exceeds `cap` nothing is written and the host redoes the chunk through the windowed path.
+__global__ void __launch_bounds__(SCAN_T) scan_expand_kernel(const uint2 *__restrict__ iv, uint64_t n, const uint64_t *sums, uint64_t nb,
+                                                             uint2 *__restrict__ tasks, uint64_t cap, unsigned long long *n_tasks_out) {
+    __shared__ unsigned long long ws[SCAN_T / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t total = sums[nb];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_tasks_out = total;
+    if (total > cap) return;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_E;
+    uint2 it[SCAN_E];
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_E; j++) {
+        it[j] = base + j < n ? iv[base + j] : make_uint2(0u, 0u);
+        if (it[j].y & IV_LONG) it[j].y = 0;         // long wildcard intervals are scanned by firstcheck_kernel
+        tot += it[j].y;
+    }
+    unsigned long long inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    unsigned long long run = sums[blockIdx.x] + inc - tot;
+    for (uint32_t w = 0; w < warp; w++) run += ws[w];
+#pragma unroll
+    for (int j = 0; j < SCAN_E; j++) {
+        const uint32_t len = it[j].y, item = (uint32_t)(base + j);
+        if (len && len <= 8)
+            for (uint32_t q = 0; q < len; q++) tasks[run + q] = make_uint2(it[j].x + q, item);
+        unsigned mask = __ballot_sync(FULL, len > 8);
+        while (mask) {                              // long intervals are written by the whole warp
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t r0 = __shfl_sync(FULL, it[j].x, src), ln = __shfl_sync(FULL, len, src), im = __shfl_sync(FULL, item, src);
+            const unsigned long long d = __shfl_sync(FULL, run, src);
+            for (uint32_t q = lane; q < ln; q += 32) tasks[d + q] = make_uint2(r0 + q, im);
+        }
+        run += len;
+    }
+}
+
+void launch_scan_expand(const uint2 *iv, uint32_t n_items, uint64_t *scratch, uint2 *tasks, uint64_t cap, unsigned long long *n_tasks_out,
+                        cudaStream_t s) {
+    if (n_items == 0) return;
+    const uint64_t nb = ((uint64_t)n_items + SCAN_B - 1) / SCAN_B;
+    scan_block_sums_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(LoadIvLen{iv}, (uint64_t)n_items, scratch);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(scratch, nb);
+    scan_expand_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(iv, (uint64_t)n_items, scratch, nb, tasks, cap, n_tasks_out);
+}
+
 size_t scan_scratch_elems(uint64_t n) { return (size_t)((n + SCAN_B - 1) / SCAN_B + 2); }
 
 template <class Load>
