@@ -696,9 +696,10 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         res->d_seqoff = seqoff.take();
     }
     res->d_counts = counts.take();
+    // Every path above ends with a statistics read (which synchronises the stream); the search kernels ran before it and the
+    // result pipeline, which runs after it in locate mode, only touches the DUPS / BIGSEG words it reads itself.
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    read_stats(ix);
     ix->batch_ctr[0] = ix->h_stats[ST_RANK] - redo_rank;
     ix->batch_ctr[1] = ix->h_stats[ST_LF];
     ix->batch_ctr[2] = ix->h_stats[ST_MARK];
