@@ -444,9 +444,11 @@ def test_config1_short_patterns_take_the_wildcard_scan(config1, key64, oracle_mo
     for L in (9, 10, 11, 12, 13):
         st = rng.integers(0, len(seq) - L, 120)
         pats += [seq[s:s + L].tobytes() for s in st]
-    pats += [b"ACGTACGTACGT", b"AAAAAAAAAAAA", b"ACGTNACGTACG"]
+    # one k-mer (tens of thousands of occurrences: the global-memory segment sort) and two (hundreds: the CTA sort)
+    pats += [b"ACGTACGTACGT", b"AAAAAAAAAAAA", b"ACGTNACGTACG", b"ACGT", b"TTTT", b"GATTACAG", b"ACGTAC"]
     data, offs = pack(pats)
     want = [orc.search(p, True) for p in pats]
+    assert max(w[0] for w in want) > 4096
     scanned = 0
     for dense in (1, 0):
         dev.set_option(capi.OPT_DENSE, dense)
