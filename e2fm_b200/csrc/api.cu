@@ -408,6 +408,24 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
     d.natural_of_compact = dev_keep_copy<uint32_t>(ix, img.natural_of_compact.data(), img.natural_of_compact.size());
     d.sym_index = dev_keep_copy<uint8_t>(ix, sym_index, 256);
     d.symbols = dev_keep_copy<uint8_t>(ix, img.syms, img.n_sym);
+    {
+        // low / high symbol parts of every k-mer (EFMIndex::backwardStepIfMatch and findWholePatternMatches compare k-mer strings
+        // position by position, EFMIndex.cpp:2011-2041, :1862-1899; here one table lookup and an integer compare)
+        const uint32_t km1 = img.k > 1 ? img.k - 1 : 0;
+        std::vector<uint32_t> low((size_t)km1 * img.A + 1), high((size_t)km1 * img.A + 1);
+        for (uint32_t f = 1; f <= km1; f++) {
+            uint64_t pf = 1, pr = 1;
+            for (uint32_t i = 0; i < f; i++) pf *= img.n_sym;
+            for (uint32_t i = 0; i < img.k - f; i++) pr *= img.n_sym;
+            for (uint32_t c = 0; c < img.A; c++) {
+                low[(size_t)(f - 1) * img.A + c] = (uint32_t)(img.natural_of_compact[c] % pf);
+                high[(size_t)(f - 1) * img.A + c] = (uint32_t)(img.natural_of_compact[c] / pr);
+            }
+        }
+        d.kmer_low = dev_keep_copy<uint32_t>(ix, low.data(), low.size());
+        d.kmer_high = dev_keep_copy<uint32_t>(ix, high.data(), high.size());
+        CK(cudaStreamSynchronize(s));   // the vectors above go out of scope
+    }
     d.terminators = dev_keep_copy<int64_t>(ix, img.terminators.data(), img.terminators.size());
     // start-interval table over pairs of super-characters (needs the finished DevIndex: it ranks through the sectors)
     if ((uint64_t)img.A * img.A <= (4u << 20)) {

@@ -58,6 +58,9 @@ struct DevIndex {
     const uint32_t *natural_of_compact;   // [A]
     const uint8_t *sym_index;   // [256] ASCII -> index in the original alphabet, 0xFF if absent
     const uint8_t *symbols;     // [n_sym] index -> ASCII
+    // per compact code c and number of fixed symbols f in 1..k-1 (tables of (k-1)*A entries, index (f-1)*A + c):
+    const uint32_t *kmer_low;   // natural(c) mod n_sym^f      — the f low-order symbols  ('?'-prefixed first super-character)
+    const uint32_t *kmer_high;  // natural(c) div n_sym^(k-f)  — the f high-order symbols ('?'-suffixed last super-character)
     const int64_t *terminators; // [n_term]
 };
 

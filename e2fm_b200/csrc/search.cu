@@ -384,29 +384,22 @@ static constexpr int FC_GROUP = 2;        // warp batches (of 32 items) per task
 
 // low[(f-1)*A + code] = the f low-order symbols of the k-mer of compact code `code` (its natural value mod n_sym^f): what a
 // '?'-prefixed first super-character with f fixed symbols has to equal. In shared memory when it fits, else recomputed.
-template <bool SMEM>
 struct FcTable {
-    const uint32_t *low;   // shared-memory table (SMEM) or unused
-    const DevIndex *ix;
+    const uint32_t *low;   // DevIndex::kmer_low (a few KB, L1-resident): entry (f-1)*A + code
     uint32_t A;
-    // `row` = low + (f-1)*A for the interval at hand
-    __device__ __forceinline__ bool match(const uint32_t *row, uint32_t code, uint32_t pw, uint32_t want) const {
-        if (SMEM) return row[code] == want;
-        return __ldg(ix->natural_of_compact + code) % pw == want;
-    }
 };
 
 // 8-bit mask of the matching rows among the 8 consecutive rows [c, c+8) (c a multiple of 8, loaded as v) that fall in [s0, s0+ln)
-template <bool SMEM>
-__device__ __forceinline__ uint32_t fc_eval(const FcTable<SMEM> &tab, const uint4 v, uint32_t c, uint32_t s0, uint32_t ln, uint32_t f,
+__device__ __forceinline__ uint32_t fc_eval(const FcTable &tab, const uint4 v, uint32_t c, uint32_t s0, uint32_t ln, uint32_t f,
                                             uint32_t pw, uint32_t want) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     const uint32_t *row = tab.low + (f - 1) * tab.A;
     uint32_t m = 0;
+    (void)pw;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         const uint32_t code = (w[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;
-        m |= (tab.match(row, code, pw, want) ? 1u : 0u) << t;
+        m |= (__ldg(row + code) == want ? 1u : 0u) << t;
     }
     // rows of the group that belong to the interval: [max(s0,c), min(s0+ln, c+8))
     const uint32_t lo = s0 > c ? s0 - c : 0u, hi = min(s0 + ln - c, 8u);
@@ -414,22 +407,14 @@ __device__ __forceinline__ uint32_t fc_eval(const FcTable<SMEM> &tab, const uint
 }
 static constexpr int FC_UNROLL = 4;   // 16-byte loads in flight per lane: an interval of up to 1024 rows costs one DRAM round trip
 
-template <int KT, bool SMEM>
+template <int KT>
 __global__ void __launch_bounds__(256) firstcheck_kernel(SearchArgs a) {
-    extern __shared__ uint32_t fc_low[];
     if (a.stats[ST_ANY_LONG] == 0) return;              // no long wildcard interval in this chunk (the usual case for long patterns)
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym;
     const uint32_t n_items = a.pv.count * k;
-    FcTable<SMEM> tab{fc_low, &ix, ix.A};
-    if (SMEM) {
-        for (uint32_t t = threadIdx.x; t < (k - 1) * ix.A; t += blockDim.x) {
-            const uint32_t f = t / ix.A + 1, code = t - (f - 1) * ix.A;
-            fc_low[t] = ix.natural_of_compact[code] % ipow(no, f);
-        }
-        __syncthreads();
-    }
+    const FcTable tab{ix.kmer_low, ix.A};
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long n_rows = 0;
     for (uint32_t g0 = warp_global * (32u * FC_GROUP); g0 < n_items; g0 += n_warps * (32u * FC_GROUP)) {
@@ -553,11 +538,8 @@ void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s) {
     if (n_items == 0 || a.ix.k < 2) return;
     const uint64_t groups = (n_items + 32 * FC_GROUP - 1) / (32 * FC_GROUP);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((groups + 7) / 8, (uint64_t)n_sm * 8);
-    const size_t tab_bytes = (size_t)(a.ix.k - 1) * a.ix.A * 4;
-    const bool use_smem = tab_bytes <= 40 * 1024;
-    if (a.ix.k == 4 && use_smem) firstcheck_kernel<4, true><<<blocks, 256, tab_bytes, s>>>(a);
-    else if (use_smem) firstcheck_kernel<0, true><<<blocks, 256, tab_bytes, s>>>(a);
-    else firstcheck_kernel<0, false><<<blocks, 256, 0, s>>>(a);
+    if (a.ix.k == 4) firstcheck_kernel<4><<<blocks, 256, 0, s>>>(a);
+    else firstcheck_kernel<0><<<blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- scans
@@ -960,24 +942,12 @@ void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
 // EFMIndex::extractSuperCharacter walks to). 1-3 independent gathers per task, one task per thread. What a row has to
 // match was computed once per (pattern, shift) by the backward search (firstw / hatw); the per-symbol parts of every
 // k-mer come from two small shared-memory tables, so a task touches no pattern bytes.
-template <int KT, bool SMEM>
+template <int KT>
 __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
-    extern __shared__ uint32_t rs_tab[];
     const DevIndex &ix = a.ix;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const uint32_t k = KT ? (uint32_t)KT : ix.k, no = ix.n_sym, A = ix.A;
-    // low[(f-1)*A + c]  = natural(c) mod no^f      (f low-order symbols:  '?'-prefixed first super-character)
-    // high[(f-1)*A + c] = natural(c) div no^(k-f)  (f high-order symbols: '?'-suffixed last super-character)
-    uint32_t *low = rs_tab, *high = rs_tab + (k - 1) * A;
-    if (SMEM) {
-        for (uint32_t t = threadIdx.x; t < (k - 1) * A; t += blockDim.x) {
-            const uint32_t f = t / A + 1, code = t - (f - 1) * A;
-            const uint32_t nat = ix.natural_of_compact[code];
-            low[t] = nat % ipow(no, f);
-            high[t] = nat / ipow(no, k - f);
-        }
-        __syncthreads();
-    }
+    const uint32_t *low = ix.kmer_low, *high = ix.kmer_high;   // (f-1)*A + code; a few KB, L1-resident
     if (a.n_tasks_dev) {
         const unsigned long long nt = *a.n_tasks_dev;
         a.n_tasks = nt > a.n_tasks ? 0u : (uint32_t)nt;
@@ -1016,7 +986,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
                     n_g++;
                     const uint32_t f = k - sa, want = natural_value(ix, ptr, f);
                     ok = want != 0xFFFFFFFFu &&
-                         (SMEM ? low[(f - 1) * A + code] : __ldg(ix.natural_of_compact + code) % ipow(no, f)) == want;
+                         __ldg(low + (f - 1) * A + code) == want;
                 }
                 if (ok && hat) {
                     const uint32_t from = (L - 1) * k - sa;
@@ -1038,7 +1008,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
                 if (p < ix.n) {
                     const uint32_t code = __ldg(ix.text + p);
                     n_g++;
-                    ok = (SMEM ? high[(hat_f - 1) * A + code] : __ldg(ix.natural_of_compact + code) / ipow(no, k - hat_f)) == hat_want;
+                    ok = __ldg(high + (hat_f - 1) * A + code) == hat_want;
                 }
             }
             emit = ok;
@@ -1071,11 +1041,8 @@ void launch_resolve(const WalkArgs &a, int n_sm, cudaStream_t s) {
     uint64_t blocks = a.n_tasks_dev ? ~0ull : ((uint64_t)a.n_tasks + 255) / 256;
     const uint64_t cap = (uint64_t)n_sm * 16;
     if (blocks > cap) blocks = cap;
-    const size_t tab_bytes = (size_t)2 * (a.ix.k > 1 ? a.ix.k - 1 : 0) * a.ix.A * 4;
-    const bool use_smem = tab_bytes <= 48 * 1024;
-    if (a.ix.k == 4 && use_smem) resolve_kernel<4, true><<<(uint32_t)blocks, 256, tab_bytes, s>>>(a);
-    else if (use_smem) resolve_kernel<0, true><<<(uint32_t)blocks, 256, tab_bytes, s>>>(a);
-    else resolve_kernel<0, false><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    if (a.ix.k == 4) resolve_kernel<4><<<(uint32_t)blocks, 256, 0, s>>>(a);
+    else resolve_kernel<0><<<(uint32_t)blocks, 256, 0, s>>>(a);
 }
 
 // ---------------------------------------------------------------- result pipeline
