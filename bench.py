@@ -295,6 +295,8 @@ def gpu_arm(args, rank, world, local_rank):
         ix.set_option(capi.OPT_CHUNK, args.chunk)
     if args.pipe:
         ix.set_option(capi.OPT_PIPE, args.pipe)
+    if args.taper:
+        ix.set_option(capi.OPT_TAPER, 1)
     info = ix.info
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
@@ -639,6 +641,7 @@ def main():
     ap.add_argument("--pieces", type=int, default=0, help="sharded mode: pipeline pieces per batch (0 = automatic)")
     ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
+    ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")
     ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()

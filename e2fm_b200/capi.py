@@ -21,6 +21,8 @@ OPT_WINDOW = 3
 OPT_DENSE = 4
 OPT_PIPE = 5
 OPT_DENSITY = 6
+OPT_TAPER = 7
+OPT_PHASE_TIMERS = 8
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [

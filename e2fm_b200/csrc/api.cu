@@ -102,7 +102,9 @@ struct EventTimer {
     cudaStream_t s;
     EventPool *pool;
     EventTimer(cudaStream_t st, EventPool *p) : s(st), pool(p) { spans.reserve(64); }
+    bool phases = true;      // false: only the whole-batch and H2D spans (slots 0 and 6) are recorded
     int begin(int slot, cudaStream_t on = nullptr) {
+        if (!phases && slot != 0 && slot != 6) return -1;
         Span sp;
         sp.slot = slot;
         sp.a = pool->get(true);
@@ -111,7 +113,7 @@ struct EventTimer {
         spans.push_back(sp);
         return (int)spans.size() - 1;
     }
-    void end(int h, cudaStream_t on = nullptr) { CK(cudaEventRecord(spans[h].b, on ? on : s)); }
+    void end(int h, cudaStream_t on = nullptr) { if (h >= 0) CK(cudaEventRecord(spans[h].b, on ? on : s)); }
     // after the streams have been synchronised
     void collect(float *out, int n_slots) {
         for (auto &sp : spans) {
@@ -134,7 +136,9 @@ struct e2fm_index {
     int n_sm = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-buffer pipeline
-    uint64_t pipe_patterns = 1u << 19;                          // patterns per pipeline stage when the batch comes from the host
+    int phase_timers = 2;                                         // 0 never, 1 always, 2 device-resident batches only
+    bool pipe_taper = false;                                      // host batches: stage sizes halve towards the end of the batch
+    uint64_t pipe_patterns = 1u << 18;                          // patterns per pipeline stage when the batch comes from the host
     HostImage img;              // header fields (the per-row vectors stay small: terminators, C, tables)
     DevIndex dix{};
     std::vector<void *> owned;  // device allocations that live as long as the index
@@ -466,8 +470,23 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     if (b.h_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, ix->pipe_patterns));
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1024, (uint64_t)((double)ix->window_tasks / ix->tasks_per_pattern)));
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
+    // chunk boundaries. Device batches: equal chunks. Host batches: stages of DECREASING size (each half the previous, down to
+    // an eighth of the first): the end-to-end time of the pipeline is the H2D time of the whole batch plus the search of the
+    // LAST stage only, so the last stage should be small, while big early stages keep the per-stage overheads few.
+    std::vector<uint64_t> bounds(1, 0);
+    {
+        uint64_t sz = chunk;
+        const uint64_t floor_sz = std::max<uint64_t>(1, chunk / 8);
+        while (bounds.back() < b.n) {
+            bounds.push_back(std::min<uint64_t>(b.n, bounds.back() + sz));
+            if (b.h_bytes && ix->pipe_taper) sz = std::max<uint64_t>(floor_sz, sz / 2);
+        }
+    }
     auto byte_at = [&](uint64_t i) -> uint64_t { return b.h_off ? b.h_off[i] : i * (uint64_t)b.fixed_len; };
 
+    // every CUDA call on the launch path costs the host a few microseconds, and a pipeline stage of a host batch holds only
+    // ~0.1 ms of kernels: per-phase event pairs are recorded for device batches only (E2FM_OPT_PHASE_TIMERS overrides)
+    tm.phases = ix->phase_timers == 1 || (ix->phase_timers == 2 && !b.h_bytes);
     // ---- host batches: every chunk's H2D copy is queued up front on the copy stream; the search of chunk c waits for its
     // own event only, so copies of later chunks overlap the kernels of earlier ones
     std::vector<cudaEvent_t> h2d_ev;
@@ -476,9 +495,8 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         CK(cudaEventRecord(ready, s));                       // the device buffers were allocated in order on s
         CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
         const int h = tm.begin(0, ix->h2d_stream);
-        for (uint64_t first = 0; first < b.n; first += chunk) {
-            const uint64_t last = std::min<uint64_t>(b.n, first + chunk);
-            const uint64_t lo = byte_at(first), hi = byte_at(last);
+        for (size_t c = 0; c + 1 < bounds.size(); c++) {
+            const uint64_t lo = byte_at(bounds[c]), hi = byte_at(bounds[c + 1]);
             if (hi > lo) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b.d_bytes) + lo, b.h_bytes + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
             cudaEvent_t e = ix->events.get(false);
             h2d_ev.push_back(e);
@@ -533,7 +551,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // intervals straight on as row tasks / wildcard intervals, the task count stays on the device. Row tasks go into a
     // buffer of `cap` entries (density learned from earlier batches); a chunk whose tasks do not fit is redone below.
     const bool fast = ix->use_dense && dix.sa && dix.bwt16;
-    const uint64_t n_chunks = b.n ? (b.n + chunk - 1) / chunk : 0;
+    const uint64_t n_chunks = bounds.size() - 1;
     const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(ix->window_tasks, (uint64_t)(ix->tasks_per_pattern * (double)chunk) + 1024));
     WsBuf<unsigned long long> chunk_ctr(ix, WS_CHUNK_CTR, std::max<uint64_t>(n_chunks, 1), s);   // row tasks of every chunk
     chunk_ctr.zero(std::max<uint64_t>(n_chunks, 1));
@@ -555,13 +573,12 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         // overflow instead of writing past the end
         if (mode == E2FM_MODE_LOCATE)
             grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
-        uint64_t chunk_no = 0;
-        for (uint64_t first = 0; first < b.n; first += chunk, chunk_no++) {
-            const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
+        for (uint64_t chunk_no = 0; chunk_no < n_chunks; chunk_no++) {
+            const uint64_t first = bounds[chunk_no];
+            const uint32_t cnt = (uint32_t)(bounds[chunk_no + 1] - first);
             PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
             encode_chunk(first, cnt, chunk_no);
-            CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
-            CK(cudaMemsetAsync(ix->d_stats + ST_ANY_LONG, 0, 8, s));
+            CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 16, s));   // work-queue cursor + ST_ANY_LONG
             int h = tm.begin(1);
             SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u | k3_opts, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
             launch_backward_search(sa, ix->n_sm, s);
@@ -604,8 +621,8 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     for (uint64_t c = 0; c < n_chunks; c++) {
         if (!redo[c]) continue;
         if (fast) n_redone++;
-        const uint64_t first = c * chunk;
-        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, b.n - first);
+        const uint64_t first = bounds[c];
+        const uint32_t cnt = (uint32_t)(bounds[c + 1] - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
         unsigned long long rank0 = 0, sect0 = 0;
         if (fast) {
@@ -1105,7 +1122,9 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
         case E2FM_OPT_DENSITY:   // test hook: forget the learned densities (value = per-mille of one task / result per pattern)
             ix->tasks_per_pattern = ix->results_per_pattern = (double)value / 1000.0;
             return E2FM_OK;
-        case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 19); return E2FM_OK;
+        case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
+        case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;
+        case E2FM_OPT_PHASE_TIMERS: ix->phase_timers = (int)std::min<uint64_t>(value, 2); return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");
             ix->use_dense = value != 0;

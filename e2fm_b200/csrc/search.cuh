@@ -28,12 +28,13 @@ enum {
     ST_BIGSEG = 5,   // result segments longer than the per-thread sort limit
     ST_DUPS = 6,     // duplicate positions removed (EFMIndex.cpp:2296-2299)
     ST_QUEUE = 7,    // work-queue cursor of the running kernel
-    ST_SECT_BS = 8,  // distinct 32-byte rank sectors gathered by the backward-search kernel
+    ST_ANY_LONG = 8, // set by the backward search when the chunk has a long wildcard interval (firstcheck_kernel has work);
+                     // kept next to ST_QUEUE so that one 16-byte memset resets both
+    ST_SECT_BS = 13, // distinct 32-byte rank sectors gathered by the backward-search kernel
     ST_GATHER = 9,   // dependent 8-byte gathers issued by the walk kernel
     ST_RES_OVF = 10, // occurrences that did not fit the result store (the host then redoes the batch with exact sizes)
     ST_SCAN_ROWS = 11, // rows streamed by firstcheck_kernel (2 bytes each)
-    ST_ANY_LONG = 12,  // set by the backward search when the chunk has a long wildcard interval (firstcheck_kernel has work)
-    ST_N = 13
+    ST_N = 14
 };
 
 struct SearchArgs {

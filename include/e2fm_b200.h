@@ -133,7 +133,11 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
-#define E2FM_OPT_PIPE 5          /* patterns per pipeline stage of a host-buffer batch (0 = default 2^19) */
+#define E2FM_OPT_PIPE 5          /* patterns per pipeline stage of a host-buffer batch (0 = default 2^18) */
+#define E2FM_OPT_TAPER 7         /* 1: pipeline stages of a host batch halve in size towards its end (down to 1/8 of the first), so that only a
+                                    small stage is left to search when the last bytes arrive; 0 (default): equal stages */
+#define E2FM_OPT_PHASE_TIMERS 8  /* per-phase CUDA-event pairs (e2fm_last_batch_ms slots 1-5, 7): 0 never, 1 always, 2 (default) only for
+                                    device-resident batches — on a pipelined host batch the extra event calls cost more than they show */
 #define E2FM_OPT_DENSITY 6       /* test hook: preset the learned row-task / occurrence densities (per-mille per pattern) that size the
                                     fast path's buffers; too small a value forces the overflow -> windowed-path redo */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
