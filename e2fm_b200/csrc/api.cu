@@ -586,7 +586,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             tm.end(h);
             h = tm.begin(2);
             launch_scan_expand(iv.p, cnt * k, scratch.p, tasks.p, cap, chunk_ctr.p + chunk_no, s);   // sets the chunk's task count
-            launches += 3;
+            launches += 2;
             tm.end(h);
             h = tm.begin(7);
             launch_firstcheck(sa, ix->n_sm, s);                                                      // appends the wildcard survivors

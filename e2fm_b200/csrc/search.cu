@@ -639,9 +639,22 @@ __global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(Load in, uint64_t n,
 // count goes to *n_tasks_out; when it exceeds `cap` nothing is written and the host redoes the chunk through the windowed path.
 __global__ void __launch_bounds__(SCAN_T) scan_expand_kernel(const uint2 *__restrict__ iv, uint64_t n, const uint64_t *sums, uint64_t nb,
                                                              uint2 *__restrict__ tasks, uint64_t cap, unsigned long long *n_tasks_out) {
-    __shared__ unsigned long long ws[SCAN_T / 32];
+    __shared__ unsigned long long ws[SCAN_T / 32], red[2][SCAN_T / 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t total = sums[nb];
+    // prefix of this block and the chunk's total, straight from the block sums (a few thousand at most): no separate launch
+    unsigned long long pre = 0, all = 0;
+    for (uint64_t i = threadIdx.x; i < nb; i += SCAN_T) {
+        const unsigned long long v = sums[i];
+        all += v;
+        if (i < blockIdx.x) pre += v;
+    }
+    pre = warp_sum(pre);
+    all = warp_sum(all);
+    if (lane == 0) { red[0][warp] = pre; red[1][warp] = all; }
+    __syncthreads();
+    unsigned long long block_prefix = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_T / 32; w++) { block_prefix += red[0][w]; total += red[1][w]; }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_tasks_out = total;
     if (total > cap) return;
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_E;
@@ -661,7 +674,7 @@ __global__ void __launch_bounds__(SCAN_T) scan_expand_kernel(const uint2 *__rest
     }
     if (lane == 31) ws[warp] = inc;
     __syncthreads();
-    unsigned long long run = sums[blockIdx.x] + inc - tot;
+    unsigned long long run = block_prefix + inc - tot;
     for (uint32_t w = 0; w < warp; w++) run += ws[w];
 #pragma unroll
     for (int j = 0; j < SCAN_E; j++) {
@@ -685,7 +698,6 @@ void launch_scan_expand(const uint2 *iv, uint32_t n_items, uint64_t *scratch, ui
     if (n_items == 0) return;
     const uint64_t nb = ((uint64_t)n_items + SCAN_B - 1) / SCAN_B;
     scan_block_sums_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(LoadIvLen{iv}, (uint64_t)n_items, scratch);
-    scan_sums_kernel<<<1, 1024, 0, s>>>(scratch, nb);
     scan_expand_kernel<<<(uint32_t)nb, SCAN_T, 0, s>>>(iv, (uint64_t)n_items, scratch, nb, tasks, cap, n_tasks_out);
 }
 

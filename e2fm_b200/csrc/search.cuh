@@ -78,7 +78,7 @@ void launch_backward_search(const SearchArgs &a, int n_sm, cudaStream_t s);
 void launch_firstcheck(const SearchArgs &a, int n_sm, cudaStream_t s);
 // exclusive scan of iv[i].y (interval lengths) into off[0..n_items] (off[n_items] = total)
 void launch_task_scan(const uint2 *iv, uint64_t *off, uint32_t n_items, uint64_t *scratch, cudaStream_t s);
-// fast path: scan the interval lengths and write the row tasks in one go (block sums, scan of the sums, scan + expand);
+// fast path: scan the interval lengths and write the row tasks in one go (block sums, then scan + expand);
 // *n_tasks_out receives the chunk's task count, nothing is written when it exceeds cap
 void launch_scan_expand(const uint2 *iv, uint32_t n_items, uint64_t *scratch, uint2 *tasks, uint64_t cap, unsigned long long *n_tasks_out,
                         cudaStream_t s);
