@@ -960,6 +960,8 @@ void launch_walk(const WalkArgs &a, int n_sm, cudaStream_t s) {
 // EFMIndex::extractSuperCharacter walks to). 1-3 independent gathers per task, one task per thread. What a row has to
 // match was computed once per (pattern, shift) by the backward search (firstw / hatw); the per-symbol parts of every
 // k-mer come from two small shared-memory tables, so a task touches no pattern bytes.
+static constexpr uint32_t RS_FLUSH = 1024, RS_CAP = RS_FLUSH + 256;   // CTA staging buffer of resolve_kernel
+
 template <int KT>
 __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
     const DevIndex &ix = a.ix;
@@ -972,9 +974,34 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
     }
     uint32_t n_g = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    // whole warps iterate together so that the result compaction below stays warp-uniform
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < a.n_tasks; base += stride) {
-        const uint32_t idx = base + lane;
+    // Located occurrences are staged per CTA in shared memory and handed over RS_FLUSH at a time: a same-address returning
+    // atomic per warp iteration (10^5..10^7 per launch) serialises at about one per nanosecond and was most of this kernel.
+    __shared__ uint32_t rs_pat[RS_CAP];
+    __shared__ uint64_t rs_pos[RS_CAP];
+    __shared__ uint32_t rs_cnt;
+    __shared__ unsigned long long rs_base;
+    const bool locate = a.mode == E2FM_MODE_LOCATE;
+    if (threadIdx.x == 0) rs_cnt = 0;
+    __syncthreads();
+    auto flush = [&]() {                                   // called by the whole CTA, rs_cnt stable
+        const uint32_t c = rs_cnt;
+        if (threadIdx.x == 0) rs_base = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)c);
+        __syncthreads();
+        const unsigned long long b0 = rs_base;
+        uint32_t lost = 0;
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+            const unsigned long long slot = b0 + i;
+            if (slot < a.res_cap) { a.res_pat[slot] = rs_pat[i]; a.res_pos[slot] = rs_pos[i]; }
+            else lost++;
+        }
+        if (lost) atomicAdd(a.stats + ST_RES_OVF, (unsigned long long)lost);
+        __syncthreads();
+        if (threadIdx.x == 0) rs_cnt = 0;
+        __syncthreads();
+    };
+    // the whole CTA iterates together (uniform trip count: the staging buffer is flushed between iterations)
+    for (uint32_t base = blockIdx.x * blockDim.x; base < a.n_tasks; base += stride) {
+        const uint32_t idx = base + threadIdx.x;
         bool emit = false;
         uint32_t item = 0, tp = 0;
         if (idx < a.n_tasks) {
@@ -1035,20 +1062,26 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
         if (em) {
             const uint32_t pl = item / k, sa = item - pl * k;
             if (emit) atomicAdd(a.counts + a.pv.first + pl, 1ull);
-            if (a.mode == E2FM_MODE_LOCATE) {
-                unsigned long long b = 0;
+            if (locate) {
+                uint32_t b = 0;
                 const int leader = __ffs(em) - 1;
-                if ((int)lane == leader) b = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)__popc(em));
+                if ((int)lane == leader) b = atomicAdd(&rs_cnt, (uint32_t)__popc(em));      // shared-memory atomic
                 b = __shfl_sync(FULL, b, leader);
                 if (emit) {
-                    const unsigned long long slot = b + __popc(em & lt);
-                    if (slot < a.res_cap) {
-                        a.res_pat[slot] = (uint32_t)(a.pv.first + pl);
-                        a.res_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;
-                    } else atomicAdd(a.stats + ST_RES_OVF, 1ull);
+                    const uint32_t slot = b + __popc(em & lt);                               // < RS_FLUSH + 256 = RS_CAP
+                    rs_pat[slot] = (uint32_t)(a.pv.first + pl);
+                    rs_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;
                 }
             }
         }
+        if (locate) {
+            __syncthreads();
+            if (rs_cnt >= RS_FLUSH) flush();
+        }
+    }
+    if (locate) {
+        __syncthreads();
+        if (rs_cnt) flush();
     }
     const unsigned long long g = warp_sum((unsigned long long)n_g);
     if (lane == 0 && g) atomicAdd(a.stats + ST_GATHER, g);
