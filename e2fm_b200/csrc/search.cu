@@ -1,17 +1,24 @@
 // search.cu — batched exact-pattern search over the flattened device index.
 //
+//   encode_patterns_kernel       k-mer compact code at every pattern byte (ScrambledSuperAlphabet::getCode + charactersRemappings,
+//                                EFMIndex.cpp:2186-2191), so that a backward step costs one 2-byte load.
 //   K3  backward_search_kernel   EFMIndex::computeSuperPatterns + exactMatch(interval) + backwardStep
 //                                (EFMIndex.cpp:2055-2207, :1901-1963, :1966-2001) for every (pattern, shift):
 //                                one (pattern, shift) per LANE, lanes refilled from a warp-local slice of a global
-//                                work queue, one 32-byte rank sector per occ() instead of the reference's
-//                                super-bucket + bucket + position-list chain (SuperBucket.cpp:82, Bucket.cpp:656-779).
-//   K4  walk_kernel              one BWT row per lane: backwardStepIfMatch (EFMIndex.cpp:2011-2041), getRowPosition
-//                                (:2468-2497) + Bucket::getMarkedTextPosition (Bucket.cpp:823), findWholePatternMatches +
-//                                extractSuperCharacter (:1862-1899, :2216-2269). One dependent 8-byte gather per
-//                                step; results compacted with warp-aggregated atomics.
+//                                work queue; start interval + first step from the pair table, then one 32-byte rank
+//                                sector per step instead of the reference's super-bucket + bucket + position-list
+//                                chain (SuperBucket.cpp:82, Bucket.cpp:656-779).
+//   scan / expand                the interval each shift ends with -> row tasks {row, item}
+//   firstcheck_kernel            EFMIndex::backwardStepIfMatch (:2011-2041) over whole long intervals: streams bwt16[]
+//   K4  resolve_kernel           row tasks answered from the dense sa[] / text[] tables: getRowPosition (:2468-2497),
+//                                findWholePatternMatches + extractSuperCharacter (:1862-1899, :2216-2269)
+//   K4' walk_kernel              the same row tasks by per-query walks from the marked rows (dense tables off): one
+//                                dependent 8-byte gather per LF step, Bucket::getMarkedTextPosition (Bucket.cpp:823)
 //   result pipeline              per-pattern CSR (scan + scatter), segmented sort + adjacent de-duplication
 //                                (EFMIndex::locateOccurrences, :2281-2301), position -> (sequence, offset)
 //                                (EFMCollection::search, EFMCollection.cpp:124-148).
+//   extract_kernel               EFMIndex::extractSnippet (:2325-2452) from text[]
+//   gather_bench_kernel          the random-gather roofline measurement
 #include "search.cuh"
 
 #include <algorithm>
