@@ -747,6 +747,14 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[9] = n_redone;
 }
 
+// a failed batch may have copies queued that still read the caller's host buffers: nothing is in flight when the call returns
+void quiesce(e2fm_index *ix) {
+    if (ix->h2d_stream) cudaStreamSynchronize(ix->h2d_stream);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->d2h_stream) cudaStreamSynchronize(ix->d2h_stream);
+    cudaGetLastError();
+}
+
 int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
                   bool on_device, int mode, e2fm_result **out, uint64_t *counts_out = nullptr) {
     if (!ix || !out || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
@@ -790,12 +798,15 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
         CK(cudaStreamSynchronize(s));
         tm.collect(ix->batch_ms, 8);
     } catch (const CudaError &e) {
+        quiesce(ix);
         e2fm_result_free(res);
         return fail(E2FM_ERR_CUDA, e.what());
     } catch (const std::bad_alloc &) {
+        quiesce(ix);
         e2fm_result_free(res);
         return fail(E2FM_ERR_OOM, "out of host memory");
     } catch (const std::exception &e) {
+        quiesce(ix);
         e2fm_result_free(res);
         return fail(E2FM_ERR_FORMAT, e.what());
     }

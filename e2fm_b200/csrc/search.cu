@@ -1081,10 +1081,9 @@ __global__ void __launch_bounds__(256) resolve_kernel(WalkArgs a) {
                 }
             }
         }
-        if (locate) {
-            __syncthreads();
-            if (rs_cnt >= RS_FLUSH) flush();
-        }
+        // The decision is taken THROUGH the barrier: a thread that read rs_cnt after it could see the next iteration's
+        // additions of a faster warp and flush alone. The last read before the barrier sees every addition of this iteration.
+        if (locate && __syncthreads_or(rs_cnt >= RS_FLUSH)) flush();
     }
     if (locate) {
         __syncthreads();

@@ -76,7 +76,9 @@ void *e2fm_index_stream(const e2fm_index *ix);
 
 /* Batched replacement of the per-pattern loop around EFMCollection::search (Main.cpp:1055-1079,
  * EFMCollection.cpp:115): patterns are `n` byte strings, pattern i = bytes[offsets[i] .. offsets[i+1]).
- * HOST buffers; the call copies them to the device, runs the search and leaves the result on the device. */
+ * HOST buffers; the call copies them to the device, runs the search and leaves the result on the device.
+ * offsets[] must be non-decreasing and offsets[n] the size of bytes[] (they are the caller's own bookkeeping and are not
+ * re-validated per batch); an empty pattern has zero occurrences. */
 int e2fm_search_batch(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint64_t n, int mode,
                       e2fm_result **out);
 /* Fixed-length batch: pattern i = bytes[i*length .. (i+1)*length) (no offsets array to ship). */
