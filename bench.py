@@ -191,6 +191,17 @@ def measured_peak():
 
 # ------------------------------------------------------------------ CPU reference
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def reference_procs(prep) -> int:
     """processes the host can run side by side: one per core, but each holds the whole index plus what it decodes lazily
     (about 12x the index file: bucketText u32 + charactersPositions u64 per super-character)"""
@@ -258,7 +269,8 @@ def reference_arm(args, prep):
         "config": {"workload": w["name"], "mode": "count+locate" if w["locate"] else "count", "k": K, "bucket_size": BUCKET,
                    "mrp": MRP, "sample_patterns": sample},
         "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": procs, "kind": "reference", "sample": desc,
-                         "cold_value": float(np.mean(colds)), "host_cores": cores},
+                         "cold_value": float(np.mean(colds)), "host_cores": cores, "cpu_model": cpu_model(),
+                         "per_process": value / procs},
         "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall_all,
     }
@@ -497,7 +509,7 @@ def gpu_arm(args, rank, world, local_rank):
                 wall = 0.0
                 line["cpu_baseline_error"] = str(e)
             line["cpu_baseline"] = {"value": v, "unit": "patterns/s", "cores": procs, "kind": "reference", "host_cores": cores,
-                                    "cold_value": c,
+                                    "cold_value": c, "cpu_model": cpu_model(), "per_process": (v / procs) if v else None,
                                     "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified "
                                               f"reference (1 matcher thread each), warm pass; cold pass {c} patterns/s; {wall:.1f}s wall"}
         emit(line)
