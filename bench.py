@@ -418,6 +418,17 @@ def gpu_arm(args, rank, world, local_rank):
         except Exception as e:   # noqa: BLE001
             gg = None
             log(f"[bench] gather microbenchmark failed: {e}")
+        # ... and, when the image is smaller than that floor (L2-resident indexes), the same measurement over a buffer of the
+        # image's own size: what a dependent-gather kernel could reach out of the L2
+        gg_ws, ws_buf = None, 16 << 20
+        try:
+            while ws_buf < info.device_bytes:
+                ws_buf *= 2
+            if ws_buf < gbuf:
+                gg_ws = capi.gather_bench(ws_buf, 1 << 29, local_rank)
+        except Exception as e:   # noqa: BLE001
+            gg_ws = None
+            log(f"[bench] working-set gather microbenchmark failed: {e}")
         value = world * npat * steps / (dev_ms_max / 1e3)
         e2e_value = world * npat * steps / (e2e_ms_max / 1e3)
         # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
@@ -468,6 +479,10 @@ def gpu_arm(args, rank, world, local_rank):
                         "giga_gathers_per_s": gg, "sector_gbs": gg * 32.0, "frac_of_hbm_peak": gg * 32.0 / peak,
                         "achieved_frac_of_random_gather": kern[dom]["layout_sector_gbs"] / (gg * 32.0),
                         "buffer_MB": gbuf >> 20,
+                        "working_set": None if not gg_ws else {
+                            "buffer_MB": ws_buf >> 20, "giga_gathers_per_s": gg_ws,
+                            "achieved_frac": kern[dom]["layout_sector_gbs"] / (gg_ws * 32.0),
+                            "note": "the device image fits the L2: same microbenchmark over a buffer of the image's size"},
                         "how": "independent 8-byte loads at hashed addresses of a buffer the size of the device image (power of two, "
                                ">= 256 MB), 2^29 gathers, best of 3 (e2fm_debug_gather_bench); one 32-byte sector per gather"},
                     "note": "achieved = 32 B x sectors this layout must gather (distinct rank sectors / row-task gathers), per launch, "
