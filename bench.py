@@ -1,18 +1,28 @@
 #!/usr/bin/env python
 """bench.py — batched pattern search throughput (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ecoli|collection100|config1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload human|collection100|chr1|ecoli|config1] [--impl reference]
+                    [--sharded]
 
-A step = one pass of the hot path over one batch of synthetic patterns (count, or count+locate).
-  value      whole-job patterns/s with the pattern batch already resident in HBM (device time, CUDA events on
-             the library's stream, max over ranks)
-  e2e        the same through the C ABI with HOST (pinned) buffers: H2D of the patterns and D2H of the counts
-             (and positions) inside the timed region
-  roofline   dominant kernel: algorithmic bytes (160 B/rank + 224 B/lf + 64 B/mark, operation
-             counts measured by the kernels and pinned to the oracle's by tests) / its CUDA-event time
-  cpu_baseline  the UNMODIFIED reference (oracle/_ref/e2fm_ref) on the host cores over a bounded sample
---impl reference times that CPU reference as the main line.
-The index is always built by the reference's own CPU builder (north star: index construction stays on the CPU).
+Default workload = BASELINE.json configs[3], the north-star configuration: 3.1 Gbp synthetic collection (24 sequences),
+10 M patterns of length 50, count + locate. A step = one pass of the hot path over the whole 10 M-pattern batch.
+
+  N = 1    one replica of the index searches the whole batch.
+  N > 1    STRONG scaling: every GPU holds a replica, the one batch is partitioned by pattern (contiguous slices), results land
+           back in ONE host buffer (POSIX shared memory, page-locked by every rank): replicas + pattern partition, the
+           throughput mode of SURVEY.md 8(e). `--sharded` times the other mode (collection sharded by sequence, patterns
+           broadcast, NCCL merge) and is also reported as the `sharded` object of the default line when N > 1.
+
+  value         whole-job patterns/s, patterns already resident in HBM (CUDA events on the library's stream, max over ranks)
+  e2e           same batch through the C ABI from HOST buffers: H2D of the patterns and D2H of what EFMCollection::search
+                returns (per-pattern occurrence offsets, sequence index, offset in the sequence) inside the timed region
+  roofline      dominant kernel: 32 B x the sectors it has to gather / its CUDA-event time, against the measured HBM copy peak
+                AND against the random-gather rate measured on this box for a working set of the index's size
+  parity        the first patterns of the TIMED batch compared with the unmodified reference's own CPU search (exit 1 on mismatch)
+  cpu_baseline  the unmodified reference (oracle/_ref/e2fm_ref) on the host cores over a bounded sample of the same batch
+--impl reference times that CPU reference as the main line (rank 0 only).
+The index is always built by the reference's own CPU builder (north star: index construction stays on the CPU) and cached
+under data/bench_cache together with the pattern batch.
 """
 import argparse
 import json
@@ -30,30 +40,32 @@ from e2fm_b200 import synth  # noqa: E402
 
 CACHE = os.path.join(ROOT, "data", "bench_cache")
 
+HG = [248_956_422, 242_193_529, 198_295_559, 190_214_555, 181_538_259, 170_805_979, 159_345_973, 145_138_636,
+      138_394_717, 133_797_422, 135_086_622, 133_275_309, 114_364_328, 107_043_718, 101_991_189, 90_338_345,
+      83_257_441, 80_373_285, 58_617_616, 64_444_167, 46_709_983, 50_818_468, 156_040_895, 57_227_415]
 WORKLOADS = {
+    # BASELINE.json configs[3]: human-genome-sized 3.1 Gbp collection (24 sequences, hg38-like proportions), 10M patterns len 50
+    "human": dict(seq_lens=HG, seed=44, n_patterns=10_000_000, pat_len=50, locate=True,
+                  name="configs[3]: 3.1 Gbp human-genome-sized synthetic collection (24 sequences), 10M patterns len 50, count+locate"),
     # BASELINE.json configs[1]: E. coli-sized 4.6 Mbp synthetic genome, 1M patterns len 32, count only, 1 GPU
     "ecoli": dict(seq_lens=[4_641_652], seed=43, n_patterns=1_000_000, pat_len=32, locate=False,
                   name="configs[1]: 4.6 Mbp synthetic genome, 1M patterns len 32, count"),
     # BASELINE.json configs[0]: 10 Mbp random ACGT, 10k patterns len 20, count+locate
     "config1": dict(seq_lens=[10_000_000], seed=42, n_patterns=10_000, pat_len=20, locate=True,
                     name="configs[0]: 10 Mbp random ACGT, 10k patterns len 20, count+locate"),
-    # BASELINE.json configs[2] on ONE GPU (whole collection in one index): larger than L2, HBM-bound
+    # BASELINE.json configs[2] (whole collection in one index per GPU)
     "collection100": dict(seq_lens=[4_641_652] * 100, seed=1000, n_patterns=10_000_000, pat_len=24, locate=True,
                           name="configs[2]: 100 x 4.6 Mbp synthetic genomes, 10M patterns len 24, count+locate"),
     # BASELINE.json configs[4]: chr1-sized 248 Mbp single sequence, locate-heavy short patterns (len 12)
     "chr1": dict(seq_lens=[248_956_422], seed=45, n_patterns=1_000_000, pat_len=12, locate=True,
                  name="configs[4]: 248 Mbp chr1-sized synthetic sequence, 1M patterns len 12, count+locate"),
-    # BASELINE.json configs[3]: human-genome-sized 3.1 Gbp collection (24 sequences, hg38-like proportions), 10M patterns len 50
-    "human": dict(seq_lens=[248_956_422, 242_193_529, 198_295_559, 190_214_555, 181_538_259, 170_805_979, 159_345_973, 145_138_636,
-                            138_394_717, 133_797_422, 135_086_622, 133_275_309, 114_364_328, 107_043_718, 101_991_189, 90_338_345,
-                            83_257_441, 80_373_285, 58_617_616, 64_444_167, 46_709_983, 50_818_468, 156_040_895, 57_227_415],
-                  seed=44, n_patterns=10_000_000, pat_len=50, locate=True,
-                  name="configs[3]: 3.1 Gbp human-genome-sized synthetic collection (24 sequences), 10M patterns len 50, count+locate"),
     # a collection100 shard-sized index for quicker HBM-bound runs
     "collection25": dict(seq_lens=[4_641_652] * 25, seed=1000, n_patterns=4_000_000, pat_len=24, locate=True,
                          name="25 x 4.6 Mbp synthetic genomes, 4M patterns len 24, count+locate"),
 }
 K, BUCKET, MRP = 4, 4096, 2   # the authors' regime (Main.cpp:469,747)
+PARITY_PATTERNS = 2000
+L2_BYTES = 126 << 20
 
 
 def log(*a):
@@ -86,42 +98,76 @@ def ref_bin():
     return p
 
 
-def prepare(workload: str, rank: int = 0):
-    """Synthetic collection + reference-built index (cached on disk) -> dict"""
-    w = WORKLOADS[workload]
-    os.makedirs(CACHE, exist_ok=True)
-    lens = synth.safe_lengths(w["seq_lens"], K, 100 // MRP)
-    seqs = []
-    for i, L in enumerate(lens):
-        seqs += synth.random_sequences([L], w["seed"] + i)
-    base = os.path.join(CACHE, f"{workload}_k{K}_b{BUCKET}_m{MRP}")
-    keyfile = os.path.join(CACHE, "key.bin")
-    efm = base + ".efm"
-    if rank == 0:
-        if not os.path.exists(keyfile):
-            with open(keyfile, "wb") as f:
-                f.write(synth.test_key())
-        if not os.path.exists(efm):
-            t0 = time.time()
-            fa = base + ".fa"
-            synth.write_fasta(fa, seqs)
-            threads = str(min(32, os.cpu_count() or 2))
-            r = subprocess.run([ref_bin(), "build", fa, efm + ".tmp", keyfile, str(K), str(BUCKET), str(MRP), threads],
-                               capture_output=True, text=True)
-            if r.returncode != 0 or not os.path.exists(efm + ".tmp"):
-                raise SystemExit("reference index build failed: " + r.stderr[-400:])
-            os.replace(efm + ".tmp", efm)
-            os.remove(fa)
-            log(f"[bench] reference built {efm} ({os.path.getsize(efm) / 1e6:.1f} MB) in {time.time() - t0:.1f}s")
-    return dict(w=w, seqs=seqs, efm=efm, keyfile=keyfile)
-
-
 def wait_for(path, timeout=3600):
     t0 = time.time()
     while not os.path.exists(path):
         if time.time() - t0 > timeout:
             raise SystemExit("timed out waiting for " + path)
         time.sleep(0.5)
+
+
+def workload_lens(w):
+    return synth.safe_lengths(w["seq_lens"], K, 100 // MRP)
+
+
+def make_sequences(w, lens=None):
+    lens = lens or workload_lens(w)
+    seqs = []
+    for i, L in enumerate(lens):
+        seqs += synth.random_sequences([L], w["seed"] + i)
+    return seqs
+
+
+def build_index(fa_seqs, efm, keyfile, threads):
+    t0 = time.time()
+    fa = efm[:-4] + ".fa"
+    synth.write_fasta(fa, fa_seqs)
+    r = subprocess.run([ref_bin(), "build", fa, efm + ".tmp", keyfile, str(K), str(BUCKET), str(MRP), str(threads)],
+                       capture_output=True, text=True)
+    if r.returncode != 0 or not os.path.exists(efm + ".tmp"):
+        raise SystemExit("reference index build failed: " + r.stderr[-400:])
+    os.replace(efm + ".tmp", efm)
+    os.remove(fa)
+    log(f"[bench] reference built {efm} ({os.path.getsize(efm) / 1e6:.1f} MB) in {time.time() - t0:.1f}s")
+
+
+def prepare(workload: str, rank: int = 0):
+    """Synthetic collection -> reference-built index + the pattern batch, both cached on disk (rank 0 makes them, the
+    other ranks wait). The batch is SURVEY.md 8(d)'s: substrings sampled inside sequences plus 5 % uniformly random strings,
+    shuffled, cut to the configured size."""
+    w = WORKLOADS[workload]
+    os.makedirs(CACHE, exist_ok=True)
+    base = os.path.join(CACHE, f"{workload}_k{K}_b{BUCKET}_m{MRP}")
+    keyfile = os.path.join(CACHE, "key.bin")
+    efm = base + ".efm"
+    patf = base + f"_p{w['n_patterns']}x{w['pat_len']}.npy"
+    if rank == 0:
+        if not os.path.exists(keyfile):
+            with open(keyfile + ".tmp", "wb") as f:
+                f.write(synth.test_key())
+            os.replace(keyfile + ".tmp", keyfile)
+        if not (os.path.exists(efm) and os.path.exists(patf)):
+            seqs = make_sequences(w)
+            if not os.path.exists(patf):
+                t0 = time.time()
+                pats = synth.sample_patterns(seqs, w["n_patterns"], w["pat_len"], w["seed"] + 1)
+                perm = np.random.Generator(np.random.PCG64(w["seed"] + 2)).permutation(len(pats))[:w["n_patterns"]]
+                np.save(patf + ".tmp.npy", pats[perm])
+                os.replace(patf + ".tmp.npy", patf)
+                del pats
+                log(f"[bench] pattern batch {patf} in {time.time() - t0:.1f}s")
+            if not os.path.exists(efm):
+                build_index(seqs, efm, keyfile, min(32, os.cpu_count() or 2))
+            del seqs
+    else:
+        wait_for(keyfile)
+        wait_for(patf)
+        wait_for(efm)
+    return dict(w=w, efm=efm, keyfile=keyfile, patf=patf, workload=workload)
+
+
+def load_patterns(prep):
+    return np.load(prep["patf"], mmap_mode="r")
 
 
 class ClockSampler:
@@ -215,20 +261,34 @@ def reference_procs(prep) -> int:
     return int(max(1, min(cores, 32, (avail // 2) // per_proc)))
 
 
-def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdir: str):
-    """P independent processes of the unmodified reference, each over a 1/P slice (the reference is serial and not
-    re-entrant per object); 1 matcher thread each; 2 passes: cold (lazy bucket decode) and warm.
-    Returns (patterns/s warm aggregate, patterns/s cold aggregate, wall seconds)."""
+def reference_sample_size(prep, procs: int) -> int:
+    """Bounded sample: the whole batch when the CPU finishes it in seconds, else a fixed leading part.
+    The cold pass costs one bucket decode per bucket touched, so big indexes get fewer patterns per process."""
+    w = prep["w"]
+    size = os.path.getsize(prep["efm"])
+    if size <= (64 << 20):
+        per_proc = w["n_patterns"] if w["pat_len"] >= 20 else 2_000   # the full batch takes the CPU a few seconds
+    else:
+        per_proc = 500 if w["pat_len"] >= 20 else 100
+    return int(min(w["n_patterns"], procs * per_proc))
+
+
+def run_reference(prep, pats: np.ndarray, locate: bool, procs: int, tmpdir: str, warm_passes: int = 1):
+    """P independent processes of the unmodified reference, each over a contiguous 1/P slice (the reference is serial and not
+    re-entrant per object); 1 matcher thread each; pass 0 is cold (lazy bucket decode), the others warm.
+    Returns (per-pass wall ms = max over processes, [result dict per slice], [slice index arrays], wall seconds)."""
+    from oracle import oracle
     slices = np.array_split(np.arange(len(pats)), procs)
     ps = []
     t0 = time.time()
     for i, sl in enumerate(slices):
         pf = os.path.join(tmpdir, f"p{i}.txt")
-        synth.write_patterns(pf, pats[sl])
+        synth.write_patterns(pf, np.ascontiguousarray(pats[sl[0]:sl[-1] + 1]) if len(sl) else pats[:0])
         ps.append(subprocess.Popen([ref_bin(), "search", prep["efm"], prep["keyfile"], pf, os.path.join(tmpdir, f"r{i}.res"),
-                                    "1" if locate else "0", "1", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    cold = warm = 0.0
-    for p, sl in zip(ps, slices):
+                                    "1" if locate else "0", "1", str(1 + warm_passes)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.PIPE, text=True))
+    pass_ms = np.zeros(1 + warm_passes)
+    for p in ps:
         out, err = p.communicate()
         line = [l for l in out.splitlines() if l.startswith("{")]
         if p.returncode != 0 or not line:
@@ -236,48 +296,129 @@ def run_reference_sample(prep, pats: np.ndarray, locate: bool, procs: int, tmpdi
                 if q.poll() is None:
                     q.kill()
             raise RuntimeError(f"reference search failed (exit code {p.returncode}): {(err or out)[-300:].strip()}")
-        j = json.loads(line[-1])
-        cold = max(cold, j["pass_ms"][0])
-        warm = max(warm, j["pass_ms"][1])
-    return len(pats) / (warm / 1e3), len(pats) / (cold / 1e3), time.time() - t0
+        pass_ms = np.maximum(pass_ms, np.array(json.loads(line[-1])["pass_ms"], dtype=np.float64))
+    res = [oracle.read_result_file(os.path.join(tmpdir, f"r{i}.res")) for i in range(len(slices))]
+    return pass_ms, res, slices, time.time() - t0
 
 
 def reference_arm(args, prep):
     w = prep["w"]
     cores = os.cpu_count() or 1
     procs = reference_procs(prep)
-    big = os.path.getsize(prep["efm"]) > (200 << 20)
-    per_proc = (500 if big else 4000) if w["pat_len"] >= 20 else 400
-    sample = min(w["n_patterns"], procs * per_proc)
-    pats = synth.sample_patterns(prep["seqs"], sample, w["pat_len"], w["seed"] + 1)[:sample]
-    vals, colds = [], []
+    sample = reference_sample_size(prep, procs)
+    pats = np.ascontiguousarray(load_patterns(prep)[:sample])
     with tempfile.TemporaryDirectory() as td:
         t_all = time.time()
-        for step in range(args.warmup + args.steps):
-            v, c, wall = run_reference_sample(prep, pats, w["locate"], procs, td)
-            if step >= args.warmup:
-                vals.append(v); colds.append(c)
+        pass_ms, _res, _sl, _wall = run_reference(prep, pats, w["locate"], procs, td, warm_passes=args.warmup + args.steps)
         wall_all = time.time() - t_all
-    value = float(np.mean(vals))
-    desc = (f"{sample} of {w['n_patterns']} patterns (len {w['pat_len']}) split over {procs} processes of the unmodified "
-            f"reference, 1 matcher thread each; value = warm pass (2nd pass, buckets already decoded), cold pass = "
-            f"{float(np.mean(colds)):.0f} patterns/s")
+    timed = pass_ms[1 + args.warmup:]
+    ms = float(np.mean(timed))
+    value = sample / (ms / 1e3)
+    cold = sample / (pass_ms[0] / 1e3)
+    desc = (f"first {sample} of the {w['n_patterns']} patterns (len {w['pat_len']}) split over {procs} processes of the unmodified "
+            f"reference, 1 matcher thread each; a step = one warm pass over that sample (buckets already decoded by the cold pass, "
+            f"which ran at {cold:.0f} patterns/s)")
     line = {
         "impl": "reference", "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": w["name"], "mode": "count+locate" if w["locate"] else "count", "k": K, "bucket_size": BUCKET,
-                   "mrp": MRP, "sample_patterns": sample},
+                   "mrp": MRP, "patterns": w["n_patterns"], "pattern_len": w["pat_len"], "sample_patterns": sample},
         "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": procs, "kind": "reference", "sample": desc,
-                         "cold_value": float(np.mean(colds)), "host_cores": cores, "cpu_model": cpu_model(),
-                         "per_process": value / procs},
+                         "cold_value": cold, "host_cores": cores, "cpu_model": cpu_model(), "per_process": value / procs},
         "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall_all,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ shared host buffer (N > 1: one batch, one result, one host)
+
+class SharedHost:
+    """The batch and its result live in ONE host buffer per array: POSIX shared memory mapped by every rank and page-locked
+    with cudaHostRegister, so that each GPU copies its slice of the patterns straight out of it and its slice of the result
+    straight into it. With one rank it is plain pinned memory from the library."""
+
+    def __init__(self, tag: str, world: int, rank: int, capi):
+        self.tag, self.world, self.rank, self.capi = tag, world, rank, capi
+        self.arrays = {}
+        self._keep = []
+
+    def array(self, name: str, shape, dtype):
+        dtype = np.dtype(dtype)
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        if self.world == 1:
+            pa = self.capi.PinnedArray(shape, dtype)
+            self._keep.append(pa)
+            self.arrays[name] = pa.array
+            return pa.array
+        import torch
+        nbytes = max(int(np.prod(shape, dtype=np.int64)) * dtype.itemsize, 4096)
+        path = f"/dev/shm/e2fm_bench_{self.tag}_{name}"
+        if self.rank == 0:
+            with open(path + ".tmp", "wb") as f:
+                f.truncate(nbytes)
+            os.replace(path + ".tmp", path)
+        else:
+            wait_for(path, 600)
+        mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister({name}) failed: {rc}")
+        self._keep.append(mm)
+        a = mm[:int(np.prod(shape, dtype=np.int64)) * dtype.itemsize].view(dtype).reshape(shape)
+        self.arrays[name] = a
+        return a
+
+    def close(self):
+        if self.world > 1:
+            import torch
+            for mm in self._keep:
+                try:
+                    torch.cuda.cudart().cudaHostUnregister(mm.ctypes.data)
+                except Exception:
+                    pass
+            if self.rank == 0:
+                for name in self.arrays:
+                    try:
+                        os.remove(f"/dev/shm/e2fm_bench_{self.tag}_{name}")
+                    except OSError:
+                        pass
+        self.arrays.clear()
+        self._keep.clear()
+
+
 # ------------------------------------------------------------------ GPU arm
+
+def compare_with_reference(ref_res, slices, got, n_checked):
+    """bit-exact comparison of counts, occurrence counts, (sequence, offset) and global positions of the first patterns"""
+    mism = 0
+    first_bad = None
+    for res, sl in zip(ref_res, slices):
+        if len(sl) == 0:
+            continue
+        a, b = int(sl[0]), int(sl[-1]) + 1
+        ok = np.array_equal(res["counts"], got["counts"][a:b])
+        if got.get("pos_offsets") is not None and ok:
+            o0, o1 = int(got["pos_offsets"][a]), int(got["pos_offsets"][b])
+            ok = np.array_equal(np.diff(res["pos_offsets"].astype(np.int64)), np.diff(got["pos_offsets"][a:b + 1].astype(np.int64)))
+            ok = ok and np.array_equal(res["seq"], got["seq"][o0:o1]) and np.array_equal(res["off"], got["off"][o0:o1])
+            if ok and got.get("positions") is not None:
+                ok = np.array_equal(res["positions"], got["positions"][o0:o1])
+        if not ok:
+            # count the patterns that differ
+            for j in range(a, b):
+                c_ok = int(res["counts"][j - a]) == int(got["counts"][j])
+                if got.get("pos_offsets") is not None:
+                    r0, r1 = int(res["pos_offsets"][j - a]), int(res["pos_offsets"][j - a + 1])
+                    g0, g1 = int(got["pos_offsets"][j]), int(got["pos_offsets"][j + 1])
+                    c_ok = c_ok and np.array_equal(res["seq"][r0:r1], got["seq"][g0:g1]) and np.array_equal(res["off"][r0:r1], got["off"][g0:g1])
+                if not c_ok:
+                    mism += 1
+                    if first_bad is None:
+                        first_bad = j
+    return {"checked": int(n_checked), "mismatches": int(mism), "first_mismatch": first_bad}
+
 
 def gpu_arm(args, rank, world, local_rank):
     import torch
@@ -293,7 +434,6 @@ def gpu_arm(args, rank, world, local_rank):
     prep = prepare(args.workload, rank)
     if world > 1:
         dist.barrier()
-    wait_for(prep["efm"])
     w = prep["w"]
     locate = w["locate"]
     with open(prep["efm"], "rb") as f:
@@ -301,6 +441,7 @@ def gpu_arm(args, rank, world, local_rank):
     t0 = time.time()
     ix = capi.DeviceIndex(raw, synth.test_key(), local_rank)
     load_s = time.time() - t0
+    del raw
     if args.walk:
         ix.set_option(capi.OPT_DENSE, 0)
     if args.chunk:
@@ -313,16 +454,28 @@ def gpu_arm(args, rank, world, local_rank):
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
 
-    # weak scaling: every rank searches its own batch of the workload's size against its replica of the index
-    # (single-sequence workloads do not shard: replicas only)
-    npat, L = w["n_patterns"], w["pat_len"]
-    pats = synth.sample_patterns(prep["seqs"], npat, L, w["seed"] + 1 + 7919 * rank)[:npat]
-    pin_p = capi.PinnedArray((npat, L), np.uint8)
-    pin_p.array[:] = pats
-    pin_counts = capi.PinnedArray(npat, np.uint64)
-    d_pats = torch.from_numpy(pats).to(dev_t)
+    # strong scaling: the ONE batch is partitioned by pattern; rank r owns the contiguous slice [lo, hi)
+    npat_all, L = w["n_patterns"], w["pat_len"]
+    lo, hi = npat_all * rank // world, npat_all * (rank + 1) // world
+    npat = hi - lo
+    all_pats = load_patterns(prep)
+    shm = SharedHost(f"{os.environ.get('MASTER_PORT', '0')}_{args.workload}", world, rank, capi)
+    h_pats = shm.array("patterns", (npat_all, L), np.uint8)
+    if world > 1:
+        dist.barrier()
+    h_pats[lo:hi] = all_pats[lo:hi]
+    # result buffers of the whole batch (every rank writes its own part): what EFMCollection::search returns
+    occ_cap = int(npat_all * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
+    h_counts = shm.array("counts", npat_all, np.uint64)
+    h_noff = shm.array("occ_offsets", (world, npat_all // world + 2), np.uint64) if locate else None
+    h_seq = shm.array("seq", occ_cap, np.uint32) if locate else None
+    h_off = shm.array("off", occ_cap, np.uint64) if locate else None
+    d_pats = torch.from_numpy(np.ascontiguousarray(all_pats[lo:hi])).to(dev_t)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)   # > 126 MB L2
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        totals_t = torch.zeros(world, dtype=torch.int64, device=dev_t)
 
     def l2_flush():
         if os.environ.get("E2FM_BENCH_NOFLUSH"):
@@ -338,28 +491,29 @@ def gpu_arm(args, rank, world, local_rank):
         r.free()
         return ms, ctr, tot
 
-    pin_pos = {}
     e2e_dev_ms = []
+    e2e_state = {}
 
     def step_e2e():
+        """host patterns -> host result, through the C ABI; N > 1: the result parts are placed behind one another in the one
+        shared buffer (an all-gather of the per-rank totals gives every rank its place)"""
         t0 = time.perf_counter()
-        r = ix.search_stream(pin_p.array, locate, pin_counts.array)
+        r = ix.search_stream(h_pats[lo:hi], locate, h_counts[lo:hi])
+        base = 0
         if locate:
-            need = max(r.total, 1)
-            if pin_pos.get("n", 0) < need:
-                for k_ in ("pos", "off"):
-                    if k_ in pin_pos:
-                        pin_pos[k_].free()
-                pin_pos["pos"] = capi.PinnedArray(int(need * 1.2) + 16, np.uint64)
-                pin_pos["off"] = capi.PinnedArray(npat + 1, np.uint64)
-                pin_pos["n"] = int(need * 1.2) + 16
-            r.fetch_positions(pos_offsets=pin_pos["off"].array, positions=pin_pos["pos"].array[:r.total])
-        else:
-            pass   # count mode: the counts were streamed into pin_counts chunk by chunk (e2fm_search_batch_stream)
+            if world > 1:
+                mine = torch.tensor([r.total], dtype=torch.int64, device=dev_t)
+                dist.all_gather_into_tensor(totals_t, mine)
+                tl = totals_t.tolist()
+                base = int(sum(tl[:rank]))
+            if base + r.total > occ_cap:
+                raise SystemExit("bench: occurrence buffer too small; pass a larger --occ-per-pattern")
+            r.fetch_occurrences(h_noff[rank][:npat + 1], h_seq[base:base + r.total], h_off[base:base + r.total])
         dt = time.perf_counter() - t0
         tot = r.total
         r.free()
         e2e_dev_ms.append(ix.last_batch_ms()["total"])
+        e2e_state.update(base=base, total=tot)
         return dt, tot
 
     for _ in range(args.warmup):
@@ -373,17 +527,17 @@ def gpu_arm(args, rank, world, local_rank):
     if not os.environ.get("E2FM_BENCH_NOSAMPLER"):
         sampler.start()
     wall0 = time.perf_counter()
-    dev_ms, bs_ms, walk_ms, exp_ms, res_ms, enc_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
-    ctr_sum = {"rank": 0, "lf": 0, "mark": 0, "launches": 0, "tasks": 0, "rank_sectors": 0, "walk_gathers": 0, "scan_rows": 0,
-               "chunks_redone": 0}
-    fc_ms = 0.0
+    phases = ["total", "backward_search", "walk", "expand", "results", "encode", "firstcheck"]
+    ph_ms = {k_: 0.0 for k_ in phases}
+    ctr_sum = {}
     occ_total = 0
     for _ in range(args.steps):
         l2_flush()
         ms, ctr, tot = step_device()
-        dev_ms += ms["total"]; bs_ms += ms["backward_search"]; walk_ms += ms["walk"]; exp_ms += ms["expand"]; res_ms += ms["results"]; enc_ms += ms["encode"]; fc_ms += ms["firstcheck"]
-        for k_ in ctr_sum:
-            ctr_sum[k_] += ctr[k_]
+        for k_ in phases:
+            ph_ms[k_] += ms[k_]
+        for k_, v in ctr.items():
+            ctr_sum[k_] = ctr_sum.get(k_, 0) + v
         occ_total += tot
     torch.cuda.synchronize()
     if world > 1:
@@ -392,6 +546,8 @@ def gpu_arm(args, rank, world, local_rank):
     e2e_s = 0.0
     for _ in range(args.steps):
         l2_flush()
+        if world > 1:
+            dist.barrier()     # a step = the whole batch: all ranks start it together
         dt, _tot = step_e2e()
         e2e_s += dt
     torch.cuda.synchronize()
@@ -399,139 +555,141 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     clocks = sampler.stop()
 
-    # max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3, bs_ms, walk_ms], dtype=torch.float64, device=dev_t)
+    # max over ranks (times), sum over ranks (work)
+    t = torch.tensor([ph_ms["total"], e2e_s * 1e3, ph_ms["backward_search"], ph_ms["walk"]], dtype=torch.float64, device=dev_t)
+    cnt = torch.tensor([occ_total, ctr_sum.get("launches", 0)], dtype=torch.int64, device=dev_t)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, bs_ms_max, walk_ms_max = [float(x) for x in t.tolist()]
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    occ_all, launches_all = int(cnt[0]), int(cnt[1])
+    steps = args.steps
+
+    # ---- parity of the TIMED batch + CPU baseline (rank 0, outside the timed region): the unmodified reference searches the first
+    # patterns of the batch on the host cores; its answers must equal what the last timed e2e step left in the host buffers
+    parity = None
+    cpu_base = None
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        procs = reference_procs(prep)
+        sample = min(npat, max(PARITY_PATTERNS, 0 if args.no_cpu_baseline else reference_sample_size(prep, procs)))
+        got = {"counts": h_counts[:sample + 1]}
+        if locate:
+            got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq, off=h_off, positions=None)
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                pass_ms, ref_res, slices, wall = run_reference(prep, np.ascontiguousarray(all_pats[:sample]), locate, procs, td)
+            parity = compare_with_reference(ref_res, slices, got, sample)
+            parity["against"] = "oracle/_ref/e2fm_ref search (the unmodified reference) on the first patterns of the timed batch"
+            v, c = sample / (pass_ms[1] / 1e3), sample / (pass_ms[0] / 1e3)
+            cpu_base = {"value": v, "unit": "patterns/s", "cores": procs, "kind": "reference", "host_cores": cores, "cold_value": c,
+                        "cpu_model": cpu_model(), "per_process": v / procs,
+                        "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified reference "
+                                  f"(1 matcher thread each), warm pass; cold pass {c:.0f} patterns/s; {wall:.1f}s wall"}
+        except RuntimeError as e:
+            parity = {"checked": 0, "mismatches": None, "error": str(e)}
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        steps = args.steps
-        # the random-gather roofline of THIS box for a working set of this index's size: independent 8-byte gathers over a
-        # buffer as large as the device image (power of two, at least 256 MB), one 32-byte sector each
-        gbuf = 256 << 20
-        while gbuf < info.device_bytes and gbuf < (64 << 30):
-            gbuf *= 2
-        try:
-            gg = capi.gather_bench(gbuf, 1 << 29, local_rank)
-        except Exception as e:   # noqa: BLE001
-            gg = None
-            log(f"[bench] gather microbenchmark failed: {e}")
-        # ... and, when the image is smaller than that floor (L2-resident indexes), the same measurement over a buffer of the
-        # image's own size: what a dependent-gather kernel could reach out of the L2
-        gg_ws, ws_buf = None, 16 << 20
-        try:
-            while ws_buf < info.device_bytes:
-                ws_buf *= 2
-            if ws_buf < gbuf:
-                gg_ws = capi.gather_bench(ws_buf, 1 << 29, local_rank)
-        except Exception as e:   # noqa: BLE001
-            gg_ws = None
-            log(f"[bench] working-set gather microbenchmark failed: {e}")
-        value = world * npat * steps / (dev_ms_max / 1e3)
-        e2e_value = world * npat * steps / (e2e_ms_max / 1e3)
-        # algorithmic bytes, SURVEY.md 8(d): rank 160 B, lf 224 B, mark 64 B per reference operation
-        # SURVEY.md 8(d) reference-model bytes: only meaningful where the reference's operations are executed one for one
-        bytes_bs = 160.0 * ctr_sum["rank"]
-        bytes_walk = 224.0 * ctr_sum["lf"] + 64.0 * ctr_sum["mark"]
-        # what THIS layout has to touch at minimum: 32 B per distinct sector gathered by the backward search,
-        # 32 B per gather of the walk / resolve kernel, 2 B per row streamed (twice) by the wildcard scan
-        lay = {"backward_search_kernel": 32.0 * ctr_sum["rank_sectors"],
-               "walk_kernel": 32.0 * ctr_sum["walk_gathers"],
-               "firstcheck_kernel": 4.0 * ctr_sum["scan_rows"]}
-        tms = {"backward_search_kernel": bs_ms, "walk_kernel": walk_ms, "firstcheck_kernel": fc_ms}
-        ref = {"backward_search_kernel": bytes_bs, "walk_kernel": bytes_walk, "firstcheck_kernel": 0.0}
-        kern = {}
-        for name in lay:
-            t = tms[name]
-            kern[name] = {"ms_per_step": t / steps, "alg_bytes_per_step": ref[name] / steps,
-                          "achieved_gbs": ref[name] / (t / 1e3) / 1e9 if t else 0.0,
-                          "layout_sector_bytes_per_step": lay[name] / steps,
-                          "layout_sector_gbs": lay[name] / (t / 1e3) / 1e9 if t else 0.0}
-        dom = max(tms, key=lambda n: tms[n])
-        traffic = None
-        short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}.get(args.workload, args.workload)
-        try:
-            import glob
-            tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
-            if tfiles:
-                with open(tfiles[-1]) as f:
-                    tj = json.load(f)
-                want = ("walk_kernel" if args.walk else "resolve_kernel") if dom == "walk_kernel" else dom
-                for name, d in tj.items():
-                    if name.startswith(f"prof_{short}_") and want in d:
-                        traffic = d[want]
-        except Exception:
-            traffic = None
-        # roofline.achieved = 32 B x the sectors THIS layout has to gather / the kernel's CUDA-event time;
-        # reference_model = SURVEY.md 8(d)'s per-operation bytes of the REFERENCE's structure x the operations counted
-        roofline = {"bound": "hbm", "kernel": dom + (" (resolve_kernel: dense tables)" if dom == "walk_kernel" and not args.walk else ""),
-                    "achieved": kern[dom]["layout_sector_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["layout_sector_gbs"] / peak, "traffic": traffic, "peak_source": peak_kind,
-                    "algorithmic_bytes_per_launch": kern[dom]["layout_sector_bytes_per_step"],
-                    "reference_model": {"bytes_per_launch": kern[dom]["alg_bytes_per_step"], "gbs": kern[dom]["achieved_gbs"],
-                                        "frac": kern[dom]["achieved_gbs"] / peak,
-                                        "note": "160 B/rank + 224 B/lf + 64 B/mark (SURVEY.md 8(d)) x operations the kernels executed; "
-                                                "above the peak by construction: one sector per rank instead of five, and with the dense "
-                                                "tables the walks are not executed at all"},
-                    "random_gather": None if not gg else {
-                        "giga_gathers_per_s": gg, "sector_gbs": gg * 32.0, "frac_of_hbm_peak": gg * 32.0 / peak,
-                        "achieved_frac_of_random_gather": kern[dom]["layout_sector_gbs"] / (gg * 32.0),
-                        "buffer_MB": gbuf >> 20,
-                        "working_set": None if not gg_ws else {
-                            "buffer_MB": ws_buf >> 20, "giga_gathers_per_s": gg_ws,
-                            "achieved_frac": kern[dom]["layout_sector_gbs"] / (gg_ws * 32.0),
-                            "note": "the device image fits the L2: same microbenchmark over a buffer of the image's size"},
-                        "how": "independent 8-byte loads at hashed addresses of a buffer the size of the device image (power of two, "
-                               ">= 256 MB), 2^29 gathers, best of 3 (e2fm_debug_gather_bench); one 32-byte sector per gather"},
-                    "note": "achieved = 32 B x sectors this layout must gather (distinct rank sectors / row-task gathers), per launch, "
-                            "over the kernel's average CUDA-event duration; traffic = ncu dram read+write of one launch (profiles/)",
-                    "kernels": kern}
+        value = npat_all * steps / (dev_ms_max / 1e3)
+        e2e_value = npat_all * steps / (e2e_ms_max / 1e3)
+        roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind)
+        h2d = int(npat * L)
+        d2h = int(npat * 8 + ((npat + 1) * 8 + (occ_total // max(steps, 1)) * 12 if locate else 0))
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic",
+            "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["name"], "mode": "count+locate" if locate else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
-                       "patterns_per_gpu": npat, "pattern_len": L, "parallelism": f"replicas x{world} (pattern batch per GPU)",
+                       "patterns": npat_all, "pattern_len": L,
+                       "parallelism": (f"{world} index replicas, the one batch partitioned by pattern ({npat} per GPU), results gathered in one "
+                                       f"shared host buffer" if world > 1 else "one index replica, whole batch"),
                        "l2": "256 MB flush between timed iterations",
                        "locate_tables": "per-query walks from marked rows" if args.walk else "dense sa[]/text[] built at load",
                        "index_device_MB": round(info.device_bytes / 1e6, 1), "index_load_s": round(load_s, 3)},
-            "occurrences_per_s": (world * occ_total / (dev_ms_max / 1e3)) if locate else None,
-            "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": int(npat * L),
-                    "d2h_bytes_per_step": int(npat * 8 + ((npat + 1) * 8 + (occ_total // max(steps, 1)) * 8 if locate else 0)),
-                    "ms_per_step": e2e_ms_max / steps,
-                    "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None},
-            "gpu_launches": int(ctr_sum["launches"]),
+            "occurrences_per_s": (occ_all / (dev_ms_max / 1e3)) if locate else None,
+            "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
+                    "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e2e_ms_max / steps,
+                    "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None,
+                    "what": "ASCII patterns from page-locked host memory; counts (u64), per-pattern occurrence offsets (u64), sequence index (u32) "
+                            "and offset in the sequence (u64) of every occurrence back into page-locked host memory"},
+            "gpu_launches": launches_all,
             "roofline": roofline,
-            "ops_per_pattern": {"rank": ctr_sum["rank"] / (npat * steps), "lf": ctr_sum["lf"] / (npat * steps),
-                                "mark": ctr_sum["mark"] / (npat * steps)},
-            "phase_ms_per_step": {"encode": enc_ms / steps, "backward_search": bs_ms / steps, "scan_expand": exp_ms / steps,
-                                  "firstcheck": fc_ms / steps, "walk_or_resolve": walk_ms / steps, "results": res_ms / steps},
+            "parity": parity,
+            "ops_per_pattern": {k_: ctr_sum.get(k_, 0) / (npat * steps) for k_ in ("rank", "lf", "mark", "rank_sectors", "walk_gathers")},
+            "phase_ms_per_step": {"encode": ph_ms["encode"] / steps, "backward_search": ph_ms["backward_search"] / steps,
+                                  "scan_expand": ph_ms["expand"] / steps, "firstcheck": ph_ms["firstcheck"] / steps,
+                                  "walk_or_resolve": ph_ms["walk"] / steps, "results": ph_ms["results"] / steps},
             "clocks": clocks, "wall_s_timed_device_loop": wall_dev,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            procs = reference_procs(prep)
-            big = os.path.getsize(prep["efm"]) > (200 << 20)
-            per_proc = (500 if big else 4000) if L >= 20 else 400
-            sample = min(npat, procs * per_proc)
-            try:
-                with tempfile.TemporaryDirectory() as td:
-                    v, c, wall = run_reference_sample(prep, pats[:sample], locate, procs, td)
-            except RuntimeError as e:
-                v = c = None
-                wall = 0.0
-                line["cpu_baseline_error"] = str(e)
-            line["cpu_baseline"] = {"value": v, "unit": "patterns/s", "cores": procs, "kind": "reference", "host_cores": cores,
-                                    "cold_value": c, "cpu_model": cpu_model(), "per_process": (v / procs) if v else None,
-                                    "sample": f"first {sample} patterns of the same batch over {procs} processes of the unmodified "
-                                              f"reference (1 matcher thread each), warm pass; cold pass {c} patterns/s; {wall:.1f}s wall"}
+        if cpu_base is not None and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_base
         emit(line)
     ix.close()
+    shm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and parity.get("mismatches"):
+        log(f"[bench] PARITY FAILURE: {parity}")
+        sys.exit(1)
+
+
+def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind):
+    """roofline of the dominant kernel. This layout's contract (replaces SURVEY.md 8(d)'s table, which prices
+    the REFERENCE's five-to-seven-sector operations): 32 B per sector the kernel has to gather (rank sectors, pair-table entries,
+    sa / text / record gathers), 2 B x 2 per row streamed by the wildcard scan."""
+    resident = info.device_bytes < L2_BYTES
+    # random-gather rate of THIS box for a working set of the index's size (power of two >= the image, at least 16 MB)
+    ws_buf = 16 << 20
+    while ws_buf < info.device_bytes and ws_buf < (64 << 30):
+        ws_buf *= 2
+    try:
+        gg = capi.gather_bench(ws_buf, 1 << 29, local_rank)
+    except Exception as e:   # noqa: BLE001
+        gg = None
+        log(f"[bench] gather microbenchmark failed: {e}")
+    lay = {"backward_search_kernel": 32.0 * ctr_sum.get("rank_sectors", 0),
+           "walk_kernel" if args.walk else "resolve_kernel": 32.0 * ctr_sum.get("walk_gathers", 0),
+           "firstcheck_kernel": 4.0 * ctr_sum.get("scan_rows", 0)}
+    tms = {"backward_search_kernel": ph_ms["backward_search"], ("walk_kernel" if args.walk else "resolve_kernel"): ph_ms["walk"],
+           "firstcheck_kernel": ph_ms["firstcheck"]}
+    kern = {}
+    for name in lay:
+        t = tms[name]
+        kern[name] = {"ms_per_step": t / steps, "algorithmic_bytes_per_step": lay[name] / steps,
+                      "achieved_gbs": lay[name] / (t / 1e3) / 1e9 if t else 0.0}
+    dom = max(tms, key=lambda n: tms[n])
+    traffic = None
+    short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}.get(args.workload, args.workload)
+    try:
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
+        if tfiles:
+            with open(tfiles[-1]) as f:
+                tj = json.load(f)
+            for name, d in tj.items():
+                if name.startswith(f"prof_{short}_") and dom in d:
+                    traffic = d[dom]
+    except Exception:
+        traffic = None
+    achieved = kern[dom]["achieved_gbs"]
+    ref_bytes = 160.0 * ctr_sum.get("rank", 0) + 224.0 * ctr_sum.get("lf", 0) + 64.0 * ctr_sum.get("mark", 0)
+    return {"bound": "l2" if resident else "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+            "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes_per_step"],
+            "random_gather": None if not gg else {
+                "giga_gathers_per_s": gg, "peak_gbs": gg * 32.0, "frac": achieved / (gg * 32.0), "buffer_MB": ws_buf >> 20,
+                "frac_of_hbm_copy_peak": gg * 32.0 / peak,
+                "how": "independent 8-byte loads at hashed addresses of a buffer of the device image's size (next power of two), 2^29 "
+                       "gathers, best of 3 (e2fm_debug_gather_bench); one 32-byte sector per gather"},
+            "note": ("the device image fits the 126 MB L2: HBM fraction is low by construction, read random_gather.frac" if resident else
+                     "achieved = 32 B x sectors this layout must gather, per step, over the kernel's CUDA-event time; "
+                     "traffic = ncu dram read+write of the same kernel (profiles/)"),
+            "reference_model": {"bytes_per_step": ref_bytes / steps,
+                                "note": "SURVEY.md 8(d): 160 B/rank + 224 B/lf + 64 B/mark x the REFERENCE operations this batch stands for; "
+                                        "not a measure of this layout (one sector per rank, no walks)"},
+            "kernels": kern}
 
 
 def sharded_arm(args, rank, world, local_rank):
@@ -555,7 +713,7 @@ def sharded_arm(args, rank, world, local_rank):
     locate = w["locate"]
     # every shard's own super-text length must dodge the reference's load-time quirks: lengthen the
     # last sequence of an unlucky shard by k bases until all shards are clean (deterministic, so every rank agrees)
-    lens = synth.safe_lengths(w["seq_lens"], K, 100 // MRP)
+    lens = workload_lens(w)
     for _ in range(1000):
         plan = sharded.plan_shards(lens, world, K)
         bad = None
@@ -577,17 +735,7 @@ def sharded_arm(args, rank, world, local_rank):
         seqs += synth.random_sequences([lens[i]], w["seed"] + i)
     efm = os.path.join(CACHE, f"{args.workload}_shard{rank}of{world}_k{K}_b{BUCKET}_m{MRP}.efm")
     if not os.path.exists(efm):
-        t0 = time.time()
-        fa = efm[:-4] + ".fa"
-        # every shard must dodge the reference's load-time quirks on its own
-        synth.write_fasta(fa, seqs)
-        threads = str(max(4, min(32, (os.cpu_count() or 2) // world)))
-        r = subprocess.run([ref_bin(), "build", fa, efm + ".tmp", keyfile, str(K), str(BUCKET), str(MRP), threads], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise SystemExit("reference shard build failed: " + r.stderr[-400:])
-        os.replace(efm + ".tmp", efm)
-        os.remove(fa)
-        log(f"[bench r{rank}] reference built shard {efm} in {time.time() - t0:.1f}s")
+        build_index(seqs, efm, keyfile, max(4, min(32, (os.cpu_count() or 2) // world)))
     with open(efm, "rb") as f:
         raw = f.read()
     col = sharded.ShardedCollection(raw, synth.test_key(), local_rank, first, text_base)
@@ -597,9 +745,7 @@ def sharded_arm(args, rank, world, local_rank):
     pats0 = None
     if rank == 0:
         # patterns are sampled from the WHOLE collection: rank 0 regenerates the sequences it does not index
-        all_seqs = []
-        for i in range(len(lens)):
-            all_seqs += synth.random_sequences([lens[i]], w["seed"] + i)
+        all_seqs = make_sequences(w, lens)
         pats0 = torch.from_numpy(synth.sample_patterns(all_seqs, npat, L, w["seed"] + 1)[:npat]).pin_memory()
         del all_seqs
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
@@ -608,11 +754,8 @@ def sharded_arm(args, rank, world, local_rank):
     def step():
         flush.add_(1)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record()
         m = col.search_batch(pats0, (npat, L), locate, args.pieces or None)
-        e1.record()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         phases.append(dict(col.last_phase_ms))
@@ -660,11 +803,12 @@ def sharded_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
-    ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="human", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--occ-per-pattern", type=float, default=1.0, help="expected occurrences per pattern (sizes the host result buffers)")
     ap.add_argument("--pieces", type=int, default=0, help="sharded mode: pipeline pieces per batch (0 = automatic)")
     ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
@@ -673,6 +817,8 @@ def main():
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    if args.workload == "chr1" and args.occ_per_pattern < 20:
+        args.occ_per_pattern = 20.0
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -23,6 +23,7 @@ OPT_PIPE = 5
 OPT_DENSITY = 6
 OPT_TAPER = 7
 OPT_PHASE_TIMERS = 8
+OPT_SEED = 9
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
@@ -33,6 +34,8 @@ EXPORTS = [
     "e2fm_result_free", "e2fm_last_batch_ms", "e2fm_last_batch_counters", "e2fm_set_option",
     "e2fm_debug_gather_bench", "e2fm_debug_keystream", "e2fm_debug_salsa20", "e2fm_debug_bwt", "e2fm_debug_marks", "e2fm_debug_lf",
     "e2fm_debug_rank", "e2fm_last_error", "e2fm_version",
+    "e2fm_packed_stride", "e2fm_pack_patterns", "e2fm_search_batch_packed", "e2fm_search_batch_packed_device",
+    "e2fm_result_fetch_compact", "e2fm_debug_seed",
 ]
 
 
@@ -47,7 +50,8 @@ class Info(C.Structure):
                 ("n_buckets", C.c_uint64), ("n_superbuckets", C.c_uint64), ("n_sequences", C.c_uint64),
                 ("initial_n", C.c_uint64), ("device_bytes", C.c_uint64), ("k", C.c_uint32), ("n_symbols", C.c_uint32),
                 ("compact_alphabet", C.c_uint32), ("marked_rows_percentage", C.c_uint32), ("marking_rate", C.c_uint32),
-                ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("dense", C.c_uint32), ("load_ms", C.c_float * 8)]
+                ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("dense", C.c_uint32), ("seed_chars", C.c_uint32),
+                ("seed_table_mb", C.c_uint32), ("load_ms", C.c_float * 8)]
 
 
 _lib = None
@@ -84,6 +88,13 @@ def lib():
     L.e2fm_search_batch_stream.argtypes = [vp, vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
     L.e2fm_search_batch_device.argtypes = [vp, vp, vp, u64, u64, i32, C.POINTER(vp)]
     L.e2fm_search_batch_device_fixed.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_packed_stride.restype = u32
+    L.e2fm_packed_stride.argtypes = [u32]
+    L.e2fm_pack_patterns.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
+    L.e2fm_search_batch_packed.argtypes = [vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
+    L.e2fm_search_batch_packed_device.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
+    L.e2fm_result_fetch_compact.argtypes = [vp, vp, vp, vp, vp]
+    L.e2fm_debug_seed.argtypes = [vp, vp, u64, vp]
     L.e2fm_extract.argtypes = [vp, u64, u64, vp, u64, C.POINTER(u64)]
     L.e2fm_result_patterns.restype = u64
     L.e2fm_result_patterns.argtypes = [vp]
@@ -185,6 +196,19 @@ class Result:
     def fetch_positions(self, pos_offsets, positions):
         """D2H of the CSR offsets and positions only (counts already streamed back)"""
         check(lib().e2fm_result_fetch(self._h, None, pos_offsets.ctypes.data, positions.ctypes.data if positions.size else None, None, None))
+
+    def fetch_occurrences(self, pos_offsets, seq_index, seq_offset):
+        """D2H of what EFMCollection::search returns per pattern (FMCollection.h:23-44): CSR offsets, sequence index and
+        offset in the sequence of every occurrence (counts already streamed back)"""
+        check(lib().e2fm_result_fetch(self._h, None, pos_offsets.ctypes.data, None,
+                                      seq_index.ctypes.data if seq_index.size else None,
+                                      seq_offset.ctypes.data if seq_offset.size else None))
+
+    def fetch_compact(self, counts=None, pos_offsets=None, seq_index=None, seq_offset=None):
+        """32-bit D2H of whichever arrays are given (e2fm_result_fetch_compact)"""
+        p = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
+        check(lib().e2fm_result_fetch_compact(self._h, p(counts), pos_offsets.ctypes.data if pos_offsets is not None else None,
+                                              p(seq_index), p(seq_offset)))
 
     def device_ptrs(self):
         ptrs = [C.c_void_p() for _ in range(5)]
@@ -296,6 +320,27 @@ class DeviceIndex:
                                              MODE_LOCATE if locate else MODE_COUNT, counts_out.ctypes.data, C.byref(h)))
         return Result(h, locate)
 
+    def search_packed(self, packed: np.ndarray, n: int, length: int, locate: bool, counts_out: np.ndarray = None) -> Result:
+        """packed: host uint8 array of n * packed_stride(length) bytes (pinned for full overlap)"""
+        assert packed.dtype == np.uint8 and packed.flags.c_contiguous and packed.size >= n * packed_stride(length)
+        h = C.c_void_p()
+        check(lib().e2fm_search_batch_packed(self._h, packed.ctypes.data if packed.size else None, n, length,
+                                             MODE_LOCATE if locate else MODE_COUNT,
+                                             counts_out.ctypes.data if counts_out is not None else None, C.byref(h)))
+        return Result(h, locate)
+
+    def search_packed_device(self, d_ptr: int, n: int, length: int, locate: bool) -> Result:
+        h = C.c_void_p()
+        check(lib().e2fm_search_batch_packed_device(self._h, d_ptr, n, length, MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
+        return Result(h, locate)
+
+    def debug_seed(self, codes) -> np.ndarray:
+        """codes: (count, seed_chars) compact codes -> (count, 3) [start, rows, exact]"""
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        out = np.zeros((codes.shape[0], 3), dtype=np.uint32)
+        check(lib().e2fm_debug_seed(self._h, codes.ctypes.data, codes.shape[0], out.ctypes.data))
+        return out
+
     def search_device_fixed(self, d_ptr: int, n: int, length: int, locate: bool) -> Result:
         h = C.c_void_p()
         check(lib().e2fm_search_batch_device_fixed(self._h, d_ptr, n, length, MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
@@ -318,7 +363,7 @@ class DeviceIndex:
         a = (C.c_uint64 * 16)()
         check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
         return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers", "scan_rows",
-                         "chunks_redone"], [int(x) for x in a]))
+                         "chunks_redone", "complex_patterns", "seeded"], [int(x) for x in a]))
 
     # ---- test hooks
     def debug_bwt(self, row0: int, count: int) -> np.ndarray:
@@ -343,6 +388,21 @@ class DeviceIndex:
         out = np.zeros(len(rows), dtype=np.uint64)
         check(lib().e2fm_debug_rank(self._h, codes.ctypes.data, rows.ctypes.data, len(rows), out.ctypes.data))
         return out
+
+
+def packed_stride(length: int) -> int:
+    return int(lib().e2fm_packed_stride(length))
+
+
+def pack_patterns(pats: np.ndarray, out: np.ndarray = None):
+    """(n, L) ASCII uint8 -> (packed uint8 array of n * packed_stride(L) bytes, number of patterns with a byte outside ACGT)"""
+    assert pats.dtype == np.uint8 and pats.ndim == 2 and pats.flags.c_contiguous
+    n, L = pats.shape
+    if out is None:
+        out = np.zeros(n * packed_stride(L), dtype=np.uint8)
+    bad = C.c_uint64(0)
+    check(lib().e2fm_pack_patterns(pats.ctypes.data if pats.size else None, n, L, out.ctypes.data if out.size else None, C.byref(bad)))
+    return out, int(bad.value)
 
 
 def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count: int, device: int = 0) -> np.ndarray:

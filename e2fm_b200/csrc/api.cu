@@ -20,6 +20,7 @@
 #include "host_format.h"
 #include "index_build.cuh"
 #include "search.cuh"
+#include "seed.cuh"
 
 using namespace e2fm;
 
@@ -143,12 +144,15 @@ struct e2fm_index {
     DevIndex dix{};
     std::vector<void *> owned;  // device allocations that live as long as the index
     uint64_t device_bytes = 0;
+    uint64_t seed_bytes = 0;
+    uint64_t max_seq_len = 0;   // longest span between terminators (a 32-bit offset in the sequence fits when it is below 2^32)
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
     uint64_t batch_ctr[16] = {0};
     double results_per_pattern = 2.0; // learned occurrence density: sizes the fast path's result store
     double tasks_per_pattern = 2.0;   // learned row-task density: sizes the fast path's task buffer
     bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
+    bool use_seed = false;      // fixed-length batches through the seed table (E2FM_OPT_SEED)
     uint64_t chunk_patterns = 4u << 20;
     uint64_t window_tasks = 64u << 20;
     unsigned long long *d_stats = nullptr;
@@ -156,7 +160,7 @@ struct e2fm_index {
     EventPool events;
     // work buffers of the search path: grow-only, reused by every batch (allocation calls cost more than the kernels of a
     // 1M-pattern batch)
-    struct Slot { void *p = nullptr; size_t bytes = 0; } ws[16];
+    struct Slot { void *p = nullptr; size_t bytes = 0; } ws[24];
 };
 
 struct e2fm_result {
@@ -189,7 +193,7 @@ T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
 
 // view of a workspace slot with the DBuf interface; contents are preserved across a growth only when asked
 enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SPARE, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_FIRSTW, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
-       WS_CURSOR, WS_BIG_LIST, WS_HATW };
+       WS_CURSOR, WS_BIG_LIST, WS_HATW, WS_PACKED, WS_PFLAG, WS_CLIST, WS_SUB, WS_NARROW, WS_N };
 template <class T>
 struct WsBuf {
     e2fm_index *ix;
@@ -437,6 +441,63 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
         launch_pair_build(d, pt, s);
         d.pair_tab = pt;
     }
+    // ---- 2-bit packed patterns: packed k-mer (base i at bits 2i) -> compact code
+    for (int b4 = 0; b4 < 4; b4++) d.sym4[b4] = sym_index[(uint8_t)"ACGT"[b4]];
+    d.packed_code = nullptr;
+    if (img.k >= 1 && img.k <= 7) {
+        const uint32_t np = 1u << (2 * img.k);
+        std::vector<uint16_t> pc(np, 0xFFFF);
+        for (uint32_t v = 0; v < np; v++) {
+            uint64_t nat = 0;
+            bool bad = false;
+            for (uint32_t i = 0; i < img.k; i++) {
+                const uint8_t si = d.sym4[(v >> (2 * i)) & 3u];
+                bad |= si == 0xFF;
+                nat = nat * img.n_sym + si;
+            }
+            if (!bad && nat < img.compact_of_natural.size()) pc[v] = img.compact_of_natural[nat];
+        }
+        d.packed_code = dev_keep_copy<uint16_t>(ix, pc.data(), pc.size());
+        CK(cudaStreamSynchronize(s));
+    }
+    // ---- seed table (seed.cuh): j = the fewest super-characters with A^j >= n/2 (E2FM_SEED_CHARS overrides, 0 = none)
+    d.seed_tab = nullptr;
+    d.seed_chars = 0;
+    d.seed_gph = (img.A + SEED_GROUP - 1) / SEED_GROUP;
+    if (sa && text && img.A >= 2) {
+        uint32_t j = 2;
+        double seeds = (double)img.A * img.A;
+        while (j < 4 && seeds < (double)img.n / 2) { seeds *= img.A; j++; }
+        if (const char *ov = getenv("E2FM_SEED_CHARS")) j = (uint32_t)atoi(ov);
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        auto table_bytes = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi * d.seed_gph * 32.0; };
+        auto hi_values = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi; };
+        while (j >= 2 && (table_bytes(j) > 0.25 * (double)free_b || hi_values(j) > 2147483648.0)) j--;
+        if (j >= 2 && j <= 8) {
+            h = tm.begin(6);
+            const uint64_t n_sectors = (uint64_t)hi_values(j) * d.seed_gph;
+            uint4 *tab = dev_keep<uint4>(ix, n_sectors * 2);
+            SeedBuildParams sp{img.n, img.A, j, d.seed_gph, sa, text, tab, d_status.p};
+            launch_seed_build(sp, n_sectors, s);
+            tm.end(h);
+            uint32_t st = 0;
+            CK(cudaMemcpyAsync(&st, d_status.p, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            CK(cudaGetLastError());
+            if (st & BUILD_ERR_SEED) {
+                // rows not in seed order (never seen on a reference-built index): search without the table
+                CK(cudaFree(tab));
+                ix->owned.pop_back();
+                ix->device_bytes -= n_sectors * 32;
+            } else {
+                d.seed_tab = tab;
+                d.seed_chars = j;
+                ix->seed_bytes = n_sectors * 32;
+            }
+        }
+    }
+    ix->use_seed = d.seed_tab != nullptr && d.packed_code != nullptr && !(getenv("E2FM_SEED") && atoi(getenv("E2FM_SEED")) == 0);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     tm.collect(ix->load_ms, 7);
@@ -453,74 +514,109 @@ struct Batch {
     const uint8_t *h_bytes = nullptr;     // patterns on the host: copied chunk by chunk on the H2D stream while earlier chunks search
     const uint64_t *h_off = nullptr;      // their offsets (ragged batches)
     uint64_t *h_counts = nullptr;         // optional: counts are copied back chunk by chunk on the D2H stream
+    // 2-bit packed input (e2fm_search_batch_packed*): d_bytes / h_bytes hold 16 * ceil(fixed_len / 64) bytes per pattern
+    bool packed_in = false;
+    uint64_t unit() const { return packed_in ? 16ull * ((fixed_len + 63) / 64) : (uint64_t)fixed_len; }   // input bytes per fixed-length pattern
 };
 
-void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, EventTimer &tm) {
-    cudaStream_t s = ix->stream;
-    const DevIndex &dix = ix->dix;
-    const uint32_t k = dix.k;
-    uint64_t launches = 0;
-    res->n = b.n;
-    res->located = mode == E2FM_MODE_LOCATE;
-    DBuf<unsigned long long> counts(std::max<uint64_t>(b.n, 1), s);
-    counts.zero();
-    CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
-
-    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ix->chunk_patterns, (1ull << 31) / k));
-    if (b.h_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, ix->pipe_patterns));
-    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1024, (uint64_t)((double)ix->window_tasks / ix->tasks_per_pattern)));
-    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
-    // chunk boundaries. Device batches: equal chunks. Host batches: stages of DECREASING size (each half the previous, down to
-    // an eighth of the first): the end-to-end time of the pipeline is the H2D time of the whole batch plus the search of the
-    // LAST stage only, so the last stage should be small, while big early stages keep the per-stage overheads few.
-    std::vector<uint64_t> bounds(1, 0);
-    {
-        uint64_t sz = chunk;
-        const uint64_t floor_sz = std::max<uint64_t>(1, chunk / 8);
-        while (bounds.back() < b.n) {
-            bounds.push_back(std::min<uint64_t>(b.n, bounds.back() + sz));
-            if (b.h_bytes && ix->pipe_taper) sz = std::max<uint64_t>(floor_sz, sz / 2);
-        }
+// what the search paths of one batch share: the counts, the list of located occurrences, the bookkeeping
+struct RunState {
+    e2fm_index *ix;
+    cudaStream_t s;
+    int mode;
+    EventTimer &tm;
+    unsigned long long *counts;           // [batch n], device
+    WsBuf<uint32_t> res_pat;
+    WsBuf<uint64_t> res_pos;
+    uint64_t n_results = 0, total_tasks = 0, launches = 0, n_redone = 0;
+    unsigned long long redo_rank = 0, redo_sect = 0;
+    bool fast_used = false;
+    RunState(e2fm_index *ix_, int mode_, EventTimer &tm_, unsigned long long *counts_)
+        : ix(ix_), s(ix_->stream), mode(mode_), tm(tm_), counts(counts_), res_pat(ix_, WS_RES_PAT, ix_->stream), res_pos(ix_, WS_RES_POS, ix_->stream) {}
+    void grow_results(uint64_t need) {
+        if (res_pos.n >= need && res_pat.n >= need) return;
+        const uint64_t cap = std::max<uint64_t>(need, res_pos.n + res_pos.n / 2);
+        res_pat.alloc(cap, n_results);
+        res_pos.alloc(cap, n_results);
     }
-    auto byte_at = [&](uint64_t i) -> uint64_t { return b.h_off ? b.h_off[i] : i * (uint64_t)b.fixed_len; };
+    uint64_t res_cap() const { return std::min(res_pat.n, res_pos.n); }
+};
 
-    // every CUDA call on the launch path costs the host a few microseconds, and a pipeline stage of a host batch holds only
-    // ~0.1 ms of kernels: per-phase event pairs are recorded for device batches only (E2FM_OPT_PHASE_TIMERS overrides)
-    tm.phases = ix->phase_timers == 1 || (ix->phase_timers == 2 && !b.h_bytes);
-    // ---- host batches: every chunk's H2D copy is queued up front on the copy stream; the search of chunk c waits for its
-    // own event only, so copies of later chunks overlap the kernels of earlier ones
+// chunk boundaries + the H2D copies of a host batch, queued up front on the copy stream: the search of chunk c waits for its
+// own event only, so copies of later chunks overlap the kernels of earlier ones
+struct Staging {
+    std::vector<uint64_t> bounds;
     std::vector<cudaEvent_t> h2d_ev;
+};
+
+Staging stage_batch(e2fm_index *ix, const Batch &b, uint64_t chunk, EventTimer &tm) {
+    cudaStream_t s = ix->stream;
+    Staging st;
+    st.bounds.assign(1, 0);
+    // Device batches: equal chunks. Host batches (option TAPER): stages of DECREASING size (each half the previous, down to an
+    // eighth of the first): the end-to-end time of the pipeline is the H2D time of the whole batch plus the search of the LAST
+    // stage only, so the last stage should be small, while big early stages keep the per-stage overheads few.
+    uint64_t sz = chunk;
+    const uint64_t floor_sz = std::max<uint64_t>(1, chunk / 8);
+    while (st.bounds.back() < b.n) {
+        st.bounds.push_back(std::min<uint64_t>(b.n, st.bounds.back() + sz));
+        if (b.h_bytes && ix->pipe_taper) sz = std::max<uint64_t>(floor_sz, sz / 2);
+    }
     if (b.h_bytes) {
+        auto byte_at = [&](uint64_t i) -> uint64_t { return b.h_off ? b.h_off[i] : i * b.unit(); };
         cudaEvent_t ready = ix->events.get(false);
         CK(cudaEventRecord(ready, s));                       // the device buffers were allocated in order on s
         CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
         const int h = tm.begin(0, ix->h2d_stream);
-        for (size_t c = 0; c + 1 < bounds.size(); c++) {
-            const uint64_t lo = byte_at(bounds[c]), hi = byte_at(bounds[c + 1]);
+        for (size_t c = 0; c + 1 < st.bounds.size(); c++) {
+            const uint64_t lo = byte_at(st.bounds[c]), hi = byte_at(st.bounds[c + 1]);
             if (hi > lo) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b.d_bytes) + lo, b.h_bytes + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
             cudaEvent_t e = ix->events.get(false);
-            h2d_ev.push_back(e);
+            st.h2d_ev.push_back(e);
             CK(cudaEventRecord(e, ix->h2d_stream));
         }
         tm.end(h, ix->h2d_stream);
     }
+    return st;
+}
+
+uint64_t pick_chunk(e2fm_index *ix, const Batch &b) {
+    const uint32_t k = ix->dix.k;
+    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ix->chunk_patterns, (1ull << 31) / k));
+    if (b.h_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, ix->pipe_patterns));
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1024, (uint64_t)((double)ix->window_tasks / ix->tasks_per_pattern)));
+    return std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
+}
+
+// The generic path (search.cu): any batch — ragged, any k, dense tables or per-query walks. `allow_fast` = false keeps to the
+// windowed path (exact sizes, no overflow redo): the sub-batch of a seed search must not disturb what is already in the result list.
+void generic_search(RunState &st, const Batch &b, bool allow_fast) {
+    e2fm_index *ix = st.ix;
+    cudaStream_t s = st.s;
+    EventTimer &tm = st.tm;
+    const int mode = st.mode;
+    const DevIndex &dix = ix->dix;
+    const uint32_t k = dix.k;
+    uint64_t &launches = st.launches, &n_results = st.n_results, &total_tasks = st.total_tasks;
+    unsigned long long *counts = st.counts;
+
+    const uint64_t chunk = pick_chunk(ix, b);
+    const Staging sg = stage_batch(ix, b, chunk, tm);
+    const std::vector<uint64_t> &bounds = sg.bounds;
+    auto byte_at = [&](uint64_t i) -> uint64_t { return b.h_off ? b.h_off[i] : i * (uint64_t)b.fixed_len; };
+
     const uint64_t items_cap = chunk * k;
     WsBuf<uint2> iv(ix, WS_IV, items_cap, s);
     WsBuf<uint32_t> firstw(ix, WS_FIRSTW, items_cap, s), hatw(ix, WS_HATW, items_cap, s);
     WsBuf<uint64_t> task_off(ix, WS_TASK_OFF, items_cap + 1, s);
     WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(items_cap, b.n)), s);
     WsBuf<uint2> tasks(ix, WS_TASKS, s);
-    WsBuf<uint32_t> res_pat(ix, WS_RES_PAT, s);
-    WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s);
-    uint64_t n_results = 0, total_tasks = 0;
-    unsigned long long redo_rank = 0, redo_sect = 0;
     // The single-row step of the backward search (one 8-byte record instead of a rank sector once the interval is one row)
     // saves instructions while everything is L2-resident, but on an HBM-resident index it adds a second large array to the
     // gather working set and loses (measured: 4.6 Mbp 0.164 vs 0.170 ms; 116 Mbp 0.65 vs 0.56 ms; 3.1 Gbp 5.6 vs 4.9 ms per
     // batch): it is used only while rec[] + occ[] fit the L2. E2FM_K3_OPTS (2 = off, 4 = no pair-table start) overrides.
     uint32_t k3_opts = (uint64_t)dix.n * 12 > (96ull << 20) ? 2u : 0u;
     if (const char *ov = getenv("E2FM_K3_OPTS")) k3_opts = (uint32_t)atoi(ov) & 6u;
-    uint64_t n_redone = 0;
 
     // ---- pre-pass: k-mer code at every pattern byte (device batches: all at once; host batches: per chunk, as it arrives)
     WsBuf<uint16_t> codes(ix, WS_CODES, b.total_bytes + 8, s);
@@ -538,19 +634,14 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         cudaEvent_t e = ix->events.get(false);
         CK(cudaEventRecord(e, s));
         CK(cudaStreamWaitEvent(ix->d2h_stream, e, 0));
-        CK(cudaMemcpyAsync(b.h_counts + first, counts.p + first, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h_stream));
-    };
-    auto grow_results = [&](uint64_t need) {
-        if (res_pos.n >= need && res_pat.n >= need) return;
-        const uint64_t cap = std::max<uint64_t>(need, res_pos.n + res_pos.n / 2);
-        res_pat.alloc(cap, n_results);
-        res_pos.alloc(cap, n_results);
+        CK(cudaMemcpyAsync(b.h_counts + first, counts + first, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h_stream));
     };
 
     // ---- FAST PATH (dense tables): every chunk is queued without a host round trip. The backward search hands its
     // intervals straight on as row tasks / wildcard intervals, the task count stays on the device. Row tasks go into a
     // buffer of `cap` entries (density learned from earlier batches); a chunk whose tasks do not fit is redone below.
-    const bool fast = ix->use_dense && dix.sa && dix.bwt16;
+    const bool fast = allow_fast && ix->use_dense && dix.sa && dix.bwt16;
+    st.fast_used = fast;
     const uint64_t n_chunks = bounds.size() - 1;
     const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(ix->window_tasks, (uint64_t)(ix->tasks_per_pattern * (double)chunk) + 1024));
     WsBuf<unsigned long long> chunk_ctr(ix, WS_CHUNK_CTR, std::max<uint64_t>(n_chunks, 1), s);   // row tasks of every chunk
@@ -561,7 +652,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     bool full_redo = false;
     auto encode_chunk = [&](uint64_t first, uint32_t cnt, uint64_t chunk_no) {
         if (!b.h_bytes) return;
-        CK(cudaStreamWaitEvent(s, h2d_ev[chunk_no], 0));
+        CK(cudaStreamWaitEvent(s, sg.h2d_ev[chunk_no], 0));
         const int h = tm.begin(4);
         launch_encode_patterns(dix, all, byte_at(first), byte_at(first + cnt), b.total_bytes, codes.p, ix->n_sm, s);
         launches++;
@@ -572,7 +663,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         // result store: every row task yields at most one occurrence; sized from the learned density, the kernels flag an
         // overflow instead of writing past the end
         if (mode == E2FM_MODE_LOCATE)
-            grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
+            st.grow_results(std::min<uint64_t>(n_chunks * cap, (uint64_t)(ix->results_per_pattern * (double)b.n) + 4096));
         for (uint64_t chunk_no = 0; chunk_no < n_chunks; chunk_no++) {
             const uint64_t first = bounds[chunk_no];
             const uint32_t cnt = (uint32_t)(bounds[chunk_no + 1] - first);
@@ -580,7 +671,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             encode_chunk(first, cnt, chunk_no);
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 16, s));   // work-queue cursor + ST_ANY_LONG
             int h = tm.begin(1);
-            SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u | k3_opts, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts.p, ix->d_stats};
+            SearchArgs sa{dix, pv, mode, codes.p, iv.p, 1u | k3_opts, firstw.p, hatw.p, tasks.p, chunk_ctr.p + chunk_no, cap, counts, ix->d_stats};
             launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -593,7 +684,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             launches++;
             tm.end(h);
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts, st.res_pat.p, st.res_pos.p, st.res_cap(), ix->d_stats};
             launch_resolve(wa, ix->n_sm, s);
             launches++;
             tm.end(h);
@@ -608,7 +699,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         }
         if (ix->h_stats[ST_RES_OVF]) {
             // the result store was too small: start the whole batch over through the exact-size path
-            CK(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(b.n, 1) * 8, s));
+            CK(cudaMemsetAsync(counts, 0, std::max<uint64_t>(b.n, 1) * 8, s));
             CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
             n_results = 0;
             full_redo = true;
@@ -620,21 +711,21 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // per (pattern, shift), scanned and expanded into row-task windows sized from the host.
     for (uint64_t c = 0; c < n_chunks; c++) {
         if (!redo[c]) continue;
-        if (fast) n_redone++;
+        if (fast) st.n_redone++;
         const uint64_t first = bounds[c];
         const uint32_t cnt = (uint32_t)(bounds[c + 1] - first);
         PatternView pv{b.d_bytes, b.d_off, b.fixed_len, first, cnt};
         unsigned long long rank0 = 0, sect0 = 0;
         if (fast) {
             // the fast path already added this chunk's directly counted intervals: start its counts over
-            CK(cudaMemsetAsync(counts.p + first, 0, (size_t)cnt * 8, s));
+            CK(cudaMemsetAsync(counts + first, 0, (size_t)cnt * 8, s));
             read_stats(ix);
             rank0 = ix->h_stats[ST_RANK];
             sect0 = ix->h_stats[ST_SECT_BS];
         } else encode_chunk(first, cnt, c);
         CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
         int h = tm.begin(1);
-        SearchArgs sa{dix, pv, mode, codes.p, iv.p, k3_opts, firstw.p, hatw.p, nullptr, nullptr, 0, counts.p, ix->d_stats};
+        SearchArgs sa{dix, pv, mode, codes.p, iv.p, k3_opts, firstw.p, hatw.p, nullptr, nullptr, 0, counts, ix->d_stats};
         launch_backward_search(sa, ix->n_sm, s);
         launches++;
         tm.end(h);
@@ -646,8 +737,8 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         CK(cudaMemcpyAsync(&n_tasks, task_off.p + (size_t)cnt * k, 8, cudaMemcpyDeviceToHost, s));
         read_stats(ix);
         if (fast && !full_redo) {   // the backward search ran twice for this chunk: keep its operations counted once
-            redo_rank += ix->h_stats[ST_RANK] - rank0;
-            redo_sect += ix->h_stats[ST_SECT_BS] - sect0;
+            st.redo_rank += ix->h_stats[ST_RANK] - rank0;
+            st.redo_sect += ix->h_stats[ST_SECT_BS] - sect0;
         }
         if (!fast) total_tasks += n_tasks;
         const uint64_t win = std::min<uint64_t>(n_tasks, ix->window_tasks);
@@ -658,10 +749,10 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
             launch_expand(iv.p, task_off.p, cnt * k, w0, w1, tasks.p, nullptr, s);
             launches++;
             tm.end(h);
-            if (mode == E2FM_MODE_LOCATE) grow_results(n_results + (w1 - w0));   // every row task yields at most one occurrence
+            if (mode == E2FM_MODE_LOCATE) st.grow_results(n_results + (w1 - w0));   // every row task yields at most one occurrence
             CK(cudaMemsetAsync(ix->d_stats + ST_QUEUE, 0, 8, s));
             h = tm.begin(3);
-            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)(w1 - w0), nullptr, counts.p, res_pat.p, res_pos.p, std::min(res_pat.n, res_pos.n), ix->d_stats};
+            WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)(w1 - w0), nullptr, counts, st.res_pat.p, st.res_pos.p, st.res_cap(), ix->d_stats};
             if (ix->use_dense && dix.sa) launch_resolve(wa, ix->n_sm, s);
             else launch_walk(wa, ix->n_sm, s);
             launches++;
@@ -672,10 +763,120 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         stream_counts_back(first, cnt);
     }
     if (b.h_counts) CK(cudaStreamSynchronize(ix->d2h_stream));
-    // learn the task density for the next batch's capacity (x1.5 head room)
+}
+
+// The seed path (seed_search.cu): fixed-length batches whose every shift holds a whole seed; ASCII input is packed on the
+// device first. Patterns it cannot finish (several rows left at the end of a shift, a saturated seed counter, an index symbol
+// outside ACGT) are searched by the generic path as a sub-batch.
+void seed_search(RunState &st, const Batch &b) {
+    e2fm_index *ix = st.ix;
+    cudaStream_t s = st.s;
+    EventTimer &tm = st.tm;
+    const DevIndex &dix = ix->dix;
+    const uint32_t m = b.fixed_len, nw = (m + 63) / 64;
+    const bool locate = st.mode == E2FM_MODE_LOCATE;
+
+    uint64_t chunk = std::max<uint64_t>(1, ix->chunk_patterns);
+    if (b.h_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(chunk, ix->pipe_patterns));
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(b.n, 1));
+    const Staging sg = stage_batch(ix, b, chunk, tm);
+    const uint64_t n_chunks = sg.bounds.size() - 1;
+
+    const uint4 *packed = reinterpret_cast<const uint4 *>(b.d_bytes);
+    const uint8_t *pflag = nullptr;
+    WsBuf<uint4> packed_ws(ix, WS_PACKED, s);
+    WsBuf<uint8_t> pflag_ws(ix, WS_PFLAG, s);
+    if (!b.packed_in) {
+        packed_ws.alloc(b.n * nw + 1);
+        pflag_ws.alloc(b.n + 1);
+        packed = packed_ws.p;
+        pflag = pflag_ws.p;
+    }
+    WsBuf<uint32_t> clist(ix, WS_CLIST, std::max<uint64_t>(b.n, 1), s);
+    if (locate) st.grow_results((uint64_t)(ix->results_per_pattern * (double)b.n) + 4096);
+
+    uint64_t n_complex = 0;
+    for (int attempt = 0;; attempt++) {
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            const uint64_t first = sg.bounds[c];
+            const uint32_t cnt = (uint32_t)(sg.bounds[c + 1] - first);
+            if (b.h_bytes && attempt == 0) CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
+            if (!b.packed_in && attempt == 0) {
+                const int h = tm.begin(4);
+                launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s);
+                st.launches++;
+                tm.end(h);
+            }
+            const int h = tm.begin(1);
+            SeedArgs sa{dix, packed, pflag, m, first, cnt, st.mode, st.counts, st.res_pat.p, st.res_pos.p, st.res_cap(), clist.p, ix->d_stats};
+            launch_seed_search(sa, nw, s);
+            st.launches++;
+            tm.end(h);
+        }
+        read_stats(ix);
+        if (!ix->h_stats[ST_RES_OVF]) break;
+        // the result store (sized from the density of earlier batches) was too small: enlarge it and search again
+        const uint64_t need = ix->h_stats[ST_RESULTS] + ix->h_stats[ST_RES_OVF];
+        st.n_results = 0;
+        st.grow_results(need + need / 8 + 4096);
+        CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
+        st.n_redone++;
+    }
+    st.n_results = ix->h_stats[ST_RESULTS];
+    n_complex = ix->h_stats[ST_COMPLEX];
+    if (n_complex) {
+        // ---- what the seed search left: an ASCII sub-batch with local pattern numbers through the generic path
+        WsBuf<uint8_t> sub(ix, WS_SUB, n_complex * m + 16, s);
+        launch_materialize(clist.p, (uint32_t)n_complex, m, nw, b.packed_in ? nullptr : b.d_bytes, packed, sub.p, s);
+        st.launches++;
+        DBuf<unsigned long long> sub_counts(n_complex, s);
+        sub_counts.zero();
+        Batch sb{sub.p, nullptr, m, n_complex, n_complex * m};
+        RunState sub_st(ix, st.mode, tm, sub_counts.p);
+        sub_st.n_results = st.n_results;
+        generic_search(sub_st, sb, false);
+        launch_sub_merge(clist.p, (uint32_t)n_complex, sub_counts.p, st.counts, sub_st.res_pat.p, st.n_results, sub_st.n_results, s);
+        st.launches += sub_st.launches + 1;
+        st.total_tasks += sub_st.total_tasks;
+        st.n_results = sub_st.n_results;
+        st.res_pat.p = sub_st.res_pat.p; st.res_pat.n = sub_st.res_pat.n;     // the list may have grown
+        st.res_pos.p = sub_st.res_pos.p; st.res_pos.n = sub_st.res_pos.n;
+        CK(cudaStreamSynchronize(s));                                          // sub_counts goes out of scope
+    }
+    ix->batch_ctr[10] = n_complex;
+    if (b.h_counts && b.n) {
+        CK(cudaMemcpyAsync(b.h_counts, st.counts, b.n * 8, cudaMemcpyDeviceToHost, s));
+    }
+}
+
+void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, EventTimer &tm) {
+    cudaStream_t s = ix->stream;
+    const DevIndex &dix = ix->dix;
+    res->n = b.n;
+    res->located = mode == E2FM_MODE_LOCATE;
+    DBuf<unsigned long long> counts(std::max<uint64_t>(b.n, 1), s);
+    CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
+    // every CUDA call on the launch path costs the host a few microseconds, and a pipeline stage of a host batch holds only
+    // ~0.1 ms of kernels: per-phase event pairs are recorded for device batches only (E2FM_OPT_PHASE_TIMERS overrides)
+    tm.phases = ix->phase_timers == 1 || (ix->phase_timers == 2 && !b.h_bytes);
+    ix->batch_ctr[10] = 0;
+
+    RunState st(ix, mode, tm, counts.p);
+    const bool seeded = ix->use_seed && ix->use_dense && !b.d_off && !b.h_off && b.n > 0 && seed_search_supported(dix, b.fixed_len);
+    if (b.packed_in && !seeded) throw std::runtime_error("packed patterns need the seed search: dense tables and seed table built, k <= 7, "
+                                                         "pattern length <= 128 with a whole seed in every shift (use the ASCII entry points)");
+    if (seeded) seed_search(st, b);        // writes every count itself
+    else {
+        counts.zero();
+        generic_search(st, b, true);
+    }
+    uint64_t n_results = st.n_results;
+    uint64_t &launches = st.launches;
+    WsBuf<uint64_t> scratch(ix, WS_SCRATCH, scan_scratch_elems(std::max<uint64_t>(b.n, 1)), s);
+    // learn the densities for the next batch's capacities (x1.5 head room)
     if (b.n) {
-        if (fast) ix->tasks_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)total_tasks / (double)b.n));
-        if (mode == E2FM_MODE_LOCATE) ix->results_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)n_results / (double)b.n));
+        if (st.fast_used) ix->tasks_per_pattern = std::min(1.0e6, std::max(2.0, 1.5 * (double)st.total_tasks / (double)b.n));
+        if (mode == E2FM_MODE_LOCATE) ix->results_per_pattern = std::min(1.0e6, std::max(seeded ? 1.25 : 2.0, (seeded ? 1.2 : 1.5) * (double)n_results / (double)b.n));
     }
 
     // ---- result pipeline (locate): CSR offsets, scatter, segmented sort + de-duplication, sequence mapping
@@ -688,7 +889,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
         DBuf<uint64_t> pos(std::max<uint64_t>(n_results, 1), s);
         WsBuf<uint32_t> cursor(ix, WS_CURSOR, std::max<uint64_t>(b.n, 1), s);
         cursor.zero(std::max<uint64_t>(b.n, 1));
-        launch_scatter(res_pat.p, res_pos.p, n_results, off.p, cursor.p, pos.p, s);
+        launch_scatter(st.res_pat.p, st.res_pos.p, n_results, off.p, cursor.p, pos.p, s);
         launches++;
         WsBuf<uint32_t> big_list(ix, WS_BIG_LIST, n_results / 24 + 1, s);
         uint32_t *ulen = cursor.p;   // the cursors are dead after the scatter
@@ -735,16 +936,17 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // result pipeline, which runs after it in locate mode, only touches the DUPS / BIGSEG words it reads itself.
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    ix->batch_ctr[0] = ix->h_stats[ST_RANK] - redo_rank;
+    ix->batch_ctr[0] = ix->h_stats[ST_RANK] - st.redo_rank;
     ix->batch_ctr[1] = ix->h_stats[ST_LF];
     ix->batch_ctr[2] = ix->h_stats[ST_MARK];
-    ix->batch_ctr[3] = total_tasks;
-    ix->batch_ctr[4] = ix->h_stats[ST_SECT_BS] - redo_sect;
+    ix->batch_ctr[3] = st.total_tasks;
+    ix->batch_ctr[4] = ix->h_stats[ST_SECT_BS] - st.redo_sect;
     ix->batch_ctr[5] = launches;
     ix->batch_ctr[6] = n_results;
     ix->batch_ctr[7] = ix->h_stats[ST_GATHER];
     ix->batch_ctr[8] = ix->h_stats[ST_SCAN_ROWS];
-    ix->batch_ctr[9] = n_redone;
+    ix->batch_ctr[9] = st.n_redone;
+    ix->batch_ctr[11] = seeded ? 1 : 0;
 }
 
 // a failed batch may have copies queued that still read the caller's host buffers: nothing is in flight when the call returns
@@ -756,7 +958,7 @@ void quiesce(e2fm_index *ix) {
 }
 
 int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets, uint32_t fixed_len, uint64_t n, uint64_t total_bytes,
-                  bool on_device, int mode, e2fm_result **out, uint64_t *counts_out = nullptr) {
+                  bool on_device, int mode, e2fm_result **out, uint64_t *counts_out = nullptr, bool packed_in = false) {
     if (!ix || !out || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
     if (n && !bytes && total_bytes) return fail(E2FM_ERR_ARG, "pattern bytes missing");
     if (n >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 patterns in one batch");
@@ -778,6 +980,7 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
         WsBuf<uint8_t> d_bytes(ix, WS_BYTES, s);
         WsBuf<uint64_t> d_off(ix, WS_OFF, s);
         Batch b{bytes, offsets, fixed_len, n, total_bytes};
+        b.packed_in = packed_in;
         if (!on_device) {
             // the pattern bytes travel chunk by chunk inside run_batch (H2D stream); only the offsets go ahead of them
             d_bytes.alloc(total_bytes + 16);
@@ -917,6 +1120,13 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
         const double t0 = now_ms();
         parse_index_header(file, size, key64, ix->img);
         ix->load_ms[0] = (float)(now_ms() - t0);
+        {
+            const HostImage &g = ix->img;
+            const uint64_t text_end = g.n * g.k + g.initial_n;
+            uint64_t prev = 0, mx = g.terminators.empty() ? text_end : 0;
+            for (int64_t t : g.terminators) { mx = std::max<uint64_t>(mx, (uint64_t)t - prev); prev = (uint64_t)t; }
+            ix->max_seq_len = std::max<uint64_t>(mx, text_end > prev ? text_end - prev : 0);
+        }
         CK(cudaSetDevice(device));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
@@ -982,6 +1192,8 @@ int e2fm_index_info(const e2fm_index *ix, e2fm_info *o) {
     o->rank_block = 1u << ix->dix.blk_shift;
     o->quirks = g.quirks;
     o->dense = ix->dix.sa ? (ix->use_dense ? 1u : 2u) : 0u;
+    o->seed_chars = ix->dix.seed_tab ? ix->dix.seed_chars : 0u;
+    o->seed_table_mb = (uint32_t)(ix->seed_bytes >> 20);
     memcpy(o->load_ms, ix->load_ms, sizeof(o->load_ms));
     return E2FM_OK;
 }
@@ -1021,6 +1233,47 @@ int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint6
 }
 int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
     return search_common(ix, d_bytes, nullptr, length, n, n * length, true, mode, out);
+}
+
+uint32_t e2fm_packed_stride(uint32_t length) { return 16u * ((length + 63u) / 64u); }
+
+int e2fm_pack_patterns(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable) {
+    if ((n && (!ascii || !packed_out)) || length == 0) return fail(E2FM_ERR_ARG, "bad argument");
+    const uint32_t stride = e2fm_packed_stride(length);
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *src = ascii + i * length;
+        uint64_t *dst = reinterpret_cast<uint64_t *>(packed_out + i * stride);
+        bool ok = true;
+        for (uint32_t w = 0; w < stride / 8; w++) {
+            uint64_t cur = 0;
+            const uint32_t end = std::min<uint32_t>(length, (w + 1) * 32);
+            for (uint32_t j = w * 32, sh = 0; j < end; j++, sh += 2) {
+                uint32_t c;
+                switch (src[j]) {
+                    case 'A': c = 0; break;
+                    case 'C': c = 1; break;
+                    case 'G': c = 2; break;
+                    case 'T': c = 3; break;
+                    default: c = 0; ok = false;
+                }
+                cur |= (uint64_t)c << sh;
+            }
+            dst[w] = cur;
+        }
+        if (!ok) bad++;
+    }
+    if (n_unpackable) *n_unpackable = bad;
+    return E2FM_OK;
+}
+
+int e2fm_search_batch_packed(e2fm_index *ix, const uint8_t *packed, uint64_t n, uint32_t length, int mode, uint64_t *counts_out,
+                             e2fm_result **out) {
+    return search_common(ix, packed, nullptr, length, n, n * e2fm_packed_stride(length), false, mode, out, counts_out, true);
+}
+int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
+    if (d_packed && (reinterpret_cast<uintptr_t>(d_packed) & 15u)) return fail(E2FM_ERR_ARG, "packed patterns must be 16-byte aligned");
+    return search_common(ix, d_packed, nullptr, length, n, n * e2fm_packed_stride(length), true, mode, out, nullptr, true);
 }
 
 int e2fm_extract(e2fm_index *ix, uint64_t from, uint64_t to, char *out, uint64_t cap, uint64_t *out_len) {
@@ -1090,6 +1343,43 @@ int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, u
     return E2FM_OK;
 }
 
+int e2fm_result_fetch_compact(e2fm_result *r, uint32_t *counts, uint32_t *pos_offsets, uint32_t *seq_index, uint32_t *seq_offset) {
+    if (!r) return fail(E2FM_ERR_ARG, "bad argument");
+    if (r->total >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 occurrences: use e2fm_result_fetch");
+    try {
+        e2fm_index *ix = r->ix;
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t s = ix->stream;
+        const uint64_t need = (counts ? r->n : 0) + (pos_offsets && r->located ? r->n + 1 : 0) + (seq_offset && r->located ? r->total : 0);
+        WsBuf<uint32_t> tmp(ix, WS_NARROW, need + 4, s);
+        uint32_t *q = tmp.p;
+        if (counts && r->n) {
+            launch_narrow(r->d_counts, q, r->n, s);
+            CK(cudaMemcpyAsync(counts, q, r->n * 4, cudaMemcpyDeviceToHost, s));
+            q += r->n;
+        }
+        if (pos_offsets) {
+            if (r->located) {
+                launch_narrow(reinterpret_cast<const unsigned long long *>(r->d_off), q, r->n + 1, s);
+                CK(cudaMemcpyAsync(pos_offsets, q, (r->n + 1) * 4, cudaMemcpyDeviceToHost, s));
+                q += r->n + 1;
+            } else memset(pos_offsets, 0, (r->n + 1) * 4);
+        }
+        if (r->located && r->total) {
+            if (seq_index) CK(cudaMemcpyAsync(seq_index, r->d_seq, r->total * 4, cudaMemcpyDeviceToHost, s));
+            if (seq_offset) {
+                if (ix->max_seq_len >= (1ull << 32)) return fail(E2FM_ERR_ARG, "a sequence is longer than 2^32-1: use e2fm_result_fetch");
+                launch_narrow(reinterpret_cast<const unsigned long long *>(r->d_seqoff), q, r->total, s);
+                CK(cudaMemcpyAsync(seq_offset, q, r->total * 4, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        CK(cudaStreamSynchronize(s));
+    } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
 int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uint64_t **d_pos_offsets, const uint64_t **d_positions,
                             const uint32_t **d_seq_index, const uint64_t **d_seq_offset) {
     if (!r) return fail(E2FM_ERR_ARG, "bad argument");
@@ -1136,6 +1426,10 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;
         case E2FM_OPT_PHASE_TIMERS: ix->phase_timers = (int)std::min<uint64_t>(value, 2); return E2FM_OK;
+        case E2FM_OPT_SEED:
+            if (value && !(ix->dix.seed_tab && ix->dix.packed_code)) return fail(E2FM_ERR_UNSUPPORTED, "the seed table was not built for this index");
+            ix->use_seed = value != 0;
+            return E2FM_OK;
         case E2FM_OPT_DENSE:
             if (value && !ix->dix.sa) return fail(E2FM_ERR_UNSUPPORTED, "the dense locate tables were not built for this index");
             ix->use_dense = value != 0;
@@ -1264,6 +1558,18 @@ int e2fm_debug_rank(const e2fm_index *ix, const uint32_t *codes, const uint64_t 
         }
         launch_debug_rank(ix->dix, d_c.p, d_in.p, count, d.p, s);
         if (count) CK(cudaMemcpyAsync(out, d.p, count * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+
+int e2fm_debug_seed(const e2fm_index *ix, const uint32_t *codes, uint64_t count, uint32_t *out) {
+    if (!ix || !ix->dix.seed_tab) return fail(E2FM_ERR_UNSUPPORTED, "the seed table was not built for this index");
+    return debug_call(ix, [&](cudaStream_t s) {
+        const uint32_t j = ix->dix.seed_chars;
+        DBuf<uint32_t> d_c(std::max<uint64_t>(count * j, 1), s), d(std::max<uint64_t>(count * 3, 1), s);
+        if (count) CK(cudaMemcpyAsync(d_c.p, codes, count * j * 4, cudaMemcpyHostToDevice, s));
+        launch_debug_seed(ix->dix, d_c.p, count, d.p, s);
+        if (count) CK(cudaMemcpyAsync(out, d.p, count * 3 * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     });
 }

@@ -62,6 +62,14 @@ struct DevIndex {
     const uint32_t *kmer_low;   // natural(c) mod n_sym^f      — the f low-order symbols  ('?'-prefixed first super-character)
     const uint32_t *kmer_high;  // natural(c) div n_sym^(k-f)  — the f high-order symbols ('?'-suffixed last super-character)
     const int64_t *terminators; // [n_term]
+    // seed table (seed.cuh): the interval of the last seed_chars super-characters of a shift in one gather; nullptr = none
+    const uint4 *seed_tab;
+    uint32_t seed_chars;        // j
+    uint32_t seed_gph;          // sectors per value of the first j-1 super-characters = ceil(A / 56)
+    // 2-bit packed patterns (A C G T = 0 1 2 3, base i of a k-mer at bits 2i): packed k-mer -> compact code, 0xFFFF when the
+    // k-mer does not occur in the text or one of its symbols is not in the index's alphabet; nullptr when k > 7
+    const uint16_t *packed_code; // [4^k]
+    uint8_t sym4[4];            // index of A, C, G, T in the original alphabet (0xFF: not a symbol of this index)
 };
 
 struct OpCounters { unsigned long long rank, lf, mark; };

@@ -13,6 +13,9 @@
 
 #include "bits.h"
 #include "salsa20.h"
+#include "seed.cuh"
+
+#include <algorithm>
 
 namespace e2fm {
 
@@ -558,6 +561,70 @@ __global__ void __launch_bounds__(256) pair_build_kernel(DevIndex ix, uint2 *__r
 void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s) {
     const uint32_t n = ix.A * ix.A;
     if (n) pair_build_kernel<<<(n + 255) / 256, 256, 0, s>>>(ix, pair_tab);
+}
+
+// ---------------------------------------------------------------- seed table (seed.cuh)
+
+// every sector: base = n (no row at or beyond the group's first seed), all counters 0
+__global__ void __launch_bounds__(256) seed_fill_kernel(uint4 *__restrict__ tab, uint64_t n_sectors, uint32_t n_rows) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sectors; i += (uint64_t)gridDim.x * blockDim.x) {
+        tab[2 * i] = make_uint4(n_rows, 0u, 0u, 0u);
+        tab[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// the first j super-characters of the rotation that row `row` stands for: all but the last packed in `hi`, the last in `cl`
+__device__ __forceinline__ void seed_of_row(const SeedBuildParams &p, uint32_t row, uint32_t &hi, uint32_t &cl) {
+    uint64_t pos = p.sa[row];
+    uint32_t h = 0;
+    for (uint32_t i = 0; i + 1 < p.j; i++) {
+        h = h * p.A + p.text[pos];
+        pos = pos + 1 == p.n ? 0 : pos + 1;
+    }
+    hi = h;
+    cl = p.text[pos];
+}
+
+// One thread per row. Rows are sorted by rotation, so rows with the same seed are consecutive and seeds never decrease
+// with the row number (checked: a violation sets BUILD_ERR_SEED and the table is dropped). The first row of every run
+// writes the run's length into the seed's counter and the base of every group that begins between the previous row's
+// seed and its own.
+__global__ void __launch_bounds__(256) seed_build_kernel(SeedBuildParams p) {
+    const uint64_t r64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r64 >= p.n) return;
+    const uint32_t r = (uint32_t)r64;
+    uint32_t hi, cl;
+    seed_of_row(p, r, hi, cl);
+    const uint64_t key = (uint64_t)hi * p.A + cl;
+    const uint64_t g = (uint64_t)hi * p.gph + cl / SEED_GROUP;
+    uint64_t g_first = 0;            // first group whose base this row sets
+    bool start = true;
+    if (r > 0) {
+        uint32_t hp, cp;
+        seed_of_row(p, r - 1, hp, cp);
+        const uint64_t keyp = (uint64_t)hp * p.A + cp;
+        if (keyp > key) atomicOr(p.status, BUILD_ERR_SEED);
+        start = keyp != key;
+        g_first = (uint64_t)hp * p.gph + cp / SEED_GROUP + 1;
+    }
+    if (!start) return;
+    uint32_t cnt = 1;
+    for (uint64_t rr = r64 + 1; cnt < SEED_SAT && rr < p.n; rr++) {
+        uint32_t h2, c2;
+        seed_of_row(p, (uint32_t)rr, h2, c2);
+        if ((uint64_t)h2 * p.A + c2 != key) break;
+        cnt++;
+    }
+    uint32_t *words = reinterpret_cast<uint32_t *>(p.tab);
+    const uint32_t slot = cl % SEED_GROUP;
+    atomicOr(words + g * 8 + 1 + (slot >> 3), cnt << ((slot & 7u) * 4u));
+    for (uint64_t gg = g_first; gg <= g; gg++) words[gg * 8] = r;
+}
+
+void launch_seed_build(const SeedBuildParams &p, uint64_t n_sectors, cudaStream_t s) {
+    if (p.n == 0 || n_sectors == 0) return;
+    seed_fill_kernel<<<(uint32_t)std::min<uint64_t>((n_sectors + 255) / 256, 148 * 32), 256, 0, s>>>(p.tab, n_sectors, (uint32_t)p.n);
+    seed_build_kernel<<<(uint32_t)((p.n + 255) / 256), 256, 0, s>>>(p);
 }
 
 }  // namespace e2fm

@@ -31,6 +31,16 @@ constexpr uint32_t BUILD_ERR_BOUNDS = 1;     // a field points outside the file
 constexpr uint32_t BUILD_ERR_LENGTH = 2;     // decoded bucket length != expected (wrong key / corrupt text)
 constexpr uint32_t BUILD_ERR_ALPHABET = 4;   // bitset size mismatch
 constexpr uint32_t BUILD_ERR_MARKS = 8;      // marked value out of range / duplicate
+constexpr uint32_t BUILD_ERR_SEED = 16;      // rows are not sorted by their first super-characters: the seed table is dropped
+
+struct SeedBuildParams {
+    uint64_t n;
+    uint32_t A, j, gph;         // j super-characters per seed, gph sectors per value of the first j-1
+    const uint32_t *sa;
+    const uint16_t *text;
+    uint4 *tab;
+    uint32_t *status;
+};
 
 struct RankBuildParams {
     uint64_t n;
@@ -67,6 +77,9 @@ void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn
 void launch_bwt16_build(const uint64_t *rec, uint64_t n, uint16_t *bwt16, cudaStream_t s);
 // pair_tab[a*A + b] = {s,e}: [C[a], C[a+1]) after one backward step with b
 void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s);
+
+// seed table (seed.cuh) from the dense tables: fill + one thread per row
+void launch_seed_build(const SeedBuildParams &p, uint64_t n_sectors, cudaStream_t s);
 
 // standalone K1 test hook
 void launch_keystream_debug(const uint32_t key[8], uint64_t nonce, uint32_t bits, uint64_t start, uint64_t count,

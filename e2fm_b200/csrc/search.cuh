@@ -34,6 +34,7 @@ enum {
     ST_GATHER = 9,   // dependent 8-byte gathers issued by the walk kernel
     ST_RES_OVF = 10, // occurrences that did not fit the result store (the host then redoes the batch with exact sizes)
     ST_SCAN_ROWS = 11, // rows streamed by firstcheck_kernel (2 bytes each)
+    ST_COMPLEX = 12, // patterns seed_search_kernel handed to the generic path
     ST_N = 14
 };
 
@@ -69,6 +70,34 @@ struct WalkArgs {
     unsigned long long res_cap;      // capacity of the two arrays above
     unsigned long long *stats;
 };
+
+// seed_search.cu: fixed-length batches over 2-bit packed patterns, one thread per pattern
+struct SeedArgs {
+    DevIndex ix;
+    const uint4 *packed;             // [batch n * nw] packed patterns (16 bytes per 64 bases)
+    const uint8_t *pflag;            // [batch n] 0 plain, 1 index symbol outside ACGT, 2 foreign symbol; nullptr: all plain
+    uint32_t m;                      // pattern length
+    uint64_t first;                  // first pattern of the chunk
+    uint32_t count;
+    int mode;
+    unsigned long long *counts;      // [batch n]
+    uint32_t *res_pat;
+    uint64_t *res_pos;
+    unsigned long long res_cap;
+    uint32_t *complex_list;          // [batch n] patterns for the generic path, ST_COMPLEX of them
+    unsigned long long *stats;
+};
+// true when every shift of an m-base pattern has at least seed_chars fixed super-characters (and the tables exist)
+bool seed_search_supported(const DevIndex &ix, uint32_t m);
+void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t first, uint32_t count, uint32_t m, uint32_t nw,
+                          uint4 *packed, uint8_t *pflag, cudaStream_t s);
+void launch_seed_search(const SeedArgs &a, uint32_t nw, cudaStream_t s);
+void launch_materialize(const uint32_t *sel, uint32_t n_sel, uint32_t m, uint32_t nw, const uint8_t *ascii, const uint4 *packed,
+                        uint8_t *out, cudaStream_t s);
+void launch_sub_merge(const uint32_t *sel, uint32_t n_sel, const unsigned long long *sub_counts, unsigned long long *counts,
+                      uint32_t *res_pat, uint64_t r0, uint64_t r1, cudaStream_t s);
+void launch_narrow(const unsigned long long *in, uint32_t *out, uint64_t n, cudaStream_t s);
+void launch_debug_seed(const DevIndex &ix, const uint32_t *codes, uint64_t count, uint32_t *out, cudaStream_t s);
 
 // codes[j] for the pattern bytes [j_begin, j_end) of a batch of n_bytes bytes (pv describes all its patterns; j_end is a pattern end)
 void launch_encode_patterns(const DevIndex &ix, const PatternView &pv, uint64_t j_begin, uint64_t j_end, uint64_t n_bytes, uint16_t *codes,

@@ -49,6 +49,8 @@ typedef struct e2fm_info {
     uint32_t quirks;             /* bit0: floor(n/rate) is a power of two (reference locate is corrupt, EFMIndex.cpp:399 vs :1280)
                                     bit1: n % rate == 0 (reference reads one junk marked-row entry, EFMIndex.cpp:1278) */
     uint32_t dense;              /* 0: no dense locate tables (HBM short); 1: built and in use; 2: built, switched off (E2FM_OPT_DENSE) */
+    uint32_t seed_chars;         /* super-characters per entry of the seed table (0: not built) */
+    uint32_t seed_table_mb;      /* its size in MiB (included in device_bytes) */
     float load_ms[8];            /* one-time costs: [0] host parse, [1] H2D, [2] superbucket parse, [3] bucket decrypt+decode,
                                     [4] histogram, [5] scan, [6] rank sectors + LF fill, [7] total device */
 } e2fm_info;
@@ -94,6 +96,20 @@ int e2fm_search_batch_device(e2fm_index *ix, const uint8_t *d_bytes, const uint6
                              uint64_t total_bytes, int mode, e2fm_result **out);
 int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint64_t n, uint32_t length, int mode,
                                    e2fm_result **out);
+/* 2-bit packed fixed-length patterns: A C G T = 0 1 2 3, base i of a pattern at bits [2i, 2i+2) of its little-endian bit string,
+ * e2fm_packed_stride(length) = 16 * ceil(length / 64) bytes per pattern, unused bits zero. A quarter of the PCIe bytes of the ASCII
+ * entry points, and no pattern pre-pass on the device. Only for batches the seed search takes (e2fm_info.seed_chars > 0, k <= 7,
+ * length <= 128 and long enough for every shift to hold a whole seed: about (seed_chars + 2) * k bases); E2FM_ERR_FORMAT otherwise.
+ * Same search, same results as the per-pattern loop around EFMCollection::search (Main.cpp:1055-1079). counts_out: optional host
+ * array of n counts (NULL: fetch them with the result). */
+uint32_t e2fm_packed_stride(uint32_t length);
+/* host helper: ASCII (n x length) -> packed; *n_unpackable = patterns holding a byte other than A C G T (packed as if it were A:
+ * send such batches through the ASCII entry points, which handle every symbol of the index's alphabet) */
+int e2fm_pack_patterns(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable);
+int e2fm_search_batch_packed(e2fm_index *ix, const uint8_t *packed, uint64_t n, uint32_t length, int mode, uint64_t *counts_out,
+                             e2fm_result **out);
+int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uint64_t n, uint32_t length, int mode,
+                                    e2fm_result **out);
 /* Page-locked host memory for pattern / result buffers (plain malloc'ed buffers work too, only slower). */
 void *e2fm_host_alloc(size_t bytes);
 void e2fm_host_free(void *p);
@@ -114,6 +130,11 @@ uint64_t e2fm_result_total_positions(const e2fm_result *r);
  *   seq_index[total], seq_offset[total]   Occurrence{sequenceIndex, patternPosition} (EFMCollection.cpp:124-148) */
 int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, uint64_t *positions,
                       uint32_t *seq_index, uint64_t *seq_offset);
+/* The same in 32 bits (a third of the PCIe bytes): counts[n], pos_offsets[n+1], seq_index[total], seq_offset[total] — whichever are
+ * non-NULL. What EFMCollection::search returns per pattern is (sequenceIndex, patternPosition) of every occurrence
+ * (FMCollection.h:23-44): pos_offsets + seq_index + seq_offset. E2FM_ERR_ARG when a value does not fit (2^32 occurrences, a
+ * sequence of 2^32 bases); counts above 2^32-1 are truncated (a count is bounded by k times the text length). */
+int e2fm_result_fetch_compact(e2fm_result *r, uint32_t *counts, uint32_t *pos_offsets, uint32_t *seq_index, uint32_t *seq_offset);
 /* device pointers of the same arrays (valid until e2fm_result_free) */
 int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uint64_t **d_pos_offsets,
                             const uint64_t **d_positions, const uint32_t **d_seq_index,
@@ -131,7 +152,7 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
  * [3] row tasks, [4] distinct 32-byte sectors gathered by the backward-search kernel (rank sectors, pair-table entries, records),
  * [5] kernels launched by the batch, [6] located occurrences, [7] gathers issued by the walk / resolve kernel,
  * [8] rows streamed by firstcheck_kernel (2 bytes each, read twice), [9] chunks redone through the windowed path,
- * [10..15] reserved */
+ * [10] patterns the seed search handed to the generic path, [11] 1 when the batch went through the seed search, [12..15] reserved */
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
@@ -142,6 +163,9 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
                                     device-resident batches — on a pipelined host batch the extra event calls cost more than they show */
 #define E2FM_OPT_DENSITY 6       /* test hook: preset the learned row-task / occurrence densities (per-mille per pattern) that size the
                                     fast path's buffers; too small a value forces the overflow -> windowed-path redo */
+#define E2FM_OPT_SEED 9          /* 1 (default when the seed table was built): fixed-length batches whose every shift holds a whole seed
+                                    go through seed_search_kernel (seed table + dense tables); 0: always the generic backward search.
+                                    Same results either way. */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).
@@ -164,6 +188,9 @@ int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint
 int e2fm_debug_bwt(const e2fm_index *ix, uint64_t row0, uint64_t count, uint32_t *out);
 /* marked value of each row in [row0,row0+count) or UINT64_MAX if the row is not marked */
 int e2fm_debug_marks(const e2fm_index *ix, uint64_t row0, uint64_t count, uint64_t *out);
+/* seed table against the rank structure: `count` seeds of seed_chars compact codes each (text order) -> out[3*i] = interval start,
+ * out[3*i+1] = rows, out[3*i+2] = 1 when exact (0: a saturated counter, the search falls back to backward steps) */
+int e2fm_debug_seed(const e2fm_index *ix, const uint32_t *codes, uint64_t count, uint32_t *out);
 /* LF-mapping of rows (device rank structure) */
 int e2fm_debug_lf(const e2fm_index *ix, const uint64_t *rows, uint64_t count, uint64_t *out);
 /* C[c] + occ(c,row) for `count` (code,row) pairs — the rank primitive of EFMIndex::backwardStep (EFMIndex.cpp:1966) */

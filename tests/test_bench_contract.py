@@ -12,7 +12,7 @@ from conftest import ROOT
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "e2fm_ref")), reason="oracle/_ref not built")
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ecoli", "--steps", "2", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -26,6 +26,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "configs[1]" in d["config"]["workload"]
+    assert d["config"]["sample_patterns"] == d["config"]["patterns"] == 1_000_000   # the whole batch: the CPU finishes it in seconds
 
 
 def test_reference_arm_on_other_ranks_is_silent():
