@@ -459,18 +459,34 @@ def gpu_arm(args, rank, world, local_rank):
     lo, hi = npat_all * rank // world, npat_all * (rank + 1) // world
     npat = hi - lo
     all_pats = load_patterns(prep)
+    # 2-bit packed patterns (e2fm_search_batch_packed) when the seed search takes this batch shape, else ASCII
+    stride = capi.packed_stride(L)
+    packed_api = not args.ascii
+    if packed_api:
+        try:
+            probe, _ = capi.pack_patterns(np.ascontiguousarray(all_pats[:1]))
+            ix.search_packed(probe, 1, L, locate).free()
+        except capi.E2FMError:
+            packed_api = False
+    unit = stride if packed_api else L
     shm = SharedHost(f"{os.environ.get('MASTER_PORT', '0')}_{args.workload}", world, rank, capi)
-    h_pats = shm.array("patterns", (npat_all, L), np.uint8)
+    h_pats = shm.array("patterns", (npat_all, unit), np.uint8)
     if world > 1:
         dist.barrier()
-    h_pats[lo:hi] = all_pats[lo:hi]
-    # result buffers of the whole batch (every rank writes its own part): what EFMCollection::search returns
+    mine = np.ascontiguousarray(all_pats[lo:hi])
+    if packed_api:
+        _, bad = capi.pack_patterns(mine, h_pats[lo:hi].reshape(-1))
+        assert bad == 0, "the synthetic batch holds only A C G T"
+    else:
+        h_pats[lo:hi] = mine
+    # result buffers of the whole batch (every rank writes its own part): what EFMCollection::search returns, in 32 bits
     occ_cap = int(npat_all * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
-    h_counts = shm.array("counts", npat_all, np.uint64)
-    h_noff = shm.array("occ_offsets", (world, npat_all // world + 2), np.uint64) if locate else None
+    h_counts = shm.array("counts", npat_all, np.uint32)
+    h_noff = shm.array("occ_offsets", (world, npat_all // world + 2), np.uint32) if locate else None
     h_seq = shm.array("seq", occ_cap, np.uint32) if locate else None
-    h_off = shm.array("off", occ_cap, np.uint64) if locate else None
-    d_pats = torch.from_numpy(np.ascontiguousarray(all_pats[lo:hi])).to(dev_t)
+    h_off = shm.array("off", occ_cap, np.uint32) if locate else None
+    d_pats = torch.from_numpy(np.array(h_pats[lo:hi])).to(dev_t)
+    del mine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)   # > 126 MB L2
     torch.cuda.synchronize()
     if world > 1:
@@ -484,7 +500,10 @@ def gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step_device():
-        r = ix.search_device_fixed(d_pats.data_ptr(), npat, L, locate)
+        if packed_api:
+            r = ix.search_packed_device(d_pats.data_ptr(), npat, L, locate)
+        else:
+            r = ix.search_device_fixed(d_pats.data_ptr(), npat, L, locate)
         ms = ix.last_batch_ms()
         ctr = ix.last_batch_counters()
         tot = r.total
@@ -492,29 +511,34 @@ def gpu_arm(args, rank, world, local_rank):
         return ms, ctr, tot
 
     e2e_dev_ms = []
-    e2e_state = {}
+    e2e_state = {"result": None}
 
     def step_e2e():
         """host patterns -> host result, through the C ABI; N > 1: the result parts are placed behind one another in the one
         shared buffer (an all-gather of the per-rank totals gives every rank its place)"""
+        if e2e_state["result"] is not None:
+            e2e_state["result"].free()
+            e2e_state["result"] = None
         t0 = time.perf_counter()
-        r = ix.search_stream(h_pats[lo:hi], locate, h_counts[lo:hi])
+        if packed_api:
+            r = ix.search_packed(h_pats[lo:hi].reshape(-1), npat, L, locate)
+        else:
+            r = ix.search_fixed(h_pats[lo:hi], locate)
         base = 0
         if locate:
             if world > 1:
-                mine = torch.tensor([r.total], dtype=torch.int64, device=dev_t)
-                dist.all_gather_into_tensor(totals_t, mine)
-                tl = totals_t.tolist()
-                base = int(sum(tl[:rank]))
+                mine_t = torch.tensor([r.total], dtype=torch.int64, device=dev_t)
+                dist.all_gather_into_tensor(totals_t, mine_t)
+                base = int(sum(totals_t.tolist()[:rank]))
             if base + r.total > occ_cap:
                 raise SystemExit("bench: occurrence buffer too small; pass a larger --occ-per-pattern")
-            r.fetch_occurrences(h_noff[rank][:npat + 1], h_seq[base:base + r.total], h_off[base:base + r.total])
+            r.fetch_compact(None, h_noff[rank][:npat + 1], h_seq[base:base + r.total], h_off[base:base + r.total])
+        else:
+            r.fetch_compact(h_counts[lo:hi], None, None, None)
         dt = time.perf_counter() - t0
-        tot = r.total
-        r.free()
         e2e_dev_ms.append(ix.last_batch_ms()["total"])
-        e2e_state.update(base=base, total=tot)
-        return dt, tot
+        e2e_state.update(base=base, total=r.total, result=r)
+        return dt, r.total
 
     for _ in range(args.warmup):
         l2_flush(); step_device()
@@ -573,9 +597,14 @@ def gpu_arm(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         procs = reference_procs(prep)
         sample = min(npat, max(PARITY_PATTERNS, 0 if args.no_cpu_baseline else reference_sample_size(prep, procs)))
-        got = {"counts": h_counts[:sample + 1]}
+        # counts and global positions of the same (last timed) batch come from an untimed 64-bit fetch of its result
+        full = e2e_state["result"].fetch()
+        got = {"counts": full["counts"]}
         if locate:
-            got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq, off=h_off, positions=None)
+            got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq, off=h_off, positions=full["positions"])
+            assert np.array_equal(full["pos_offsets"][:sample + 1], h_noff[0][:sample + 1]) and np.array_equal(full["seq"], h_seq[:len(full["seq"])])
+        else:
+            assert np.array_equal(full["counts"], h_counts[:npat])
         try:
             with tempfile.TemporaryDirectory() as td:
                 pass_ms, ref_res, slices, wall = run_reference(prep, np.ascontiguousarray(all_pats[:sample]), locate, procs, td)
@@ -594,8 +623,8 @@ def gpu_arm(args, rank, world, local_rank):
         value = npat_all * steps / (dev_ms_max / 1e3)
         e2e_value = npat_all * steps / (e2e_ms_max / 1e3)
         roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind)
-        h2d = int(npat * L)
-        d2h = int(npat * 8 + ((npat + 1) * 8 + (occ_total // max(steps, 1)) * 12 if locate else 0))
+        h2d = int(npat * unit)
+        d2h = int(((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else npat * 4)
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -606,25 +635,35 @@ def gpu_arm(args, rank, world, local_rank):
                                        f"shared host buffer" if world > 1 else "one index replica, whole batch"),
                        "l2": "256 MB flush between timed iterations",
                        "locate_tables": "per-query walks from marked rows" if args.walk else "dense sa[]/text[] built at load",
+                       "patterns_in": "2-bit packed (16 B per 64 bases)" if packed_api else "ASCII", "seed_chars": int(info.seed_chars),
+                       "seed_table_MB": int(info.seed_table_mb),
                        "index_device_MB": round(info.device_bytes / 1e6, 1), "index_load_s": round(load_s, 3)},
             "occurrences_per_s": (occ_all / (dev_ms_max / 1e3)) if locate else None,
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                     "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e2e_ms_max / steps,
                     "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None,
-                    "what": "ASCII patterns from page-locked host memory; counts (u64), per-pattern occurrence offsets (u64), sequence index (u32) "
-                            "and offset in the sequence (u64) of every occurrence back into page-locked host memory"},
+                    "what": (("2-bit packed patterns (e2fm_search_batch_packed, 16 B per 64 bases)" if packed_api else "ASCII patterns") +
+                             " from page-locked host memory; " +
+                             ("per-pattern occurrence offsets, sequence index and offset in the sequence of every occurrence (what "
+                              "EFMCollection::search returns, FMCollection.h:23-44), 32 bits each" if locate else "32-bit counts") +
+                             " back into page-locked host memory (e2fm_result_fetch_compact)")},
             "gpu_launches": launches_all,
             "roofline": roofline,
             "parity": parity,
-            "ops_per_pattern": {k_: ctr_sum.get(k_, 0) / (npat * steps) for k_ in ("rank", "lf", "mark", "rank_sectors", "walk_gathers")},
-            "phase_ms_per_step": {"encode": ph_ms["encode"] / steps, "backward_search": ph_ms["backward_search"] / steps,
+            "ops_per_pattern": {k_: ctr_sum.get(k_, 0) / (npat * steps) for k_ in ("rank", "lf", "mark", "rank_sectors", "walk_gathers",
+                                                                                    "complex_patterns")},
+            "phase_ms_per_step": {"encode_or_pack": ph_ms["encode"] / steps, "backward_or_seed_search": ph_ms["backward_search"] / steps,
                                   "scan_expand": ph_ms["expand"] / steps, "firstcheck": ph_ms["firstcheck"] / steps,
-                                  "walk_or_resolve": ph_ms["walk"] / steps, "results": ph_ms["results"] / steps},
+                                  "walk_resolve_or_seed_verify": ph_ms["walk"] / steps, "results": ph_ms["results"] / steps},
             "clocks": clocks, "wall_s_timed_device_loop": wall_dev,
         }
         if cpu_base is not None and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_base
+        if world == 1 and not args.no_cpp:
+            line["e2e_cpp"] = cpp_host_arm(prep, local_rank)
         emit(line)
+    if e2e_state["result"] is not None:
+        e2e_state["result"].free()
     ix.close()
     shm.close()
     if world > 1:
@@ -633,6 +672,25 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0 and parity is not None and parity.get("mismatches"):
         log(f"[bench] PARITY FAILURE: {parity}")
         sys.exit(1)
+
+
+def cpp_host_arm(prep, device):
+    """the same batch through the C++ host classes (e2fm_b200/host): std::vector<std::string> in, the 32-bit CSR or the reference's
+    std::vector<SearchResult> out; host wall clock of the whole call, measured by e2fm_bench_host"""
+    exe = os.path.join(ROOT, "e2fm_b200", "e2fm_bench_host")
+    if not os.path.exists(exe):
+        return {"error": "e2fm_b200/e2fm_bench_host not built"}
+    w = prep["w"]
+    with open(prep["patf"], "rb") as f:
+        np.lib.format.read_magic(f)
+        np.lib.format.read_array_header_1_0(f)
+        skip = f.tell()
+    r = subprocess.run([exe, prep["efm"], prep["keyfile"], prep["patf"], str(w["n_patterns"]), str(w["pat_len"]),
+                        "locate" if w["locate"] else "count", "3", str(device), str(skip)], capture_output=True, text=True)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not line:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    return json.loads(line[-1])
 
 
 def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind):
@@ -649,11 +707,12 @@ def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, pea
     except Exception as e:   # noqa: BLE001
         gg = None
         log(f"[bench] gather microbenchmark failed: {e}")
-    lay = {"backward_search_kernel": 32.0 * ctr_sum.get("rank_sectors", 0),
-           "walk_kernel" if args.walk else "resolve_kernel": 32.0 * ctr_sum.get("walk_gathers", 0),
+    seeded = ctr_sum.get("seeded", 0) > 0
+    k3 = "seed_lookup_kernel" if seeded else "backward_search_kernel"
+    k4 = "seed_verify_kernel" if seeded else ("walk_kernel" if args.walk else "resolve_kernel")
+    lay = {k3: 32.0 * ctr_sum.get("rank_sectors", 0), k4: 32.0 * ctr_sum.get("walk_gathers", 0),
            "firstcheck_kernel": 4.0 * ctr_sum.get("scan_rows", 0)}
-    tms = {"backward_search_kernel": ph_ms["backward_search"], ("walk_kernel" if args.walk else "resolve_kernel"): ph_ms["walk"],
-           "firstcheck_kernel": ph_ms["firstcheck"]}
+    tms = {k3: ph_ms["backward_search"], k4: ph_ms["walk"], "firstcheck_kernel": ph_ms["firstcheck"]}
     kern = {}
     for name in lay:
         t = tms[name]
@@ -808,12 +867,14 @@ def main():
     ap.add_argument("--impl", default="e2fm_b200", choices=["e2fm_b200", "reference"])
     ap.add_argument("--workload", default="human", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpp", action="store_true", help="skip the e2e_cpp figure (C++ host classes)")
     ap.add_argument("--occ-per-pattern", type=float, default=1.0, help="expected occurrences per pattern (sizes the host result buffers)")
     ap.add_argument("--pieces", type=int, default=0, help="sharded mode: pipeline pieces per batch (0 = automatic)")
     ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")
     ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
+    ap.add_argument("--ascii", action="store_true", help="ASCII patterns through e2fm_search_batch_fixed even when the packed entry point would take the batch")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)

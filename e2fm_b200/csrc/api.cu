@@ -151,6 +151,7 @@ struct e2fm_index {
     uint64_t batch_ctr[16] = {0};
     double results_per_pattern = 2.0; // learned occurrence density: sizes the fast path's result store
     double tasks_per_pattern = 2.0;   // learned row-task density: sizes the fast path's task buffer
+    double seed_tasks_per_pattern = 2.0;   // the same for the seed search (rows of seed intervals per pattern)
     bool use_dense = false;     // answer row tasks from sa[] / text[] instead of walking (E2FM_OPT_DENSE)
     bool use_seed = false;      // fixed-length batches through the seed table (E2FM_OPT_SEED)
     uint64_t chunk_patterns = 4u << 20;
@@ -794,9 +795,17 @@ void seed_search(RunState &st, const Batch &b) {
     }
     WsBuf<uint32_t> clist(ix, WS_CLIST, std::max<uint64_t>(b.n, 1), s);
     if (locate) st.grow_results((uint64_t)(ix->results_per_pattern * (double)b.n) + 4096);
+    // row tasks of a chunk (seed_lookup_kernel -> seed_verify_kernel): capacity from the density of earlier batches; the kernels
+    // never write past it and the host searches again with room when a chunk needed more
+    WsBuf<uint2> tasks(ix, WS_TASKS, s);
+    uint64_t cap = (uint64_t)(ix->seed_tasks_per_pattern * (double)chunk) + 4096;
+    WsBuf<unsigned long long> chunk_ctr(ix, WS_CHUNK_CTR, std::max<uint64_t>(n_chunks, 1), s);
+    std::vector<unsigned long long> h_chunk_tasks(n_chunks, 0);
 
-    uint64_t n_complex = 0;
+    uint64_t n_complex = 0, seed_tasks = 0;
     for (int attempt = 0;; attempt++) {
+        tasks.alloc(cap);
+        chunk_ctr.zero(std::max<uint64_t>(n_chunks, 1));
         for (uint64_t c = 0; c < n_chunks; c++) {
             const uint64_t first = sg.bounds[c];
             const uint32_t cnt = (uint32_t)(sg.bounds[c + 1] - first);
@@ -807,21 +816,35 @@ void seed_search(RunState &st, const Batch &b) {
                 st.launches++;
                 tm.end(h);
             }
-            const int h = tm.begin(1);
-            SeedArgs sa{dix, packed, pflag, m, first, cnt, st.mode, st.counts, st.res_pat.p, st.res_pos.p, st.res_cap(), clist.p, ix->d_stats};
-            launch_seed_search(sa, nw, s);
-            st.launches++;
+            SeedArgs sa{dix, packed, pflag, m, first, cnt, st.mode, st.counts, st.res_pat.p, st.res_pos.p, st.res_cap(), clist.p,
+                        tasks.p, cap, chunk_ctr.p + c, ix->d_stats};
+            int h = tm.begin(1);
+            launch_seed_lookup(sa, nw, ix->n_sm, s);
             tm.end(h);
+            h = tm.begin(3);
+            launch_seed_verify(sa, nw, ix->n_sm, s);
+            tm.end(h);
+            st.launches += 2;
         }
+        if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_ctr.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
         read_stats(ix);
-        if (!ix->h_stats[ST_RES_OVF]) break;
-        // the result store (sized from the density of earlier batches) was too small: enlarge it and search again
-        const uint64_t need = ix->h_stats[ST_RESULTS] + ix->h_stats[ST_RES_OVF];
-        st.n_results = 0;
-        st.grow_results(need + need / 8 + 4096);
+        uint64_t most = 0;
+        seed_tasks = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) { most = std::max<uint64_t>(most, h_chunk_tasks[c]); seed_tasks += h_chunk_tasks[c]; }
+        const bool task_ovf = most > cap, res_ovf = ix->h_stats[ST_RES_OVF] != 0;
+        if (!task_ovf && !res_ovf) break;
+        // a store sized from the density of earlier batches was too small: enlarge it and search again
+        if (task_ovf) cap = most + most / 8 + 4096;
+        if (locate) {
+            const uint64_t need = std::max<uint64_t>(ix->h_stats[ST_RESULTS] + ix->h_stats[ST_RES_OVF], task_ovf ? seed_tasks : 0);
+            st.n_results = 0;
+            st.grow_results(need + need / 8 + 4096);
+        }
         CK(cudaMemsetAsync(ix->d_stats, 0, ST_N * sizeof(unsigned long long), s));
         st.n_redone++;
     }
+    st.total_tasks += seed_tasks;
+    if (b.n) ix->seed_tasks_per_pattern = std::min(1.0e6, std::max(1.5, 1.3 * (double)seed_tasks / (double)b.n));
     st.n_results = ix->h_stats[ST_RESULTS];
     n_complex = ix->h_stats[ST_COMPLEX];
     if (n_complex) {
@@ -863,7 +886,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
 
     RunState st(ix, mode, tm, counts.p);
     const bool seeded = ix->use_seed && ix->use_dense && !b.d_off && !b.h_off && b.n > 0 && seed_search_supported(dix, b.fixed_len);
-    if (b.packed_in && !seeded) throw std::runtime_error("packed patterns need the seed search: dense tables and seed table built, k <= 7, "
+    if (b.packed_in && !seeded && b.n > 0) throw std::runtime_error("packed patterns need the seed search: dense tables and seed table built, k <= 7, "
                                                          "pattern length <= 128 with a whole seed in every shift (use the ASCII entry points)");
     if (seeded) seed_search(st, b);        // writes every count itself
     else {
@@ -1421,7 +1444,7 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
         case E2FM_OPT_CHUNK: ix->chunk_patterns = value ? value : (4u << 20); return E2FM_OK;
         case E2FM_OPT_WINDOW: ix->window_tasks = value ? value : (64u << 20); return E2FM_OK;
         case E2FM_OPT_DENSITY:   // test hook: forget the learned densities (value = per-mille of one task / result per pattern)
-            ix->tasks_per_pattern = ix->results_per_pattern = (double)value / 1000.0;
+            ix->tasks_per_pattern = ix->results_per_pattern = ix->seed_tasks_per_pattern = (double)value / 1000.0;
             return E2FM_OK;
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;

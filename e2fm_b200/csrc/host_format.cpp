@@ -78,10 +78,34 @@ static uint32_t symbol_index(const HostImage &img, uint8_t c) {
 // "1-bit flag, unaligned i64 size, bits" (EFMIndex.cpp:1200-1215). The flag selects the RLE form
 // (BitSetRLEEncoder), which the reference never writes for alphabets (tryToStoreCompressedBitmaps=false,
 // EFMIndex.h:406) but can read.
-static std::vector<uint8_t> read_bitset(BitCursor &r, uint64_t limit_bits) {
+// Tail-safe reader for the host parse: the caller's buffer is NOT padded (unlike the device copy), so a field that starts
+// within 8 bytes of the end — or, in a truncated or corrupt file, beyond it — reads zeros instead of foreign memory.
+struct HostCursor {
+    const uint8_t *p;
+    uint64_t size;     // bytes
+    uint64_t bit;
+    uint64_t get(uint32_t n) {
+        const uint64_t byte = bit >> 3;
+        uint64_t v;
+        if (byte + 8 <= size) v = read_bits(p, bit, n);
+        else {
+            uint8_t tmp[8] = {0};
+            for (uint64_t i = 0; i < 8 && byte + i < size; i++) tmp[i] = p[byte + i];
+            v = read_bits(tmp, bit & 7, n);
+        }
+        bit += n;
+        return v;
+    }
+    uint64_t get64() { uint64_t hi = get(56); return (hi << 8) | get(8); }   // MemoryBitReader::getInt64 :51
+    void align() { bit = (bit + 7) & ~7ull; }                                // gotoNextByteStart :82
+};
+
+static std::vector<uint8_t> read_bitset(HostCursor &r, uint64_t max_bits) {
     bool compressed = r.get(1) == 1;
     uint64_t sz = r.get64();
-    if (sz > limit_bits) throw std::runtime_error("corrupt index: bitset larger than the file");
+    // the stored form is never longer than the bitset it stands for (max_bits, known from the header) plus the RLE's own
+    // overhead, and it must lie inside the file: checked BEFORE anything is allocated
+    if (sz > 2 * max_bits + 64 || r.bit + sz > r.size * 8) throw std::runtime_error("corrupt index: bitset larger than the file");
     std::vector<uint8_t> raw(sz);
     for (uint64_t i = 0; i < sz; i++) raw[i] = (uint8_t)r.get(1);
     if (!compressed) return raw;
@@ -90,7 +114,10 @@ static std::vector<uint8_t> read_bitset(BitCursor &r, uint64_t limit_bits) {
     uint32_t x = 0;
     bool pending = false;
     auto flush = [&]() {
-        if (x > 0) out.insert(out.end(), (size_t)((1ull << x) + N - 1), 0);
+        if (x > 0) {
+            if (x >= 40 || out.size() + ((1ull << x) + N - 1) > max_bits + 1) throw std::runtime_error("corrupt index: bitset run past its size");
+            out.insert(out.end(), (size_t)((1ull << x) + N - 1), 0);
+        }
         out.push_back(1);
         N = 0;
         x = 0;
@@ -112,7 +139,7 @@ void parse_index_header(const uint8_t *file, size_t size, const uint8_t key64[64
         throw std::runtime_error("File type is not Encrypted and Compressed Genomic Index");   // EFMIndex.cpp:1155
     if (size < 64) throw std::runtime_error("corrupt index: truncated header");
     const uint64_t file_bits = (uint64_t)size * 8;
-    BitCursor r{file, 16};
+    HostCursor r{file, (uint64_t)size, 16};
     img.n_sym = (uint32_t)r.get(8);
     if (img.n_sym == 0 || 3 + (uint64_t)img.n_sym + 100 > size) throw std::runtime_error("corrupt index: bad symbol table");
     for (uint32_t i = 0; i < img.n_sym; i++) img.syms[i] = (uint8_t)r.get(8);
@@ -171,7 +198,7 @@ void parse_index_header(const uint8_t *file, size_t size, const uint8_t key64[64
     }
 
     // compact alphabet (EFMIndex.cpp:1200-1239): compact code = rank of the scrambled code in the bitset
-    std::vector<uint8_t> abits = read_bitset(r, file_bits);
+    std::vector<uint8_t> abits = read_bitset(r, card);
     if (abits.size() != card) throw std::runtime_error("corrupt index or wrong alphabet: bitset size mismatch");
     std::vector<int32_t> compact_of_scr(card, -1);
     img.A = 0;
@@ -255,7 +282,7 @@ void parse_index_header(const uint8_t *file, size_t size, const uint8_t key64[64
     for (uint64_t i = 0; i < cnt; i++) { tp += (int64_t)r.get(tb); img.terminators[i] = tp; }
     // FASTA headers (EFMCollection::loadFastaHeaders, EFMCollection.cpp:97-104): i32 size + bytes
     if (fasta_start + 4 <= size) {
-        BitCursor h{file, fasta_start * 8};
+        HostCursor h{file, (uint64_t)size, fasta_start * 8};
         uint64_t hs = h.get(32);
         if (fasta_start + 4 + hs <= size) img.fasta_headers.assign((const char *)file + fasta_start + 4, hs);
     }

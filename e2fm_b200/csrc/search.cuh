@@ -85,13 +85,17 @@ struct SeedArgs {
     uint64_t *res_pos;
     unsigned long long res_cap;
     uint32_t *complex_list;          // [batch n] patterns for the generic path, ST_COMPLEX of them
+    uint2 *tasks;                    // row tasks {row, chunk-local item} of the chunk: seed_lookup_kernel -> seed_verify_kernel
+    unsigned long long task_cap;
+    unsigned long long *task_cursor; // device-resident number of row tasks of the chunk
     unsigned long long *stats;
 };
 // true when every shift of an m-base pattern has at least seed_chars fixed super-characters (and the tables exist)
 bool seed_search_supported(const DevIndex &ix, uint32_t m);
 void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t first, uint32_t count, uint32_t m, uint32_t nw,
                           uint4 *packed, uint8_t *pflag, cudaStream_t s);
-void launch_seed_search(const SeedArgs &a, uint32_t nw, cudaStream_t s);
+void launch_seed_lookup(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s);
+void launch_seed_verify(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s);
 void launch_materialize(const uint32_t *sel, uint32_t n_sel, uint32_t m, uint32_t nw, const uint8_t *ascii, const uint4 *packed,
                         uint8_t *out, cudaStream_t s);
 void launch_sub_merge(const uint32_t *sel, uint32_t n_sel, const unsigned long long *sub_counts, unsigned long long *counts,

@@ -81,231 +81,272 @@ void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t fir
                                                                reinterpret_cast<unsigned long long *>(packed), pflag);
 }
 
-// ---------------------------------------------------------------- the search
+// ---------------------------------------------------------------- the search: seed lookup, then verification
 
-// bits [off, off + width) of the pattern's bit string (width <= 32)
-template <int NW>
-__device__ __forceinline__ uint32_t pk_field(const unsigned long long (&pk)[2 * NW], uint32_t off, uint32_t mask) {
-    const uint32_t wi = off >> 6, sh = off & 63u;
-    unsigned long long a = 0, b = 0;
-#pragma unroll
-    for (int i = 0; i < 2 * NW; i++) {
-        if (wi == (uint32_t)i) a = pk[i];
-        if (wi + 1 == (uint32_t)i) b = pk[i];
-    }
-    unsigned long long v = a >> sh;
-    if (sh) v |= b << (64 - sh);
-    return (uint32_t)v & mask;
+// which super-characters of shift sa are searched: l = their end (exclusive), lo = the first fixed one, or l <= 0 when the shift
+// yields nothing (EFMIndex.cpp:2132 / :1745)
+__host__ __device__ __forceinline__ void shift_geometry(uint32_t m, uint32_t k, uint32_t sa, uint32_t &L, bool &last_var, int &l, int &lo) {
+    L = (m + sa + k - 1) / k;
+    last_var = (m + sa) % k != 0;
+    l = -1;
+    if (!last_var) { if (!(L == 1 && sa > 0)) l = (int)L; }
+    else if (L > 1 && (L > 2 || sa == 0)) l = (int)L - 1;
+    lo = sa > 0 ? 1 : 0;
 }
 
-// natural value (base n_sym, first base most significant) of the f bases at bit offset off: what kmer_low / kmer_high hold
+// A pattern's bit string in registers: NW x 128 bits. bits(off, mask): up to 32 bits at bit offset off.
 template <int NW>
-__device__ __forceinline__ uint32_t pk_natural(const DevIndex &ix, const unsigned long long (&pk)[2 * NW], uint32_t off, uint32_t f) {
-    const uint32_t bits = pk_field<NW>(pk, off, f >= 16 ? 0xFFFFFFFFu : ((1u << (2 * f)) - 1u));
-    uint32_t v = 0;
-    bool bad = false;
-    for (uint32_t i = 0; i < f; i++) {
-        const uint32_t s = ix.sym4[(bits >> (2 * i)) & 3u];
-        bad |= s == 0xFFu;
-        v = v * ix.n_sym + s;
-    }
-    return bad ? 0xFFFFFFFFu : v;
-}
-
-template <int KT, int NW>
-__global__ void __launch_bounds__(256) seed_search_kernel(SeedArgs a) {
-    extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code
-    __shared__ uint32_t warp_tot[8];
-    __shared__ unsigned long long blk_base;
-    const DevIndex &ix = a.ix;
-    constexpr uint32_t k = KT;
-    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
-    for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t < a.count;
-    const uint64_t p = a.first + t;
-    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A;
-    const uint32_t blk_shift = ix.blk_shift, blk_mask = (1u << blk_shift) - 1;
-    const long long n = (long long)ix.n;
-
-    unsigned long long pk[2 * NW];
-#pragma unroll
-    for (int i = 0; i < 2 * NW; i++) pk[i] = 0;
-    uint32_t flag = 2;
-    if (valid) {
-        const uint4 *src = a.packed + p * NW;
+struct PatRegs {
+    uint32_t w[4 * NW];
+    __device__ __forceinline__ void load(const uint4 *src) {
 #pragma unroll
         for (int i = 0; i < NW; i++) {
             const uint4 v = __ldg(src + i);
-            pk[2 * i] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-            pk[2 * i + 1] = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
-        flag = a.pflag ? a.pflag[p] : 0;
     }
-    // the packed form holds nothing beyond base m-1
-    uint32_t cnt_total = 0, nres = 0, n_sect = 0, n_rank = 0;
-    unsigned long long respos[KT];
-    bool complex = flag == 1;
-
-    if (flag == 0) {
-        // ---- EFMIndex::computeSuperPatterns (:2055-2207) + the seed of every shift: k independent sector gathers in flight
-        Sector sec[KT];
-        uint32_t slot[KT];
-        int nexti[KT];        // next super-character to process, -2: the shift is dead
+    __device__ __forceinline__ uint32_t bits(uint32_t off, uint32_t mask) const {
+        const uint32_t wi = off >> 5;
+        uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int sa = 0; sa < KT; sa++) {
-            const uint32_t L = (m + sa + k - 1) / k;
-            const bool last_var = (m + sa) % k != 0;
-            int l = -1;
-            if (!last_var) { if (!(L == 1 && sa > 0)) l = (int)L; }
-            else if (L > 1 && (L > 2 || sa == 0)) l = (int)L - 1;
-            nexti[sa] = -2;
-            slot[sa] = 0;
-            if (l > 0) {                               // the host only takes this path when every such shift has >= j fixed characters
+        for (int i = 0; i < 4 * NW; i++) {
+            if (wi == (uint32_t)i) lo = w[i];
+            if (wi + 1 == (uint32_t)i) hi = w[i];
+        }
+        return __funnelshift_r(lo, hi, off & 31u) & mask;
+    }
+    // natural value (base n_sym, first base most significant) of the f bases at bit offset off: what kmer_low / kmer_high hold
+    __device__ __forceinline__ uint32_t natural(const DevIndex &ix, uint32_t off, uint32_t f) const {
+        const uint32_t b = bits(off, f >= 16 ? 0xFFFFFFFFu : ((1u << (2 * f)) - 1u));
+        uint32_t v = 0;
+        bool bad = false;
+        for (uint32_t i = 0; i < f; i++) {
+            const uint32_t s = ix.sym4[(b >> (2 * i)) & 3u];
+            bad |= s == 0xFFu;
+            v = v * ix.n_sym + s;
+        }
+        return bad ? 0xFFFFFFFFu : v;
+    }
+};
+
+static constexpr uint32_t SL_FLUSH = 1024;                       // staged row tasks handed over per reservation
+static constexpr uint32_t SL_CAP = SL_FLUSH + 256 * 14;          // a tile adds at most 14 rows per lane (exact counters stop at 14)
+
+// K_a: one LANE per (pattern, shift). EFMIndex::computeSuperPatterns (:2055-2207) for the last j fixed super-characters of the shift
+// from the packed pattern, ONE sector gather of the seed table (start interval :1728-1748 + j-1 backwardSteps :1966), and the rows
+// of the interval — at most 14 — become row tasks {row, item}. The k lanes of a pattern sit next to each other in a warp: when one
+// of them meets a saturated counter the whole pattern goes to the generic path instead.
+template <int KT, int NW>
+__global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
+    extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code
+    __shared__ uint2 st_task[SL_CAP];
+    __shared__ uint32_t st_cnt;
+    __shared__ unsigned long long st_base;
+    const DevIndex &ix = a.ix;
+    constexpr uint32_t k = KT, PPW = 32 / KT, PPC = 8 * PPW;
+    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
+    if (threadIdx.x == 0) st_cnt = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t pl = lane / k, sa = lane - pl * k;
+    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A;
+    uint32_t L;
+    bool last_var;
+    int l, lo;
+    shift_geometry(m, k, sa, L, last_var, l, lo);
+    const unsigned group = (pl < PPW ? ((1u << k) - 1u) << (pl * k) : 0u);
+    unsigned long long n_sect = 0;
+    auto flush = [&]() {                               // whole CTA, st_cnt stable
+        const uint32_t c = st_cnt;
+        if (threadIdx.x == 0) st_base = atomicAdd(a.task_cursor, (unsigned long long)c);
+        __syncthreads();
+        const unsigned long long b0 = st_base;
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x)
+            if (b0 + i < a.task_cap) a.tasks[b0 + i] = st_task[i];
+        __syncthreads();
+        if (threadIdx.x == 0) st_cnt = 0;
+        __syncthreads();
+    };
+    for (uint32_t tile = blockIdx.x; (unsigned long long)tile * PPC < a.count; tile += gridDim.x) {
+        const uint32_t p_local = tile * PPC + warp * PPW + pl;
+        const bool valid = pl < PPW && p_local < a.count;
+        uint32_t cnt = 0, s = 0;
+        bool irregular = false;
+        if (valid) {
+            const uint64_t p = a.first + p_local;
+            const uint32_t flag = a.pflag ? a.pflag[p] : 0;
+            if (sa == 0) a.counts[p] = 0;              // seed_verify_kernel (and the generic path for list members) add to it
+            irregular = flag == 1;
+            if (flag == 0 && l > 0) {
+                PatRegs<NW> pat;
+                pat.load(a.packed + p * NW);
                 uint32_t hi = 0, cl = 0;
                 bool absent = false;
                 for (uint32_t q = 0; q < j; q++) {
                     const uint32_t c = (uint32_t)l - j + q;
-                    const uint32_t code = ctab[pk_field<NW>(pk, 2 * (c * k - sa), KMASK)];
+                    const uint32_t code = ctab[pat.bits(2 * (c * k - sa), KMASK)];
                     absent |= code == 0xFFFFu;
                     if (q + 1 < j) hi = hi * A + code; else cl = code;
                 }
                 if (!absent) {
-                    sec[sa] = seed_load(ix, seed_sector(ix, hi, cl, slot[sa]));
-                    nexti[sa] = l - (int)j - 1;
+                    uint32_t slot;
+                    const size_t sector = seed_sector(ix, hi, cl, slot);
+                    const SeedHit h = seed_decode(seed_load(ix, sector), slot);
                     n_sect++;
+                    if (!h.exact) irregular = true;
+                    else { s = h.s; cnt = h.cnt; }
                 }
             }
         }
-#pragma unroll
-        for (int sa = 0; sa < KT; sa++) {
-            if (nexti[sa] == -2 || complex) continue;
-            const SeedHit h = seed_decode(sec[sa], slot[sa]);
-            if (!h.exact) { complex = true; continue; }
-            if (h.cnt == 0) continue;
-            const uint32_t L = (m + sa + k - 1) / k;
-            const bool last_var = (m + sa) % k != 0;
-            const int l = last_var ? (int)L - 1 : (int)L;
-            const int lo = sa > 0 ? 1 : 0;
-            uint32_t s = h.s, e = h.s + h.cnt;
-            int i = nexti[sa];
-            // ---- EFMIndex::backwardStep (:1966-2001) over rank sectors while several rows are left
-            while (e - s > 1 && i >= lo) {
-                const uint32_t cc = ctab[pk_field<NW>(pk, 2 * ((uint32_t)i * k - sa), KMASK)];
-                if (cc == 0xFFFFu) { e = s; break; }
-                const uint32_t re = e - 1;
-                const Sector se = load_sector(ix, cc, re >> blk_shift);
-                uint32_t ns;
-                if (s == 0) ns = (uint32_t)__ldg(ix.C + cc);
-                else {
-                    const uint32_t rs = s - 1;
-                    if ((rs >> blk_shift) == (re >> blk_shift)) ns = sector_rank(ix, se, rs & blk_mask);
-                    else {
-                        const Sector ss = load_sector(ix, cc, rs >> blk_shift);
-                        ns = sector_rank(ix, ss, rs & blk_mask);
-                        n_sect++;
-                    }
-                }
-                e = sector_rank(ix, se, re & blk_mask);
-                s = ns;
-                n_sect++;
-                n_rank += 2;
-                i--;
-            }
-            if (e <= s) continue;
-            if (e - s > 1) { complex = true; continue; }     // several rows at the end: expanded and resolved by the generic path
-            // ---- one row left: its suffix starts at text position pos; super-character c of the shift lies at pos - (i + 1 - c)
-            const long long pos = (long long)__ldg(ix.sa + s);
-            n_sect++;
-            auto at = [&](long long x) -> uint32_t {
-                if (x < 0) x += n; else if (x >= n) x -= n;
-                return (uint32_t)__ldg(ix.text + x);
-            };
-            bool ok = true;
-            for (int c = i; c >= lo; c--) {
-                const uint32_t code = ctab[pk_field<NW>(pk, 2 * ((uint32_t)c * k - sa), KMASK)];
-                ok &= code == at(pos - (long long)(i + 1 - c));
-            }
-            long long tp = pos - (long long)(i + 1);          // text position of super-character 0 of the shift
-            if (tp < 0) tp += n;
-            if (sa > 0) {
-                // EFMIndex::backwardStepIfMatch (:2011-2041): the k - sa fixed symbols of the '?'-prefixed first super-character
-                const uint32_t f = k - sa;
-                const uint32_t want = pk_natural<NW>(ix, pk, 0, f);
-                const uint32_t code = (uint32_t)__ldg(ix.text + tp);
-                ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code) == want;
-            }
-            if (last_var) {
-                // EFMIndex::findWholePatternMatches (:1862-1899): the fixed symbols of the '?'-suffixed last super-character
-                const long long ph = tp + (long long)L - 1;
-                if (ph >= n) ok = false;
-                else {
-                    const uint32_t from = (L - 1) * k - sa, f = m - from;
-                    const uint32_t want = pk_natural<NW>(ix, pk, 2 * from, f);
-                    const uint32_t code = (uint32_t)__ldg(ix.text + ph);
-                    ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_high + (f - 1) * A + code) == want;
-                }
-            }
-            {   // distinct 32-byte sectors of text[] this touched: the run [tp or tp+lo, pos-1] and the hat character
-                const long long a0 = (sa > 0 ? tp : pos - (long long)(i + 1 - lo)), a1 = pos - 1;
-                if (a1 >= a0 && a0 >= 0) n_sect += (uint32_t)((a1 >> 4) - (a0 >> 4) + 1); else n_sect += 2;
-                if (last_var && ((tp + (long long)L - 1) >> 4) != ((pos - 1) >> 4)) n_sect++;
-            }
-            if (ok) {
-                cnt_total++;
-                respos[nres++] = (unsigned long long)tp * k + sa + ix.initial_n;      // EFMIndex.cpp:2312-2319
+        // a pattern with an irregular shift is searched by the generic path, all its shifts
+        const unsigned irr = __ballot_sync(FULL, irregular);
+        if (irr & group) {
+            cnt = 0;
+            if (valid && sa == 0) {
+                const unsigned long long at = atomicAdd(a.stats + ST_COMPLEX, 1ull);
+                a.complex_list[at] = (uint32_t)(a.first + p_local);
             }
         }
-    }
-    if (complex) { cnt_total = 0; nres = 0; }
-    if (valid) {
-        a.counts[p] = cnt_total;                               // countOccurrences (:2273); the generic path adds to it for list members
-        if (complex) {
-            const unsigned long long at = atomicAdd(a.stats + ST_COMPLEX, 1ull);
-            a.complex_list[at] = (uint32_t)p;
-        }
-    }
-    // ---- located occurrences: one reservation per CTA
-    if (a.mode == E2FM_MODE_LOCATE) {
-        uint32_t incl = nres;
+        // ---- rows of the interval -> staged row tasks
+        uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_up_sync(FULL, incl, d);
             if ((int)lane >= d) incl += v;
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const uint32_t v = warp_tot[w];
-            if ((uint32_t)w < warp) before += v;
-            total += v;
+        const uint32_t wtot = __shfl_sync(FULL, incl, 31);
+        uint32_t wbase = 0;
+        if (wtot) {
+            if (lane == 0) wbase = atomicAdd(&st_cnt, wtot);
+            wbase = __shfl_sync(FULL, wbase, 0);
+            const uint32_t item = p_local * k + sa;
+            for (uint32_t q = 0; q < cnt; q++) st_task[wbase + incl - cnt + q] = make_uint2(s + q, item);
         }
-        if (threadIdx.x == 0 && total) blk_base = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)total);
-        __syncthreads();
-        if (nres) {
-            unsigned long long slot0 = blk_base + before + incl - nres;
-            uint32_t lost = 0;
+        (void)lt;
+        if (__syncthreads_or(st_cnt >= SL_FLUSH)) flush();
+    }
+    __syncthreads();
+    if (st_cnt) flush();
 #pragma unroll
-            for (int q = 0; q < KT; q++) {
-                if ((uint32_t)q < nres) {
-                    if (slot0 + q < a.res_cap) { a.res_pat[slot0 + q] = (uint32_t)p; a.res_pos[slot0 + q] = respos[q]; }
-                    else lost++;
+    for (int d = 16; d > 0; d >>= 1) n_sect += __shfl_xor_sync(FULL, n_sect, d);
+    if (lane == 0 && n_sect) atomicAdd(a.stats + ST_SECT_BS, n_sect);
+}
+
+// K_b: one thread per row task {row, item}. The row's suffix starts at text position sa[row] with the j seed super-characters; what
+// is left of EFMIndex::exactMatch(interval) (:1901-1963) for this row — the fixed super-characters before the seed, the '?'-prefixed
+// first one (backwardStepIfMatch, :2011-2041) and the '?'-suffixed last one (findWholePatternMatches, :1862-1899) — is compared with
+// the run of text[] around that position, and the occurrence reported at the position getRowPosition (:2468-2497) would walk to.
+// A backward step from a single row r with character c succeeds iff text[sa[r] - 1] == c, and then leads to the row of sa[r] - 1.
+static constexpr uint32_t SV_FLUSH = 1024, SV_CAP = SV_FLUSH + 256;
+
+template <int KT, int NW>
+__global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
+    extern __shared__ uint16_t ctab[];
+    __shared__ uint32_t rs_pat[SV_CAP];
+    __shared__ uint64_t rs_pos[SV_CAP];
+    __shared__ uint32_t rs_cnt;
+    __shared__ unsigned long long rs_base;
+    const DevIndex &ix = a.ix;
+    constexpr uint32_t k = KT;
+    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
+    if (threadIdx.x == 0) rs_cnt = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A, n = (uint32_t)ix.n;
+    const bool locate = a.mode == E2FM_MODE_LOCATE;
+    const unsigned long long nt = *a.task_cursor;
+    const uint32_t n_tasks = (uint32_t)(nt > a.task_cap ? 0ull : nt);     // an overflowing chunk is searched again by the host
+    unsigned long long n_sect = 0;
+    auto flush = [&]() {
+        const uint32_t c = rs_cnt;
+        if (threadIdx.x == 0) rs_base = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)c);
+        __syncthreads();
+        const unsigned long long b0 = rs_base;
+        uint32_t lost = 0;
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+            if (b0 + i < a.res_cap) { a.res_pat[b0 + i] = rs_pat[i]; a.res_pos[b0 + i] = rs_pos[i]; }
+            else lost++;
+        }
+        if (lost) atomicAdd(a.stats + ST_RES_OVF, (unsigned long long)lost);
+        __syncthreads();
+        if (threadIdx.x == 0) rs_cnt = 0;
+        __syncthreads();
+    };
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_tasks; base += stride) {
+        const uint32_t idx = base + threadIdx.x;
+        bool ok = false;
+        uint32_t sa = 0, tp = 0;
+        uint64_t p = 0;
+        if (idx < n_tasks) {
+            const uint2 tk = __ldg(a.tasks + idx);
+            const uint32_t pos = __ldg(ix.sa + tk.x);
+            const uint32_t pl = tk.y / k;
+            sa = tk.y - pl * k;
+            p = a.first + pl;
+            PatRegs<NW> pat;
+            pat.load(a.packed + p * NW);
+            uint32_t L;
+            bool last_var;
+            int l, lo;
+            shift_geometry(m, k, sa, L, last_var, l, lo);
+            const int i = l - (int)j - 1;              // first super-character left of the seed
+            auto back = [&](uint32_t d) -> uint32_t { return pos >= d ? pos - d : pos + (n - d); };   // (pos - d) mod n
+            ok = true;
+            for (int c = i; c >= lo; c--) {
+                const uint32_t code = ctab[pat.bits(2 * ((uint32_t)c * k - sa), KMASK)];
+                ok &= code == (uint32_t)__ldg(ix.text + back((uint32_t)(i + 1 - c)));
+            }
+            tp = back((uint32_t)(i + 1));              // text position of super-character 0 of the shift
+            if (sa > 0) {
+                const uint32_t f = k - sa;
+                const uint32_t want = pat.natural(ix, 0, f);
+                const uint32_t code = (uint32_t)__ldg(ix.text + tp);
+                ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code) == want;
+            }
+            if (last_var) {
+                const unsigned long long ph = (unsigned long long)tp + L - 1;
+                if (ph >= ix.n) ok = false;
+                else {
+                    const uint32_t from = (L - 1) * k - sa, f = m - from;
+                    const uint32_t want = pat.natural(ix, 2 * from, f);
+                    const uint32_t code = (uint32_t)__ldg(ix.text + ph);
+                    ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_high + (f - 1) * A + code) == want;
                 }
             }
-            if (lost) atomicAdd(a.stats + ST_RES_OVF, (unsigned long long)lost);
+            {   // sa[] + the distinct 32-byte sectors of text[]: the run that ends at pos - 1 and the hat character
+                const uint32_t run = (uint32_t)(i + 1 - (sa > 0 ? 0 : lo));
+                n_sect += 1;
+                if (run) n_sect += pos >= run ? ((pos - 1) >> 4) - ((pos - run) >> 4) + 1 : 2;
+                if (last_var && ((tp + L - 1) >> 4) != ((pos == 0 ? 0 : pos - 1) >> 4)) n_sect++;
+            }
         }
+        const unsigned em = __ballot_sync(FULL, ok);
+        if (em) {
+            if (ok) atomicAdd(a.counts + p, 1ull);                                    // countOccurrences (:2273)
+            if (locate) {
+                uint32_t b = 0;
+                const int leader = __ffs(em) - 1;
+                if ((int)lane == leader) b = atomicAdd(&rs_cnt, (uint32_t)__popc(em));
+                b = __shfl_sync(FULL, b, leader);
+                if (ok) {
+                    const uint32_t slot = b + __popc(em & lt);
+                    rs_pat[slot] = (uint32_t)p;
+                    rs_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;              // EFMIndex.cpp:2312-2319
+                }
+            }
+        }
+        if (locate && __syncthreads_or(rs_cnt >= SV_FLUSH)) flush();
     }
-    unsigned long long q = n_sect, r = n_rank;
+    if (locate) {
+        __syncthreads();
+        if (rs_cnt) flush();
+    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { q += __shfl_xor_sync(FULL, q, d); r += __shfl_xor_sync(FULL, r, d); }
-    if (lane == 0) {
-        if (q) atomicAdd(a.stats + ST_SECT_BS, q);
-        if (r) atomicAdd(a.stats + ST_RANK, r);
-    }
+    for (int d = 16; d > 0; d >>= 1) n_sect += __shfl_xor_sync(FULL, n_sect, d);
+    if (lane == 0 && n_sect) atomicAdd(a.stats + ST_GATHER, n_sect);
 }
 
 bool seed_search_supported(const DevIndex &ix, uint32_t m) {
@@ -325,25 +366,36 @@ bool seed_search_supported(const DevIndex &ix, uint32_t m) {
 }
 
 template <int KT>
-static void launch_seed_kt(const SeedArgs &a, uint32_t nw, cudaStream_t s) {
-    const uint32_t blocks = (a.count + 255) / 256;
+static void launch_seed_kt(const SeedArgs &a, uint32_t nw, int n_sm, bool verify, cudaStream_t s) {
+    constexpr uint32_t PPC = 8 * (32 / KT);
     const size_t smem = (size_t)2 << (2 * KT);
-    if (nw == 1) seed_search_kernel<KT, 1><<<blocks, 256, smem, s>>>(a);
-    else seed_search_kernel<KT, 2><<<blocks, 256, smem, s>>>(a);
+    const uint32_t tiles = (a.count + PPC - 1) / PPC;
+    const uint32_t lookup_blocks = std::min<uint32_t>(tiles, (uint32_t)n_sm * 6);
+    const uint32_t verify_blocks = (uint32_t)n_sm * 8;
+    if (!verify) {
+        if (nw == 1) seed_lookup_kernel<KT, 1><<<lookup_blocks, 256, smem, s>>>(a);
+        else seed_lookup_kernel<KT, 2><<<lookup_blocks, 256, smem, s>>>(a);
+    } else {
+        if (nw == 1) seed_verify_kernel<KT, 1><<<verify_blocks, 256, smem, s>>>(a);
+        else seed_verify_kernel<KT, 2><<<verify_blocks, 256, smem, s>>>(a);
+    }
 }
 
-void launch_seed_search(const SeedArgs &a, uint32_t nw, cudaStream_t s) {
+static void launch_seed_any(const SeedArgs &a, uint32_t nw, int n_sm, bool verify, cudaStream_t s) {
     if (a.count == 0) return;
     switch (a.ix.k) {
-        case 2: launch_seed_kt<2>(a, nw, s); break;
-        case 3: launch_seed_kt<3>(a, nw, s); break;
-        case 4: launch_seed_kt<4>(a, nw, s); break;
-        case 5: launch_seed_kt<5>(a, nw, s); break;
-        case 6: launch_seed_kt<6>(a, nw, s); break;
-        case 7: launch_seed_kt<7>(a, nw, s); break;
+        case 2: launch_seed_kt<2>(a, nw, n_sm, verify, s); break;
+        case 3: launch_seed_kt<3>(a, nw, n_sm, verify, s); break;
+        case 4: launch_seed_kt<4>(a, nw, n_sm, verify, s); break;
+        case 5: launch_seed_kt<5>(a, nw, n_sm, verify, s); break;
+        case 6: launch_seed_kt<6>(a, nw, n_sm, verify, s); break;
+        case 7: launch_seed_kt<7>(a, nw, n_sm, verify, s); break;
         default: break;
     }
 }
+// seed lookup (row tasks), then verification (counts, located occurrences)
+void launch_seed_lookup(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s) { launch_seed_any(a, nw, n_sm, false, s); }
+void launch_seed_verify(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s) { launch_seed_any(a, nw, n_sm, true, s); }
 
 // ---------------------------------------------------------------- sub-batch for the generic path
 

@@ -1,10 +1,13 @@
 // e2fm_host.cpp — see e2fm_host.h. Thin: file I/O, key handling, marshalling to / from the C ABI.
 #include "e2fm_host.h"
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
+#include <thread>
 
 #include "../../include/e2fm_b200.h"
 
@@ -13,7 +16,34 @@ namespace e2fm {
 namespace {
 [[noreturn]] void raise_last(const char *what) { throw std::runtime_error(std::string(what) + ": " + e2fm_last_error()); }
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// fn(begin, end) over [0, n) on all host threads (the marshalling of 10^7 std::strings is the host's share of a batch)
+template <class F>
+void parallel_for(uint64_t n, F fn) {
+    unsigned t = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32));
+    if (n < 65536) t = 1;
+    if (t == 1) { fn((uint64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < t; i++) th.emplace_back([=]() { fn(n * i / t, n * (i + 1) / t); });
+    for (auto &x : th) x.join();
+}
 }  // namespace
+
+void *EFMIndex::Pinned::ensure(size_t need) {
+    if (need > bytes) {
+        release();
+        const size_t want = need + need / 4 + 4096;
+        p = e2fm_host_alloc(want);
+        if (!p) throw std::runtime_error(std::string("e2fm_host_alloc: ") + e2fm_last_error());
+        bytes = want;
+    }
+    return p;
+}
+void EFMIndex::Pinned::release() {
+    if (p) e2fm_host_free(p);
+    p = nullptr;
+    bytes = 0;
+}
 
 EFMIndex::EFMIndex()
     : handle_(nullptr), device_(0), numberOfThreads_(1), haveKey_(false), infoBucketSize_(0), infoSuperBucketSize_(0), infoBuckets_(0),
@@ -84,6 +114,7 @@ void EFMIndex::close() {
     clearMatches();
     if (handle_) e2fm_index_close(handle_);
     handle_ = nullptr;
+    for (Pinned *b : {&stageIn_, &stageOffs_, &stageCounts_, &stageCsr_, &stageSeq_, &stageOff_}) b->release();
 }
 
 void EFMIndex::requireLoaded() const {
@@ -111,6 +142,89 @@ BatchResult EFMIndex::searchBatch(const std::vector<std::string> &patterns, Mode
                                out.sequenceOffset.data());
     e2fm_result_free(r);
     if (rc != E2FM_OK) raise_last("e2fm_result_fetch");
+    e2fm_last_batch_ms(handle_, out.deviceMs);
+    out.elapsedMs = now_ms() - t0;
+    return out;
+}
+
+CompactBatchResult EFMIndex::searchBatchCompact(const std::vector<std::string> &patterns, Mode mode) {
+    requireLoaded();
+    const double t0 = now_ms();
+    CompactBatchResult out;
+    const uint64_t n = patterns.size();
+    out.n = n;
+    e2fm_result *r = nullptr;
+    const uint32_t len = n ? (uint32_t)patterns[0].size() : 0;
+    bool packed = n > 0 && len > 0 && len <= 128;
+    if (packed) {
+        // one pass over the strings on all host threads: 2 bits per base into page-locked memory; a different length or a byte
+        // outside A C G T sends the batch through the ASCII entry point instead
+        const uint32_t stride = e2fm_packed_stride(len);
+        uint8_t *dst = (uint8_t *)stageIn_.ensure(n * stride);
+        std::atomic<bool> ok(true);
+        parallel_for(n, [&](uint64_t a, uint64_t b) {
+            bool fine = true;
+            for (uint64_t i = a; i < b && fine; i++) {
+                const std::string &p = patterns[i];
+                if (p.size() != len) { fine = false; break; }
+                uint64_t *w = reinterpret_cast<uint64_t *>(dst + i * stride);
+                for (uint32_t q = 0; q < stride / 8; q++) {
+                    uint64_t cur = 0;
+                    const uint32_t end = std::min<uint32_t>(len, (q + 1) * 32);
+                    for (uint32_t j = q * 32, sh = 0; j < end; j++, sh += 2) {
+                        uint64_t c;
+                        switch (p[j]) {
+                            case 'A': c = 0; break;
+                            case 'C': c = 1; break;
+                            case 'G': c = 2; break;
+                            case 'T': c = 3; break;
+                            default: c = 0; fine = false;
+                        }
+                        cur |= c << sh;
+                    }
+                    w[q] = cur;
+                }
+            }
+            if (!fine) ok.store(false);
+        });
+        packed = ok.load();
+        if (packed) {
+            out.packMs = now_ms() - t0;
+            if (e2fm_search_batch_packed(handle_, dst, n, len, (int)mode, nullptr, &r) != E2FM_OK) {
+                r = nullptr;      // this batch shape is not for the seed search (short patterns, no seed table): ASCII below
+                packed = false;
+            }
+        }
+    }
+    if (!packed) {
+        uint64_t *offs = (uint64_t *)stageOffs_.ensure((n + 1) * 8);
+        offs[0] = 0;
+        for (uint64_t i = 0; i < n; i++) offs[i + 1] = offs[i] + patterns[i].size();
+        uint8_t *bytes = (uint8_t *)stageIn_.ensure(offs[n] + 1);
+        parallel_for(n, [&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; i++) memcpy(bytes + offs[i], patterns[i].data(), patterns[i].size());
+        });
+        out.packMs = now_ms() - t0;
+        if (e2fm_search_batch(handle_, bytes, offs, n, (int)mode, &r) != E2FM_OK) throw std::runtime_error(e2fm_last_error());
+    }
+    out.packed = packed;
+    out.total = e2fm_result_total_positions(r);
+    int rc;
+    if (mode == Mode::Count) {
+        uint32_t *c = (uint32_t *)stageCounts_.ensure((n + 1) * 4);
+        rc = e2fm_result_fetch_compact(r, c, nullptr, nullptr, nullptr);
+        out.counts = c;
+    } else {
+        uint32_t *o = (uint32_t *)stageCsr_.ensure((n + 1) * 4);
+        uint32_t *sq = (uint32_t *)stageSeq_.ensure((out.total + 1) * 4);
+        uint32_t *so = (uint32_t *)stageOff_.ensure((out.total + 1) * 4);
+        rc = e2fm_result_fetch_compact(r, nullptr, o, sq, so);
+        out.offsets = o;
+        out.sequenceIndex = sq;
+        out.sequenceOffset = so;
+    }
+    e2fm_result_free(r);
+    if (rc != E2FM_OK) raise_last("e2fm_result_fetch_compact");
     e2fm_last_batch_ms(handle_, out.deviceMs);
     out.elapsedMs = now_ms() - t0;
     return out;
@@ -180,18 +294,27 @@ std::string EFMCollection::getDescription(uint32_t sequenceIndex) {
 }
 
 std::vector<SearchResult> EFMCollection::searchBatch(const std::vector<std::string> &patterns, Mode mode, bool retrieveSequenceDescriptions) {
-    BatchResult b = EFMIndex::searchBatch(patterns, mode);
+    const double t0 = now_ms();
+    const CompactBatchResult b = searchBatchCompact(patterns, mode);
     std::vector<SearchResult> out(patterns.size());
-    const double per = patterns.empty() ? 0 : b.elapsedMs / (double)patterns.size();
-    for (size_t i = 0; i < patterns.size(); i++) {
-        out[i].pattern = patterns[i];
-        out[i].elapsedTime = per;
-        for (uint64_t j = b.offsets[i]; j < b.offsets[i + 1]; j++) {
-            const uint32_t s = b.sequenceIndex[j];
-            out[i].occurrences.emplace_back(s, (retrieveSequenceDescriptions && s != 0xFFFFFFFFu) ? getDescription(s) : std::string(),
-                                            b.sequenceOffset[j]);
+    if (retrieveSequenceDescriptions && getSize()) getDescription(0);      // split the headers once, before the threads read them
+    // 10^7 SearchResult objects are 2 x 10^7 heap allocations: built by all host threads, every vector reserved to its final size
+    parallel_for(patterns.size(), [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; i++) {
+            SearchResult &sr = out[i];
+            sr.pattern = patterns[i];
+            if (mode != Mode::Locate) continue;
+            const uint32_t a = b.offsets[i], e = b.offsets[i + 1];
+            sr.occurrences.reserve(e - a);
+            for (uint32_t j = a; j < e; j++) {
+                const uint32_t s = b.sequenceIndex[j];
+                if (retrieveSequenceDescriptions && s != 0xFFFFFFFFu) sr.occurrences.emplace_back(s, fastaHeaders_.at(s), (uint64_t)b.sequenceOffset[j]);
+                else sr.occurrences.emplace_back(s, std::string(), (uint64_t)b.sequenceOffset[j]);
+            }
         }
-    }
+    });
+    const double per = patterns.empty() ? 0 : (now_ms() - t0) / (double)patterns.size();
+    for (SearchResult &sr : out) sr.elapsedTime = per;
     return out;
 }
 

@@ -55,6 +55,20 @@ struct BatchResult {
     float deviceMs[8] = {0};             // e2fm_last_batch_ms
 };
 
+// The same CSR in 32 bits, in page-locked buffers OWNED BY THE INDEX OBJECT (valid until its next search or close): what a
+// caller with millions of patterns reads instead of 10^7 SearchResult objects. counts is filled in Count mode, the other three
+// in Locate mode (a pattern's occurrences are [offsets[i], offsets[i+1])).
+struct CompactBatchResult {
+    uint64_t n = 0, total = 0;
+    const uint32_t *counts = nullptr;
+    const uint32_t *offsets = nullptr;
+    const uint32_t *sequenceIndex = nullptr;
+    const uint32_t *sequenceOffset = nullptr;
+    bool packed = false;                 // the batch went to the device as 2-bit codes (e2fm_search_batch_packed)
+    double elapsedMs = 0, packMs = 0;    // whole call / its host-side marshalling part
+    float deviceMs[8] = {0};
+};
+
 class EFMIndex {
 public:
     EFMIndex();
@@ -84,8 +98,11 @@ public:
     uint8_t getMarkedRowsPercentage();
     uint8_t getSuperAlphabetOrder() const;
     uint64_t getTextLength() const;             // super-text length n
-    // --- batched entry point (new)
+    // --- batched entry points (new)
     BatchResult searchBatch(const std::vector<std::string> &patterns, Mode mode);
+    // patterns of one length over A C G T are packed to 2 bits per base by all host threads straight into page-locked memory
+    // and searched through e2fm_search_batch_packed; anything else goes through the ASCII entry point. Same answers.
+    CompactBatchResult searchBatchCompact(const std::vector<std::string> &patterns, Mode mode);
 
     std::vector<Match *> allSuperPatternMatches;   // protected in the reference (EFMIndex.h:431); public here for drivers
 
@@ -102,6 +119,13 @@ protected:
     std::string headersBuffer_;
     uint64_t infoBucketSize_, infoSuperBucketSize_, infoBuckets_, infoSuperBuckets_, infoN_;
     uint32_t infoK_, infoMrp_;
+    // grow-only page-locked staging (e2fm_host_alloc): patterns in, 32-bit results out
+    struct Pinned {
+        void *p = nullptr;
+        size_t bytes = 0;
+        void *ensure(size_t need);
+        void release();
+    } stageIn_, stageOffs_, stageCounts_, stageCsr_, stageSeq_, stageOff_;
 };
 
 // FMCollection.h:65-95 (the part that load + search use)

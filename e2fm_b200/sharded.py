@@ -34,19 +34,29 @@ def padded_length(seq_len: int, k: int) -> int:
 
 
 def plan_shards(seq_lens, world: int, k: int):
-    """Contiguous groups balanced by length -> list of (first_seq, n_seqs, text_base) per rank."""
+    """Contiguous groups balanced by length -> list of (first_seq, n_seqs, text_base) per rank.
+
+    A group is closed after the sequence that brings the running total to its share, at most one group per sequence, and never
+    so late that a later rank would be left without a sequence: with at least `world` sequences every rank gets one or more
+    (an empty shard has no index to build), however skewed the lengths are."""
     lens = [int(x) for x in seq_lens]
+    n = len(lens)
     total = sum(lens)
     bounds = [0]
     acc = 0
     for i, L in enumerate(lens):
         acc += L
-        # close a group once it reaches its share (keep at least one sequence per remaining rank when possible)
-        while len(bounds) < world and acc >= total * len(bounds) / world and i + 1 <= len(lens) - (world - len(bounds)):
+        g = len(bounds)                       # the group being filled is g-1; groups g..world-1 still need sequences
+        if g >= world:
+            break
+        left_after = n - (i + 1)
+        must = left_after == world - g        # closing later would starve a later rank
+        may = left_after >= world - g         # closing now leaves one sequence or more for every later rank
+        if must or (may and acc * world >= total * g):
             bounds.append(i + 1)
     while len(bounds) < world:
-        bounds.append(len(lens))
-    bounds.append(len(lens))
+        bounds.append(n)
+    bounds.append(n)
     out = []
     base = 0
     for r in range(world):

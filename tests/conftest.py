@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GOLDEN_SEARCH_CASES = ["col3_k4", "one_k3", "col2_k2"]
+GOLDEN_SEARCH_CASES = ["col3_k4", "one_k3", "col2_k2", "two_k5"]
 
 
 def pytest_configure(config):

@@ -31,7 +31,11 @@ CASES = [
     ("one_k3", [24000], 3, 128, 5, 8, [3, 4, 6, 7, 10, 15, 20]),
     ("col2_k4_nomarks", [12000, 8000], 4, 256, 0, 9, [8, 12, 20]),
     ("col2_k2", [9000, 5000], 2, 512, 4, 10, [2, 3, 5, 8, 13]),
+    # the authors' second regime (Main.cpp:623-626): k = 5, bucketSize 8192 (super-buckets of 131072 rows). 19 buckets: a
+    # super-bucket boundary at bucket 16, and an even LAST bucket, which the odd-bucket rule excludes (EFMIndex.cpp:898-901)
+    ("two_k5", [520003, 230002], 5, 8192, 2, 11, [10, 14, 15, 19, 25, 40, 50]),
 ]
+NO_FASTA = {"two_k5"}     # too big to commit: synth.random_sequences(lens, seed) regenerates it
 
 
 def main():
@@ -43,7 +47,10 @@ def main():
     keyfile = os.path.join(OUT, "key.bin")
     with open(keyfile, "wb") as f:
         f.write(key)
+    only = set(sys.argv[1:])
     for name, lens, k, bs, mrp, seed, plens in CASES:
+        if only and name not in only:
+            continue
         rate = 100 // mrp if mrp else 0
         lens = synth.safe_lengths(lens, k, rate)
         seqs = synth.random_sequences(lens, seed)
@@ -83,6 +90,8 @@ def main():
                     bad += 1
         print(f"{name}: n_patterns={len(pats)} occurrences={len(res['positions'])} index={os.path.getsize(base + '.efm')} B "
               f"reference-vs-naive mismatches={bad}")
+        if name in NO_FASTA:
+            os.remove(base + ".fa")
         if name in ("col3_k4", "one_k3"):
             # extract / getSequence / extractSnippet (EFMCollection.cpp:43,67; EFMIndex.cpp:2325) from the reference
             rng = np.random.default_rng(seed + 77)

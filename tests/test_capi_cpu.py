@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import GOLDEN, ROOT
 from e2fm_b200 import capi
 
 
@@ -27,9 +27,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_info_struct_layout_matches_header():
-    # 8 u64 + 8 u32 + 8 float
+    # 8 u64 + 10 u32 + 8 float
     import ctypes
-    assert ctypes.sizeof(capi.Info) == 8 * 8 + 8 * 4 + 8 * 4
+    assert ctypes.sizeof(capi.Info) == 8 * 8 + 10 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback(golden, key64):
@@ -93,3 +93,24 @@ def test_host_header_parse_errors(golden, key64):
     for cut in (10, 60, 200, len(idx) // 3):
         with pytest.raises(capi.E2FMError):
             capi.parse_header(idx[:cut], key64)
+
+
+def test_header_parse_never_reads_outside_the_buffer(tmp_path):
+    """truncated and corrupted index files under AddressSanitizer: the host parse works on the caller's unpadded buffer and must
+    reject (or parse) every one of them without touching memory outside it"""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "asan_header_fuzz")
+    src = [os.path.join(ROOT, "tests", "asan_header_fuzz.cpp"), os.path.join(ROOT, "e2fm_b200", "csrc", "host_format.cpp")]
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe] + src,
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "asan" in (r.stderr or "").lower():
+        pytest.skip("AddressSanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("col3_k4", "col2_k2"):
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".efm"), os.path.join(GOLDEN, "key.bin")], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        assert "parsed=" in r.stdout

@@ -512,3 +512,174 @@ def test_cpp_host_extract_matches_reference(gpu, golden):
     with open(g["base"] + ".extract.out") as f:
         want = f.read().split("\n")[:-1]
     assert got == want
+
+
+# ---------------------------------------------------------------- seed table + seed search (fixed-length batches, packed patterns)
+
+def _subset(res, idxs, locate=True):
+    """the reference's answers for the patterns idxs, re-packed as a CSR of their own"""
+    counts = res["counts"][idxs]
+    segs = [(int(res["pos_offsets"][i]), int(res["pos_offsets"][i + 1])) for i in idxs]
+    offs = np.zeros(len(idxs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([b - a for a, b in segs])
+    cat = lambda a: np.concatenate([a[x:y] for x, y in segs]) if segs else a[:0]  # noqa: E731
+    return {"counts": counts, "pos_offsets": offs, "positions": cat(res["positions"]), "seq": cat(res["seq"]), "off": cat(res["off"])}
+
+
+def _by_length(patterns):
+    groups = {}
+    for i, p in enumerate(patterns):
+        groups.setdefault(len(p), []).append(i)
+    return groups
+
+
+def _check_out(out, want, locate, what):
+    assert np.array_equal(out["counts"], want["counts"]), what
+    if locate:
+        assert np.array_equal(out["pos_offsets"], want["pos_offsets"]), what
+        assert np.array_equal(out["positions"], want["positions"]), what
+        assert np.array_equal(out["seq"], want["seq"]) and np.array_equal(out["off"], want["off"]), what
+
+
+@pytest.mark.parametrize("name,seed_chars", [(n, j) for n in GOLDEN_SEARCH_CASES for j in (None, 2, 3)] + [("col3_k4", 4)])
+def test_seed_search_matches_reference(gpu, golden, key64, name, seed_chars):
+    """fixed-length batches go through seed_search_kernel when every shift holds a whole seed: same counts, positions and
+    (sequence, offset) as the reference, for the automatic seed length and forced ones, from ASCII and from packed patterns,
+    and the same again with the seed search switched off"""
+    g = golden[name]
+    if seed_chars is None:
+        os.environ.pop("E2FM_SEED_CHARS", None)
+    else:
+        os.environ["E2FM_SEED_CHARS"] = str(seed_chars)
+    try:
+        dev = capi.DeviceIndex(g["index"], key64)
+    finally:
+        os.environ.pop("E2FM_SEED_CHARS", None)
+    try:
+        j = int(dev.info.seed_chars)
+        assert j >= 2 and (seed_chars is None or j == seed_chars)
+        # the table against the rank structure: random seeds + every seed of a few rows' own first characters
+        rng = np.random.default_rng(11)
+        A, n = int(dev.info.compact_alphabet), int(dev.info.text_length)
+        codes = rng.integers(0, A, (4000, j), dtype=np.uint32)
+        bwt = dev.debug_bwt(0, n)
+        _, C, _ = capi.parse_header(g["index"], key64)
+        C = C.astype(np.int64)
+        # 1000 seeds that do occur: j consecutive super-characters of the text, read off the BWT (F[r] preceded by bwt[r],
+        # preceded by bwt[LF(r)], ...)
+        rr = rng.integers(0, n, 1000).astype(np.uint64)
+        codes[:1000, j - 1] = np.searchsorted(C, rr.astype(np.int64), side="right") - 1
+        for q in range(j - 2, -1, -1):
+            codes[:1000, q] = bwt[rr.astype(np.int64)]
+            rr = dev.debug_lf(rr)
+        got = dev.debug_seed(codes)
+        c = codes[:, j - 1].astype(np.int64)
+        s, e = C[c].copy(), C[c + 1].copy()
+        for q in range(j - 2, -1, -1):                               # EFMIndex::backwardStep (:1966) through the rank hook
+            c = codes[:, q].astype(np.uint32)
+            live = e > s
+            lo_rows = np.where(s > 0, s - 1, 0).astype(np.uint64)
+            ns = np.where(s > 0, dev.debug_rank(c, lo_rows).astype(np.int64), C[c.astype(np.int64)])
+            ne = dev.debug_rank(c, np.where(live, e - 1, 0).astype(np.uint64)).astype(np.int64)
+            s, e = np.where(live, ns, s), np.where(live, ne, e)
+        rows = np.maximum(e - s, 0)
+        exact = got[:, 2] == 1
+        assert np.array_equal(got[exact, 1].astype(np.int64), rows[exact])
+        hit = exact & (rows > 0)
+        assert np.array_equal(got[hit, 0].astype(np.int64), s[hit])
+        assert np.all(rows[:1000] > 0)
+        if A ** j >= 4 * n:                                           # about one row per seed or fewer: counters hardly ever saturate
+            assert hit.sum() >= 900 and exact.sum() > len(codes) * 0.9
+        seeded_any = False
+        for L, idxs in sorted(_by_length(g["patterns"]).items()):
+            if L == 0:
+                continue
+            arr = np.frombuffer(b"".join(g["patterns"][i] for i in idxs), dtype=np.uint8).reshape(len(idxs), L).copy()
+            want = _subset(g["res"], idxs)
+            for locate in (False, True):
+                r = dev.search_fixed(arr, locate)
+                seeded = dev.last_batch_counters()["seeded"]
+                _check_out(r.fetch(), want, locate, (name, L, "seed" if seeded else "generic"))
+                r.free()
+                if seeded:
+                    seeded_any = True
+                    dev.set_option(capi.OPT_SEED, 0)
+                    r = dev.search_fixed(arr, locate)
+                    assert dev.last_batch_counters()["seeded"] == 0
+                    _check_out(r.fetch(), want, locate, (name, L, "seed off"))
+                    r.free()
+                    dev.set_option(capi.OPT_SEED, 1)
+                    # packed entry point: only batches of pure ACGT patterns
+                    keep = [q for q, i in enumerate(idxs) if all(ch in b"ACGT" for ch in g["patterns"][i])]
+                    if not keep:
+                        continue
+                    sub = np.ascontiguousarray(arr[keep])
+                    packed, bad = capi.pack_patterns(sub)
+                    assert bad == 0
+                    cnt = np.zeros(len(keep), dtype=np.uint64)
+                    r = dev.search_packed(packed, len(keep), L, locate, cnt)
+                    wsub = _subset(g["res"], [idxs[q] for q in keep])
+                    out = r.fetch()
+                    _check_out(out, wsub, locate, (name, L, "packed"))
+                    assert np.array_equal(cnt, wsub["counts"])
+                    if locate:
+                        c32 = np.zeros(len(keep), dtype=np.uint32)
+                        o32 = np.zeros(len(keep) + 1, dtype=np.uint32)
+                        s32 = np.zeros(r.total, dtype=np.uint32)
+                        f32 = np.zeros(r.total, dtype=np.uint32)
+                        r.fetch_compact(c32, o32, s32, f32)
+                        assert np.array_equal(c32, wsub["counts"]) and np.array_equal(o32, wsub["pos_offsets"])
+                        assert np.array_equal(s32, wsub["seq"]) and np.array_equal(f32, wsub["off"])
+                    r.free()
+        assert seeded_any, "no batch of this golden went through the seed search"
+    finally:
+        dev.close()
+
+
+def test_seed_search_hands_repeats_and_odd_symbols_to_the_generic_path(gpu, golden, key64, oracle_mod):
+    """a pattern that ends with several rows in some shift (it occurs more than once), meets a saturated seed counter, or holds
+    an index symbol outside ACGT leaves the seed search untouched and is answered by the generic path; a foreign symbol means no
+    match at all (EFMIndex.cpp:1702-1717)"""
+    g = golden["col3_k4"]
+    dev = capi.DeviceIndex(g["index"], key64)
+    orc = oracle_mod.OracleIndex(g["index"], key64)
+    try:
+        seqs = synth.random_sequences(synth.safe_lengths([30011, 20003, 9001], 4, 50), 7)   # tests/golden/make_golden.py
+        text = synth.collection_text(seqs, 4)
+        L = 12
+        pats = [text[100:100 + L], text[30009:30009 + L], b"ACGTACGTACGT", b"A" * L, b"ACGTNNNNACGT", b"ACGT&&&&ACGT",
+                text[30000:30000 + L], b"acgtacgtacgt", text[59020:59020 + L], b"$$$$$$$$$$$$", text[5:5 + L]]
+        # 12-mers that occur twice in the text: the seed search must hand those to the generic path
+        seen, twice = {}, []
+        whole = seqs[0].tobytes()
+        for i in range(len(whole) - L):
+            w = whole[i:i + L]
+            if w in seen and len(twice) < 20:
+                twice.append(w)
+            seen[w] = i
+        pats += twice
+        arr = np.frombuffer(b"".join(pats), dtype=np.uint8).reshape(len(pats), L).copy()
+        for locate in (False, True):
+            r = dev.search_fixed(arr, locate)
+            c = dev.last_batch_counters()
+            assert c["seeded"] == 1
+            out = r.fetch()
+            for i, p in enumerate(pats):
+                cnt, pos = orc.search(p, True)
+                assert int(out["counts"][i]) == cnt, (p, locate)
+                if locate:
+                    a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+                    assert np.array_equal(out["positions"][a:b], pos), p
+            assert c["complex_patterns"] >= 2       # at least the '&' pattern and poly-A / the repeats
+            r.free()
+        # tiny result store: the seed search flags the overflow and is run again with room
+        dev.set_option(capi.OPT_DENSITY, 1)
+        big = np.ascontiguousarray(np.tile(arr[:1], (5000, 1)))
+        r = dev.search_fixed(big, True)
+        out = r.fetch()
+        assert r.total == 5000 and np.all(out["counts"] == 1) and np.all(out["positions"] == out["positions"][0])
+        assert dev.last_batch_counters()["chunks_redone"] >= 1
+        r.free()
+    finally:
+        dev.close()
+        orc.close()

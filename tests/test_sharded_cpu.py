@@ -34,6 +34,28 @@ def test_plan_shards_is_contiguous_and_balanced():
     assert sharded.plan_shards([30011, 20003, 9001], 2, 4) == [(0, 1, 0), (1, 2, 30016)]
 
 
+def test_plan_shards_never_starves_a_rank():
+    """skewed lengths: one long sequence must not close several groups at once (an empty shard has no index to build and its
+    rank would hang the collective); with at least `world` sequences every rank gets one or more"""
+    import random
+    assert [p[1] for p in sharded.plan_shards([100, 1, 1], 3, 4)] == [1, 1, 1]
+    assert [p[1] for p in sharded.plan_shards([1000, 10, 10, 10], 4, 4)] == [1, 1, 1, 1]
+    assert [p[1] for p in sharded.plan_shards([1, 1, 1000], 3, 4)] == [1, 1, 1]
+    rnd = random.Random(5)
+    for _ in range(300):
+        world = rnd.randint(1, 8)
+        lens = [rnd.choice([1, 3, 10, 1000, 10 ** 6]) for _ in range(rnd.randint(1, 30))]
+        plan = sharded.plan_shards(lens, world, 4)
+        assert len(plan) == world and plan[0][0] == 0 and sum(p[1] for p in plan) == len(lens)
+        assert all(plan[i][0] + plan[i][1] == plan[i + 1][0] for i in range(world - 1))
+        if len(lens) >= world:
+            assert all(p[1] >= 1 for p in plan), (lens, world, plan)
+        base = 0
+        for first, cnt, tb in plan:
+            assert tb == base
+            base += sum(sharded.padded_length(L, 4) for L in lens[first:first + cnt])
+
+
 def _worker(rank, world, port, locate, q):
     import sys
     sys.path.insert(0, ROOT)
