@@ -36,6 +36,8 @@ EXPORTS = [
     "e2fm_debug_rank", "e2fm_last_error", "e2fm_version",
     "e2fm_packed_stride", "e2fm_pack_patterns", "e2fm_search_batch_packed", "e2fm_search_batch_packed_device",
     "e2fm_result_fetch_compact", "e2fm_debug_seed",
+    "e2fm_shardset_unique_id", "e2fm_shardset_create", "e2fm_shardset_destroy", "e2fm_shardset_slice", "e2fm_shardset_search",
+    "e2fm_shardset_last_ms",
 ]
 
 
@@ -95,6 +97,14 @@ def lib():
     L.e2fm_search_batch_packed_device.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
     L.e2fm_result_fetch_compact.argtypes = [vp, vp, vp, vp, vp]
     L.e2fm_debug_seed.argtypes = [vp, vp, u64, vp]
+    L.e2fm_shardset_unique_id.argtypes = [vp]
+    L.e2fm_shardset_create.argtypes = [vp, vp, i32, i32, u64, u64, C.POINTER(vp)]
+    L.e2fm_shardset_destroy.argtypes = [vp]
+    L.e2fm_shardset_destroy.restype = None
+    L.e2fm_shardset_slice.restype = u64
+    L.e2fm_shardset_slice.argtypes = [u64, i32, i32, C.POINTER(u64)]
+    L.e2fm_shardset_search.argtypes = [vp, vp, u64, u32, i32, i32, C.POINTER(vp)]
+    L.e2fm_shardset_last_ms.argtypes = [vp, C.POINTER(C.c_float * 8)]
     L.e2fm_extract.argtypes = [vp, u64, u64, vp, u64, C.POINTER(u64)]
     L.e2fm_result_patterns.restype = u64
     L.e2fm_result_patterns.argtypes = [vp]
@@ -388,6 +398,57 @@ class DeviceIndex:
         out = np.zeros(len(rows), dtype=np.uint64)
         check(lib().e2fm_debug_rank(self._h, codes.ctypes.data, rows.ctypes.data, len(rows), out.ctypes.data))
         return out
+
+
+def shardset_unique_id() -> bytes:
+    """128 bytes of a fresh NCCL unique id (rank 0 calls this and hands them to the other ranks)"""
+    buf = (C.c_uint8 * 128)()
+    check(lib().e2fm_shardset_unique_id(buf))
+    return bytes(buf)
+
+
+def shardset_slice(n_total: int, world: int, rank: int):
+    """(first pattern, number of patterns) of the batch that `rank` supplies to e2fm_shardset_search"""
+    cnt = C.c_uint64(0)
+    lo = lib().e2fm_shardset_slice(n_total, world, rank, C.byref(cnt))
+    return int(lo), int(cnt.value)
+
+
+class ShardSet:
+    """one rank's shard of a collection sharded by sequence + the NCCL communicator (e2fm_shardset)"""
+
+    def __init__(self, index: "DeviceIndex", unique_id: bytes, rank: int, world: int, first_sequence: int, text_base: int):
+        assert len(unique_id) == 128
+        self.index = index                      # borrowed: keep it alive
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().e2fm_shardset_create(index._h, idbuf, rank, world, first_sequence, text_base, C.byref(h)))
+        self._h = h
+
+    def search(self, slice_host: np.ndarray, n_total: int, length: int, packed: bool, locate: bool) -> "Result":
+        """slice_host: this rank's patterns [lo, lo+count) of the batch (shardset_slice), uint8, ASCII or packed"""
+        h = C.c_void_p()
+        ptr = slice_host.ctypes.data if slice_host is not None and slice_host.size else None
+        check(lib().e2fm_shardset_search(self._h, ptr, n_total, length, 1 if packed else 0, MODE_LOCATE if locate else MODE_COUNT,
+                                         C.byref(h)))
+        return Result(h, locate)
+
+    def last_ms(self):
+        a = (C.c_float * 8)()
+        check(lib().e2fm_shardset_last_ms(self._h, C.byref(a)))
+        return dict(zip(["h2d_allgather", "search", "merge_comm", "merge_kernels", "total"], [float(x) for x in a[:5]]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().e2fm_shardset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def packed_stride(length: int) -> int:

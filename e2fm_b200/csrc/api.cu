@@ -19,6 +19,7 @@
 #include "device_index.cuh"
 #include "host_format.h"
 #include "index_build.cuh"
+#include "internal.h"
 #include "search.cuh"
 #include "seed.cuh"
 
@@ -132,7 +133,17 @@ uint32_t floor_pow2(uint32_t v) {
 
 }  // namespace
 
+// A result may outlive its index (Python's garbage collector frees them in any order): both hold this token. While the index is
+// alive a result's arrays are freed stream-ordered on the index's stream; afterwards synchronously.
+struct Lifetime {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool alive = true;
+    int refs = 1;
+};
+
 struct e2fm_index {
+    Lifetime *life = nullptr;
     int device = 0;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
@@ -165,7 +176,8 @@ struct e2fm_index {
 };
 
 struct e2fm_result {
-    e2fm_index *ix = nullptr;
+    e2fm_index *ix = nullptr;   // valid only while life->alive
+    Lifetime *life = nullptr;
     uint64_t n = 0, total = 0;
     bool located = false;
     unsigned long long *d_counts = nullptr;
@@ -993,6 +1005,8 @@ int search_common(e2fm_index *ix, const uint8_t *bytes, const uint64_t *offsets,
     e2fm_result *res = new (std::nothrow) e2fm_result();
     if (!res) return fail(E2FM_ERR_OOM, "out of host memory");
     res->ix = ix;
+    res->life = ix->life;
+    ix->life->refs++;
     try {
         CK(cudaSetDevice(ix->device));
         cudaStream_t s = ix->stream;
@@ -1155,6 +1169,9 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
         CK(cudaGetDeviceProperties(&prop, device));
         ix->n_sm = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        ix->life = new Lifetime();
+        ix->life->device = device;
+        ix->life->stream = ix->stream;
         CK(cudaStreamCreateWithFlags(&ix->h2d_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ix->d2h_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
@@ -1191,6 +1208,10 @@ void e2fm_index_close(e2fm_index *ix) {
     if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);
     if (ix->d2h_stream) cudaStreamDestroy(ix->d2h_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->life) {
+        ix->life->alive = false;                 // results that are still around free their arrays synchronously from now on
+        if (--ix->life->refs == 0) delete ix->life;
+    }
     cudaGetLastError();
     delete ix;
 }
@@ -1346,6 +1367,7 @@ uint64_t e2fm_result_total_positions(const e2fm_result *r) { return r ? r->total
 int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, uint64_t *positions, uint32_t *seq_index,
                       uint64_t *seq_offset) {
     if (!r) return fail(E2FM_ERR_ARG, "bad argument");
+    if (!r->life || !r->life->alive) return fail(E2FM_ERR_ARG, "the index of this result has been closed");
     try {
         CK(cudaSetDevice(r->ix->device));
         cudaStream_t s = r->ix->stream;
@@ -1368,6 +1390,7 @@ int e2fm_result_fetch(e2fm_result *r, uint64_t *counts, uint64_t *pos_offsets, u
 
 int e2fm_result_fetch_compact(e2fm_result *r, uint32_t *counts, uint32_t *pos_offsets, uint32_t *seq_index, uint32_t *seq_offset) {
     if (!r) return fail(E2FM_ERR_ARG, "bad argument");
+    if (!r->life || !r->life->alive) return fail(E2FM_ERR_ARG, "the index of this result has been closed");
     if (r->total >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 occurrences: use e2fm_result_fetch");
     try {
         e2fm_index *ix = r->ix;
@@ -1416,16 +1439,39 @@ int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uin
 
 void e2fm_result_free(e2fm_result *r) {
     if (!r) return;
-    if (r->ix) {
-        cudaSetDevice(r->ix->device);
-        cudaStream_t s = r->ix->stream;
-        if (r->d_counts) cudaFreeAsync(r->d_counts, s);
-        if (r->d_off) cudaFreeAsync(r->d_off, s);
-        if (r->d_pos) cudaFreeAsync(r->d_pos, s);
-        if (r->d_seq) cudaFreeAsync(r->d_seq, s);
-        if (r->d_seqoff) cudaFreeAsync(r->d_seqoff, s);
+    Lifetime *life = r->life;
+    void *arrays[5] = {r->d_counts, r->d_off, r->d_pos, r->d_seq, r->d_seqoff};
+    if (life) {
+        cudaSetDevice(life->device);
+        for (void *p : arrays) {
+            if (!p) continue;
+            if (life->alive) cudaFreeAsync(p, life->stream);
+            else cudaFree(p);                    // the index (and its stream) are gone
+        }
+        if (--life->refs == 0) delete life;
+        cudaGetLastError();
     }
     delete r;
+}
+
+int e2fm_internal_device(const e2fm_index *ix) { return ix ? ix->device : 0; }
+void e2fm_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+e2fm_result *e2fm_internal_make_result(e2fm_index *ix, uint64_t n, uint64_t total, bool located, unsigned long long *d_counts,
+                                       uint64_t *d_csr, uint64_t *d_pos, uint32_t *d_seq, uint64_t *d_seqoff) {
+    e2fm_result *r = new (std::nothrow) e2fm_result();
+    if (!r) return nullptr;
+    r->ix = ix;
+    r->life = ix->life;
+    ix->life->refs++;
+    r->n = n;
+    r->total = total;
+    r->located = located;
+    r->d_counts = d_counts;
+    r->d_off = d_csr;
+    r->d_pos = d_pos;
+    r->d_seq = d_seq;
+    r->d_seqoff = d_seqoff;
+    return r;
 }
 
 int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]) {

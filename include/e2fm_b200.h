@@ -24,12 +24,14 @@ extern "C" {
 #define E2FM_ERR_ARG (-3)       /* bad argument */
 #define E2FM_ERR_UNSUPPORTED (-4) /* e.g. locate on an index without marked rows (EFMIndex.cpp:2305) */
 #define E2FM_ERR_OOM (-5)
+#define E2FM_ERR_NCCL (-6)      /* NCCL error / libnccl not found (e2fm_shardset_* only) */
 
 #define E2FM_MODE_COUNT 0        /* EFMIndex::exactMatch + countOccurrences           (EFMIndex.cpp:1694,2273) */
 #define E2FM_MODE_LOCATE 1       /* ... + locateOccurrences + (sequence, offset) map   (EFMIndex.cpp:2281, EFMCollection.cpp:115) */
 
 typedef struct e2fm_index e2fm_index;     /* device-resident flattened index (one GPU) */
-typedef struct e2fm_result e2fm_result;   /* device-resident result of one batch */
+typedef struct e2fm_result e2fm_result;   /* device-resident result of one batch; may be fetched until its index is closed, freed at any time */
+typedef struct e2fm_shardset e2fm_shardset; /* one rank's shard of a collection sharded by sequence + the NCCL communicator */
 
 typedef struct e2fm_info {
     uint64_t text_length;        /* n, super-text length (EFMIndex.h:372) */
@@ -140,6 +142,31 @@ int e2fm_result_device_ptrs(e2fm_result *r, const uint64_t **d_counts, const uin
                             const uint64_t **d_positions, const uint32_t **d_seq_index,
                             const uint64_t **d_seq_offset);
 void e2fm_result_free(e2fm_result *r);
+
+/* ---- collections sharded by sequence over the GPUs of one box (one process per GPU) ----
+ * The reference has no distribution. What makes sharding exact is EFMCollection.cpp:218-225: every sequence is padded to a multiple
+ * of k and followed by a k-long terminator, so a pattern never spans two sequences and an occurrence has the same (sequence, offset)
+ * in a shard as in the whole collection. Rank r opens the index the reference built for the r-th contiguous group of sequences
+ * (first_sequence = index of its first sequence in the collection, text_base = padded length of everything before it).
+ *   e2fm_shardset_unique_id   one rank creates the NCCL id and hands the 128 bytes to the others (file, socket, MPI, ...)
+ *   e2fm_shardset_create      ncclCommInitRank; the shard set borrows ix (close it after e2fm_shardset_destroy)
+ *   e2fm_shardset_search      ONE exchange step for a fixed-length batch of n_total patterns: this rank supplies ITS slice of the
+ *                             batch from host memory — patterns [lo, lo + count) with lo = e2fm_shardset_slice(n_total, world, rank,
+ *                             &count), `packed` != 0: 2-bit packed (e2fm_packed_stride bytes each), else ASCII —, the slices are
+ *                             all-gathered over NVLink, every rank searches the whole batch against its shard, counts are
+ *                             all-reduced and the per-pattern occurrence lists concatenated in shard order (already sorted,
+ *                             EFMIndex.cpp:2291). EVERY rank gets the whole merged result: the same arrays, bit for bit, as the
+ *                             unsharded index gives (e2fm_result_fetch / _fetch_compact / _free as usual).
+ *   e2fm_shardset_last_ms     [0] H2D + batch all-gather, [1] local search, [2] NCCL merge traffic, [3] merge kernels, [4] whole step
+ * All ranks must call create / search / destroy in the same order. */
+int e2fm_shardset_unique_id(uint8_t id_out[128]);
+int e2fm_shardset_create(e2fm_index *ix, const uint8_t id[128], int rank, int world, uint64_t first_sequence, uint64_t text_base,
+                         e2fm_shardset **out);
+void e2fm_shardset_destroy(e2fm_shardset *ss);
+uint64_t e2fm_shardset_slice(uint64_t n_total, int world, int rank, uint64_t *count);
+int e2fm_shardset_search(e2fm_shardset *ss, const uint8_t *slice, uint64_t n_total, uint32_t length, int packed, int mode,
+                         e2fm_result **out);
+int e2fm_shardset_last_ms(const e2fm_shardset *ss, float out[8]);
 
 /* Per-phase device times (ms, CUDA events on the index stream) of the most recent batch:
  * [0] pattern H2D, [1] backward search kernel, [2] interval scan + expansion, [3] row-walk kernel, [4] pattern pre-pass (k-mer codes),
