@@ -59,6 +59,9 @@ WORKLOADS = {
     # BASELINE.json configs[4]: chr1-sized 248 Mbp single sequence, locate-heavy short patterns (len 12)
     "chr1": dict(seq_lens=[248_956_422], seed=45, n_patterns=1_000_000, pat_len=12, locate=True,
                  name="configs[4]: 248 Mbp chr1-sized synthetic sequence, 1M patterns len 12, count+locate"),
+    # a sixth of configs[3] (same pattern shape) for quicker HBM-bound kernel iterations
+    "mid50": dict(seq_lens=[30_000_000] * 16, seed=46, n_patterns=4_000_000, pat_len=50, locate=True,
+                  name="16 x 30 Mbp synthetic sequences, 4M patterns len 50, count+locate"),
     # a collection100 shard-sized index for quicker HBM-bound runs
     "collection25": dict(seq_lens=[4_641_652] * 25, seed=1000, n_patterns=4_000_000, pat_len=24, locate=True,
                          name="25 x 4.6 Mbp synthetic genomes, 4M patterns len 24, count+locate"),
@@ -479,19 +482,19 @@ def gpu_arm(args, rank, world, local_rank):
         assert bad == 0, "the synthetic batch holds only A C G T"
     else:
         h_pats[lo:hi] = mine
-    # result buffers of the whole batch (every rank writes its own part): what EFMCollection::search returns, in 32 bits
-    occ_cap = int(npat_all * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
+    # result buffers of the whole batch, ONE host buffer per array (every rank writes its own region of it): what
+    # EFMCollection::search returns, in 32 bits. Region r holds rank r's occurrences; its offsets index that region.
+    occ_cap = int((npat_all // world + 1) * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
     h_counts = shm.array("counts", npat_all, np.uint32)
     h_noff = shm.array("occ_offsets", (world, npat_all // world + 2), np.uint32) if locate else None
-    h_seq = shm.array("seq", occ_cap, np.uint32) if locate else None
-    h_off = shm.array("off", occ_cap, np.uint32) if locate else None
+    h_seq = shm.array("seq", (world, occ_cap), np.uint32) if locate else None
+    h_off = shm.array("off", (world, occ_cap), np.uint32) if locate else None
     d_pats = torch.from_numpy(np.array(h_pats[lo:hi])).to(dev_t)
     del mine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)   # > 126 MB L2
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        totals_t = torch.zeros(world, dtype=torch.int64, device=dev_t)
 
     def l2_flush():
         if os.environ.get("E2FM_BENCH_NOFLUSH"):
@@ -511,34 +514,33 @@ def gpu_arm(args, rank, world, local_rank):
         return ms, ctr, tot
 
     e2e_dev_ms = []
-    e2e_state = {"result": None}
+    e2e_state = {}
 
     def step_e2e():
-        """host patterns -> host result, through the C ABI; N > 1: the result parts are placed behind one another in the one
-        shared buffer (an all-gather of the per-rank totals gives every rank its place)"""
-        if e2e_state["result"] is not None:
-            e2e_state["result"].free()
-            e2e_state["result"] = None
+        """host patterns -> host result through ONE call of the C ABI (e2fm_search_hits: H2D, search and D2H pipelined by stage);
+        --e2e-api fetch: the two-call form (e2fm_search_batch_packed / _fixed, then e2fm_result_fetch_compact)"""
         t0 = time.perf_counter()
-        if packed_api:
-            r = ix.search_packed(h_pats[lo:hi].reshape(-1), npat, L, locate)
+        if args.e2e_api == "hits":
+            total = ix.search_hits(h_pats[lo:hi].reshape(-1), npat, L, packed_api, locate, h_counts[lo:hi],
+                                   h_noff[rank][:npat + 1] if locate else None, h_seq[rank] if locate else None,
+                                   h_off[rank] if locate else None)
         else:
-            r = ix.search_fixed(h_pats[lo:hi], locate)
-        base = 0
-        if locate:
-            if world > 1:
-                mine_t = torch.tensor([r.total], dtype=torch.int64, device=dev_t)
-                dist.all_gather_into_tensor(totals_t, mine_t)
-                base = int(sum(totals_t.tolist()[:rank]))
-            if base + r.total > occ_cap:
+            if packed_api:
+                r = ix.search_packed(h_pats[lo:hi].reshape(-1), npat, L, locate)
+            else:
+                r = ix.search_fixed(h_pats[lo:hi], locate)
+            total = r.total
+            if total > occ_cap:
                 raise SystemExit("bench: occurrence buffer too small; pass a larger --occ-per-pattern")
-            r.fetch_compact(None, h_noff[rank][:npat + 1], h_seq[base:base + r.total], h_off[base:base + r.total])
-        else:
-            r.fetch_compact(h_counts[lo:hi], None, None, None)
+            if locate:
+                r.fetch_compact(h_counts[lo:hi], h_noff[rank][:npat + 1], h_seq[rank][:total], h_off[rank][:total])
+            else:
+                r.fetch_compact(h_counts[lo:hi], None, None, None)
+            r.free()
         dt = time.perf_counter() - t0
         e2e_dev_ms.append(ix.last_batch_ms()["total"])
-        e2e_state.update(base=base, total=r.total, result=r)
-        return dt, r.total
+        e2e_state.update(total=total, stages=ix.last_batch_counters().get("hits_stages", 0))
+        return dt, total
 
     for _ in range(args.warmup):
         l2_flush(); step_device()
@@ -597,14 +599,18 @@ def gpu_arm(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         procs = reference_procs(prep)
         sample = min(npat, max(PARITY_PATTERNS, 0 if args.no_cpu_baseline else reference_sample_size(prep, procs)))
-        # counts and global positions of the same (last timed) batch come from an untimed 64-bit fetch of its result
-        full = e2e_state["result"].fetch()
-        got = {"counts": full["counts"]}
+        # what the last timed e2e step left in the host buffers, plus the global positions of the same patterns from an untimed
+        # 64-bit fetch (the timed arrays must agree with it)
+        chk = ix.search_packed(h_pats[lo:lo + sample].reshape(-1), sample, L, locate) if packed_api else ix.search_fixed(h_pats[lo:lo + sample], locate)
+        full = chk.fetch()
+        chk.free()
+        got = {"counts": h_counts[:sample].astype(np.uint64)}
+        assert np.array_equal(full["counts"], got["counts"]), "timed counts differ from the 64-bit fetch"
         if locate:
-            got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq, off=h_off, positions=full["positions"])
-            assert np.array_equal(full["pos_offsets"][:sample + 1], h_noff[0][:sample + 1]) and np.array_equal(full["seq"], h_seq[:len(full["seq"])])
-        else:
-            assert np.array_equal(full["counts"], h_counts[:npat])
+            got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq[0], off=h_off[0], positions=full["positions"])
+            tot = int(h_noff[0][sample])
+            assert np.array_equal(full["pos_offsets"], h_noff[0][:sample + 1]) and np.array_equal(full["seq"], h_seq[0][:tot]) and \
+                np.array_equal(full["off"], h_off[0][:tot]), "timed occurrence arrays differ from the 64-bit fetch"
         try:
             with tempfile.TemporaryDirectory() as td:
                 pass_ms, ref_res, slices, wall = run_reference(prep, np.ascontiguousarray(all_pats[:sample]), locate, procs, td)
@@ -624,7 +630,7 @@ def gpu_arm(args, rank, world, local_rank):
         e2e_value = npat_all * steps / (e2e_ms_max / 1e3)
         roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind)
         h2d = int(npat * unit)
-        d2h = int(((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else npat * 4)
+        d2h = int(npat * 4 + (((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else 0))
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -646,7 +652,10 @@ def gpu_arm(args, rank, world, local_rank):
                              " from page-locked host memory; " +
                              ("per-pattern occurrence offsets, sequence index and offset in the sequence of every occurrence (what "
                               "EFMCollection::search returns, FMCollection.h:23-44), 32 bits each" if locate else "32-bit counts") +
-                             " back into page-locked host memory (e2fm_result_fetch_compact)")},
+                             " back into page-locked host memory; " +
+                             (f"one call, e2fm_search_hits, {e2e_state.get('stages', 0)} pipeline stages" if args.e2e_api == "hits"
+                              else "two calls: search, then e2fm_result_fetch_compact")),
+                    "api": "e2fm_search_hits" if args.e2e_api == "hits" else "e2fm_search_batch_* + e2fm_result_fetch_compact"},
             "gpu_launches": launches_all,
             "roofline": roofline,
             "parity": parity,
@@ -662,8 +671,6 @@ def gpu_arm(args, rank, world, local_rank):
         if world == 1 and not args.no_cpp:
             line["e2e_cpp"] = cpp_host_arm(prep, local_rank)
         emit(line)
-    if e2e_state["result"] is not None:
-        e2e_state["result"].free()
     ix.close()
     shm.close()
     if world > 1:
@@ -875,6 +882,7 @@ def main():
     ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")
     ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
     ap.add_argument("--ascii", action="store_true", help="ASCII patterns through e2fm_search_batch_fixed even when the packed entry point would take the batch")
+    ap.add_argument("--e2e-api", default="hits", choices=["hits", "fetch"], help="end-to-end leg: the pipelined one-call form or search + fetch")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)

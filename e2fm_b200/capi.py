@@ -24,6 +24,7 @@ OPT_DENSITY = 6
 OPT_TAPER = 7
 OPT_PHASE_TIMERS = 8
 OPT_SEED = 9
+OPT_HITS_STAGE = 10
 
 # every symbol include/e2fm_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
@@ -37,7 +38,7 @@ EXPORTS = [
     "e2fm_packed_stride", "e2fm_pack_patterns", "e2fm_search_batch_packed", "e2fm_search_batch_packed_device",
     "e2fm_result_fetch_compact", "e2fm_debug_seed",
     "e2fm_shardset_unique_id", "e2fm_shardset_create", "e2fm_shardset_destroy", "e2fm_shardset_slice", "e2fm_shardset_search",
-    "e2fm_shardset_last_ms",
+    "e2fm_shardset_last_ms", "e2fm_search_hits", "e2fm_debug_gather_bench_ex",
 ]
 
 
@@ -54,6 +55,11 @@ class Info(C.Structure):
                 ("compact_alphabet", C.c_uint32), ("marked_rows_percentage", C.c_uint32), ("marking_rate", C.c_uint32),
                 ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("dense", C.c_uint32), ("seed_chars", C.c_uint32),
                 ("seed_table_mb", C.c_uint32), ("load_ms", C.c_float * 8)]
+
+
+class Hits(C.Structure):
+    _fields_ = [("counts", C.c_void_p), ("occ_offsets", C.c_void_p), ("seq_index", C.c_void_p), ("seq_offset", C.c_void_p),
+                ("capacity", C.c_uint64), ("total", C.c_uint64)]
 
 
 _lib = None
@@ -97,6 +103,7 @@ def lib():
     L.e2fm_search_batch_packed_device.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
     L.e2fm_result_fetch_compact.argtypes = [vp, vp, vp, vp, vp]
     L.e2fm_debug_seed.argtypes = [vp, vp, u64, vp]
+    L.e2fm_search_hits.argtypes = [vp, vp, u64, u32, i32, i32, C.POINTER(Hits)]
     L.e2fm_shardset_unique_id.argtypes = [vp]
     L.e2fm_shardset_create.argtypes = [vp, vp, i32, i32, u64, u64, C.POINTER(vp)]
     L.e2fm_shardset_destroy.argtypes = [vp]
@@ -339,6 +346,26 @@ class DeviceIndex:
                                              counts_out.ctypes.data if counts_out is not None else None, C.byref(h)))
         return Result(h, locate)
 
+    def search_hits(self, patterns: np.ndarray, n: int, length: int, packed: bool, locate: bool, counts: np.ndarray = None,
+                    occ_offsets: np.ndarray = None, seq_index: np.ndarray = None, seq_offset: np.ndarray = None) -> int:
+        """e2fm_search_hits: host patterns (ASCII n x length, or packed) -> 32-bit results in the caller's host arrays, pipelined.
+        Returns the number of occurrences written (locate)."""
+        assert patterns.dtype == np.uint8 and patterns.flags.c_contiguous
+        for a in (counts, occ_offsets, seq_index, seq_offset):
+            assert a is None or (a.dtype == np.uint32 and a.flags.c_contiguous)
+        h = Hits()
+        h.counts = counts.ctypes.data if counts is not None else None
+        h.occ_offsets = occ_offsets.ctypes.data if occ_offsets is not None else None
+        h.seq_index = seq_index.ctypes.data if seq_index is not None else None
+        h.seq_offset = seq_offset.ctypes.data if seq_offset is not None else None
+        h.capacity = min(seq_index.size, seq_offset.size) if (seq_index is not None and seq_offset is not None) else 0
+        self.last_hits_total = 0
+        rc = lib().e2fm_search_hits(self._h, patterns.ctypes.data if patterns.size else None, n, length, 1 if packed else 0,
+                                    MODE_LOCATE if locate else MODE_COUNT, C.byref(h))
+        self.last_hits_total = int(h.total)
+        check(rc)
+        return int(h.total)
+
     def search_packed_device(self, d_ptr: int, n: int, length: int, locate: bool) -> Result:
         h = C.c_void_p()
         check(lib().e2fm_search_batch_packed_device(self._h, d_ptr, n, length, MODE_LOCATE if locate else MODE_COUNT, C.byref(h)))
@@ -373,7 +400,7 @@ class DeviceIndex:
         a = (C.c_uint64 * 16)()
         check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
         return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers", "scan_rows",
-                         "chunks_redone", "complex_patterns", "seeded"], [int(x) for x in a]))
+                         "chunks_redone", "complex_patterns", "seeded", "hits_stages"], [int(x) for x in a]))
 
     # ---- test hooks
     def debug_bwt(self, row0: int, count: int) -> np.ndarray:
@@ -472,10 +499,12 @@ def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count:
     return out
 
 
-def gather_bench(buffer_bytes: int = 8 << 30, n_gathers: int = 1 << 30, device: int = 0) -> float:
-    """HBM random-gather roofline in 10^9 gathers/s (one 32-byte sector each)"""
+def gather_bench(buffer_bytes: int = 8 << 30, n_gathers: int = 1 << 30, device: int = 0, variant: int = 0) -> float:
+    """HBM random-gather roofline in 10^9 gathers/s (one 32-byte sector each); variant = the load instruction (e2fm_b200.h)"""
     out = C.c_double(0)
-    check(lib().e2fm_debug_gather_bench(device, buffer_bytes, n_gathers, C.byref(out)))
+    L = lib()
+    L.e2fm_debug_gather_bench_ex.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    check(L.e2fm_debug_gather_bench_ex(device, buffer_bytes, n_gathers, variant, C.byref(out)))
     return float(out.value)
 
 

@@ -172,7 +172,10 @@ struct e2fm_index {
     EventPool events;
     // work buffers of the search path: grow-only, reused by every batch (allocation calls cost more than the kernels of a
     // 1M-pattern batch)
-    struct Slot { void *p = nullptr; size_t bytes = 0; } ws[24];
+    struct Slot { void *p = nullptr; size_t bytes = 0; } ws[40];
+    HitsStageInfo *h_stage_info = nullptr;   // pinned, written by hits_tail_kernel
+    size_t h_stage_cap = 0;
+    uint64_t hits_stage_patterns = 1u << 19;   // patterns per pipeline stage of e2fm_search_hits
 };
 
 struct e2fm_result {
@@ -206,7 +209,9 @@ T *dev_keep_copy(e2fm_index *ix, const T *src, size_t count) {
 
 // view of a workspace slot with the DBuf interface; contents are preserved across a growth only when asked
 enum { WS_BYTES = 0, WS_OFF, WS_CODES, WS_IV, WS_SPARE, WS_TASK_OFF, WS_SCRATCH, WS_TASKS, WS_FIRSTW, WS_CHUNK_CTR, WS_RES_PAT, WS_RES_POS,
-       WS_CURSOR, WS_BIG_LIST, WS_HATW, WS_PACKED, WS_PFLAG, WS_CLIST, WS_SUB, WS_NARROW, WS_N };
+       WS_CURSOR, WS_BIG_LIST, WS_HATW, WS_PACKED, WS_PFLAG, WS_CLIST, WS_SUB, WS_NARROW, WS_HCOUNTS, WS_STAGE_STATS, WS_STAGE_OFF, WS_STAGE_POS,
+       WS_RUN, WS_OUT_CNT, WS_OUT_OFF, WS_OUT_SEQ, WS_OUT_SOFF, WS_N };
+static_assert(WS_N <= 40, "e2fm_index::ws is too small");
 template <class T>
 struct WsBuf {
     e2fm_index *ix;
@@ -390,7 +395,7 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
         if ((double)img.n * 6.0 < 0.5 * (double)free_b) {
             h = tm.begin(6);
             sa = dev_keep<uint32_t>(ix, img.n);
-            text = dev_keep<uint16_t>(ix, img.n);
+            text = dev_keep<uint16_t>(ix, img.n + 32);   // seed_verify_kernel reads whole 32-byte sectors
             launch_dense_build(rec, mark_tab, mrn, img.rate, img.n, sa, text, d_status.p, s);
             bwt16 = dev_keep<uint16_t>(ix, img.n + 16);   // firstcheck_kernel reads aligned 16-byte groups
             launch_bwt16_build(rec, img.n, bwt16, s);
@@ -984,6 +989,165 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[11] = seeded ? 1 : 0;
 }
 
+// e2fm_search_hits, the pipelined path: host patterns in, host results out, stage by stage. Stage c is copied in on the H2D stream
+// while stage c-1 runs on the compute stream (seed lookup, verification, the stage's result pipeline of hits.cu) and the results of
+// stage c-2 leave on the D2H stream. Nothing on the compute stream needs the host: counts stay on the device, the device carries the
+// running occurrence total, and each stage reports {first occurrence, occurrences, trouble} into page-locked host memory, which is
+// all the host needs to queue the stage's D2H copies. Returns false when a store sized from earlier batches was too small or a
+// pattern needs the generic path (an index symbol outside ACGT): the caller then runs the plain path, which sizes exactly.
+bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, bool packed_in, int mode, e2fm_hits *hits) {
+    cudaStream_t s = ix->stream;
+    const DevIndex &dix = ix->dix;
+    const bool locate = mode == E2FM_MODE_LOCATE;
+    const uint32_t nw = (m + 63) / 64;
+    Batch b{nullptr, nullptr, m, n, 0};
+    b.packed_in = packed_in;
+    b.total_bytes = n * b.unit();
+    b.h_bytes = h_in;
+    memset(ix->batch_ms, 0, sizeof(ix->batch_ms));
+    memset(ix->batch_ctr, 0, sizeof(ix->batch_ctr));
+    ix->events.reset();
+    EventTimer tm(s, &ix->events);
+    tm.phases = false;
+    const int whole = tm.begin(6);
+    const uint64_t stage = std::max<uint64_t>(1, std::min<uint64_t>(ix->hits_stage_patterns, n));
+    const uint64_t S = (n + stage - 1) / stage;
+
+    WsBuf<uint8_t> d_in(ix, WS_BYTES, b.total_bytes + 16, s);
+    b.d_bytes = d_in.p;
+    const uint4 *packed = reinterpret_cast<const uint4 *>(d_in.p);
+    const uint8_t *pflag = nullptr;
+    WsBuf<uint4> packed_ws(ix, WS_PACKED, s);
+    WsBuf<uint8_t> pflag_ws(ix, WS_PFLAG, s);
+    if (!packed_in) {
+        packed_ws.alloc(n * nw + 1);
+        pflag_ws.alloc(n + 1);
+        packed = packed_ws.p;
+        pflag = pflag_ws.p;
+    }
+    WsBuf<unsigned long long> counts(ix, WS_HCOUNTS, n, s);
+    WsBuf<uint32_t> clist(ix, WS_CLIST, stage, s);
+    const uint64_t task_cap = (uint64_t)(ix->seed_tasks_per_pattern * (double)stage) + 4096;
+    WsBuf<uint2> tasks(ix, WS_TASKS, task_cap, s);
+    WsBuf<unsigned long long> task_ctr(ix, WS_CHUNK_CTR, S, s);
+    task_ctr.zero(S);
+    WsBuf<unsigned long long> stage_stats(ix, WS_STAGE_STATS, S * ST_N, s);
+    stage_stats.zero(S * ST_N);
+    WsBuf<unsigned long long> run(ix, WS_RUN, 2, s);
+    run.zero(2);
+    WsBuf<uint32_t> cnt32(ix, WS_OUT_CNT, n, s);
+    const uint64_t res_cap = locate ? (uint64_t)(ix->results_per_pattern * (double)stage) + 4096 : 0;
+    const uint64_t out_cap = locate ? std::min<uint64_t>(hits->capacity, (uint64_t)(ix->results_per_pattern * (double)n) + 65536) : 0;
+    WsBuf<uint32_t> res_pat(ix, WS_RES_PAT, s), cursor(ix, WS_CURSOR, s), big_list(ix, WS_BIG_LIST, s), off32(ix, WS_OUT_OFF, s),
+        seq32(ix, WS_OUT_SEQ, s), soff32(ix, WS_OUT_SOFF, s);
+    WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s), st_off(ix, WS_STAGE_OFF, s), st_pos(ix, WS_STAGE_POS, s), scratch(ix, WS_SCRATCH, s);
+    if (locate) {
+        res_pat.alloc(res_cap);
+        res_pos.alloc(res_cap);
+        st_off.alloc(stage + 1);
+        st_pos.alloc(res_cap);
+        cursor.alloc(stage);
+        big_list.alloc(res_cap / 24 + 1);
+        scratch.alloc(scan_scratch_elems(stage));
+        off32.alloc(n + 1);
+        seq32.alloc(out_cap + 1);
+        soff32.alloc(out_cap + 1);
+    }
+    if (ix->h_stage_cap < S) {
+        if (ix->h_stage_info) CK(cudaFreeHost(ix->h_stage_info));
+        ix->h_stage_info = nullptr;
+        ix->h_stage_cap = 0;
+        CK(cudaHostAlloc((void **)&ix->h_stage_info, (S + 8) * sizeof(HitsStageInfo), cudaHostAllocDefault));
+        ix->h_stage_cap = S + 8;
+    }
+    HitsStageInfo *info = ix->h_stage_info;
+    memset(info, 0, S * sizeof(HitsStageInfo));
+
+    const Staging sg = stage_batch(ix, b, stage, tm);          // every H2D copy queued up front, one event per stage
+    std::vector<cudaEvent_t> done(S);
+    uint64_t launches = 0;
+    auto enqueue = [&](uint64_t c) {
+        const uint64_t first = sg.bounds[c];
+        const uint32_t cnt = (uint32_t)(sg.bounds[c + 1] - first);
+        unsigned long long *st = stage_stats.p + c * ST_N;
+        CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
+        if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
+        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st};
+        launch_seed_lookup(sa, nw, ix->n_sm, s);
+        launch_seed_verify(sa, nw, ix->n_sm, s);
+        launches += 2;
+        if (locate) {
+            launch_scan_u64(counts.p + first, st_off.p, cnt, scratch.p, s);
+            CK(cudaMemsetAsync(cursor.p, 0, (size_t)cnt * 4, s));
+            launch_hits_scatter(res_pat.p, res_pos.p, st, res_cap, first, st_off.p, cursor.p, st_pos.p, ix->n_sm, s);
+            launch_hits_sort(st_pos.p, st_off.p, cnt, res_cap, big_list.p, cursor.p, st, ix->n_sm, s);
+            launches += 6;
+        }
+        launch_hits_finalize(dix, counts.p, first, cnt, locate ? st_off.p : nullptr, st_pos.p, run.p, out_cap, res_cap,
+                             cnt32.p, off32.p, seq32.p, soff32.p, ix->n_sm, s);
+        launch_hits_tail(locate ? st_off.p : nullptr, cnt, st, task_ctr.p + c, task_cap, res_cap, out_cap, run.p,
+                         locate && c + 1 == S ? off32.p + n : nullptr, info + c, s);
+        launches += 2;
+        done[c] = ix->events.get(false);
+        CK(cudaEventRecord(done[c], s));
+    };
+    bool trouble = false;
+    uint64_t total = 0;
+    auto drain = [&](uint64_t c) {
+        const uint64_t first = sg.bounds[c];
+        const uint64_t cnt = sg.bounds[c + 1] - first;
+        if (locate) {
+            CK(cudaEventSynchronize(done[c]));                 // the stage's report is in host memory
+            if (info[c].flags) { trouble = true; return; }
+        } else CK(cudaStreamWaitEvent(ix->d2h_stream, done[c], 0));
+        if (hits->counts) CK(cudaMemcpyAsync(hits->counts + first, cnt32.p + first, cnt * 4, cudaMemcpyDeviceToHost, ix->d2h_stream));
+        if (locate) {
+            const uint64_t base = info[c].base, tot = info[c].total;
+            if (hits->occ_offsets)
+                CK(cudaMemcpyAsync(hits->occ_offsets + first, off32.p + first, (cnt + (c + 1 == S ? 1 : 0)) * 4, cudaMemcpyDeviceToHost, ix->d2h_stream));
+            if (tot && hits->seq_index) CK(cudaMemcpyAsync(hits->seq_index + base, seq32.p + base, tot * 4, cudaMemcpyDeviceToHost, ix->d2h_stream));
+            if (tot && hits->seq_offset) CK(cudaMemcpyAsync(hits->seq_offset + base, soff32.p + base, tot * 4, cudaMemcpyDeviceToHost, ix->d2h_stream));
+            total = base + tot;
+        }
+    };
+    const uint64_t ahead = 2;                                  // stages queued on the compute stream beyond the one being drained
+    for (uint64_t c = 0; c < S && !trouble; c++) {
+        enqueue(c);
+        if (c >= ahead) drain(c - ahead);
+    }
+    for (uint64_t c = S > ahead ? S - ahead : 0; c < S && !trouble; c++) drain(c);
+    tm.end(whole);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(ix->d2h_stream));
+    CK(cudaStreamSynchronize(ix->h2d_stream));
+    CK(cudaGetLastError());
+    // what the stages report: trouble flags (count mode reads them only now), densities for the next batch's stores
+    uint64_t tasks_sum = 0, worst_tasks = 0;
+    for (uint64_t c = 0; c < S; c++) {
+        if (info[c].flags) trouble = true;
+        tasks_sum += info[c].tasks;
+        worst_tasks = std::max<uint64_t>(worst_tasks, info[c].tasks);
+    }
+    if (worst_tasks) ix->seed_tasks_per_pattern = std::min(1.0e6, std::max(1.5, 1.3 * (double)worst_tasks / (double)stage));
+    if (trouble) return false;
+    if (locate && n) ix->results_per_pattern = std::min(1.0e6, std::max(1.25, 1.2 * (double)total / (double)n));
+    hits->total = total;
+    std::vector<unsigned long long> hs(S * ST_N);
+    CK(cudaMemcpyAsync(hs.data(), stage_stats.p, S * ST_N * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint64_t c = 0; c < S; c++) {
+        ix->batch_ctr[4] += hs[c * ST_N + ST_SECT_BS];
+        ix->batch_ctr[7] += hs[c * ST_N + ST_GATHER];
+    }
+    ix->batch_ctr[3] = tasks_sum;
+    ix->batch_ctr[5] = launches;
+    ix->batch_ctr[6] = total;
+    ix->batch_ctr[11] = 1;
+    ix->batch_ctr[12] = S;
+    tm.collect(ix->batch_ms, 8);
+    return true;
+}
+
 // a failed batch may have copies queued that still read the caller's host buffers: nothing is in flight when the call returns
 void quiesce(e2fm_index *ix) {
     if (ix->h2d_stream) cudaStreamSynchronize(ix->h2d_stream);
@@ -1205,6 +1369,7 @@ void e2fm_index_close(e2fm_index *ix) {
     ix->events.destroy();
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->h_stats) cudaFreeHost(ix->h_stats);
+    if (ix->h_stage_info) cudaFreeHost(ix->h_stage_info);
     if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);
     if (ix->d2h_stream) cudaStreamDestroy(ix->d2h_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -1318,6 +1483,50 @@ int e2fm_search_batch_packed(e2fm_index *ix, const uint8_t *packed, uint64_t n, 
 int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uint64_t n, uint32_t length, int mode, e2fm_result **out) {
     if (d_packed && (reinterpret_cast<uintptr_t>(d_packed) & 15u)) return fail(E2FM_ERR_ARG, "packed patterns must be 16-byte aligned");
     return search_common(ix, d_packed, nullptr, length, n, n * e2fm_packed_stride(length), true, mode, out, nullptr, true);
+}
+
+int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32_t length, int packed, int mode, e2fm_hits *hits) {
+    if (!ix || !hits || length == 0 || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
+    if (n && !patterns) return fail(E2FM_ERR_ARG, "pattern bytes missing");
+    if (n >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 patterns in one batch");
+    const bool locate = mode == E2FM_MODE_LOCATE;
+    if (locate && (!hits->occ_offsets || ((!hits->seq_index || !hits->seq_offset) && hits->capacity)))
+        return fail(E2FM_ERR_ARG, "locate needs occ_offsets, seq_index and seq_offset");
+    if (ix->img.mrp == 0) return fail(E2FM_ERR_UNSUPPORTED, "The index doesn't contain marked rows: locate operation not supported");
+    if (locate && ix->max_seq_len >= (1ull << 32)) return fail(E2FM_ERR_ARG, "a sequence is longer than 2^32-1: use e2fm_result_fetch");
+    hits->total = 0;
+    bool piped = false;
+    if (n && ix->use_seed && ix->use_dense && seed_search_supported(ix->dix, length)) {
+        try {
+            CK(cudaSetDevice(ix->device));
+            piped = hits_pipeline(ix, patterns, n, length, packed != 0, mode, hits);
+        } catch (const CudaError &e) {
+            quiesce(ix);
+            return fail(E2FM_ERR_CUDA, e.what());
+        } catch (const std::bad_alloc &) {
+            quiesce(ix);
+            return fail(E2FM_ERR_OOM, "out of host memory");
+        } catch (const std::exception &e) {
+            quiesce(ix);
+            return fail(E2FM_ERR_FORMAT, e.what());
+        }
+    }
+    if (piped) return E2FM_OK;
+    // the plain path: whole batch, exact sizes, then the compact fetch
+    e2fm_result *r = nullptr;
+    const uint64_t unit = packed ? e2fm_packed_stride(length) : length;
+    int rc = search_common(ix, patterns, nullptr, length, n, n * unit, false, mode, &r, nullptr, packed != 0);
+    if (rc != E2FM_OK) return rc;
+    ix->batch_ctr[12] = 0;
+    hits->total = r->total;
+    if (locate && r->total > hits->capacity) {
+        e2fm_result_free(r);
+        return fail(E2FM_ERR_ARG, "e2fm_hits.capacity is too small for the occurrences of this batch (see e2fm_hits.total)");
+    }
+    rc = e2fm_result_fetch_compact(r, hits->counts, locate ? hits->occ_offsets : nullptr, locate ? hits->seq_index : nullptr,
+                                   locate ? hits->seq_offset : nullptr);
+    e2fm_result_free(r);
+    return rc;
 }
 
 int e2fm_extract(e2fm_index *ix, uint64_t from, uint64_t to, char *out, uint64_t cap, uint64_t *out_len) {
@@ -1494,6 +1703,7 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
             return E2FM_OK;
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;
+        case E2FM_OPT_HITS_STAGE: ix->hits_stage_patterns = value ? value : (1u << 19); return E2FM_OK;
         case E2FM_OPT_PHASE_TIMERS: ix->phase_timers = (int)std::min<uint64_t>(value, 2); return E2FM_OK;
         case E2FM_OPT_SEED:
             if (value && !(ix->dix.seed_tab && ix->dix.packed_code)) return fail(E2FM_ERR_UNSUPPORTED, "the seed table was not built for this index");
@@ -1532,6 +1742,10 @@ int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, ui
 }
 
 int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s) {
+    return e2fm_debug_gather_bench_ex(device, buffer_bytes, n_gathers, 0, giga_gathers_per_s);
+}
+
+int e2fm_debug_gather_bench_ex(int device, uint64_t buffer_bytes, uint64_t n_gathers, int variant, double *giga_gathers_per_s) {
     if (!giga_gathers_per_s || buffer_bytes < 4096 || n_gathers == 0) return fail(E2FM_ERR_ARG, "bad argument");
     cudaStream_t s;
     int rc = with_device(device, &s);
@@ -1549,11 +1763,11 @@ int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gather
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
         CK(cudaEventCreate(&b));
-        launch_gather_bench(buf, n_words, n_threads, per_thread, sink, s);   // warm-up
+        launch_gather_bench(buf, n_words, n_threads, per_thread, sink, variant, s);   // warm-up
         float best = 1e30f;
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaEventRecord(a, s));
-            launch_gather_bench(buf, n_words, n_threads, per_thread, sink, s);
+            launch_gather_bench(buf, n_words, n_threads, per_thread, sink, variant, s);
             CK(cudaEventRecord(b, s));
             CK(cudaEventSynchronize(b));
             float ms = 0;

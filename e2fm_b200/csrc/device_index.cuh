@@ -83,12 +83,19 @@ constexpr uint32_t SWAR_M = 0x80008000u;
 
 struct Sector { uint4 lo, hi; };
 
-__device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {
-    const uint4 *s = ix.occ + ((size_t)blk * ix.A + c) * 2;
+// One aligned 32-byte sector in ONE load instruction (LDG.E.256, sm_100): measured on a B200 (profiles/exp/gather_variants.py),
+// random sectors read with two 16-byte loads come in at 37 G sectors/s, with one 32-byte load at 47 G/s — the same rate as 8-byte
+// loads, i.e. the row-activation limit of the HBM.
+__device__ __forceinline__ Sector ld_sector(const uint4 *p) {
     Sector r;
-    r.lo = __ldg(s);
-    r.hi = __ldg(s + 1);
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+                 : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {
+    return ld_sector(ix.occ + ((size_t)blk * ix.A + c) * 2);
 }
 
 // bits 15 and 31 of the result are set iff the low / high u16 slot of w is <= x (slots and x below 0x8000):

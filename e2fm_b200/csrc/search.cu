@@ -1288,6 +1288,32 @@ void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_
 // The roofline this path lives under is not the streaming copy bandwidth but what HBM delivers for independent random
 // sector gathers. Every thread issues `per_thread` independent 8-byte loads at hashed addresses of a large buffer
 // (the access pattern of the LF / sa / text gathers, minus the dependency between steps).
+// `variant` picks the load instruction (what a gather costs in DRAM traffic depends on it, profiles/exp/):
+//   0 ld.global.nc.u64 (__ldg)   1 ld.global.u64   2 ld.global.cg.u64 (no L1)   3 ld.global.nc.v8.u32 (one 32-byte load)
+//   4 two ld.global.nc.v4.u32 of one sector   5 ld.global.nc.L2::64B.u64   6 ld.global.nc.L1::no_allocate.u64   7 ld.global.nc.L2::128B.u64
+template <int V>
+__device__ __forceinline__ unsigned long long gather_load(const uint64_t *p) {
+    unsigned long long v = 0;
+    if (V == 0) v = __ldg(p);
+    else if (V == 1) asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (V == 2) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (V == 3) {
+        uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+        const uint64_t *q = reinterpret_cast<const uint64_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)31);
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(q));
+        v = (unsigned long long)(w0 ^ w1 ^ w2 ^ w3) | ((unsigned long long)(w4 ^ w5 ^ w6 ^ w7) << 32);
+    } else if (V == 4) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)31);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        v = (unsigned long long)(a.x ^ a.y ^ a.z ^ a.w) | ((unsigned long long)(b.x ^ b.y ^ b.z ^ b.w) << 32);
+    } else if (V == 5) asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (V == 6) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (V == 7) asm volatile("ld.global.nc.L2::128B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <int V>
 __global__ void __launch_bounds__(256) gather_bench_kernel(const uint64_t *__restrict__ buf, uint64_t n_words, uint32_t per_thread,
                                                             unsigned long long *sink) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1297,13 +1323,23 @@ __global__ void __launch_bounds__(256) gather_bench_kernel(const uint64_t *__res
 #pragma unroll 8
     for (uint32_t i = 0; i < per_thread; i++) {
         x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;    // splitmix-style scramble
-        acc += __ldg(buf + (x & mask));
+        acc += gather_load<V>(buf + (x & mask));
     }
     if (acc == 0x123456789ull) *sink = acc;                        // keep the loads alive
 }
 void launch_gather_bench(const uint64_t *buf, uint64_t n_words, uint64_t n_threads, uint32_t per_thread, unsigned long long *sink,
-                         cudaStream_t s) {
-    gather_bench_kernel<<<(uint32_t)((n_threads + 255) / 256), 256, 0, s>>>(buf, n_words, per_thread, sink);
+                         int variant, cudaStream_t s) {
+    const uint32_t blocks = (uint32_t)((n_threads + 255) / 256);
+    switch (variant) {
+        case 1: gather_bench_kernel<1><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 2: gather_bench_kernel<2><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 3: gather_bench_kernel<3><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 4: gather_bench_kernel<4><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 5: gather_bench_kernel<5><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 6: gather_bench_kernel<6><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 7: gather_bench_kernel<7><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        default: gather_bench_kernel<0><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+    }
 }
 
 // ---------------------------------------------------------------- test hooks

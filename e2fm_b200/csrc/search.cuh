@@ -140,12 +140,25 @@ void launch_repack(const uint64_t *old_pos, const uint64_t *old_off, const uint6
 void launch_ulen_widen(const uint32_t *ulen, unsigned long long *out, uint64_t n, cudaStream_t s);
 void launch_map_positions(const DevIndex &ix, const uint64_t *positions, uint64_t n_pos, uint32_t *seq, uint64_t *off, cudaStream_t s);
 
+// hits.cu: result pipeline of one pipeline stage of e2fm_search_hits, without host round trips
+struct HitsStageInfo { unsigned long long base, total, flags, tasks; };   // written by the device into page-locked host memory
+enum : unsigned long long { HITS_TASK_OVF = 1, HITS_RES_OVF = 2, HITS_DUPS = 4, HITS_COMPLEX = 8, HITS_OUT_OVF = 16 };
+void launch_hits_scatter(const uint32_t *res_pat, const uint64_t *res_pos, const unsigned long long *stats, uint64_t res_cap, uint64_t first,
+                         const uint64_t *off, uint32_t *cursor, uint64_t *positions, int n_sm, cudaStream_t s);
+void launch_hits_sort(uint64_t *positions, const uint64_t *off, uint32_t cnt, uint64_t res_cap, uint32_t *big_list, uint32_t *ulen,
+                      unsigned long long *stats, int n_sm, cudaStream_t s);
+void launch_hits_finalize(const DevIndex &ix, const unsigned long long *counts, uint64_t first, uint32_t cnt, const uint64_t *off,
+                          const uint64_t *positions, const unsigned long long *run_total, uint64_t out_cap, uint64_t res_cap, uint32_t *cnt32,
+                          uint32_t *off32, uint32_t *seq32, uint32_t *soff32, int n_sm, cudaStream_t s);
+void launch_hits_tail(const uint64_t *off, uint32_t cnt, const unsigned long long *stats, const unsigned long long *task_count, uint64_t task_cap,
+                      uint64_t res_cap, uint64_t out_cap, unsigned long long *run_total, uint32_t *off32_end, HitsStageInfo *info, cudaStream_t s);
+
 // EFMIndex::extractSnippet (EFMIndex.cpp:2367): the k symbols of super-characters [st_from, st_from + count) from the dense text[] table
 void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_t *out, cudaStream_t s);
 
 // random 8-byte gathers over a buffer of n_words u64: the HBM random-gather roofline measurement
 void launch_gather_bench(const uint64_t *buf, uint64_t n_words, uint64_t n_threads, uint32_t per_thread, unsigned long long *sink,
-                         cudaStream_t s);
+                         int variant, cudaStream_t s);
 
 // test hooks
 void launch_debug_lf(const DevIndex &ix, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t s);

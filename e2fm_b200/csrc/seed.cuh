@@ -38,11 +38,7 @@ __device__ __forceinline__ size_t seed_sector(const DevIndex &ix, uint32_t hi, u
 }
 
 __device__ __forceinline__ Sector seed_load(const DevIndex &ix, size_t sector) {
-    const uint4 *p = ix.seed_tab + sector * 2;
-    Sector r;
-    r.lo = __ldg(p);
-    r.hi = __ldg(p + 1);
-    return r;
+    return ld_sector(ix.seed_tab + sector * 2);
 }
 
 __device__ __forceinline__ SeedHit seed_decode(const Sector &sec, uint32_t slot) {

@@ -105,15 +105,20 @@ struct PatRegs {
             w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
     }
+    // word i of the bit string (0 beyond its end), as a tree of selects: a dynamically indexed register array would live in local memory
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        uint32_t r = 0;
+#pragma unroll
+        for (int g = 0; g < NW; g++) {
+            const uint32_t a = (i & 1u) ? w[4 * g + 1] : w[4 * g], b = (i & 1u) ? w[4 * g + 3] : w[4 * g + 2];
+            const uint32_t v = (i & 2u) ? b : a;
+            r = (i >> 2) == (uint32_t)g ? v : r;
+        }
+        return r;
+    }
     __device__ __forceinline__ uint32_t bits(uint32_t off, uint32_t mask) const {
         const uint32_t wi = off >> 5;
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int i = 0; i < 4 * NW; i++) {
-            if (wi == (uint32_t)i) lo = w[i];
-            if (wi + 1 == (uint32_t)i) hi = w[i];
-        }
-        return __funnelshift_r(lo, hi, off & 31u) & mask;
+        return __funnelshift_r(word(wi), word(wi + 1), off & 31u) & mask;
     }
     // natural value (base n_sym, first base most significant) of the f bases at bit offset off: what kmer_low / kmer_high hold
     __device__ __forceinline__ uint32_t natural(const DevIndex &ix, uint32_t off, uint32_t f) const {
@@ -131,11 +136,31 @@ struct PatRegs {
 
 static constexpr uint32_t SL_FLUSH = 1024;                       // staged row tasks handed over per reservation
 static constexpr uint32_t SL_CAP = SL_FLUSH + 256 * 14;          // a tile adds at most 14 rows per lane (exact counters stop at 14)
+static constexpr int SEED_U = 4;                                 // independent gathers in flight per thread (tiles / tasks per iteration)
+
+// the interval of the seed c_0 .. c_{j-1} by the backward steps the table replaces (EFMIndex.cpp:1728-1748, :1966-2001): the path
+// of a lookup that met a saturated counter (a seed that occurs 15 times or more, or sits behind one in its sector)
+template <int NW>
+__device__ __forceinline__ void seed_interval_slow(const DevIndex &ix, const uint16_t *ctab, const PatRegs<NW> &pat, uint32_t first_bit,
+                                                uint32_t k, uint32_t kmask, uint32_t j, uint32_t &s, uint32_t &e) {
+    const uint32_t blk_mask = (1u << ix.blk_shift) - 1;
+    uint32_t cc = ctab[pat.bits(first_bit + 2 * (j - 1) * k, kmask)];
+    s = (uint32_t)__ldg(ix.C + cc);
+    e = (uint32_t)__ldg(ix.C + cc + 1);
+    for (int q = (int)j - 2; q >= 0 && e > s; q--) {
+        cc = ctab[pat.bits(first_bit + 2 * (uint32_t)q * k, kmask)];
+        const uint32_t re = e - 1;
+        const uint32_t ns = s == 0 ? (uint32_t)__ldg(ix.C + cc) : rank_c(ix, cc, s - 1);
+        e = sector_rank(ix, load_sector(ix, cc, re >> ix.blk_shift), re & blk_mask);
+        s = ns;
+    }
+}
 
 // K_a: one LANE per (pattern, shift). EFMIndex::computeSuperPatterns (:2055-2207) for the last j fixed super-characters of the shift
 // from the packed pattern, ONE sector gather of the seed table (start interval :1728-1748 + j-1 backwardSteps :1966), and the rows
-// of the interval — at most 14 — become row tasks {row, item}. The k lanes of a pattern sit next to each other in a warp: when one
-// of them meets a saturated counter the whole pattern goes to the generic path instead.
+// of the interval become row tasks {row, item}. The k lanes of a pattern sit next to each other in a warp. Every thread works on
+// SEED_U tiles at a time: their pattern loads, then their seed gathers, are in flight together (the kernel lives on memory-level
+// parallelism: one dependent chain per thread reaches half the random-gather rate of the part).
 template <int KT, int NW>
 __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
     extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code
@@ -145,16 +170,18 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
     const DevIndex &ix = a.ix;
     constexpr uint32_t k = KT, PPW = 32 / KT, PPC = 8 * PPW;
     constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    constexpr int U = SEED_U;
     for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
     if (threadIdx.x == 0) st_cnt = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t pl = lane / k, sa = lane - pl * k;
     const uint32_t m = a.m, j = ix.seed_chars, A = ix.A;
     uint32_t L;
     bool last_var;
     int l, lo;
     shift_geometry(m, k, sa, L, last_var, l, lo);
+    const uint32_t first_bit = l > 0 ? 2u * (((uint32_t)l - j) * k - sa) : 0u;   // bit offset of the seed's first super-character
     const unsigned group = (pl < PPW ? ((1u << k) - 1u) << (pl * k) : 0u);
     unsigned long long n_sect = 0;
     auto flush = [&]() {                               // whole CTA, st_cnt stable
@@ -168,63 +195,99 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
         if (threadIdx.x == 0) st_cnt = 0;
         __syncthreads();
     };
-    for (uint32_t tile = blockIdx.x; (unsigned long long)tile * PPC < a.count; tile += gridDim.x) {
-        const uint32_t p_local = tile * PPC + warp * PPW + pl;
-        const bool valid = pl < PPW && p_local < a.count;
-        uint32_t cnt = 0, s = 0;
-        bool irregular = false;
-        if (valid) {
-            const uint64_t p = a.first + p_local;
-            const uint32_t flag = a.pflag ? a.pflag[p] : 0;
-            if (sa == 0) a.counts[p] = 0;              // seed_verify_kernel (and the generic path for list members) add to it
-            irregular = flag == 1;
-            if (flag == 0 && l > 0) {
-                PatRegs<NW> pat;
-                pat.load(a.packed + p * NW);
+    const uint32_t tiles = (a.count + PPC - 1) / PPC;
+    for (uint32_t g = blockIdx.x * U; g < tiles; g += gridDim.x * U) {
+        uint32_t p_local[U], slot[U], flag[U];
+        size_t sector[U];
+        bool look[U];
+        PatRegs<NW> pat[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // the patterns of U tiles
+            p_local[u] = (g + u) * PPC + warp * PPW + pl;
+            look[u] = pl < PPW && g + u < tiles && p_local[u] < a.count;
+            flag[u] = 0;
+            if (look[u]) {
+                const uint64_t p = a.first + p_local[u];
+                pat[u].load(a.packed + p * NW);
+                if (a.pflag) flag[u] = a.pflag[p];
+                if (sa == 0) a.counts[p] = 0;          // seed_verify_kernel (and the generic path for list members) add to it
+            }
+        }
+        Sector sec[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // their seed gathers
+            sector[u] = 0;
+            slot[u] = 0;
+            const bool valid = look[u];
+            look[u] = false;
+            if (valid && flag[u] == 0 && l > 0) {
                 uint32_t hi = 0, cl = 0;
                 bool absent = false;
                 for (uint32_t q = 0; q < j; q++) {
-                    const uint32_t c = (uint32_t)l - j + q;
-                    const uint32_t code = ctab[pat.bits(2 * (c * k - sa), KMASK)];
+                    const uint32_t code = ctab[pat[u].bits(first_bit + 2 * q * k, KMASK)];
                     absent |= code == 0xFFFFu;
                     if (q + 1 < j) hi = hi * A + code; else cl = code;
                 }
                 if (!absent) {
-                    uint32_t slot;
-                    const size_t sector = seed_sector(ix, hi, cl, slot);
-                    const SeedHit h = seed_decode(seed_load(ix, sector), slot);
+                    sector[u] = seed_sector(ix, hi, cl, slot[u]);
+                    sec[u] = seed_load(ix, sector[u]);
+                    look[u] = true;
                     n_sect++;
-                    if (!h.exact) irregular = true;
-                    else { s = h.s; cnt = h.cnt; }
                 }
             }
+            flag[u] = (valid && flag[u] == 1) ? 1u : 0u;   // from here on: 1 = the pattern goes to the generic path
         }
-        // a pattern with an irregular shift is searched by the generic path, all its shifts
-        const unsigned irr = __ballot_sync(FULL, irregular);
-        if (irr & group) {
-            cnt = 0;
-            if (valid && sa == 0) {
-                const unsigned long long at = atomicAdd(a.stats + ST_COMPLEX, 1ull);
-                a.complex_list[at] = (uint32_t)(a.first + p_local);
-            }
-        }
-        // ---- rows of the interval -> staged row tasks
-        uint32_t incl = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, d);
-            if ((int)lane >= d) incl += v;
+        for (int u = 0; u < U; u++) {                  // rows of the intervals -> staged row tasks
+            uint32_t cnt = 0, s = 0, big = 0;
+            if (look[u]) {
+                const SeedHit h = seed_decode(sec[u], slot[u]);
+                if (h.exact) { s = h.s; cnt = h.cnt; }
+                else {
+                    uint32_t e;
+                    seed_interval_slow<NW>(ix, ctab, pat[u], first_bit, k, KMASK, j, s, e);
+                    big = e > s ? e - s : 0u;
+                    if (big <= 14) { cnt = big; big = 0; }
+                }
+            }
+            // a pattern with an index symbol outside ACGT is searched by the generic path, all its shifts
+            const unsigned irr = __ballot_sync(FULL, flag[u] != 0);
+            if (irr & group) {
+                cnt = 0;
+                big = 0;
+                if (flag[u] && sa == 0) {
+                    const unsigned long long at = atomicAdd(a.stats + ST_COMPLEX, 1ull);
+                    a.complex_list[at] = (uint32_t)(a.first + p_local[u]);
+                }
+            }
+            const uint32_t item = p_local[u] * k + sa;
+            // long intervals (a repeat: 15 rows and more) are written by the whole warp, straight to the task list
+            unsigned bigm = __ballot_sync(FULL, big != 0);
+            while (bigm) {
+                const int src = __ffs(bigm) - 1;
+                bigm &= bigm - 1;
+                const uint32_t r0 = __shfl_sync(FULL, s, src), ln = __shfl_sync(FULL, big, src), im = __shfl_sync(FULL, item, src);
+                unsigned long long b0 = 0;
+                if (lane == 0) b0 = atomicAdd(a.task_cursor, (unsigned long long)ln);
+                b0 = __shfl_sync(FULL, b0, 0);
+                for (uint32_t q = lane; q < ln; q += 32)
+                    if (b0 + q < a.task_cap) a.tasks[b0 + q] = make_uint2(r0 + q, im);
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const uint32_t wtot = __shfl_sync(FULL, incl, 31);
+            if (wtot) {
+                uint32_t wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&st_cnt, wtot);
+                wbase = __shfl_sync(FULL, wbase, 0);
+                for (uint32_t q = 0; q < cnt; q++) st_task[wbase + incl - cnt + q] = make_uint2(s + q, item);
+            }
+            if (__syncthreads_or(st_cnt >= SL_FLUSH)) flush();
         }
-        const uint32_t wtot = __shfl_sync(FULL, incl, 31);
-        uint32_t wbase = 0;
-        if (wtot) {
-            if (lane == 0) wbase = atomicAdd(&st_cnt, wtot);
-            wbase = __shfl_sync(FULL, wbase, 0);
-            const uint32_t item = p_local * k + sa;
-            for (uint32_t q = 0; q < cnt; q++) st_task[wbase + incl - cnt + q] = make_uint2(s + q, item);
-        }
-        (void)lt;
-        if (__syncthreads_or(st_cnt >= SL_FLUSH)) flush();
     }
     __syncthreads();
     if (st_cnt) flush();
@@ -233,23 +296,41 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
     if (lane == 0 && n_sect) atomicAdd(a.stats + ST_SECT_BS, n_sect);
 }
 
-// K_b: one thread per row task {row, item}. The row's suffix starts at text position sa[row] with the j seed super-characters; what
-// is left of EFMIndex::exactMatch(interval) (:1901-1963) for this row — the fixed super-characters before the seed, the '?'-prefixed
-// first one (backwardStepIfMatch, :2011-2041) and the '?'-suffixed last one (findWholePatternMatches, :1862-1899) — is compared with
-// the run of text[] around that position, and the occurrence reported at the position getRowPosition (:2468-2497) would walk to.
-// A backward step from a single row r with character c succeeds iff text[sa[r] - 1] == c, and then leads to the row of sa[r] - 1.
-static constexpr uint32_t SV_FLUSH = 1024, SV_CAP = SV_FLUSH + 256;
+// text[] is read as whole aligned sectors (one 32-byte load each): with narrower loads a sector is requested from L2 once per load,
+// because thousands of gathers in flight per SM thrash the L1
+struct Sec8 { uint32_t w[8]; };
+__device__ __forceinline__ Sec8 ld_sector256(const void *p) {
+    const Sector s = ld_sector(reinterpret_cast<const uint4 *>(p));
+    Sec8 r;
+    r.w[0] = s.lo.x; r.w[1] = s.lo.y; r.w[2] = s.lo.z; r.w[3] = s.lo.w;
+    r.w[4] = s.hi.x; r.w[5] = s.hi.y; r.w[6] = s.hi.z; r.w[7] = s.hi.w;
+    return r;
+}
+
+// K_b: one thread per row task {row, item}, SEED_UV tasks at a time. The row's suffix starts at text position sa[row] with the j seed
+// super-characters; what is left of EFMIndex::exactMatch(interval) (:1901-1963) for this row — the fixed super-characters before the
+// seed, the '?'-prefixed first one (backwardStepIfMatch, :2011-2041) and the '?'-suffixed last one (findWholePatternMatches,
+// :1862-1899) — is compared with the run of text[] around that position, and the occurrence reported at the position getRowPosition
+// (:2468-2497) would walk to. A backward step from a single row r with character c succeeds iff text[sa[r] - 1] == c, and then leads
+// to the row of sa[r] - 1.
+// The run is read as the two aligned sectors that end with text[sa[r] - 1] (one 32-byte load each, issued for all the thread's tasks
+// before any is used) and laid into a per-thread column of shared memory, from where the characters are picked; the few characters
+// outside that window (long patterns, the hat character behind the seed) are single loads.
+static constexpr int SEED_UV = 2;
+static constexpr uint32_t SV_FLUSH = 1024, SV_CAP = SV_FLUSH + 256 * SEED_UV;
 
 template <int KT, int NW>
 __global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
     extern __shared__ uint16_t ctab[];
     __shared__ uint32_t rs_pat[SV_CAP];
     __shared__ uint64_t rs_pos[SV_CAP];
+    __shared__ uint32_t win[16 * 256];                 // [word][thread]: the 32 text codes that end with text[sa[row] - 1]'s sector
     __shared__ uint32_t rs_cnt;
     __shared__ unsigned long long rs_base;
     const DevIndex &ix = a.ix;
     constexpr uint32_t k = KT;
     constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    constexpr int U = SEED_UV;
     for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
     if (threadIdx.x == 0) rs_cnt = 0;
     __syncthreads();
@@ -274,67 +355,113 @@ __global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
         if (threadIdx.x == 0) rs_cnt = 0;
         __syncthreads();
     };
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n_tasks; base += stride) {
-        const uint32_t idx = base + threadIdx.x;
-        bool ok = false;
-        uint32_t sa = 0, tp = 0;
-        uint64_t p = 0;
-        if (idx < n_tasks) {
-            const uint2 tk = __ldg(a.tasks + idx);
-            const uint32_t pos = __ldg(ix.sa + tk.x);
-            const uint32_t pl = tk.y / k;
-            sa = tk.y - pl * k;
-            p = a.first + pl;
-            PatRegs<NW> pat;
-            pat.load(a.packed + p * NW);
-            uint32_t L;
-            bool last_var;
-            int l, lo;
-            shift_geometry(m, k, sa, L, last_var, l, lo);
-            const int i = l - (int)j - 1;              // first super-character left of the seed
-            auto back = [&](uint32_t d) -> uint32_t { return pos >= d ? pos - d : pos + (n - d); };   // (pos - d) mod n
-            ok = true;
-            for (int c = i; c >= lo; c--) {
-                const uint32_t code = ctab[pat.bits(2 * ((uint32_t)c * k - sa), KMASK)];
-                ok &= code == (uint32_t)__ldg(ix.text + back((uint32_t)(i + 1 - c)));
-            }
-            tp = back((uint32_t)(i + 1));              // text position of super-character 0 of the shift
-            if (sa > 0) {
-                const uint32_t f = k - sa;
-                const uint32_t want = pat.natural(ix, 0, f);
-                const uint32_t code = (uint32_t)__ldg(ix.text + tp);
-                ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code) == want;
-            }
-            if (last_var) {
-                const unsigned long long ph = (unsigned long long)tp + L - 1;
-                if (ph >= ix.n) ok = false;
-                else {
-                    const uint32_t from = (L - 1) * k - sa, f = m - from;
-                    const uint32_t want = pat.natural(ix, 2 * from, f);
-                    const uint32_t code = (uint32_t)__ldg(ix.text + ph);
-                    ok &= want != 0xFFFFFFFFu && __ldg(ix.kmer_high + (f - 1) * A + code) == want;
-                }
-            }
-            {   // sa[] + the distinct 32-byte sectors of text[]: the run that ends at pos - 1 and the hat character
-                const uint32_t run = (uint32_t)(i + 1 - (sa > 0 ? 0 : lo));
-                n_sect += 1;
-                if (run) n_sect += pos >= run ? ((pos - 1) >> 4) - ((pos - run) >> 4) + 1 : 2;
-                if (last_var && ((tp + L - 1) >> 4) != ((pos == 0 ? 0 : pos - 1) >> 4)) n_sect++;
+    const uint16_t *text = ix.text;
+    uint32_t *col = win + threadIdx.x;                  // word w of this thread's window: col[w * 256]
+    const uint32_t stride = gridDim.x * blockDim.x * U;
+    for (uint32_t base = blockIdx.x * blockDim.x * U; base < n_tasks; base += stride) {
+        uint2 tk[U];
+        bool ok[U];
+        uint32_t pos[U];
+        PatRegs<NW> pat[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + (uint32_t)u * blockDim.x + threadIdx.x;
+            ok[u] = idx < n_tasks;
+            tk[u] = ok[u] ? __ldg(a.tasks + idx) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // sa[] gathers and pattern loads of the thread's tasks in flight together
+            pos[u] = 0;
+            if (ok[u]) {
+                pos[u] = __ldg(ix.sa + tk[u].x);
+                pat[u].load(a.packed + (a.first + tk[u].y / k) * NW);
             }
         }
-        const unsigned em = __ballot_sync(FULL, ok);
-        if (em) {
-            if (ok) atomicAdd(a.counts + p, 1ull);                                    // countOccurrences (:2273)
-            if (locate) {
-                uint32_t b = 0;
-                const int leader = __ffs(em) - 1;
-                if ((int)lane == leader) b = atomicAdd(&rs_cnt, (uint32_t)__popc(em));
-                b = __shfl_sync(FULL, b, leader);
-                if (ok) {
-                    const uint32_t slot = b + __popc(em & lt);
-                    rs_pat[slot] = (uint32_t)p;
-                    rs_pos[slot] = (uint64_t)tp * k + sa + ix.initial_n;              // EFMIndex.cpp:2312-2319
+        uint32_t sa[U], d[U], Ls[U], wbase[U], hat[U];
+        bool lastv[U], in_win[U], two[U];
+        Sec8 secA[U], secB[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // the sectors of text[] of all tasks
+            sa[u] = tk[u].y % k;
+            int l, lo;
+            shift_geometry(m, k, sa[u], Ls[u], lastv[u], l, lo);
+            d[u] = (uint32_t)(l - (int)j);              // super-characters 0 .. l-j-1 lie at text positions pos - d .. pos - 1
+            in_win[u] = ok[u] && pos[u] >= d[u] && pos[u] >= 32u;   // (else: the run wraps around the text, or sits at its very start)
+            const uint32_t sb = in_win[u] ? ((pos[u] - 1) >> 4) : 1u;
+            wbase[u] = (sb - 1) << 4;
+            two[u] = in_win[u] && pos[u] - d[u] < (sb << 4);
+            hat[u] = 0;
+            if (in_win[u]) {
+                secB[u] = ld_sector256(text + ((size_t)sb << 4));
+                if (two[u]) secA[u] = ld_sector256(text + ((size_t)wbase[u]));
+                const unsigned long long ph = (unsigned long long)pos[u] - d[u] + Ls[u] - 1;   // the '?'-suffixed last super-character
+                if (lastv[u] && ph < ix.n && (ph >> 4) != sb) hat[u] = __ldg(text + ph);
+            }
+        }
+        uint32_t tp[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            tp[u] = pos[u] >= d[u] ? pos[u] - d[u] : pos[u] + (n - d[u]);               // text position of super-character 0
+            if (!ok[u]) continue;
+            const uint32_t lo = sa[u] > 0 ? 1u : 0u;
+            const uint32_t bit0 = 2u * (d[u] * k - sa[u]);                              // bit offset of super-character d (the seed's first)
+            if (in_win[u]) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    if (two[u]) col[w * 256] = secA[u].w[w];
+                    col[(8 + w) * 256] = secB[u].w[w];
+                }
+            }
+            // text code at position q: from the window when it is there
+            auto code_at = [&](uint32_t q) -> uint32_t {
+                const uint32_t h = q - wbase[u];
+                if (in_win[u] && h < 32u && (h >= 16u || two[u])) return (col[(h >> 1) * 256] >> ((h & 1u) * 16u)) & 0xFFFFu;
+                return (uint32_t)__ldg(text + q);
+            };
+            bool good = true;
+            // text[pos - r] against super-character d - r, r = 1 .. d - lo (the fixed ones, right to left)
+            for (uint32_t r = 1; r + lo <= d[u] && good; r++) {
+                const uint32_t code = ctab[pat[u].bits(bit0 - 2u * r * k, KMASK)];
+                const uint32_t at = pos[u] >= r ? pos[u] - r : pos[u] + (n - r);        // (pos - r) mod n
+                good = code == code_at(at);
+            }
+            if (good && sa[u] > 0) {                                                    // '?'-prefixed first super-character
+                const uint32_t f = k - sa[u];
+                const uint32_t want = pat[u].natural(ix, 0, f);
+                good = want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code_at(tp[u])) == want;
+            }
+            if (good && lastv[u]) {                                                     // '?'-suffixed last super-character
+                const unsigned long long ph = (unsigned long long)tp[u] + Ls[u] - 1;
+                if (ph >= ix.n) good = false;
+                else {
+                    const uint32_t from = (Ls[u] - 1) * k - sa[u], f = m - from;
+                    const uint32_t want = pat[u].natural(ix, 2 * from, f);
+                    const uint32_t code = (in_win[u] && (ph >> 4) != ((pos[u] - 1) >> 4)) ? hat[u] : code_at((uint32_t)ph);
+                    good = want != 0xFFFFFFFFu && __ldg(ix.kmer_high + (f - 1) * A + code) == want;
+                }
+            }
+            ok[u] = good;
+            // sa[] + the distinct 32-byte sectors of text[] this task needs: the run and the hat character
+            n_sect += 1;
+            if (d[u]) n_sect += pos[u] >= d[u] ? ((pos[u] - 1) >> 4) - ((pos[u] - d[u]) >> 4) + 1 : 2;
+            if (lastv[u] && ((tp[u] + Ls[u] - 1) >> 4) != ((pos[u] == 0 ? 0 : pos[u] - 1) >> 4)) n_sect++;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned em = __ballot_sync(FULL, ok[u]);
+            if (em) {
+                const uint64_t p = a.first + tk[u].y / k;
+                if (ok[u]) atomicAdd(a.counts + p, 1ull);                                 // countOccurrences (:2273)
+                if (locate) {
+                    uint32_t b = 0;
+                    const int leader = __ffs(em) - 1;
+                    if ((int)lane == leader) b = atomicAdd(&rs_cnt, (uint32_t)__popc(em));
+                    b = __shfl_sync(FULL, b, leader);
+                    if (ok[u]) {
+                        const uint32_t slot = b + __popc(em & lt);
+                        rs_pat[slot] = (uint32_t)p;
+                        rs_pos[slot] = (uint64_t)tp[u] * k + sa[u] + ix.initial_n;        // EFMIndex.cpp:2312-2319
+                    }
                 }
             }
         }
@@ -365,20 +492,32 @@ bool seed_search_supported(const DevIndex &ix, uint32_t m) {
     return true;
 }
 
-template <int KT>
-static void launch_seed_kt(const SeedArgs &a, uint32_t nw, int n_sm, bool verify, cudaStream_t s) {
+template <class Kern>
+static uint32_t resident_ctas(Kern kern, size_t smem, int n_sm) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return (uint32_t)per_sm * (uint32_t)n_sm;
+}
+
+template <int KT, int NW>
+static void launch_seed_nw(const SeedArgs &a, int n_sm, bool verify, cudaStream_t s) {
     constexpr uint32_t PPC = 8 * (32 / KT);
     const size_t smem = (size_t)2 << (2 * KT);
-    const uint32_t tiles = (a.count + PPC - 1) / PPC;
-    const uint32_t lookup_blocks = std::min<uint32_t>(tiles, (uint32_t)n_sm * 6);
-    const uint32_t verify_blocks = (uint32_t)n_sm * 8;
+    // persistent grids: as many CTAs as the SMs hold (a multiple of the SM count)
+    static const uint32_t lookup_max = resident_ctas(seed_lookup_kernel<KT, NW>, smem, n_sm);
+    static const uint32_t verify_max = resident_ctas(seed_verify_kernel<KT, NW>, smem, n_sm);
     if (!verify) {
-        if (nw == 1) seed_lookup_kernel<KT, 1><<<lookup_blocks, 256, smem, s>>>(a);
-        else seed_lookup_kernel<KT, 2><<<lookup_blocks, 256, smem, s>>>(a);
+        const uint32_t groups = ((a.count + PPC - 1) / PPC + SEED_U - 1) / SEED_U;
+        seed_lookup_kernel<KT, NW><<<std::max(1u, std::min(groups, lookup_max)), 256, smem, s>>>(a);
     } else {
-        if (nw == 1) seed_verify_kernel<KT, 1><<<verify_blocks, 256, smem, s>>>(a);
-        else seed_verify_kernel<KT, 2><<<verify_blocks, 256, smem, s>>>(a);
+        seed_verify_kernel<KT, NW><<<verify_max, 256, smem, s>>>(a);
     }
+}
+
+template <int KT>
+static void launch_seed_kt(const SeedArgs &a, uint32_t nw, int n_sm, bool verify, cudaStream_t s) {
+    if (nw == 1) launch_seed_nw<KT, 1>(a, n_sm, verify, s);
+    else launch_seed_nw<KT, 2>(a, n_sm, verify, s);
 }
 
 static void launch_seed_any(const SeedArgs &a, uint32_t nw, int n_sm, bool verify, cudaStream_t s) {

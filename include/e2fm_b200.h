@@ -112,6 +112,27 @@ int e2fm_search_batch_packed(e2fm_index *ix, const uint8_t *packed, uint64_t n, 
                              e2fm_result **out);
 int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uint64_t n, uint32_t length, int mode,
                                     e2fm_result **out);
+/* Host to host in ONE pipelined call: the batched replacement of the loop around EFMCollection::search (Main.cpp:1055-1079) that hands
+ * back what that loop collects — per pattern the number of matches (EFMIndex::countOccurrences) and, in locate mode, the
+ * (Occurrence::sequenceIndex, Occurrence::patternPosition) pairs of FMCollection.h:23-44 — in 32 bits, straight into the caller's
+ * host arrays. Fixed-length patterns, ASCII (packed == 0, n x length bytes) or 2-bit packed (e2fm_packed_stride bytes each). The batch
+ * is cut into stages; stage c travels to the device while stage c-1 is searched and the results of stage c-2 travel back, so the call
+ * takes about as long as the slower of the two PCIe directions. Page-locked buffers (e2fm_host_alloc) are needed for the overlap.
+ *   counts        [n]      may be NULL
+ *   occ_offsets   [n + 1]  locate: occurrences of pattern i are entries [occ_offsets[i], occ_offsets[i+1]) of the two arrays below
+ *   seq_index, seq_offset  [capacity] locate; sorted by text position within a pattern (EFMIndex.cpp:2291)
+ *   total         out: occurrences written. E2FM_ERR_ARG with total = the capacity needed when `capacity` is too small, or when a value
+ *                 does not fit 32 bits (use e2fm_search_batch_* + e2fm_result_fetch then).
+ * Batches the seed search does not take (see e2fm_search_batch_packed) run unpipelined through the generic path, same results. */
+typedef struct e2fm_hits {
+    uint32_t *counts;
+    uint32_t *occ_offsets;
+    uint32_t *seq_index;
+    uint32_t *seq_offset;
+    uint64_t capacity;
+    uint64_t total;
+} e2fm_hits;
+int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32_t length, int packed, int mode, e2fm_hits *hits);
 /* Page-locked host memory for pattern / result buffers (plain malloc'ed buffers work too, only slower). */
 void *e2fm_host_alloc(size_t bytes);
 void e2fm_host_free(void *p);
@@ -179,7 +200,8 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
  * [3] row tasks, [4] distinct 32-byte sectors gathered by the backward-search kernel (rank sectors, pair-table entries, records),
  * [5] kernels launched by the batch, [6] located occurrences, [7] gathers issued by the walk / resolve kernel,
  * [8] rows streamed by firstcheck_kernel (2 bytes each, read twice), [9] chunks redone through the windowed path,
- * [10] patterns the seed search handed to the generic path, [11] 1 when the batch went through the seed search, [12..15] reserved */
+ * [10] patterns the seed search handed to the generic path, [11] 1 when the batch went through the seed search,
+ * [12] pipeline stages of e2fm_search_hits (0: the call ran unpipelined), [13..15] reserved */
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
@@ -193,6 +215,7 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_SEED 9          /* 1 (default when the seed table was built): fixed-length batches whose every shift holds a whole seed
                                     go through seed_search_kernel (seed table + dense tables); 0: always the generic backward search.
                                     Same results either way. */
+#define E2FM_OPT_HITS_STAGE 10   /* patterns per pipeline stage of e2fm_search_hits (0 = default 2^19) */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).
@@ -208,6 +231,9 @@ int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, ui
 /* HBM random-gather roofline: independent 8-byte loads at hashed addresses of a buffer_bytes buffer (make it much larger than
  * L2); returns 10^9 gathers per second (best of 3). Every gather moves one 32-byte sector over the memory system. */
 int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s);
+/* the same with the load instruction chosen: 0 ld.global.nc.u64 (the default above), 1 ld.global.u64, 2 ld.global.cg.u64, 3 one 32-byte
+ * ld.global.nc.v8.u32, 4 two 16-byte loads of one sector, 5 / 7 ld.global.nc.L2::64B / ::128B.u64, 6 ld.global.nc.L1::no_allocate.u64 */
+int e2fm_debug_gather_bench_ex(int device, uint64_t buffer_bytes, uint64_t n_gathers, int variant, double *giga_gathers_per_s);
 /* raw Salsa20/20 blocks [first_block, first_block + n_blocks) for a 32-byte key */
 int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block,
                        uint64_t n_blocks, uint8_t *out);

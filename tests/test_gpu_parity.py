@@ -636,10 +636,10 @@ def test_seed_search_matches_reference(gpu, golden, key64, name, seed_chars):
         dev.close()
 
 
-def test_seed_search_hands_repeats_and_odd_symbols_to_the_generic_path(gpu, golden, key64, oracle_mod):
-    """a pattern that ends with several rows in some shift (it occurs more than once), meets a saturated seed counter, or holds
-    an index symbol outside ACGT leaves the seed search untouched and is answered by the generic path; a foreign symbol means no
-    match at all (EFMIndex.cpp:1702-1717)"""
+def test_seed_search_repeats_and_odd_symbols(gpu, golden, key64, oracle_mod):
+    """a pattern that occurs more than once or meets a saturated seed counter is finished by the seed search itself (backward
+    steps in place of the table entry); one that holds an index symbol outside ACGT is answered by the generic path; a foreign
+    symbol means no match at all (EFMIndex.cpp:1702-1717)"""
     g = golden["col3_k4"]
     dev = capi.DeviceIndex(g["index"], key64)
     orc = oracle_mod.OracleIndex(g["index"], key64)
@@ -648,8 +648,9 @@ def test_seed_search_hands_repeats_and_odd_symbols_to_the_generic_path(gpu, gold
         text = synth.collection_text(seqs, 4)
         L = 12
         pats = [text[100:100 + L], text[30009:30009 + L], b"ACGTACGTACGT", b"A" * L, b"ACGTNNNNACGT", b"ACGT&&&&ACGT",
-                text[30000:30000 + L], b"acgtacgtacgt", text[59020:59020 + L], b"$$$$$$$$$$$$", text[5:5 + L]]
-        # 12-mers that occur twice in the text: the seed search must hand those to the generic path
+                text[30000:30000 + L], b"acgtacgtacgt", text[59020:59020 + L], text[5:5 + L]]
+        # (a pattern of '$' only is left out: the unmodified reference itself dies with SIGSEGV on it, and so does the oracle)
+        # 12-mers that occur twice in the text
         seen, twice = {}, []
         whole = seqs[0].tobytes()
         for i in range(len(whole) - L):
@@ -670,7 +671,7 @@ def test_seed_search_hands_repeats_and_odd_symbols_to_the_generic_path(gpu, gold
                 if locate:
                     a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
                     assert np.array_equal(out["positions"][a:b], pos), p
-            assert c["complex_patterns"] >= 2       # at least the '&' pattern and poly-A / the repeats
+            assert c["complex_patterns"] >= 1       # the '&' pattern
             r.free()
         # tiny result store: the seed search flags the overflow and is run again with room
         dev.set_option(capi.OPT_DENSITY, 1)
@@ -683,3 +684,96 @@ def test_seed_search_hands_repeats_and_odd_symbols_to_the_generic_path(gpu, gold
     finally:
         dev.close()
         orc.close()
+
+
+# ---------------------------------------------------------------- e2fm_search_hits: host to host, pipelined
+
+def _hits_call(dev, arr, L, packed, locate, cap):
+    n = len(arr)
+    pats = arr
+    if packed:
+        pats, bad = capi.pack_patterns(arr)
+        assert bad == 0
+    c32 = np.full(n, 0xDEADBEEF, dtype=np.uint32)
+    o32 = np.full(n + 1, 0xDEADBEEF, dtype=np.uint32) if locate else None
+    s32 = np.full(cap, 0xDEADBEEF, dtype=np.uint32) if locate else None
+    f32 = np.full(cap, 0xDEADBEEF, dtype=np.uint32) if locate else None
+    total = dev.search_hits(np.ascontiguousarray(pats).reshape(-1), n, L, packed, locate, c32, o32, s32, f32)
+    return total, c32, o32, s32, f32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
+@pytest.mark.parametrize("stage", [0, 64, 7])
+def test_search_hits_matches_reference(gpu, golden, key64, name, stage):
+    """e2fm_search_hits (pipeline stages of 2^19, 64 and 7 patterns): counts, occurrence offsets, sequence index and offset in
+    the sequence of every occurrence equal the reference's, from ASCII and from packed patterns, count and locate"""
+    g = golden[name]
+    dev = capi.DeviceIndex(g["index"], key64)
+    try:
+        dev.set_option(capi.OPT_HITS_STAGE, stage)
+        piped_any = False
+        for L, idxs in sorted(_by_length(g["patterns"]).items()):
+            if L == 0:
+                continue
+            arr = np.frombuffer(b"".join(g["patterns"][i] for i in idxs), dtype=np.uint8).reshape(len(idxs), L).copy()
+            want = _subset(g["res"], idxs)
+            acgt = all(all(ch in b"ACGT" for ch in g["patterns"][i]) for i in idxs)
+            for packed in ((False, True) if acgt else (False,)):
+                for locate in (False, True):
+                    try:
+                        total, c32, o32, s32, f32 = _hits_call(dev, arr, L, packed, locate, len(want["seq"]) + 3)
+                    except capi.E2FMError:
+                        assert packed, "only the packed form may be refused (batch shapes the seed search does not take)"
+                        continue
+                    what = (name, L, packed, locate, stage)
+                    assert np.array_equal(c32, want["counts"].astype(np.uint32)), what
+                    stages = dev.last_batch_counters()["hits_stages"]
+                    piped_any |= stages > 0
+                    if stage and stages:
+                        assert stages == -(-len(idxs) // stage)
+                    if locate:
+                        assert total == len(want["seq"]), what
+                        assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)), what
+                        assert np.array_equal(s32[:total], want["seq"]) and np.array_equal(f32[:total], want["off"].astype(np.uint32)), what
+                        assert np.all(s32[total:] == 0xDEADBEEF) and np.all(f32[total:] == 0xDEADBEEF), what
+        assert piped_any, "no batch of this golden went through the pipeline"
+    finally:
+        dev.close()
+
+
+@pytest.mark.gpu
+def test_search_hits_undersized_stores_and_capacity(gpu, golden, key64):
+    """stores sized from earlier batches that turn out too small make the call fall back to the exact-size path (same answers);
+    a caller's capacity that is too small is an error that reports the capacity needed"""
+    g = golden["col3_k4"]
+    dev = capi.DeviceIndex(g["index"], key64)
+    try:
+        groups = _by_length(g["patterns"])
+        L = max(groups, key=lambda q: len(groups[q]))
+        idxs = [i for i in groups[L] if all(ch in b"ACGT" for ch in g["patterns"][i])]   # (others go to the generic path anyway)
+        arr = np.frombuffer(b"".join(g["patterns"][i] for i in idxs), dtype=np.uint8).reshape(len(idxs), L).copy()
+        reps = -(-40000 // len(idxs))
+        big = np.ascontiguousarray(np.tile(arr, (reps, 1)))
+        want = _subset(g["res"], idxs * reps)
+        assert len(want["seq"]) > 30000
+        dev.set_option(capi.OPT_HITS_STAGE, 8192)
+        dev.set_option(capi.OPT_DENSITY, 1)          # one task / result per 1000 patterns: every stage overflows
+        total, c32, o32, s32, f32 = _hits_call(dev, big, L, False, True, len(want["seq"]) + 8)
+        assert dev.last_batch_counters()["hits_stages"] == 0, "the call must have fallen back"
+        assert total == len(want["seq"]) and np.array_equal(c32, want["counts"].astype(np.uint32))
+        assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)) and np.array_equal(s32[:total], want["seq"])
+        # now the densities are learned: the same call is pipelined
+        total, c32, o32, s32, f32 = _hits_call(dev, big, L, False, True, len(want["seq"]) + 8)
+        assert dev.last_batch_counters()["hits_stages"] > 1
+        assert total == len(want["seq"]) and np.array_equal(f32[:total], want["off"].astype(np.uint32))
+        assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)) and np.array_equal(s32[:total], want["seq"])
+        with pytest.raises(capi.E2FMError):
+            _hits_call(dev, big, L, False, True, len(want["seq"]) - 1)
+        assert dev.last_hits_total == len(want["seq"])
+        # empty batch
+        e = np.zeros((0, L), dtype=np.uint8)
+        total, c32, o32, s32, f32 = _hits_call(dev, e, L, False, True, 4)
+        assert total == 0 and o32[0] == 0
+    finally:
+        dev.close()
