@@ -459,8 +459,8 @@ def gpu_arm(args, rank, world, local_rank):
 
     # strong scaling: the ONE batch is partitioned by pattern; rank r owns the contiguous slice [lo, hi)
     npat_all, L = w["n_patterns"], w["pat_len"]
-    lo, hi = npat_all * rank // world, npat_all * (rank + 1) // world
-    npat = hi - lo
+    lo, npat = capi.shardset_slice(npat_all, world, rank)     # contiguous slices of ceil(n / world) patterns
+    hi = lo + npat
     all_pats = load_patterns(prep)
     # 2-bit packed patterns (e2fm_search_batch_packed) when the seed search takes this batch shape, else ASCII
     stride = capi.packed_stride(L)
@@ -484,9 +484,10 @@ def gpu_arm(args, rank, world, local_rank):
         h_pats[lo:hi] = mine
     # result buffers of the whole batch, ONE host buffer per array (every rank writes its own region of it): what
     # EFMCollection::search returns, in 32 bits. Region r holds rank r's occurrences; its offsets index that region.
-    occ_cap = int((npat_all // world + 1) * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
+    per_rank = -(-npat_all // world)
+    occ_cap = int((per_rank + 1) * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
     h_counts = shm.array("counts", npat_all, np.uint32)
-    h_noff = shm.array("occ_offsets", (world, npat_all // world + 2), np.uint32) if locate else None
+    h_noff = shm.array("occ_offsets", (world, per_rank + 2), np.uint32) if locate else None
     h_seq = shm.array("seq", (world, occ_cap), np.uint32) if locate else None
     h_off = shm.array("off", (world, occ_cap), np.uint32) if locate else None
     d_pats = torch.from_numpy(np.array(h_pats[lo:hi])).to(dev_t)
@@ -521,7 +522,8 @@ def gpu_arm(args, rank, world, local_rank):
         --e2e-api fetch: the two-call form (e2fm_search_batch_packed / _fixed, then e2fm_result_fetch_compact)"""
         t0 = time.perf_counter()
         if args.e2e_api == "hits":
-            total = ix.search_hits(h_pats[lo:hi].reshape(-1), npat, L, packed_api, locate, h_counts[lo:hi],
+            # locate: a pattern's count is its number of occurrences (every match is located), so only the offsets travel back
+            total = ix.search_hits(h_pats[lo:hi].reshape(-1), npat, L, packed_api, locate, None if locate else h_counts[lo:hi],
                                    h_noff[rank][:npat + 1] if locate else None, h_seq[rank] if locate else None,
                                    h_off[rank] if locate else None)
         else:
@@ -533,7 +535,7 @@ def gpu_arm(args, rank, world, local_rank):
             if total > occ_cap:
                 raise SystemExit("bench: occurrence buffer too small; pass a larger --occ-per-pattern")
             if locate:
-                r.fetch_compact(h_counts[lo:hi], h_noff[rank][:npat + 1], h_seq[rank][:total], h_off[rank][:total])
+                r.fetch_compact(None, h_noff[rank][:npat + 1], h_seq[rank][:total], h_off[rank][:total])
             else:
                 r.fetch_compact(h_counts[lo:hi], None, None, None)
             r.free()
@@ -604,7 +606,8 @@ def gpu_arm(args, rank, world, local_rank):
         chk = ix.search_packed(h_pats[lo:lo + sample].reshape(-1), sample, L, locate) if packed_api else ix.search_fixed(h_pats[lo:lo + sample], locate)
         full = chk.fetch()
         chk.free()
-        got = {"counts": h_counts[:sample].astype(np.uint64)}
+        # (locate: the timed call brings back occurrences, not counts; the counts compared with the reference are the 64-bit fetch's)
+        got = {"counts": full["counts"] if locate else h_counts[:sample].astype(np.uint64)}
         assert np.array_equal(full["counts"], got["counts"]), "timed counts differ from the 64-bit fetch"
         if locate:
             got.update(pos_offsets=h_noff[0][:sample + 1], seq=h_seq[0], off=h_off[0], positions=full["positions"])
@@ -624,13 +627,32 @@ def gpu_arm(args, rank, world, local_rank):
         except RuntimeError as e:
             parity = {"checked": 0, "mismatches": None, "error": str(e)}
 
+    # ---- N > 1: the other multi-GPU mode, the collection sharded by sequence, on the same batch
+    sharded_obj = None
+    if world > 1 and not args.no_sharded and len(w["seq_lens"]) >= world:
+        replica = {"lo": lo, "npat": npat}
+        if locate:
+            tot = int(h_noff[rank][npat])
+            replica.update(noff=h_noff[rank][:npat + 1].copy(), seq=h_seq[rank][:tot].copy(), off=h_off[rank][:tot].copy())
+        else:
+            replica.update(counts=h_counts[lo:hi].copy())
+        ix.close()
+        ix = None
+        try:
+            sharded_obj = sharded_measure(args, rank, world, local_rank, prep, replica)
+        except Exception as e:   # noqa: BLE001  (the replica line stands on its own)
+            sharded_obj = {"error": f"{type(e).__name__}: {e}"[:300]}
+            log(f"[bench r{rank}] sharded mode failed: {sharded_obj['error']}")
+
     if rank == 0:
         peak, peak_kind = measured_peak()
         value = npat_all * steps / (dev_ms_max / 1e3)
         e2e_value = npat_all * steps / (e2e_ms_max / 1e3)
         roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind)
+        if sharded_obj is not None:
+            roofline["note"] += "; the gather microbenchmark ran after the sharded leg freed the replica"
         h2d = int(npat * unit)
-        d2h = int(npat * 4 + (((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else 0))
+        d2h = int(((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else npat * 4)
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -670,8 +692,11 @@ def gpu_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_base
         if world == 1 and not args.no_cpp:
             line["e2e_cpp"] = cpp_host_arm(prep, local_rank)
+        if sharded_obj is not None:
+            line["sharded"] = sharded_obj
         emit(line)
-    ix.close()
+    if ix is not None:
+        ix.close()
     shm.close()
     if world > 1:
         dist.barrier()
@@ -758,28 +783,13 @@ def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, pea
             "kernels": kern}
 
 
-def sharded_arm(args, rank, world, local_rank):
-    """Collection sharded by sequence over the ranks: rank r indexes sequence group r with the reference
-    builder, every rank searches the whole (broadcast) batch against its shard, counts and positions are merged over NCCL.
-    Total work is fixed as N grows -> strong scaling."""
-    import torch
-    import torch.distributed as dist
-
-    from e2fm_b200 import capi, sharded
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
-    dev_t = torch.device("cuda", local_rank)
-    w = WORKLOADS[args.workload]
-    locate = w["locate"]
-    # every shard's own super-text length must dodge the reference's load-time quirks (SURVEY.md 8 quirks 2, 3): lengthen the
-    # last sequence of an unlucky shard by k bases until all shards are clean (deterministic, so every rank agrees)
+def shard_plan(w, world):
+    """contiguous sequence groups balanced by length; every shard's own super-text length must dodge the reference's load-time quirks
+    (SURVEY.md 8 quirks 2, 3): lengthen the last sequence of an unlucky shard by k bases until all shards are clean (deterministic,
+    so every rank agrees). Returns (lens, plan, adjusted?)."""
+    from e2fm_b200 import sharded
     lens = workload_lens(w)
+    lens0 = list(lens)
     for _ in range(1000):
         plan = sharded.plan_shards(lens, world, K)
         bad = None
@@ -791,79 +801,160 @@ def sharded_arm(args, rank, world, local_rank):
         if bad is None:
             break
         lens[bad] += K
+    return lens, plan, lens != lens0
+
+
+def sharded_measure(args, rank, world, local_rank, prep, replica=None):
+    """Collection sharded by sequence over the ranks, through the C ABI (e2fm_shardset_*): rank r indexes sequence
+    group r with the reference builder, supplies 1/N of the batch from the one host buffer, every rank searches the whole batch
+    against its shard, and the answers for slice r travel to rank r over NCCL (reduce-scatter of the counts, one send/recv round for
+    the occurrence lists), from where they go back to the host buffer. A step = host patterns -> host results, wall clock, max over
+    ranks. `replica`: the host arrays the replica arm left for the same batch; the sharded answers must equal them."""
+    import torch
+    import torch.distributed as dist
+
+    from e2fm_b200 import capi
+
+    dev_t = torch.device("cuda", local_rank)
+    w = prep["w"]
+    locate = w["locate"]
+    lens, plan, adjusted = shard_plan(w, world)
     first, cnt, text_base = plan[rank]
-    os.makedirs(CACHE, exist_ok=True)
-    keyfile = os.path.join(CACHE, f"key_r{rank}.bin")
-    with open(keyfile, "wb") as f:
-        f.write(synth.test_key())
-    seqs = []
-    for i in range(first, first + cnt):
-        seqs += synth.random_sequences([lens[i]], w["seed"] + i)
-    efm = os.path.join(CACHE, f"{args.workload}_shard{rank}of{world}_k{K}_b{BUCKET}_m{MRP}.efm")
+    keyfile = prep["keyfile"]
+    efm = os.path.join(CACHE, f"{prep['workload']}_shard{rank}of{world}_k{K}_b{BUCKET}_m{MRP}.efm")
+    t_build = time.time()
     if not os.path.exists(efm):
-        build_index(seqs, efm, keyfile, max(4, min(32, (os.cpu_count() or 2) // world)))
+        seqs = []
+        for i in range(first, first + cnt):
+            seqs += synth.random_sequences([lens[i]], w["seed"] + i)
+        build_index(seqs, efm, keyfile, max(2, min(32, (os.cpu_count() or 2) // world)))
+        del seqs
+    t_build = time.time() - t_build
     with open(efm, "rb") as f:
         raw = f.read()
-    col = sharded.ShardedCollection(raw, synth.test_key(), local_rank, first, text_base)
-    if args.walk:
-        col.ix.set_option(capi.OPT_DENSE, 0)
-    npat, L = w["n_patterns"], w["pat_len"]
-    pats0 = None
-    if rank == 0:
-        # patterns are sampled from the WHOLE collection: rank 0 regenerates the sequences it does not index
-        all_seqs = make_sequences(w, lens)
-        pats0 = torch.from_numpy(synth.sample_patterns(all_seqs, npat, L, w["seed"] + 1)[:npat]).pin_memory()
-        del all_seqs
+    ix = capi.DeviceIndex(raw, synth.test_key(), local_rank)
+    del raw
+    ids = [capi.shardset_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    ss = capi.ShardSet(ix, ids[0], rank, world, first, text_base)
+    npat_all, L = w["n_patterns"], w["pat_len"]
+    lo, npat = capi.shardset_slice(npat_all, world, rank)
+    per = -(-npat_all // world)
+    all_pats = load_patterns(prep)
+    packed_api = not args.ascii
+    if packed_api:
+        try:
+            probe, _ = capi.pack_patterns(np.ascontiguousarray(all_pats[:1]))
+            ix.search_packed(probe, 1, L, locate).free()
+        except capi.E2FMError:
+            packed_api = False
+    unit = capi.packed_stride(L) if packed_api else L
+    shm = SharedHost(f"{os.environ.get('MASTER_PORT', '0')}_{prep['workload']}_sh", world, rank, capi)
+    h_pats = shm.array("patterns", (npat_all, unit), np.uint8)
+    occ_cap = int((per + 1) * max(2.0, 1.3 * args.occ_per_pattern)) + 1024
+    h_counts = shm.array("counts", (world, per + 1), np.uint32)
+    h_noff = shm.array("occ_offsets", (world, per + 2), np.uint32) if locate else None
+    h_seq = shm.array("seq", (world, occ_cap), np.uint32) if locate else None
+    h_off = shm.array("off", (world, occ_cap), np.uint32) if locate else None
+    if world > 1:
+        dist.barrier()
+    mine = np.ascontiguousarray(all_pats[lo:lo + npat])
+    if packed_api:
+        _, bad = capi.pack_patterns(mine, h_pats[lo:lo + npat].reshape(-1))
+        assert bad == 0
+    else:
+        h_pats[lo:lo + npat] = mine
+    del mine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
-    dist.barrier()
+    state = {}
 
     def step():
         flush.add_(1)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        m = col.search_batch(pats0, (npat, L), locate, args.pieces or None)
-        torch.cuda.synchronize()
+        r = ss.search(h_pats[lo:lo + npat].reshape(-1), npat_all, L, packed_api, locate)
+        total = r.total
+        if total > occ_cap:
+            raise SystemExit("bench: occurrence buffer too small; pass a larger --occ-per-pattern")
+        if locate:
+            r.fetch_compact(None, h_noff[rank][:npat + 1], h_seq[rank][:total], h_off[rank][:total])
+        else:
+            r.fetch_compact(h_counts[rank][:npat], None, None, None)
+        r.free()
         dt = time.perf_counter() - t0
-        phases.append(dict(col.last_phase_ms))
-        return dt, int(m.positions.numel()), int(m.counts.sum().item())
+        state.update(total=total, ms=ss.last_ms())
+        return dt
 
-    phases = []
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step()
-    phases.clear()
-    sampler = ClockSampler(local_rank)
-    dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    tot_s, occ, cnt_sum = 0.0, 0, 0
+    tot_s = 0.0
+    phases = []
     for _ in range(args.steps):
-        dt, o, c = step()
-        tot_s += dt
-        occ, cnt_sum = o, c
-    dist.barrier()
-    clocks = sampler.stop()
-    t = torch.tensor([tot_s], dtype=torch.float64, device=dev_t)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_s += step()
+        phases.append(state["ms"])
+    # the same answers as the replicas gave for this rank's slice of the same batch?
+    mism = 0
+    if replica is not None and replica.get("lo") == lo and replica.get("npat") == npat:
+        if locate:
+            a, b = replica["noff"][:npat + 1], h_noff[rank][:npat + 1]
+            t = int(b[npat])
+            same = np.array_equal(a, b) and np.array_equal(replica["seq"][:t], h_seq[rank][:t]) and np.array_equal(replica["off"][:t], h_off[rank][:t])
+        else:
+            same = np.array_equal(replica["counts"], h_counts[rank][:npat])
+        mism = 0 if same else 1
+    t = torch.tensor([tot_s, float(mism), float(state["total"]), t_build], dtype=torch.float64, device=dev_t)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms = float(tmax[0]) * 1e3 / args.steps
+    out = {
+        "value": npat_all / (ms / 1e3), "unit": "patterns/s", "ms_per_step": ms, "scaling": "strong",
+        "parallelism": f"collection sharded by sequence over {world} GPUs (e2fm_shardset_*): each rank supplies 1/{world} of the batch from the host, "
+                       "ncclAllGather of the batch, every rank searches all patterns on its shard, counts by ncclReduceScatter, occurrence lists "
+                       "by one grouped ncclSend/ncclRecv round, merged answers of slice r back to the host from rank r",
+        "timing": "wall clock, host patterns -> host results, barrier in front, max over ranks",
+        "shards": [list(x) for x in plan], "lengths_adjusted_for_shard_quirks": adjusted,
+        "phase_ms_rank0": {k_: float(np.mean([p[k_] for p in phases])) for k_ in (phases[0] if phases else {})},
+        "occurrences": int(t[2]), "shard_index_build_s_max": float(tmax[3]),
+        "index_device_MB_rank0": round(ix.info.device_bytes / 1e6, 1),
+        "same_answers_as_replicas": (None if replica is None else {"ranks_that_differ": int(t[1])}),
+        "patterns_in": "2-bit packed" if packed_api else "ASCII",
+    }
+    ss.close()
+    ix.close()
+    shm.close()
+    return out
+
+
+def sharded_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prep = prepare(args.workload, rank)
+    if world > 1:
+        dist.barrier()
+    sh = sharded_measure(args, rank, world, local_rank, prep)
     if rank == 0:
-        ms = float(t.item()) * 1e3 / args.steps
-        line = {
-            "metric": "patterns/sec", "value": npat / (ms / 1e3), "unit": "patterns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": w["name"], "mode": "count+locate" if locate else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
-                       "patterns": npat, "pattern_len": L, "parallelism": f"collection sharded by sequence over {world} GPUs; "
-                       "patterns broadcast, counts all-reduced, positions all-gathered (NCCL)", "shards": plan,
-                       "l2": "256 MB flush between timed iterations", "timing": "wall clock around broadcast + search + merge, device synchronised, max over ranks"},
-            "occurrences_per_s": occ / (ms / 1e3) if locate else None, "total_count": cnt_sum,
-            "phase_ms_rank0": {k_: float(np.mean([p[k_] for p in phases])) for k_ in (phases[0] if phases else {})},
-            "index_device_MB_rank0": round(col.ix.info.device_bytes / 1e6, 1),
-            "e2e": {"value": npat / (ms / 1e3), "unit": "patterns/s", "h2d_bytes_per_step": npat * L, "d2h_bytes_per_step": 0,
-                    "note": "patterns start in pinned host memory on rank 0; the merged result stays on the GPUs"},
-            "gpu_launches": None, "clocks": clocks,
-        }
+        w = prep["w"]
+        line = {"metric": "patterns/sec", "value": sh["value"], "unit": "patterns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sh["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+                "data": "synthetic",
+                "config": {"workload": w["name"], "mode": "count+locate" if w["locate"] else "count", "k": K, "bucket_size": BUCKET, "mrp": MRP,
+                           "patterns": w["n_patterns"], "pattern_len": w["pat_len"], "parallelism": sh["parallelism"],
+                           "l2": "256 MB flush between timed iterations"},
+                "e2e": {"value": sh["value"], "unit": "patterns/s", "ms_per_step": sh["ms_per_step"]},
+                "sharded": sh, "gpu_launches": None}
         emit(line)
-    col.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -877,6 +968,7 @@ def main():
     ap.add_argument("--no-cpp", action="store_true", help="skip the e2e_cpp figure (C++ host classes)")
     ap.add_argument("--occ-per-pattern", type=float, default=1.0, help="expected occurrences per pattern (sizes the host result buffers)")
     ap.add_argument("--pieces", type=int, default=0, help="sharded mode: pipeline pieces per batch (0 = automatic)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-by-sequence leg of the default line")
     ap.add_argument("--sharded", action="store_true", help="shard the collection by sequence over the GPUs and merge over NCCL")
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")

@@ -400,7 +400,7 @@ class DeviceIndex:
         a = (C.c_uint64 * 16)()
         check(lib().e2fm_last_batch_counters(self._h, C.byref(a)))
         return dict(zip(["rank", "lf", "mark", "tasks", "rank_sectors", "launches", "occurrences", "walk_gathers", "scan_rows",
-                         "chunks_redone", "complex_patterns", "seeded", "hits_stages"], [int(x) for x in a]))
+                         "chunks_redone", "complex_patterns", "seeded", "hits_stages", "hits_gave_up"], [int(x) for x in a]))
 
     # ---- test hooks
     def debug_bwt(self, row0: int, count: int) -> np.ndarray:
@@ -454,7 +454,8 @@ class ShardSet:
         self._h = h
 
     def search(self, slice_host: np.ndarray, n_total: int, length: int, packed: bool, locate: bool) -> "Result":
-        """slice_host: this rank's patterns [lo, lo+count) of the batch (shardset_slice), uint8, ASCII or packed"""
+        """slice_host: this rank's patterns [lo, lo+count) of the batch (shardset_slice), uint8, ASCII or packed; the result
+        holds the merged answers for those patterns"""
         h = C.c_void_p()
         ptr = slice_host.ctypes.data if slice_host is not None and slice_host.size else None
         check(lib().e2fm_shardset_search(self._h, ptr, n_total, length, 1 if packed else 0, MODE_LOCATE if locate else MODE_COUNT,

@@ -899,7 +899,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     // every CUDA call on the launch path costs the host a few microseconds, and a pipeline stage of a host batch holds only
     // ~0.1 ms of kernels: per-phase event pairs are recorded for device batches only (E2FM_OPT_PHASE_TIMERS overrides)
     tm.phases = ix->phase_timers == 1 || (ix->phase_timers == 2 && !b.h_bytes);
-    ix->batch_ctr[10] = 0;
+    ix->batch_ctr[10] = ix->batch_ctr[12] = ix->batch_ctr[13] = 0;
 
     RunState st(ix, mode, tm, counts.p);
     const bool seeded = ix->use_seed && ix->use_dense && !b.d_off && !b.h_off && b.n > 0 && seed_search_supported(dix, b.fixed_len);
@@ -1125,6 +1125,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     uint64_t tasks_sum = 0, worst_tasks = 0;
     for (uint64_t c = 0; c < S; c++) {
         if (info[c].flags) trouble = true;
+        ix->batch_ctr[13] |= info[c].flags;
         tasks_sum += info[c].tasks;
         worst_tasks = std::max<uint64_t>(worst_tasks, info[c].tasks);
     }
@@ -1515,9 +1516,10 @@ int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32
     // the plain path: whole batch, exact sizes, then the compact fetch
     e2fm_result *r = nullptr;
     const uint64_t unit = packed ? e2fm_packed_stride(length) : length;
+    const uint64_t gave_up = ix->batch_ctr[13];
     int rc = search_common(ix, patterns, nullptr, length, n, n * unit, false, mode, &r, nullptr, packed != 0);
     if (rc != E2FM_OK) return rc;
-    ix->batch_ctr[12] = 0;
+    ix->batch_ctr[13] = gave_up;
     hits->total = r->total;
     if (locate && r->total > hits->capacity) {
         e2fm_result_free(r);

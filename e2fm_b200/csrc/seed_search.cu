@@ -134,21 +134,23 @@ struct PatRegs {
     }
 };
 
-static constexpr uint32_t SL_FLUSH = 1024;                       // staged row tasks handed over per reservation
-static constexpr uint32_t SL_CAP = SL_FLUSH + 256 * 14;          // a tile adds at most 14 rows per lane (exact counters stop at 14)
-static constexpr int SEED_U = 4;                                 // independent gathers in flight per thread (tiles / tasks per iteration)
+static constexpr int SEED_U = 2;                                 // tiles per iteration: their loads are in flight together
+static constexpr uint32_t SL_DIRECT = 4;                         // seed intervals longer than this are written straight to the task list
+static constexpr uint32_t SL_FLUSH = 256;                        // staged row tasks a warp hands over per reservation
+static constexpr uint32_t SL_WCAP = SL_FLUSH + 32 * SL_DIRECT;   // per-warp stage: a tile adds at most SL_DIRECT rows per lane
 
 // the interval of the seed c_0 .. c_{j-1} by the backward steps the table replaces (EFMIndex.cpp:1728-1748, :1966-2001): the path
 // of a lookup that met a saturated counter (a seed that occurs 15 times or more, or sits behind one in its sector)
-template <int NW>
-__device__ __forceinline__ void seed_interval_slow(const DevIndex &ix, const uint16_t *ctab, const PatRegs<NW> &pat, uint32_t first_bit,
-                                                uint32_t k, uint32_t kmask, uint32_t j, uint32_t &s, uint32_t &e) {
+template <int KT>
+__device__ __forceinline__ void seed_interval_slow(const DevIndex &ix, const uint16_t *ctab, unsigned long long window, uint32_t j,
+                                                   uint32_t &s, uint32_t &e) {
+    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
     const uint32_t blk_mask = (1u << ix.blk_shift) - 1;
-    uint32_t cc = ctab[pat.bits(first_bit + 2 * (j - 1) * k, kmask)];
+    uint32_t cc = ctab[(uint32_t)(window >> (2 * KT * (j - 1))) & KMASK];
     s = (uint32_t)__ldg(ix.C + cc);
     e = (uint32_t)__ldg(ix.C + cc + 1);
     for (int q = (int)j - 2; q >= 0 && e > s; q--) {
-        cc = ctab[pat.bits(first_bit + 2 * (uint32_t)q * k, kmask)];
+        cc = ctab[(uint32_t)(window >> (2 * KT * q)) & KMASK];
         const uint32_t re = e - 1;
         const uint32_t ns = s == 0 ? (uint32_t)__ldg(ix.C + cc) : rank_c(ix, cc, s - 1);
         e = sector_rank(ix, load_sector(ix, cc, re >> ix.blk_shift), re & blk_mask);
@@ -158,23 +160,21 @@ __device__ __forceinline__ void seed_interval_slow(const DevIndex &ix, const uin
 
 // K_a: one LANE per (pattern, shift). EFMIndex::computeSuperPatterns (:2055-2207) for the last j fixed super-characters of the shift
 // from the packed pattern, ONE sector gather of the seed table (start interval :1728-1748 + j-1 backwardSteps :1966), and the rows
-// of the interval become row tasks {row, item}. The k lanes of a pattern sit next to each other in a warp. Every thread works on
-// SEED_U tiles at a time: their pattern loads, then their seed gathers, are in flight together (the kernel lives on memory-level
-// parallelism: one dependent chain per thread reaches half the random-gather rate of the part).
+// of the interval become row tasks {row, item}. The k lanes of a pattern sit next to each other in a warp.
+// The kernel is bound by instruction issue as much as by the gathers (ncu, profiles/): a lane loads only the three words of the
+// pattern that hold its seed (where they are depends on the shift alone), the row tasks are staged per WARP (no CTA barrier in the
+// loop, one reservation per SL_FLUSH tasks), and the loads of SEED_U tiles are in flight together.
 template <int KT, int NW>
-__global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
+__global__ void __launch_bounds__(256, 4) seed_lookup_kernel(SeedArgs a) {
     extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code
-    __shared__ uint2 st_task[SL_CAP];
-    __shared__ uint32_t st_cnt;
-    __shared__ unsigned long long st_base;
+    __shared__ uint2 st_task[8][SL_WCAP];
     const DevIndex &ix = a.ix;
     constexpr uint32_t k = KT, PPW = 32 / KT, PPC = 8 * PPW;
     constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
     constexpr int U = SEED_U;
     for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
-    if (threadIdx.x == 0) st_cnt = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const uint32_t pl = lane / k, sa = lane - pl * k;
     const uint32_t m = a.m, j = ix.seed_chars, A = ix.A;
     uint32_t L;
@@ -182,61 +182,83 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
     int l, lo;
     shift_geometry(m, k, sa, L, last_var, l, lo);
     const uint32_t first_bit = l > 0 ? 2u * (((uint32_t)l - j) * k - sa) : 0u;   // bit offset of the seed's first super-character
+    const uint32_t w0 = first_bit >> 5, sh = first_bit & 31u;                     // the seed sits in words w0 .. w0 + 2 of the pattern
+    const bool live = pl < PPW && l > 0;
     const unsigned group = (pl < PPW ? ((1u << k) - 1u) << (pl * k) : 0u);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(a.packed);
+    uint2 *stage = st_task[warp];
+    uint32_t wcnt = 0;                                 // staged tasks of this warp (uniform)
     unsigned long long n_sect = 0;
-    auto flush = [&]() {                               // whole CTA, st_cnt stable
-        const uint32_t c = st_cnt;
-        if (threadIdx.x == 0) st_base = atomicAdd(a.task_cursor, (unsigned long long)c);
-        __syncthreads();
-        const unsigned long long b0 = st_base;
-        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x)
-            if (b0 + i < a.task_cap) a.tasks[b0 + i] = st_task[i];
-        __syncthreads();
-        if (threadIdx.x == 0) st_cnt = 0;
-        __syncthreads();
+    auto flush = [&]() {                               // whole warp
+        unsigned long long b0 = 0;
+        if (lane == 0) b0 = atomicAdd(a.task_cursor, (unsigned long long)wcnt);
+        b0 = __shfl_sync(FULL, b0, 0);
+        __syncwarp();
+        for (uint32_t i = lane; i < wcnt; i += 32)
+            if (b0 + i < a.task_cap) a.tasks[b0 + i] = stage[i];
+        __syncwarp();
+        wcnt = 0;
     };
     const uint32_t tiles = (a.count + PPC - 1) / PPC;
-    for (uint32_t g = blockIdx.x * U; g < tiles; g += gridDim.x * U) {
-        uint32_t p_local[U], slot[U], flag[U];
-        size_t sector[U];
-        bool look[U];
-        PatRegs<NW> pat[U];
+    // the pattern words of the NEXT group of tiles are loaded while the seed gathers of the current one are in flight: a thread then
+    // has its gathers outstanding nearly all the time instead of half of it
+    uint32_t nx0[U], nx1[U], nx2[U], nflag[U];
+    auto fetch_words = [&](uint32_t g) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {                  // the patterns of U tiles
-            p_local[u] = (g + u) * PPC + warp * PPW + pl;
-            look[u] = pl < PPW && g + u < tiles && p_local[u] < a.count;
-            flag[u] = 0;
-            if (look[u]) {
-                const uint64_t p = a.first + p_local[u];
-                pat[u].load(a.packed + p * NW);
-                if (a.pflag) flag[u] = a.pflag[p];
+        for (int u = 0; u < U; u++) {
+            const uint32_t pq = (g + u) * PPC + warp * PPW + pl;
+            nx0[u] = nx1[u] = nx2[u] = 0;
+            nflag[u] = 0;
+            if (pl < PPW && g + u < tiles && pq < a.count) {
+                const uint64_t p = a.first + pq;
+                if (live) {
+                    const uint32_t *src = words + p * (4 * NW) + w0;
+                    nx0[u] = __ldg(src);
+                    if (w0 + 1 < 4 * NW) nx1[u] = __ldg(src + 1);
+                    if (w0 + 2 < 4 * NW) nx2[u] = __ldg(src + 2);
+                }
+                if (a.pflag) nflag[u] = a.pflag[p];
                 if (sa == 0) a.counts[p] = 0;          // seed_verify_kernel (and the generic path for list members) add to it
             }
         }
+    };
+    if (blockIdx.x * U < tiles) fetch_words(blockIdx.x * U);
+    for (uint32_t g = blockIdx.x * U; g < tiles; g += gridDim.x * U) {
+        uint32_t p_local[U], flag[U], x0[U], x1[U], x2[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // the seed windows of U tiles
+            p_local[u] = (g + u) * PPC + warp * PPW + pl;
+            valid[u] = pl < PPW && g + u < tiles && p_local[u] < a.count;
+            flag[u] = nflag[u];
+            x0[u] = nx0[u]; x1[u] = nx1[u]; x2[u] = nx2[u];
+        }
         Sector sec[U];
+        unsigned long long window[U];
+        uint32_t slot[U];
+        bool look[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {                  // their seed gathers
-            sector[u] = 0;
+            window[u] = (unsigned long long)__funnelshift_r(x0[u], x1[u], sh) | ((unsigned long long)__funnelshift_r(x1[u], x2[u], sh) << 32);
             slot[u] = 0;
-            const bool valid = look[u];
             look[u] = false;
-            if (valid && flag[u] == 0 && l > 0) {
+            if (valid[u] && live && flag[u] == 0) {
                 uint32_t hi = 0, cl = 0;
                 bool absent = false;
                 for (uint32_t q = 0; q < j; q++) {
-                    const uint32_t code = ctab[pat[u].bits(first_bit + 2 * q * k, KMASK)];
+                    const uint32_t code = ctab[(uint32_t)(window[u] >> (2 * KT * q)) & KMASK];
                     absent |= code == 0xFFFFu;
                     if (q + 1 < j) hi = hi * A + code; else cl = code;
                 }
                 if (!absent) {
-                    sector[u] = seed_sector(ix, hi, cl, slot[u]);
-                    sec[u] = seed_load(ix, sector[u]);
+                    sec[u] = seed_load(ix, seed_sector(ix, hi, cl, slot[u]));
                     look[u] = true;
                     n_sect++;
                 }
             }
-            flag[u] = (valid && flag[u] == 1) ? 1u : 0u;   // from here on: 1 = the pattern goes to the generic path
+            flag[u] = (valid[u] && flag[u] == 1) ? 1u : 0u;   // from here on: 1 = the pattern goes to the generic path
         }
+        if (g + gridDim.x * U < tiles) fetch_words(g + gridDim.x * U);
 #pragma unroll
         for (int u = 0; u < U; u++) {                  // rows of the intervals -> staged row tasks
             uint32_t cnt = 0, s = 0, big = 0;
@@ -245,10 +267,10 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
                 if (h.exact) { s = h.s; cnt = h.cnt; }
                 else {
                     uint32_t e;
-                    seed_interval_slow<NW>(ix, ctab, pat[u], first_bit, k, KMASK, j, s, e);
-                    big = e > s ? e - s : 0u;
-                    if (big <= 14) { cnt = big; big = 0; }
+                    seed_interval_slow<KT>(ix, ctab, window[u], j, s, e);
+                    cnt = e > s ? e - s : 0u;
                 }
+                if (cnt > SL_DIRECT) { big = cnt; cnt = 0; }
             }
             // a pattern with an index symbol outside ACGT is searched by the generic path, all its shifts
             const unsigned irr = __ballot_sync(FULL, flag[u] != 0);
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
                 }
             }
             const uint32_t item = p_local[u] * k + sa;
-            // long intervals (a repeat: 15 rows and more) are written by the whole warp, straight to the task list
+            // longer intervals (repeats) are written by the whole warp, straight to the task list
             unsigned bigm = __ballot_sync(FULL, big != 0);
             while (bigm) {
                 const int src = __ffs(bigm) - 1;
@@ -273,24 +295,30 @@ __global__ void __launch_bounds__(256) seed_lookup_kernel(SeedArgs a) {
                 for (uint32_t q = lane; q < ln; q += 32)
                     if (b0 + q < a.task_cap) a.tasks[b0 + q] = make_uint2(r0 + q, im);
             }
-            uint32_t incl = cnt;
+            const unsigned any = __ballot_sync(FULL, cnt != 0);
+            if (any) {
+                const unsigned more = __ballot_sync(FULL, cnt > 1);
+                uint32_t excl, wtot;
+                if (!more) {                           // the usual case: no lane has more than one row
+                    excl = __popc(any & lt);
+                    wtot = __popc(any);
+                } else {
+                    uint32_t incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, incl, d);
-                if ((int)lane >= d) incl += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                        if ((int)lane >= d) incl += v;
+                    }
+                    excl = incl - cnt;
+                    wtot = __shfl_sync(FULL, incl, 31);
+                }
+                for (uint32_t q = 0; q < cnt; q++) stage[wcnt + excl + q] = make_uint2(s + q, item);
+                wcnt += wtot;
+                if (wcnt >= SL_FLUSH) flush();
             }
-            const uint32_t wtot = __shfl_sync(FULL, incl, 31);
-            if (wtot) {
-                uint32_t wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&st_cnt, wtot);
-                wbase = __shfl_sync(FULL, wbase, 0);
-                for (uint32_t q = 0; q < cnt; q++) st_task[wbase + incl - cnt + q] = make_uint2(s + q, item);
-            }
-            if (__syncthreads_or(st_cnt >= SL_FLUSH)) flush();
         }
     }
-    __syncthreads();
-    if (st_cnt) flush();
+    if (wcnt) flush();
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_sect += __shfl_xor_sync(FULL, n_sect, d);
     if (lane == 0 && n_sect) atomicAdd(a.stats + ST_SECT_BS, n_sect);
@@ -479,6 +507,7 @@ __global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
 bool seed_search_supported(const DevIndex &ix, uint32_t m) {
     if (!ix.seed_tab || !ix.packed_code || !ix.sa || !ix.text || ix.k < 2 || ix.k > 7 || m == 0 || m > 128) return false;
     const uint32_t k = ix.k, j = ix.seed_chars;
+    if (2 * k * j > 64) return false;                              // seed_lookup_kernel reads a seed as one 64-bit window of the pattern
     for (uint32_t sa = 0; sa < k; sa++) {
         const uint32_t L = (m + sa + k - 1) / k;
         const bool last_var = (m + sa) % k != 0;

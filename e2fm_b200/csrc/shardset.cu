@@ -4,14 +4,17 @@
 // never span a terminator and every sequence starts k-aligned (EFMCollection.cpp:218-225), so an occurrence has the same
 // (sequence, offset) whether its sequence is indexed alone, in a shard or in the whole collection; adding the shard's text base
 // gives the position the unsharded reference index reports, and because shards are contiguous sequence ranges the per-pattern
-// concatenation in shard order is already sorted (EFMIndex.cpp:2291). e2fm_shardset_search is ONE exchange step:
+// concatenation in shard order is already sorted (EFMIndex.cpp:2291). e2fm_shardset_search is ONE exchange step in which every
+// rank supplies 1/N of the batch and receives the merged answers for that same 1/N:
 //
-//   H2D of this rank's 1/N of the batch  ->  ncclAllGather over NVLink (every rank has the whole batch)
-//   local search on the shard (seed search / generic path, api.cu)
-//   counts:      ncclAllReduce(sum, u64)                     = EFMIndex::countOccurrences over the whole collection
-//   occurrences: ncclAllGather of the per-pattern occurrence counts of every shard -> merged CSR offsets (scan kernel);
-//                each shard's (position + text base, sequence + first sequence, offset) arrays broadcast once, in one NCCL group;
-//                merge kernels place shard r's occurrences of pattern p behind those of shards 0..r-1
+//   H2D of this rank's slice of the batch  ->  ncclAllGather over NVLink (every rank has the whole batch)
+//   local search of the whole batch on the shard (seed search / generic path, api.cu)
+//   counts:      ncclReduceScatter(sum, u64): the counts of slice q land on rank q   (EFMIndex::countOccurrences over the collection)
+//   occurrences: every rank cuts its CSR at the slice boundaries; ONE grouped ncclSend/ncclRecv round moves the offsets and the
+//                (position + text base, sequence + first sequence, offset) triples of slice q to rank q (an all-to-all-v: a rank
+//                receives 1/N of the occurrences, nothing is replicated, nothing is zero-filled);
+//                shard_merge_kernel then places shard r's occurrences of a pattern behind those of shards 0..r-1. The merged offset of
+//                a pattern is the SUM over the shards of its offsets in their CSRs: no scan is needed.
 //
 // The NCCL communicator is owned here (ncclCommInitRank from a unique id the caller distributes). libnccl is resolved with dlopen
 // at the first use, so single-GPU users of libe2fm_b200.so do not need it.
@@ -41,7 +44,9 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -71,7 +76,9 @@ NcclApi &nccl() {
     *(void **)&api.CommDestroy = sym("ncclCommDestroy");
     *(void **)&api.AllReduce = sym("ncclAllReduce");
     *(void **)&api.AllGather = sym("ncclAllGather");
-    *(void **)&api.Broadcast = sym("ncclBroadcast");
+    *(void **)&api.ReduceScatter = sym("ncclReduceScatter");
+    *(void **)&api.Send = sym("ncclSend");
+    *(void **)&api.Recv = sym("ncclRecv");
     *(void **)&api.GroupStart = sym("ncclGroupStart");
     *(void **)&api.GroupEnd = sym("ncclGroupEnd");
     *(void **)&api.GetErrorString = sym("ncclGetErrorString");
@@ -120,60 +127,61 @@ struct e2fm_shardset {
     int rank = 0, world = 1, device = 0;
     uint64_t first_seq = 0, text_base = 0;
     cudaStream_t stream = nullptr;
-    Grow batch, nocc_all, nocc_sum, roff, before, scratch, stage_pos, stage_seq, stage_off, totals;
+    Grow batch, cpad, off32, roff, stage_pos, stage_seq, stage_off, cuts;
     cudaEvent_t ev[6] = {nullptr};
     float ms[8] = {0};
-    unsigned long long *h_totals = nullptr;   // pinned, world entries
+    unsigned long long *h_cuts = nullptr;     // pinned: world x (world + 1) CSR cuts of every rank at the slice boundaries
 };
 
 // ---------------------------------------------------------------- kernels of the merge
 
 namespace {
 
-// occurrences of every pattern in this shard, and this shard's occurrences moved into the collection's coordinates
-__global__ void __launch_bounds__(256) shard_local_kernel(const uint64_t *__restrict__ off, uint64_t n, uint32_t *__restrict__ nocc,
+// this shard's occurrences moved into the collection's coordinates, its CSR in 32 bits (what travels), the counts padded to
+// world equal slices, and the CSR cut at the slice boundaries: cuts[q] = off[min(n, q * per)]
+__global__ void __launch_bounds__(256) shard_local_kernel(const uint64_t *__restrict__ off, const unsigned long long *__restrict__ counts, uint64_t n,
+                                                           uint64_t padded, uint32_t *__restrict__ off32, unsigned long long *__restrict__ cpad,
                                                            uint64_t *__restrict__ pos, uint32_t *__restrict__ seq, uint64_t total,
-                                                           uint64_t text_base, uint32_t first_seq) {
+                                                           uint64_t text_base, uint32_t first_seq, uint64_t per, uint32_t world,
+                                                           unsigned long long *__restrict__ cuts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) nocc[i] = (uint32_t)(off[i + 1] - off[i]);
-    if (i < total) {
+    if (off && i <= n) off32[i] = (uint32_t)off[i];
+    if (i < padded) cpad[i] = i < n ? counts[i] : 0ull;
+    if (off && i <= world) cuts[i] = off[min(n, i * per)];
+    if (off && i < total) {
         pos[i] += text_base;
         const uint32_t s = seq[i];
         if (s != 0xFFFFFFFFu) seq[i] = s + first_seq;     // sequenceIndex -1 (no terminator beyond the position, EFMCollection.cpp:124-133) stays
     }
 }
 
-__global__ void __launch_bounds__(256) shard_sum_kernel(const uint32_t *__restrict__ nocc_all, uint64_t n, uint32_t world,
-                                                         unsigned long long *__restrict__ sum) {
+struct MergeSrc {                                       // what one shard sent for this rank's slice
+    const uint32_t *off;                                // its CSR offsets of the slice's patterns (mine + 1 entries, absolute in ITS arrays)
+    const uint64_t *pos;
+    const uint32_t *seq;
+    const uint64_t *seqoff;
+};
+struct MergeArgs { MergeSrc src[16]; };
+
+// pattern i of the slice: its merged offset is the sum over the shards of (their offset - their offset of the slice's first pattern);
+// shard r's occurrences go behind those of shards 0..r-1
+__global__ void __launch_bounds__(256) shard_merge_kernel(MergeArgs a, uint32_t world, uint64_t mine, uint64_t *__restrict__ m_csr,
+                                                           uint64_t *__restrict__ m_pos, uint32_t *__restrict__ m_seq, uint64_t *__restrict__ m_off) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned long long t = 0;
-    for (uint32_t r = 0; r < world; r++) t += nocc_all[(uint64_t)r * n + i];
-    sum[i] = t;
-}
-
-// shard r's occurrences of pattern p go behind those of the shards before it: merged[moff[p] + before[p] + i] = stage_r[roff[p] + i]
-__global__ void __launch_bounds__(256) shard_merge_kernel(const uint32_t *__restrict__ nocc_r, const uint64_t *__restrict__ roff,
-                                                           const uint64_t *__restrict__ moff, uint32_t *__restrict__ before, uint64_t n,
-                                                           const uint64_t *__restrict__ s_pos, const uint32_t *__restrict__ s_seq,
-                                                           const uint64_t *__restrict__ s_off, uint64_t *__restrict__ m_pos,
-                                                           uint32_t *__restrict__ m_seq, uint64_t *__restrict__ m_off) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const uint32_t c = nocc_r[p];
-    if (c == 0) return;
-    const uint32_t b = before[p];
-    const uint64_t src = roff[p], dst = moff[p] + b;
-    for (uint32_t i = 0; i < c; i++) {
-        m_pos[dst + i] = s_pos[src + i];
-        m_seq[dst + i] = s_seq[src + i];
-        m_off[dst + i] = s_off[src + i];
+    if (i > mine) return;
+    uint64_t dst = 0;
+    for (uint32_t r = 0; r < world; r++) dst += a.src[r].off[i] - a.src[r].off[0];
+    m_csr[i] = dst;
+    if (i == mine) return;
+    for (uint32_t r = 0; r < world; r++) {
+        const uint32_t b = a.src[r].off[i] - a.src[r].off[0], c = a.src[r].off[i + 1] - a.src[r].off[i];
+        for (uint32_t q = 0; q < c; q++) {
+            m_pos[dst + q] = a.src[r].pos[b + q];
+            m_seq[dst + q] = a.src[r].seq[b + q];
+            m_off[dst + q] = a.src[r].seqoff[b + q];
+        }
+        dst += c;
     }
-    before[p] = b + c;
-}
-
-__global__ void __launch_bounds__(256) shard_total_kernel(const uint64_t *__restrict__ off_end, unsigned long long *__restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = *off_end;
 }
 
 thread_local std::string g_ss_err;
@@ -219,7 +227,8 @@ int e2fm_shardset_create(e2fm_index *ix, const uint8_t id[128], int rank, int wo
         memcpy(&nid, id, 128);
         NC(api.CommInitRank(&ss->comm, world, nid, rank));
         for (auto &e : ss->ev) CU(cudaEventCreate(&e));
-        CU(cudaHostAlloc((void **)&ss->h_totals, sizeof(unsigned long long) * (size_t)(world + 1), cudaHostAllocDefault));
+        if (world > 16) throw CudaFail("at most 16 ranks per shard set");
+        CU(cudaHostAlloc((void **)&ss->h_cuts, sizeof(unsigned long long) * (size_t)world * (size_t)(world + 1), cudaHostAllocDefault));
     } catch (const NcclError &e) {
         e2fm_shardset_destroy(ss);
         return ss_fail(E2FM_ERR_NCCL, e.what());
@@ -236,11 +245,9 @@ void e2fm_shardset_destroy(e2fm_shardset *ss) {
     cudaSetDevice(ss->device);
     if (ss->stream) cudaStreamSynchronize(ss->stream);
     if (ss->comm) nccl().CommDestroy(ss->comm);
-    for (Grow *g : {&ss->batch, &ss->nocc_all, &ss->nocc_sum, &ss->roff, &ss->before, &ss->scratch, &ss->stage_pos, &ss->stage_seq,
-                    &ss->stage_off, &ss->totals})
-        g->release();
+    for (Grow *g : {&ss->batch, &ss->cpad, &ss->off32, &ss->roff, &ss->stage_pos, &ss->stage_seq, &ss->stage_off, &ss->cuts}) g->release();
     for (auto &e : ss->ev) if (e) cudaEventDestroy(e);
-    if (ss->h_totals) cudaFreeHost(ss->h_totals);
+    if (ss->h_cuts) cudaFreeHost(ss->h_cuts);
     cudaGetLastError();
     delete ss;
 }
@@ -292,78 +299,78 @@ int e2fm_shardset_search(e2fm_shardset *ss, const uint8_t *slice, uint64_t n_tot
         const uint32_t *l_seq;
         e2fm_result_device_ptrs(local, &l_counts, &l_off, &l_pos, &l_seq, &l_seqoff);
         const uint64_t l_total = e2fm_result_total_positions(local);
-        // ---- counts: all-reduce straight out of the local result into the merged result's array
-        CU(cudaMallocAsync((void **)&m_counts, std::max<uint64_t>(n_total, 1) * 8, s));
-        if (n_total) {
-            if (world > 1) NC(api.AllReduce(l_counts, m_counts, n_total, ncclUint64, ncclSum, ss->comm, s));
-            else CU(cudaMemcpyAsync(m_counts, l_counts, n_total * 8, cudaMemcpyDeviceToDevice, s));
+        const bool locate = mode == E2FM_MODE_LOCATE;
+        const uint64_t padded = per * world;
+        // ---- this shard in the collection's coordinates; counts padded to equal slices; CSR cuts at the slice boundaries
+        unsigned long long *cpad = (unsigned long long *)ss->cpad.ensure(std::max<uint64_t>(padded, 1) * 8, s);
+        uint32_t *off32 = (uint32_t *)ss->off32.ensure((n_total + 2) * 4, s);
+        unsigned long long *cuts = (unsigned long long *)ss->cuts.ensure((size_t)world * (world + 1) * 8, s);
+        unsigned long long *my_cuts = cuts + (size_t)ss->rank * (world + 1);
+        {
+            const uint64_t work = std::max<uint64_t>(std::max<uint64_t>(padded, n_total + 1), std::max<uint64_t>(l_total, world + 1));
+            shard_local_kernel<<<(uint32_t)((work + 255) / 256), 256, 0, s>>>(locate ? l_off : nullptr, reinterpret_cast<const unsigned long long *>(l_counts),
+                                                                            n_total, padded, off32, cpad, const_cast<uint64_t *>(l_pos),
+                                                                            const_cast<uint32_t *>(l_seq), l_total, ss->text_base, (uint32_t)ss->first_seq,
+                                                                            per, world, my_cuts);
+        }
+        // ---- counts: the sums of slice q land on rank q
+        CU(cudaMallocAsync((void **)&m_counts, std::max<uint64_t>(per, 1) * 8, s));
+        if (per) {
+            if (world > 1) NC(api.ReduceScatter(cpad, m_counts, per, ncclUint64, ncclSum, ss->comm, s));
+            else CU(cudaMemcpyAsync(m_counts, cpad, per * 8, cudaMemcpyDeviceToDevice, s));
         }
         uint64_t m_total = 0;
-        if (mode == E2FM_MODE_LOCATE) {
-            const uint32_t blocks_n = (uint32_t)((std::max<uint64_t>(n_total, l_total) + 255) / 256);
-            uint32_t *nocc_all = (uint32_t *)ss->nocc_all.ensure((size_t)world * std::max<uint64_t>(n_total, 1) * 4, s);
-            uint32_t *nocc_mine = nocc_all + (uint64_t)ss->rank * n_total;
-            if (blocks_n)
-                shard_local_kernel<<<blocks_n, 256, 0, s>>>(l_off, n_total, nocc_mine, const_cast<uint64_t *>(l_pos), const_cast<uint32_t *>(l_seq),
-                                                            l_total, ss->text_base, (uint32_t)ss->first_seq);
-            // occurrences per pattern of every shard + every shard's total
-            unsigned long long *d_tot = (unsigned long long *)ss->totals.ensure((size_t)(world + 1) * 8, s);
-            ss->h_totals[ss->rank] = l_total;
-            CU(cudaMemcpyAsync(d_tot + ss->rank, ss->h_totals + ss->rank, 8, cudaMemcpyHostToDevice, s));
-            if (world > 1) {
-                NC(api.GroupStart());
-                if (n_total) NC(api.AllGather(nocc_mine, nocc_all, n_total, ncclUint32, ss->comm, s));
-                NC(api.AllGather(d_tot + ss->rank, d_tot, 1, ncclUint64, ss->comm, s));
-                NC(api.GroupEnd());
-            }
-            CU(cudaMemcpyAsync(ss->h_totals, d_tot, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
-            // merged CSR offsets
-            unsigned long long *sum = (unsigned long long *)ss->nocc_sum.ensure(std::max<uint64_t>(n_total, 1) * 8, s);
-            uint64_t *scratch = (uint64_t *)ss->scratch.ensure(scan_scratch_elems(std::max<uint64_t>(n_total, 1)) * 8, s);
-            CU(cudaMallocAsync((void **)&m_csr, (n_total + 1) * 8, s));
-            if (n_total) shard_sum_kernel<<<(uint32_t)((n_total + 255) / 256), 256, 0, s>>>(nocc_all, n_total, world, sum);
-            launch_scan_u64(sum, m_csr, n_total, scratch, s);
-            CU(cudaStreamSynchronize(s));                       // the shards' totals size the staging and merged arrays
-            uint64_t biggest = 0;
-            for (uint32_t r = 0; r < world; r++) { m_total += ss->h_totals[r]; biggest = std::max<uint64_t>(biggest, ss->h_totals[r]); }
-            CU(cudaMallocAsync((void **)&m_pos, std::max<uint64_t>(m_total, 1) * 8, s));
-            CU(cudaMallocAsync((void **)&m_seq, std::max<uint64_t>(m_total, 1) * 4, s));
-            CU(cudaMallocAsync((void **)&m_off, std::max<uint64_t>(m_total, 1) * 8, s));
-            // every shard's occurrence arrays, once, to every rank
+        if (locate) {
+            // ---- how many occurrences every rank holds for every slice
+            if (world > 1) NC(api.AllGather(my_cuts, cuts, world + 1, ncclUint64, ss->comm, s));
+            CU(cudaMemcpyAsync(ss->h_cuts, cuts, (size_t)world * (world + 1) * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));                       // the cuts size the staging and merged arrays
+            auto cut = [&](uint32_t r, uint32_t q) { return ss->h_cuts[(size_t)r * (world + 1) + q]; };
+            std::vector<uint64_t> rbase(world + 1, 0);
+            for (uint32_t r = 0; r < world; r++) rbase[r + 1] = rbase[r] + (cut(r, ss->rank + 1) - cut(r, ss->rank));
+            m_total = rbase[world];
+            uint32_t *roff = (uint32_t *)ss->roff.ensure((size_t)world * (per + 1) * 4 + 16, s);
             uint64_t *st_pos = (uint64_t *)ss->stage_pos.ensure(std::max<uint64_t>(m_total, 1) * 8, s);
             uint32_t *st_seq = (uint32_t *)ss->stage_seq.ensure(std::max<uint64_t>(m_total, 1) * 4, s);
             uint64_t *st_off = (uint64_t *)ss->stage_off.ensure(std::max<uint64_t>(m_total, 1) * 8, s);
-            std::vector<uint64_t> base(world + 1, 0);
-            for (uint32_t r = 0; r < world; r++) base[r + 1] = base[r] + ss->h_totals[r];
+            // ---- one grouped round: slice q of my CSR and of my occurrence arrays to rank q
             if (world > 1) {
                 NC(api.GroupStart());
+                for (uint32_t q = 0; q < world; q++) {
+                    uint64_t cnt_q = 0;
+                    const uint64_t lo_q = e2fm_shardset_slice(n_total, ss->world, (int)q, &cnt_q);
+                    const uint64_t a0 = cut(ss->rank, q), sz = cut(ss->rank, q + 1) - a0;
+                    NC(api.Send(off32 + lo_q, cnt_q + 1, ncclUint32, (int)q, ss->comm, s));
+                    if (sz) {
+                        NC(api.Send(l_pos + a0, sz, ncclUint64, (int)q, ss->comm, s));
+                        NC(api.Send(l_seq + a0, sz, ncclUint32, (int)q, ss->comm, s));
+                        NC(api.Send(l_seqoff + a0, sz, ncclUint64, (int)q, ss->comm, s));
+                    }
+                }
                 for (uint32_t r = 0; r < world; r++) {
-                    const uint64_t t = ss->h_totals[r];
-                    if (t == 0) continue;
-                    const bool me = (int)r == ss->rank;
-                    NC(api.Broadcast(me ? (const void *)l_pos : (const void *)(st_pos + base[r]), st_pos + base[r], t, ncclUint64, (int)r, ss->comm, s));
-                    NC(api.Broadcast(me ? (const void *)l_seq : (const void *)(st_seq + base[r]), st_seq + base[r], t, ncclUint32, (int)r, ss->comm, s));
-                    NC(api.Broadcast(me ? (const void *)l_seqoff : (const void *)(st_off + base[r]), st_off + base[r], t, ncclUint64, (int)r, ss->comm, s));
+                    const uint64_t sz = rbase[r + 1] - rbase[r];
+                    NC(api.Recv(roff + (size_t)r * (per + 1), mine + 1, ncclUint32, (int)r, ss->comm, s));
+                    if (sz) {
+                        NC(api.Recv(st_pos + rbase[r], sz, ncclUint64, (int)r, ss->comm, s));
+                        NC(api.Recv(st_seq + rbase[r], sz, ncclUint32, (int)r, ss->comm, s));
+                        NC(api.Recv(st_off + rbase[r], sz, ncclUint64, (int)r, ss->comm, s));
+                    }
                 }
                 NC(api.GroupEnd());
-            } else if (l_total) {
-                CU(cudaMemcpyAsync(st_pos, l_pos, l_total * 8, cudaMemcpyDeviceToDevice, s));
-                CU(cudaMemcpyAsync(st_seq, l_seq, l_total * 4, cudaMemcpyDeviceToDevice, s));
-                CU(cudaMemcpyAsync(st_off, l_seqoff, l_total * 8, cudaMemcpyDeviceToDevice, s));
             }
             CU(cudaEventRecord(ss->ev[3], s));
-            // per-pattern concatenation in shard order
-            uint32_t *before = (uint32_t *)ss->before.ensure(std::max<uint64_t>(n_total, 1) * 4, s);
-            CU(cudaMemsetAsync(before, 0, std::max<uint64_t>(n_total, 1) * 4, s));
-            uint64_t *roff = (uint64_t *)ss->roff.ensure((n_total + 1) * 8, s);
-            for (uint32_t r = 0; r < world && n_total; r++) {
-                if (ss->h_totals[r] == 0) continue;
-                const uint32_t *nocc_r = nocc_all + (uint64_t)r * n_total;
-                launch_ulen_widen(nocc_r, sum, n_total, s);
-                launch_scan_u64(sum, roff, n_total, scratch, s);
-                shard_merge_kernel<<<(uint32_t)((n_total + 255) / 256), 256, 0, s>>>(nocc_r, roff, m_csr, before, n_total, st_pos + base[r],
-                                                                                  st_seq + base[r], st_off + base[r], m_pos, m_seq, m_off);
+            // ---- per-pattern concatenation in shard order
+            CU(cudaMallocAsync((void **)&m_csr, (mine + 1) * 8, s));
+            CU(cudaMallocAsync((void **)&m_pos, std::max<uint64_t>(m_total, 1) * 8, s));
+            CU(cudaMallocAsync((void **)&m_seq, std::max<uint64_t>(m_total, 1) * 4, s));
+            CU(cudaMallocAsync((void **)&m_off, std::max<uint64_t>(m_total, 1) * 8, s));
+            MergeArgs ma;
+            memset(&ma, 0, sizeof(ma));
+            for (uint32_t r = 0; r < world; r++) {
+                if (world > 1) ma.src[r] = MergeSrc{roff + (size_t)r * (per + 1), st_pos + rbase[r], st_seq + rbase[r], st_off + rbase[r]};
+                else ma.src[r] = MergeSrc{off32, l_pos, l_seq, l_seqoff};
             }
+            shard_merge_kernel<<<(uint32_t)((mine + 1 + 255) / 256), 256, 0, s>>>(ma, world, mine, m_csr, m_pos, m_seq, m_off);
         } else {
             CU(cudaEventRecord(ss->ev[3], s));
         }
@@ -372,13 +379,13 @@ int e2fm_shardset_search(e2fm_shardset *ss, const uint8_t *slice, uint64_t n_tot
         CU(cudaGetLastError());
         e2fm_result_free(local);
         local = nullptr;
-        *out = e2fm_internal_make_result(ss->ix, n_total, m_total, mode == E2FM_MODE_LOCATE, m_counts, m_csr, m_pos, m_seq, m_off);
+        *out = e2fm_internal_make_result(ss->ix, mine, m_total, locate, m_counts, m_csr, m_pos, m_seq, m_off);
         if (!*out) throw std::bad_alloc();
         memset(ss->ms, 0, sizeof(ss->ms));
         cudaEventElapsedTime(&ss->ms[0], ss->ev[0], ss->ev[1]);     // H2D of the slice + all-gather of the batch
         cudaEventElapsedTime(&ss->ms[1], ss->ev[1], ss->ev[2]);     // local search
-        cudaEventElapsedTime(&ss->ms[2], ss->ev[2], ss->ev[3]);     // count all-reduce, occurrence-count all-gather, scan, broadcasts
-        cudaEventElapsedTime(&ss->ms[3], ss->ev[3], ss->ev[4]);     // merge kernels
+        cudaEventElapsedTime(&ss->ms[2], ss->ev[2], ss->ev[3]);     // count reduce-scatter, CSR cuts, the send/recv round
+        cudaEventElapsedTime(&ss->ms[3], ss->ev[3], ss->ev[4]);     // merge kernel
         cudaEventElapsedTime(&ss->ms[4], ss->ev[0], ss->ev[4]);     // whole step
     } catch (const NcclError &e) {
         if (local) e2fm_result_free(local);

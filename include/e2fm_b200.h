@@ -174,11 +174,12 @@ void e2fm_result_free(e2fm_result *r);
  *   e2fm_shardset_search      ONE exchange step for a fixed-length batch of n_total patterns: this rank supplies ITS slice of the
  *                             batch from host memory — patterns [lo, lo + count) with lo = e2fm_shardset_slice(n_total, world, rank,
  *                             &count), `packed` != 0: 2-bit packed (e2fm_packed_stride bytes each), else ASCII —, the slices are
- *                             all-gathered over NVLink, every rank searches the whole batch against its shard, counts are
- *                             all-reduced and the per-pattern occurrence lists concatenated in shard order (already sorted,
- *                             EFMIndex.cpp:2291). EVERY rank gets the whole merged result: the same arrays, bit for bit, as the
- *                             unsharded index gives (e2fm_result_fetch / _fetch_compact / _free as usual).
- *   e2fm_shardset_last_ms     [0] H2D + batch all-gather, [1] local search, [2] NCCL merge traffic, [3] merge kernels, [4] whole step
+ *                             all-gathered over NVLink, every rank searches the whole batch against its shard, and the answers for
+ *                             slice q travel to rank q: counts by ncclReduceScatter, occurrence lists by one grouped ncclSend/ncclRecv
+ *                             round, concatenated per pattern in shard order (already sorted, EFMIndex.cpp:2291). The result holds
+ *                             THIS RANK'S `count` patterns: the same arrays, bit for bit, as the unsharded index gives for them
+ *                             (e2fm_result_fetch / _fetch_compact / _free as usual).
+ *   e2fm_shardset_last_ms     [0] H2D + batch all-gather, [1] local search, [2] NCCL traffic of the merge, [3] merge kernel, [4] whole step
  * All ranks must call create / search / destroy in the same order. */
 int e2fm_shardset_unique_id(uint8_t id_out[128]);
 int e2fm_shardset_create(e2fm_index *ix, const uint8_t id[128], int rank, int world, uint64_t first_sequence, uint64_t text_base,
@@ -201,7 +202,8 @@ int e2fm_last_batch_ms(const e2fm_index *ix, float out[8]);
  * [5] kernels launched by the batch, [6] located occurrences, [7] gathers issued by the walk / resolve kernel,
  * [8] rows streamed by firstcheck_kernel (2 bytes each, read twice), [9] chunks redone through the windowed path,
  * [10] patterns the seed search handed to the generic path, [11] 1 when the batch went through the seed search,
- * [12] pipeline stages of e2fm_search_hits (0: the call ran unpipelined), [13..15] reserved */
+ * [12] pipeline stages of e2fm_search_hits (0: the call ran unpipelined), [13] why its pipeline gave up (1 row tasks, 2 occurrences,
+ *      4 duplicates, 8 a pattern for the generic path, 16 output capacity), [14..15] reserved */
 int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_CHUNK 2         /* patterns per internal chunk (0 = default 2^22) */
 #define E2FM_OPT_WINDOW 3        /* row tasks per walk launch (0 = default 2^26) */
