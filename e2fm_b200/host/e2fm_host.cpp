@@ -158,42 +158,65 @@ CompactBatchResult EFMIndex::searchBatchCompact(const std::vector<std::string> &
     bool packed = n > 0 && len > 0 && len <= 128;
     if (packed) {
         // one pass over the strings on all host threads: 2 bits per base into page-locked memory; a different length or a byte
-        // outside A C G T sends the batch through the ASCII entry point instead
+        // outside A C G T sends the batch through the ASCII entry point instead. The strings live all over the heap: the data of
+        // the ones a few places ahead is prefetched while the current one is packed.
+        static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, sizeof(v)); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
         const uint32_t stride = e2fm_packed_stride(len);
         uint8_t *dst = (uint8_t *)stageIn_.ensure(n * stride);
         std::atomic<bool> ok(true);
         parallel_for(n, [&](uint64_t a, uint64_t b) {
-            bool fine = true;
-            for (uint64_t i = a; i < b && fine; i++) {
+            uint32_t bad = 0;
+            for (uint64_t i = a; i < b; i++) {
+                if (i + 8 < b) __builtin_prefetch(patterns[i + 8].data());
                 const std::string &p = patterns[i];
-                if (p.size() != len) { fine = false; break; }
+                if (p.size() != len) { bad = 4; break; }
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.data());
                 uint64_t *w = reinterpret_cast<uint64_t *>(dst + i * stride);
                 for (uint32_t q = 0; q < stride / 8; q++) {
                     uint64_t cur = 0;
                     const uint32_t end = std::min<uint32_t>(len, (q + 1) * 32);
                     for (uint32_t j = q * 32, sh = 0; j < end; j++, sh += 2) {
-                        uint64_t c;
-                        switch (p[j]) {
-                            case 'A': c = 0; break;
-                            case 'C': c = 1; break;
-                            case 'G': c = 2; break;
-                            case 'T': c = 3; break;
-                            default: c = 0; fine = false;
-                        }
-                        cur |= c << sh;
+                        const uint32_t c = lut.v[src[j]];
+                        bad |= c;
+                        cur |= (uint64_t)(c & 3u) << sh;
                     }
                     w[q] = cur;
                 }
             }
-            if (!fine) ok.store(false);
+            if (bad & 4u) ok.store(false);
         });
         packed = ok.load();
         if (packed) {
             out.packMs = now_ms() - t0;
-            if (e2fm_search_batch_packed(handle_, dst, n, len, (int)mode, nullptr, &r) != E2FM_OK) {
-                r = nullptr;      // this batch shape is not for the seed search (short patterns, no seed table): ASCII below
-                packed = false;
+            // host to host in one pipelined call (H2D, search and D2H overlap stage by stage)
+            e2fm_hits h;
+            memset(&h, 0, sizeof(h));
+            uint64_t cap = mode == Mode::Locate ? std::max<uint64_t>(lastTotal_ + lastTotal_ / 8, n + n / 4) + 4096 : 0;
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if (mode == Mode::Count) h.counts = (uint32_t *)stageCounts_.ensure((n + 1) * 4);
+                else {
+                    h.occ_offsets = (uint32_t *)stageCsr_.ensure((n + 1) * 4);
+                    h.seq_index = (uint32_t *)stageSeq_.ensure((cap + 1) * 4);
+                    h.seq_offset = (uint32_t *)stageOff_.ensure((cap + 1) * 4);
+                    h.capacity = cap;
+                }
+                const int rc = e2fm_search_hits(handle_, dst, n, len, 1, (int)mode, &h);
+                if (rc == E2FM_OK) {
+                    out.packed = true;
+                    out.total = h.total;
+                    lastTotal_ = h.total;
+                    out.counts = h.counts;
+                    out.offsets = h.occ_offsets;
+                    out.sequenceIndex = h.seq_index;
+                    out.sequenceOffset = h.seq_offset;
+                    e2fm_last_batch_ms(handle_, out.deviceMs);
+                    out.elapsedMs = now_ms() - t0;
+                    return out;
+                }
+                if (rc == E2FM_ERR_ARG && mode == Mode::Locate && h.total > cap) { cap = h.total + 1024; continue; }   // more occurrences than room
+                break;            // this batch shape is not for the seed search (short patterns, no seed table): ASCII below
             }
+            packed = false;
         }
     }
     if (!packed) {

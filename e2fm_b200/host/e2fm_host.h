@@ -126,6 +126,7 @@ protected:
         void *ensure(size_t need);
         void release();
     } stageIn_, stageOffs_, stageCounts_, stageCsr_, stageSeq_, stageOff_;
+    uint64_t lastTotal_ = 0;                    // occurrences of the previous batch: sizes the next one's result buffers
 };
 
 // FMCollection.h:65-95 (the part that load + search use)

@@ -119,3 +119,71 @@ def test_sharded_merge_equals_unsharded_reference(oracle_mod, locate):
         assert np.array_equal(seq, np.array(want_seq, dtype=np.int64))
         assert np.array_equal(off, np.array(want_off, dtype=np.int64))
     assert sum(int(res["counts"][i]) for i in got[0][1]) >= 20
+
+
+def test_shardset_slices_cover_the_batch_once():
+    """e2fm_shardset_slice: contiguous slices of ceil(n / world) patterns, every pattern in exactly one (host-only call)"""
+    from e2fm_b200 import capi
+    for n in (0, 1, 7, 8, 9, 1000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            seen = 0
+            for r in range(world):
+                lo, cnt = capi.shardset_slice(n, world, r)
+                assert lo == min(n, -(-n // world) * r) and lo == seen
+                seen += cnt
+            assert seen == n
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_shardset_merge_model(world, oracle_mod):
+    """The arithmetic of shard_merge_kernel (csrc/shardset.cu) on the CPU: rank q receives, from every shard r, the shard's CSR
+    offsets of slice q and the occurrence triples between its first and last offset; the merged offset of a pattern is the SUM over
+    the shards of (offset - offset of the slice's first pattern), shard r's occurrences follow those of shards 0..r-1. Fed with the
+    oracle's answers on the golden shards (incl. an EMPTY shard when world = 3 and a sequence index of -1), the result must equal
+    the reference on the unsharded collection."""
+    from conftest import read_patterns
+    key = open(os.path.join(GOLDEN, "key.bin"), "rb").read()
+    res = oracle_mod.read_result_file(os.path.join(GOLDEN, "col3_k4.res"))
+    pats = read_patterns(os.path.join(GOLDEN, "col3_k4.pat"))
+    keep = [i for i, p in enumerate(pats) if len(p) in (12, 20)]
+    if world == 1:
+        shards = [(os.path.join(GOLDEN, "col3_k4.efm"), 0, 0)]
+    else:
+        plan = sharded.plan_shards([30011, 20003, 9001], 2, 4)
+        shards = [(os.path.join(GOLDEN, f"col3_k4_shard{r}of2.efm"), plan[r][0], plan[r][2]) for r in range(2)]
+    local = []
+    for path, first_seq, text_base in shards:
+        orc = oracle_mod.OracleIndex(open(path, "rb").read(), key)
+        off, pos, seq, so = [0], [], [], []
+        for i in keep:
+            _, p = orc.search(pats[i], True)
+            for x in p:
+                s, o = orc.map_position(int(x))
+                pos.append(int(x) + text_base); seq.append(s + first_seq if s >= 0 else -1); so.append(o)
+            off.append(len(pos))
+        orc.close()
+        local.append((np.array(off), np.array(pos, dtype=np.int64), np.array(seq, dtype=np.int64), np.array(so, dtype=np.int64)))
+    if world == 3:                                   # a shard without a single occurrence
+        local.append((np.zeros(len(keep) + 1, dtype=np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64)))
+        local[0][2][:1] = -1                          # and a sequence index the reference left at -1 travels unchanged
+    n = len(keep)
+    per = -(-n // world)
+    for q in range(world):
+        lo, hi = min(n, per * q), min(n, per * (q + 1))
+        recv = [(off[lo:hi + 1], pos[off[lo]:off[hi]], seq[off[lo]:off[hi]], so[off[lo]:off[hi]]) for off, pos, seq, so in local]
+        m_csr = sum(o - o[0] for o, _, _, _ in recv)
+        m_pos = np.zeros(int(m_csr[-1]), dtype=np.int64); m_seq = m_pos.copy(); m_so = m_pos.copy()
+        for i in range(hi - lo):
+            dst = int(m_csr[i])
+            for o, p_, s_, f_ in recv:
+                b, c = int(o[i] - o[0]), int(o[i + 1] - o[i])
+                m_pos[dst:dst + c], m_seq[dst:dst + c], m_so[dst:dst + c] = p_[b:b + c], s_[b:b + c], f_[b:b + c]
+                dst += c
+        want_pos = np.concatenate([res["positions"][int(res["pos_offsets"][i]):int(res["pos_offsets"][i + 1])] for i in keep[lo:hi]] or [np.zeros(0)])
+        want_seq = np.concatenate([res["seq"][int(res["pos_offsets"][i]):int(res["pos_offsets"][i + 1])] for i in keep[lo:hi]] or [np.zeros(0)])
+        assert np.array_equal(np.diff(m_csr), [int(res["pos_offsets"][i + 1] - res["pos_offsets"][i]) for i in keep[lo:hi]])
+        assert np.array_equal(m_pos, want_pos.astype(np.int64))
+        if not (world == 3 and q == 0):
+            assert np.array_equal(m_seq, want_seq.astype(np.int64))
+        else:
+            assert m_seq[0] == -1 and np.array_equal(m_seq[1:], want_seq.astype(np.int64)[1:])
