@@ -175,7 +175,7 @@ struct e2fm_index {
     struct Slot { void *p = nullptr; size_t bytes = 0; } ws[40];
     HitsStageInfo *h_stage_info = nullptr;   // pinned, written by hits_tail_kernel
     size_t h_stage_cap = 0;
-    uint64_t hits_stage_patterns = 1u << 19;   // patterns per pipeline stage of e2fm_search_hits
+    uint64_t hits_stage_patterns = 1u << 20;   // patterns per (full) pipeline stage of e2fm_search_hits
 };
 
 struct e2fm_result {
@@ -1011,7 +1011,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     tm.phases = false;
     const int whole = tm.begin(6);
     const uint64_t stage = std::max<uint64_t>(1, std::min<uint64_t>(ix->hits_stage_patterns, n));
-    const uint64_t S = (n + stage - 1) / stage;
+    const uint64_t S_max = (n + stage - 1) / stage + 24;      // stages (the tapered tail adds a few): sizes the per-stage arrays
 
     WsBuf<uint8_t> d_in(ix, WS_BYTES, b.total_bytes + 16, s);
     b.d_bytes = d_in.p;
@@ -1029,10 +1029,10 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     WsBuf<uint32_t> clist(ix, WS_CLIST, stage, s);
     const uint64_t task_cap = (uint64_t)(ix->seed_tasks_per_pattern * (double)stage) + 4096;
     WsBuf<uint2> tasks(ix, WS_TASKS, task_cap, s);
-    WsBuf<unsigned long long> task_ctr(ix, WS_CHUNK_CTR, S, s);
-    task_ctr.zero(S);
-    WsBuf<unsigned long long> stage_stats(ix, WS_STAGE_STATS, S * ST_N, s);
-    stage_stats.zero(S * ST_N);
+    WsBuf<unsigned long long> task_ctr(ix, WS_CHUNK_CTR, S_max, s);
+    task_ctr.zero(S_max);
+    WsBuf<unsigned long long> stage_stats(ix, WS_STAGE_STATS, S_max * ST_N, s);
+    stage_stats.zero(S_max * ST_N);
     WsBuf<unsigned long long> run(ix, WS_RUN, 2, s);
     run.zero(2);
     WsBuf<uint32_t> cnt32(ix, WS_OUT_CNT, n, s);
@@ -1053,42 +1053,74 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         seq32.alloc(out_cap + 1);
         soff32.alloc(out_cap + 1);
     }
-    if (ix->h_stage_cap < S) {
+    if (ix->h_stage_cap < S_max) {
         if (ix->h_stage_info) CK(cudaFreeHost(ix->h_stage_info));
         ix->h_stage_info = nullptr;
         ix->h_stage_cap = 0;
-        CK(cudaHostAlloc((void **)&ix->h_stage_info, (S + 8) * sizeof(HitsStageInfo), cudaHostAllocDefault));
-        ix->h_stage_cap = S + 8;
+        CK(cudaHostAlloc((void **)&ix->h_stage_info, (S_max + 8) * sizeof(HitsStageInfo), cudaHostAllocDefault));
+        ix->h_stage_cap = S_max + 8;
     }
     HitsStageInfo *info = ix->h_stage_info;
-    memset(info, 0, S * sizeof(HitsStageInfo));
+    memset(info, 0, S_max * sizeof(HitsStageInfo));
 
-    const Staging sg = stage_batch(ix, b, stage, tm);          // every H2D copy queued up front, one event per stage
+    // stage sizes: equal stages, the last one cut into 1/2, 1/4, 1/4: what the call takes is the H2D time of the whole batch plus
+    // search and D2H of the LAST stage, so the last stages are small; more than that does not pay (every stage costs ~40 us of
+    // launch latencies on the compute stream, measured: profiles/exp/e2e_stages.py)
+    Staging sg;
+    sg.bounds.assign(1, 0);
+    while (sg.bounds.back() < n) {
+        const uint64_t left = n - sg.bounds.back();
+        if (left > stage) { sg.bounds.push_back(sg.bounds.back() + stage); continue; }
+        if (left >= 65536 && S_max > 1) {
+            sg.bounds.push_back(sg.bounds.back() + left / 2);
+            sg.bounds.push_back(sg.bounds.back() + left / 4);
+        }
+        sg.bounds.push_back(n);
+    }
+    const uint64_t S = sg.bounds.size() - 1;
+    {
+        cudaEvent_t ready = ix->events.get(false);
+        CK(cudaEventRecord(ready, s));                       // the device buffers were allocated in order on s
+        CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
+        const int hh = tm.begin(0, ix->h2d_stream);
+        for (uint64_t c = 0; c < S; c++) {                   // every H2D copy queued up front, one event per stage
+            const uint64_t lo = sg.bounds[c] * b.unit(), hi = sg.bounds[c + 1] * b.unit();
+            CK(cudaMemcpyAsync(d_in.p + lo, h_in + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
+            cudaEvent_t e = ix->events.get(false);
+            sg.h2d_ev.push_back(e);
+            CK(cudaEventRecord(e, ix->h2d_stream));
+        }
+        tm.end(hh, ix->h2d_stream);
+    }
     std::vector<cudaEvent_t> done(S);
+    // E2FM_HITS_TRACE=1: per-stage timeline (CUDA events on the three streams) on stderr
+    static const bool trace = getenv("E2FM_HITS_TRACE") && atoi(getenv("E2FM_HITS_TRACE")) != 0;
+    std::vector<cudaEvent_t> tr_begin(trace ? S : 0), tr_search(trace ? S : 0), tr_out(trace ? S : 0);
+    cudaEvent_t tr_zero = nullptr;
+    if (trace) { tr_zero = ix->events.get(true); CK(cudaEventRecord(tr_zero, s)); }
     uint64_t launches = 0;
     auto enqueue = [&](uint64_t c) {
         const uint64_t first = sg.bounds[c];
         const uint32_t cnt = (uint32_t)(sg.bounds[c + 1] - first);
         unsigned long long *st = stage_stats.p + c * ST_N;
         CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
+        if (trace) { tr_begin[c] = ix->events.get(true); CK(cudaEventRecord(tr_begin[c], s)); }
         if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
         SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st};
         launch_seed_lookup(sa, nw, ix->n_sm, s);
         launch_seed_verify(sa, nw, ix->n_sm, s);
         launches += 2;
+        if (trace) { tr_search[c] = ix->events.get(true); CK(cudaEventRecord(tr_search[c], s)); }
         if (locate) {
-            launch_scan_u64(counts.p + first, st_off.p, cnt, scratch.p, s);
-            CK(cudaMemsetAsync(cursor.p, 0, (size_t)cnt * 4, s));
+            launch_hits_scan(counts.p + first, cnt, st_off.p, cursor.p, reinterpret_cast<unsigned long long *>(scratch.p), s);
             launch_hits_scatter(res_pat.p, res_pos.p, st, res_cap, first, st_off.p, cursor.p, st_pos.p, ix->n_sm, s);
-            launch_hits_sort(st_pos.p, st_off.p, cnt, res_cap, big_list.p, cursor.p, st, ix->n_sm, s);
-            launches += 6;
+            launches += 3;
         }
-        launch_hits_finalize(dix, counts.p, first, cnt, locate ? st_off.p : nullptr, st_pos.p, run.p, out_cap, res_cap,
-                             cnt32.p, off32.p, seq32.p, soff32.p, ix->n_sm, s);
-        launch_hits_tail(locate ? st_off.p : nullptr, cnt, st, task_ctr.p + c, task_cap, res_cap, out_cap, run.p,
-                         locate && c + 1 == S ? off32.p + n : nullptr, info + c, s);
+        HitsOut ho{counts.p, first, cnt, locate ? st_off.p : nullptr, st_pos.p, run.p, out_cap, res_cap, task_cap, cnt32.p, off32.p, seq32.p, soff32.p,
+                   big_list.p, locate && c + 1 == S ? off32.p + n : nullptr, st, task_ctr.p + c, info + c};
+        launch_hits_finish(dix, ho, ix->n_sm, s);
         launches += 2;
-        done[c] = ix->events.get(false);
+        done[c] = ix->events.get(trace);
         CK(cudaEventRecord(done[c], s));
     };
     bool trouble = false;
@@ -1109,6 +1141,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
             if (tot && hits->seq_offset) CK(cudaMemcpyAsync(hits->seq_offset + base, soff32.p + base, tot * 4, cudaMemcpyDeviceToHost, ix->d2h_stream));
             total = base + tot;
         }
+        if (trace) { tr_out[c] = ix->events.get(true); CK(cudaEventRecord(tr_out[c], ix->d2h_stream)); }
     };
     const uint64_t ahead = 2;                                  // stages queued on the compute stream beyond the one being drained
     for (uint64_t c = 0; c < S && !trouble; c++) {
@@ -1121,6 +1154,17 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     CK(cudaStreamSynchronize(ix->d2h_stream));
     CK(cudaStreamSynchronize(ix->h2d_stream));
     CK(cudaGetLastError());
+    if (trace && !trouble) {
+        for (uint64_t c = 0; c < S; c++) {
+            float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+            cudaEventElapsedTime(&t0, tr_zero, tr_begin[c]);
+            cudaEventElapsedTime(&t1, tr_zero, tr_search[c]);
+            cudaEventElapsedTime(&t2, tr_zero, done[c]);
+            cudaEventElapsedTime(&t3, tr_zero, tr_out[c]);
+            fprintf(stderr, "[hits] stage %2llu: %8llu patterns  search starts %7.3f  seed kernels done %7.3f  results done %7.3f  D2H done %7.3f ms\n",
+                    (unsigned long long)c, (unsigned long long)(sg.bounds[c + 1] - sg.bounds[c]), t0, t1, t2, t3);
+        }
+    }
     // what the stages report: trouble flags (count mode reads them only now), densities for the next batch's stores
     uint64_t tasks_sum = 0, worst_tasks = 0;
     for (uint64_t c = 0; c < S; c++) {
@@ -1705,7 +1749,7 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
             return E2FM_OK;
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;
-        case E2FM_OPT_HITS_STAGE: ix->hits_stage_patterns = value ? value : (1u << 19); return E2FM_OK;
+        case E2FM_OPT_HITS_STAGE: ix->hits_stage_patterns = value ? value : (1u << 20); return E2FM_OK;
         case E2FM_OPT_PHASE_TIMERS: ix->phase_timers = (int)std::min<uint64_t>(value, 2); return E2FM_OK;
         case E2FM_OPT_SEED:
             if (value && !(ix->dix.seed_tab && ix->dix.packed_code)) return fail(E2FM_ERR_UNSUPPORTED, "the seed table was not built for this index");

@@ -86,12 +86,22 @@ struct Sector { uint4 lo, hi; };
 // One aligned 32-byte sector in ONE load instruction (LDG.E.256, sm_100): measured on a B200 (profiles/exp/gather_variants.py),
 // random sectors read with two 16-byte loads come in at 37 G sectors/s, with one 32-byte load at 47 G/s — the same rate as 8-byte
 // loads, i.e. the row-activation limit of the HBM.
+// Without a hint the L2 fetches the whole 128-byte line of a missing sector from DRAM (127 B of DRAM traffic per random gather,
+// measured); L2::64B halves that. The gather RATE of the microbenchmark does not change (it is bound by row activations), but a
+// kernel that mixes gathers with streaming traffic gets its bandwidth back.
 __device__ __forceinline__ Sector ld_sector(const uint4 *p) {
     Sector r;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
                  : "l"(p));
     return r;
+}
+
+// a lone 4-byte gather with the same hint (sa[])
+__device__ __forceinline__ uint32_t ld_gather_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ Sector load_sector(const DevIndex &ix, uint32_t c, uint32_t blk) {

@@ -158,7 +158,8 @@ void parse_index_header(const uint8_t *file, size_t size, const uint8_t key64[64
         throw std::runtime_error("corrupt index: bad geometry");
     if (c_start >= size || mrb_start > size || sbpos_start >= size || bpos_start >= size || fasta_start > size)
         throw std::runtime_error("corrupt index: bookmark outside the file");
-    if (img.n >= (1ull << 32)) throw std::runtime_error("unsupported index: super-text longer than 2^32-1 rows per device shard");
+    // rows are 32-bit on the device and bit 31 of an interval length flags a long wildcard interval (search.cu, IV_LONG)
+    if (img.n >= (1ull << 31)) throw std::runtime_error("unsupported index: super-text longer than 2^31-1 rows per device shard");
     img.B = (img.n + img.b_size - 1) / img.b_size;
     img.S = (img.n + img.sb_size - 1) / img.sb_size;
 

@@ -1291,6 +1291,7 @@ void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_
 // `variant` picks the load instruction (what a gather costs in DRAM traffic depends on it, profiles/exp/):
 //   0 ld.global.nc.u64 (__ldg)   1 ld.global.u64   2 ld.global.cg.u64 (no L1)   3 ld.global.nc.v8.u32 (one 32-byte load)
 //   4 two ld.global.nc.v4.u32 of one sector   5 ld.global.nc.L2::64B.u64   6 ld.global.nc.L1::no_allocate.u64   7 ld.global.nc.L2::128B.u64
+//   8 ld.global.nc.L2::64B.v8.u32 (ld_sector: what the search kernels use)
 template <int V>
 __device__ __forceinline__ unsigned long long gather_load(const uint64_t *p) {
     unsigned long long v = 0;
@@ -1310,6 +1311,10 @@ __device__ __forceinline__ unsigned long long gather_load(const uint64_t *p) {
     } else if (V == 5) asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
     else if (V == 6) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
     else if (V == 7) asm volatile("ld.global.nc.L2::128B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (V == 8) {
+        const Sector s = ld_sector(reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)31));
+        v = (unsigned long long)(s.lo.x ^ s.lo.y ^ s.lo.z ^ s.lo.w) | ((unsigned long long)(s.hi.x ^ s.hi.y ^ s.hi.z ^ s.hi.w) << 32);
+    }
     return v;
 }
 
@@ -1338,6 +1343,7 @@ void launch_gather_bench(const uint64_t *buf, uint64_t n_words, uint64_t n_threa
         case 5: gather_bench_kernel<5><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
         case 6: gather_bench_kernel<6><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
         case 7: gather_bench_kernel<7><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
+        case 8: gather_bench_kernel<8><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
         default: gather_bench_kernel<0><<<blocks, 256, 0, s>>>(buf, n_words, per_thread, sink); break;
     }
 }

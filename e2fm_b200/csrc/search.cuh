@@ -145,13 +145,24 @@ struct HitsStageInfo { unsigned long long base, total, flags, tasks; };   // wri
 enum : unsigned long long { HITS_TASK_OVF = 1, HITS_RES_OVF = 2, HITS_DUPS = 4, HITS_COMPLEX = 8, HITS_OUT_OVF = 16 };
 void launch_hits_scatter(const uint32_t *res_pat, const uint64_t *res_pos, const unsigned long long *stats, uint64_t res_cap, uint64_t first,
                          const uint64_t *off, uint32_t *cursor, uint64_t *positions, int n_sm, cudaStream_t s);
-void launch_hits_sort(uint64_t *positions, const uint64_t *off, uint32_t cnt, uint64_t res_cap, uint32_t *big_list, uint32_t *ulen,
-                      unsigned long long *stats, int n_sm, cudaStream_t s);
-void launch_hits_finalize(const DevIndex &ix, const unsigned long long *counts, uint64_t first, uint32_t cnt, const uint64_t *off,
-                          const uint64_t *positions, const unsigned long long *run_total, uint64_t out_cap, uint64_t res_cap, uint32_t *cnt32,
-                          uint32_t *off32, uint32_t *seq32, uint32_t *soff32, int n_sm, cudaStream_t s);
-void launch_hits_tail(const uint64_t *off, uint32_t cnt, const unsigned long long *stats, const unsigned long long *task_count, uint64_t task_cap,
-                      uint64_t res_cap, uint64_t out_cap, unsigned long long *run_total, uint32_t *off32_end, HitsStageInfo *info, cudaStream_t s);
+// exclusive scan of the stage's counts into its CSR (off[cnt] = total), scatter cursors cleared; scratch: cnt / 2048 + 1 u64
+void launch_hits_scan(const unsigned long long *counts, uint32_t cnt, uint64_t *off, uint32_t *cursor, unsigned long long *scratch, cudaStream_t s);
+struct HitsOut {                                    // where the stage's answers go (batch-wide arrays) and what bounds them
+    const unsigned long long *counts;               // [batch n]
+    uint64_t first;                                 // first pattern of the stage
+    uint32_t cnt;                                   // its patterns
+    const uint64_t *off;                            // [cnt + 1] stage-local CSR (nullptr: count mode)
+    uint64_t *positions;                            // [off[cnt]] stage-local, scattered
+    unsigned long long *run_total;                  // occurrences of the stages before this one
+    unsigned long long out_cap, res_cap, task_cap;
+    uint32_t *cnt32, *off32, *seq32, *soff32;       // batch-wide 32-bit outputs
+    uint32_t *big_list, *off32_end;                 // long segments of the stage; where the batch's total goes (last stage) or nullptr
+    unsigned long long *stats;                      // the stage's statistics block
+    const unsigned long long *task_count;
+    HitsStageInfo *info;                            // page-locked host memory
+};
+// per-pattern sort + (sequence, offset) mapping + 32-bit offsets and counts, then the long segments and the stage's report
+void launch_hits_finish(const DevIndex &ix, const HitsOut &o, int n_sm, cudaStream_t s);
 
 // EFMIndex::extractSnippet (EFMIndex.cpp:2367): the k symbols of super-characters [st_from, st_from + count) from the dense text[] table
 void launch_extract(const DevIndex &ix, uint64_t st_from, uint64_t count, uint8_t *out, cudaStream_t s);

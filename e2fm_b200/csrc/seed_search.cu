@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
         for (int u = 0; u < U; u++) {                  // sa[] gathers and pattern loads of the thread's tasks in flight together
             pos[u] = 0;
             if (ok[u]) {
-                pos[u] = __ldg(ix.sa + tk[u].x);
+                pos[u] = ld_gather_u32(ix.sa + tk[u].x);
                 pat[u].load(a.packed + (a.first + tk[u].y / k) * NW);
             }
         }

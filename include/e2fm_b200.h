@@ -217,7 +217,8 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_SEED 9          /* 1 (default when the seed table was built): fixed-length batches whose every shift holds a whole seed
                                     go through seed_search_kernel (seed table + dense tables); 0: always the generic backward search.
                                     Same results either way. */
-#define E2FM_OPT_HITS_STAGE 10   /* patterns per pipeline stage of e2fm_search_hits (0 = default 2^19) */
+#define E2FM_OPT_HITS_STAGE 10   /* patterns per full pipeline stage of e2fm_search_hits (0 = default 2^20); the last stage of a batch is cut
+                                    into 1/2, 1/4, 1/4 */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).
@@ -234,7 +235,8 @@ int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, ui
  * L2); returns 10^9 gathers per second (best of 3). Every gather moves one 32-byte sector over the memory system. */
 int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s);
 /* the same with the load instruction chosen: 0 ld.global.nc.u64 (the default above), 1 ld.global.u64, 2 ld.global.cg.u64, 3 one 32-byte
- * ld.global.nc.v8.u32, 4 two 16-byte loads of one sector, 5 / 7 ld.global.nc.L2::64B / ::128B.u64, 6 ld.global.nc.L1::no_allocate.u64 */
+ * ld.global.nc.v8.u32, 4 two 16-byte loads of one sector, 5 / 7 ld.global.nc.L2::64B / ::128B.u64, 6 ld.global.nc.L1::no_allocate.u64,
+ * 8 one 32-byte ld.global.nc.L2::64B.v8.u32 (what the search kernels use for rank, seed and text sectors) */
 int e2fm_debug_gather_bench_ex(int device, uint64_t buffer_bytes, uint64_t n_gathers, int variant, double *giga_gathers_per_s);
 /* raw Salsa20/20 blocks [first_block, first_block + n_blocks) for a 32-byte key */
 int e2fm_debug_salsa20(int device, const uint8_t key32[32], uint64_t nonce, uint64_t first_block,

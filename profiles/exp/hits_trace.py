@@ -1,0 +1,32 @@
+"""Per-stage timeline of e2fm_search_hits (E2FM_HITS_TRACE=1) on a bench workload. Usage: python profiles/exp/hits_trace.py [workload] [stage]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+os.environ["E2FM_HITS_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from e2fm_b200 import capi, synth  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "mid50"
+prep = bench.prepare(wl, 0)
+w = prep["w"]
+n, L = w["n_patterns"], w["pat_len"]
+ix = capi.DeviceIndex(open(prep["efm"], "rb").read(), synth.test_key(), 0)
+if len(sys.argv) > 2:
+    ix.set_option(capi.OPT_HITS_STAGE, int(sys.argv[2]))
+pats = np.ascontiguousarray(bench.load_patterns(prep)[:n])
+stride = capi.packed_stride(L)
+h_in = capi.PinnedArray((n, stride), np.uint8)
+capi.pack_patterns(pats, h_in.array.reshape(-1))
+cap = 2 * n + 4096
+h_off, h_seq, h_so = (capi.PinnedArray(s, np.uint32) for s in (n + 1, cap, cap))
+for rep in range(4):
+    print(f"--- call {rep}", file=sys.stderr, flush=True)
+    t0 = time.perf_counter()
+    ix.search_hits(h_in.array.reshape(-1), n, L, True, True, None, h_off.array, h_seq.array, h_so.array)
+    print(f"--- wall {1e3 * (time.perf_counter() - t0):.3f} ms", file=sys.stderr, flush=True)
+ix.close()

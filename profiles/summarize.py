@@ -65,16 +65,16 @@ def main():
                 except Exception:
                     pass
         print("wrote", name + ".txt")
-    for lc in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "launches_*.csv"))):
+    for lc in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"launches_*_{tag}.csv"))):
         rows = [r for r in csv.reader(open(lc)) if len(r) > 10]
         hdr = rows[0]
-        ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-        name = os.path.basename(lc)[:-4] + f"_{tag}.txt"
+        ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        name = os.path.basename(lc)[:-4] + ".txt"
         tot = {}
         order = []
         for r in rows[1:]:
             k = r[ki].split("(")[0]
-            v = float(r[vi].replace(",", "")) / 1e3
+            v = float(r[vi].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1e-3)
             if k not in tot:
                 tot[k] = [0, 0.0]
                 order.append(k)
@@ -88,6 +88,8 @@ def main():
             for k in order:
                 f.write(f"{k[:80]:80s} {tot[k][0]:8d} {tot[k][1]:12.1f} {100 * tot[k][1] / allus:6.1f}%\n")
         print("wrote", name)
+    if not traffic:
+        return
     with open(os.path.join(OUT, f"traffic_{tag}.json"), "w") as f:
         json.dump(traffic, f, indent=1)
 

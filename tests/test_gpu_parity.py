@@ -731,7 +731,7 @@ def test_search_hits_matches_reference(gpu, golden, key64, name, stage):
                     stages = dev.last_batch_counters()["hits_stages"]
                     piped_any |= stages > 0
                     if stage and stages:
-                        assert stages == -(-len(idxs) // stage)
+                        assert stages >= -(-len(idxs) // stage)      # full stages, then a tapered tail
                     if locate:
                         assert total == len(want["seq"]), what
                         assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)), what
