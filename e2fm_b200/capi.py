@@ -54,7 +54,7 @@ class Info(C.Structure):
                 ("initial_n", C.c_uint64), ("device_bytes", C.c_uint64), ("k", C.c_uint32), ("n_symbols", C.c_uint32),
                 ("compact_alphabet", C.c_uint32), ("marked_rows_percentage", C.c_uint32), ("marking_rate", C.c_uint32),
                 ("rank_block", C.c_uint32), ("quirks", C.c_uint32), ("dense", C.c_uint32), ("seed_chars", C.c_uint32),
-                ("seed_table_mb", C.c_uint32), ("load_ms", C.c_float * 8)]
+                ("seed_table_mb", C.c_uint32), ("vrec_mb", C.c_uint32), ("reserved", C.c_uint32), ("load_ms", C.c_float * 8)]
 
 
 class Hits(C.Structure):

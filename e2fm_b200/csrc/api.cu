@@ -155,7 +155,7 @@ struct e2fm_index {
     DevIndex dix{};
     std::vector<void *> owned;  // device allocations that live as long as the index
     uint64_t device_bytes = 0;
-    uint64_t seed_bytes = 0;
+    uint64_t seed_bytes = 0, vrec_bytes = 0;
     uint64_t max_seq_len = 0;   // longest span between terminators (a 32-bit offset in the sequence fits when it is below 2^32)
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
@@ -513,6 +513,20 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
                 d.seed_chars = j;
                 ix->seed_bytes = n_sectors * 32;
             }
+        }
+    }
+    // ---- verification records for the seed search: 32 bytes per row, when HBM allows (E2FM_VREC=0: never)
+    d.vrec = nullptr;
+    if (d.seed_tab && sa && text && !(getenv("E2FM_VREC") && atoi(getenv("E2FM_VREC")) == 0)) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if ((double)img.n * 32.0 < 0.3 * (double)free_b) {
+            h = tm.begin(6);
+            uint4 *vr = dev_keep<uint4>(ix, (size_t)img.n * 2);
+            launch_vrec_build(img.n, d.seed_chars, sa, text, vr, s);
+            tm.end(h);
+            d.vrec = vr;
+            ix->vrec_bytes = (uint64_t)img.n * 32;
         }
     }
     ix->use_seed = d.seed_tab != nullptr && d.packed_code != nullptr && !(getenv("E2FM_SEED") && atoi(getenv("E2FM_SEED")) == 0);
@@ -1448,6 +1462,7 @@ int e2fm_index_info(const e2fm_index *ix, e2fm_info *o) {
     o->dense = ix->dix.sa ? (ix->use_dense ? 1u : 2u) : 0u;
     o->seed_chars = ix->dix.seed_tab ? ix->dix.seed_chars : 0u;
     o->seed_table_mb = (uint32_t)(ix->seed_bytes >> 20);
+    o->vrec_mb = (uint32_t)(ix->vrec_bytes >> 20);
     memcpy(o->load_ms, ix->load_ms, sizeof(o->load_ms));
     return E2FM_OK;
 }

@@ -33,6 +33,7 @@
 namespace e2fm {
 
 constexpr uint64_t REC_MARKED = 1ull << 63;
+constexpr uint32_t VREC_LEFT = 12;      // super-characters before the row's text position held by a verification record
 constexpr int SECTOR_SLOTS = 14;
 constexpr int SECTOR_INLINE_OVF = 12;
 
@@ -66,6 +67,9 @@ struct DevIndex {
     const uint4 *seed_tab;
     uint32_t seed_chars;        // j
     uint32_t seed_gph;          // sectors per value of the first j-1 super-characters = ceil(A / 56)
+    // verification records (index_build.cu, vrec_build_kernel): [n] 32-byte sectors {sa[row], the VREC_LEFT super-characters before
+    // that text position, the one seed_chars behind it}; nullptr = not built (HBM short): seed_verify_kernel reads sa[] / text[]
+    const uint4 *vrec;
     // 2-bit packed patterns (A C G T = 0 1 2 3, base i of a k-mer at bits 2i): packed k-mer -> compact code, 0xFFFF when the
     // k-mer does not occur in the text or one of its symbols is not in the index's alphabet; nullptr when k > 7
     const uint16_t *packed_code; // [4^k]

@@ -504,6 +504,140 @@ __global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs a) {
     if (lane == 0 && n_sect) atomicAdd(a.stats + ST_GATHER, n_sect);
 }
 
+// K_b over the verification records (DevIndex::vrec): the same row task answered with ONE gather — the record holds sa[row], the
+// VREC_LEFT super-characters before that text position (nearest first, so the r-th comparison reads a fixed register) and the one
+// behind the seed. Only patterns with more than VREC_LEFT super-characters left of the seed read text[] for the rest.
+template <int KT, int NW>
+__global__ void __launch_bounds__(256, 4) seed_verify_rec_kernel(SeedArgs a) {
+    extern __shared__ uint16_t ctab[];
+    __shared__ uint32_t rs_pat[SV_CAP];
+    __shared__ uint64_t rs_pos[SV_CAP];
+    __shared__ uint32_t rs_cnt;
+    __shared__ unsigned long long rs_base;
+    const DevIndex &ix = a.ix;
+    constexpr uint32_t k = KT;
+    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    constexpr int U = SEED_UV;
+    for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
+    if (threadIdx.x == 0) rs_cnt = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A, n = (uint32_t)ix.n;
+    const bool locate = a.mode == E2FM_MODE_LOCATE;
+    const unsigned long long nt = *a.task_cursor;
+    const uint32_t n_tasks = (uint32_t)(nt > a.task_cap ? 0ull : nt);     // an overflowing chunk is searched again by the host
+    unsigned long long n_sect = 0;
+    auto flush = [&]() {
+        const uint32_t c = rs_cnt;
+        if (threadIdx.x == 0) rs_base = atomicAdd(a.stats + ST_RESULTS, (unsigned long long)c);
+        __syncthreads();
+        const unsigned long long b0 = rs_base;
+        uint32_t lost = 0;
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+            if (b0 + i < a.res_cap) { a.res_pat[b0 + i] = rs_pat[i]; a.res_pos[b0 + i] = rs_pos[i]; }
+            else lost++;
+        }
+        if (lost) atomicAdd(a.stats + ST_RES_OVF, (unsigned long long)lost);
+        __syncthreads();
+        if (threadIdx.x == 0) rs_cnt = 0;
+        __syncthreads();
+    };
+    const uint32_t stride = gridDim.x * blockDim.x * U;
+    for (uint32_t base = blockIdx.x * blockDim.x * U; base < n_tasks; base += stride) {
+        uint2 tk[U];
+        bool ok[U];
+        Sector rec[U];
+        PatRegs<NW> pat[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + (uint32_t)u * blockDim.x + threadIdx.x;
+            ok[u] = idx < n_tasks;
+            tk[u] = ok[u] ? __ldg(a.tasks + idx) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {                  // the records and the patterns of the thread's tasks in flight together
+            if (ok[u]) {
+                rec[u] = ld_sector(ix.vrec + 2 * (size_t)tk[u].x);
+                pat[u].load(a.packed + (a.first + tk[u].y / k) * NW);
+            }
+        }
+        uint32_t tp[U], sa[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            sa[u] = tk[u].y % k;
+            tp[u] = 0;
+            if (!ok[u]) continue;
+            uint32_t L;
+            bool last_var;
+            int l, lo_i;
+            shift_geometry(m, k, sa[u], L, last_var, l, lo_i);
+            const uint32_t d = (uint32_t)(l - (int)j), lo = (uint32_t)lo_i;   // super-characters 0 .. d-1 lie at text positions pos - d .. pos - 1
+            const uint32_t pos = rec[u].lo.x;
+            const uint32_t left[6] = {rec[u].lo.y, rec[u].lo.z, rec[u].lo.w, rec[u].hi.x, rec[u].hi.y, rec[u].hi.z};
+            const uint32_t bit0 = 2u * (d * k - sa[u]);                        // bit offset of super-character d (the seed's first)
+            tp[u] = pos >= d ? pos - d : pos + (n - d);
+            bool good = true;
+            uint32_t first_code = 0xFFFFFFFFu;                                 // text code at tp, when the record holds it
+            // text[pos - r] against super-character d - r, r = 1 .. d - lo (the fixed ones, right to left)
+#pragma unroll
+            for (uint32_t r = 1; r <= VREC_LEFT; r++) {
+                const uint32_t tv = (left[(r - 1) >> 1] >> (((r - 1) & 1u) * 16u)) & 0xFFFFu;
+                if (r + lo <= d) good &= ctab[pat[u].bits(bit0 - 2u * r * k, KMASK)] == tv;
+                if (r == d) first_code = tv;
+            }
+            for (uint32_t r = VREC_LEFT + 1; r + lo <= d && good; r++) {       // long patterns: the rest from text[]
+                const uint32_t at = pos >= r ? pos - r : pos + (n - r);
+                good = ctab[pat[u].bits(bit0 - 2u * r * k, KMASK)] == (uint32_t)__ldg(ix.text + at);
+                n_sect++;
+            }
+            if (good && sa[u] > 0) {                                           // '?'-prefixed first super-character
+                const uint32_t f = k - sa[u];
+                const uint32_t want = pat[u].natural(ix, 0, f);
+                const uint32_t code = d <= VREC_LEFT ? first_code : (uint32_t)__ldg(ix.text + tp[u]);
+                good = want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code) == want;
+            }
+            if (good && last_var) {                                            // '?'-suffixed last super-character: text[pos + j]
+                const uint32_t code = rec[u].hi.w & 0xFFFFu;
+                if (code == 0xFFFFu) good = false;                             // beyond the end of the text
+                else {
+                    const uint32_t from = (L - 1) * k - sa[u], f = m - from;
+                    const uint32_t want = pat[u].natural(ix, 2 * from, f);
+                    good = want != 0xFFFFFFFFu && __ldg(ix.kmer_high + (f - 1) * A + code) == want;
+                }
+            }
+            ok[u] = good;
+            n_sect++;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned em = __ballot_sync(FULL, ok[u]);
+            if (em) {
+                const uint64_t p = a.first + tk[u].y / k;
+                if (ok[u]) atomicAdd(a.counts + p, 1ull);                                 // countOccurrences (:2273)
+                if (locate) {
+                    uint32_t b = 0;
+                    const int leader = __ffs(em) - 1;
+                    if ((int)lane == leader) b = atomicAdd(&rs_cnt, (uint32_t)__popc(em));
+                    b = __shfl_sync(FULL, b, leader);
+                    if (ok[u]) {
+                        const uint32_t slot = b + __popc(em & lt);
+                        rs_pat[slot] = (uint32_t)p;
+                        rs_pos[slot] = (uint64_t)tp[u] * k + sa[u] + ix.initial_n;        // EFMIndex.cpp:2312-2319
+                    }
+                }
+            }
+        }
+        if (locate && __syncthreads_or(rs_cnt >= SV_FLUSH)) flush();
+    }
+    if (locate) {
+        __syncthreads();
+        if (rs_cnt) flush();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_sect += __shfl_xor_sync(FULL, n_sect, d);
+    if (lane == 0 && n_sect) atomicAdd(a.stats + ST_GATHER, n_sect);
+}
+
 bool seed_search_supported(const DevIndex &ix, uint32_t m) {
     if (!ix.seed_tab || !ix.packed_code || !ix.sa || !ix.text || ix.k < 2 || ix.k > 7 || m == 0 || m > 128) return false;
     const uint32_t k = ix.k, j = ix.seed_chars;
@@ -535,9 +669,12 @@ static void launch_seed_nw(const SeedArgs &a, int n_sm, bool verify, cudaStream_
     // persistent grids: as many CTAs as the SMs hold (a multiple of the SM count)
     static const uint32_t lookup_max = resident_ctas(seed_lookup_kernel<KT, NW>, smem, n_sm);
     static const uint32_t verify_max = resident_ctas(seed_verify_kernel<KT, NW>, smem, n_sm);
+    static const uint32_t verify_rec_max = resident_ctas(seed_verify_rec_kernel<KT, NW>, smem, n_sm);
     if (!verify) {
         const uint32_t groups = ((a.count + PPC - 1) / PPC + SEED_U - 1) / SEED_U;
         seed_lookup_kernel<KT, NW><<<std::max(1u, std::min(groups, lookup_max)), 256, smem, s>>>(a);
+    } else if (a.ix.vrec) {
+        seed_verify_rec_kernel<KT, NW><<<verify_rec_max, 256, smem, s>>>(a);
     } else {
         seed_verify_kernel<KT, NW><<<verify_max, 256, smem, s>>>(a);
     }

@@ -53,6 +53,8 @@ typedef struct e2fm_info {
     uint32_t dense;              /* 0: no dense locate tables (HBM short); 1: built and in use; 2: built, switched off (E2FM_OPT_DENSE) */
     uint32_t seed_chars;         /* super-characters per entry of the seed table (0: not built) */
     uint32_t seed_table_mb;      /* its size in MiB (included in device_bytes) */
+    uint32_t vrec_mb;            /* MiB of verification records (32 bytes per row: what the seed search reads per candidate row); 0: not built */
+    uint32_t reserved;
     float load_ms[8];            /* one-time costs: [0] host parse, [1] H2D, [2] superbucket parse, [3] bucket decrypt+decode,
                                     [4] histogram, [5] scan, [6] rank sectors + LF fill, [7] total device */
 } e2fm_info;

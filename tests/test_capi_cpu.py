@@ -27,9 +27,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_info_struct_layout_matches_header():
-    # 8 u64 + 10 u32 + 8 float
+    # 8 u64 + 12 u32 + 8 float
     import ctypes
-    assert ctypes.sizeof(capi.Info) == 8 * 8 + 10 * 4 + 8 * 4
+    assert ctypes.sizeof(capi.Info) == 8 * 8 + 12 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback(golden, key64):

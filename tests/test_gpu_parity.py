@@ -704,12 +704,18 @@ def _hits_call(dev, arr, L, packed, locate, cap):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", GOLDEN_SEARCH_CASES)
-@pytest.mark.parametrize("stage", [0, 64, 7])
-def test_search_hits_matches_reference(gpu, golden, key64, name, stage):
-    """e2fm_search_hits (pipeline stages of 2^19, 64 and 7 patterns): counts, occurrence offsets, sequence index and offset in
-    the sequence of every occurrence equal the reference's, from ASCII and from packed patterns, count and locate"""
+@pytest.mark.parametrize("stage,vrec", [(0, 1), (64, 1), (7, 1), (64, 0)])
+def test_search_hits_matches_reference(gpu, golden, key64, name, stage, vrec):
+    """e2fm_search_hits (pipeline stages of 2^20, 64 and 7 patterns; candidate rows verified through the 32-byte verification
+    records and, with E2FM_VREC=0, through sa[] / text[]): counts, occurrence offsets, sequence index and offset in the sequence of
+    every occurrence equal the reference's, from ASCII and from packed patterns, count and locate"""
     g = golden[name]
-    dev = capi.DeviceIndex(g["index"], key64)
+    os.environ["E2FM_VREC"] = str(vrec)
+    try:
+        dev = capi.DeviceIndex(g["index"], key64)
+    finally:
+        os.environ.pop("E2FM_VREC", None)
+    assert (dev.info.vrec_mb > 0 or dev.info.text_length * 32 < (1 << 20)) if vrec else dev.info.vrec_mb == 0
     try:
         dev.set_option(capi.OPT_HITS_STAGE, stage)
         piped_any = False
