@@ -648,7 +648,7 @@ def gpu_arm(args, rank, world, local_rank):
         peak, peak_kind = measured_peak()
         value = npat_all * steps / (dev_ms_max / 1e3)
         e2e_value = npat_all * steps / (e2e_ms_max / 1e3)
-        roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind)
+        roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind, npat)
         if sharded_obj is not None:
             roofline["note"] += "; the gather microbenchmark ran after the sharded leg freed the replica"
         h2d = int(npat * unit)
@@ -664,7 +664,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "l2": "256 MB flush between timed iterations",
                        "locate_tables": "per-query walks from marked rows" if args.walk else "dense sa[]/text[] built at load",
                        "patterns_in": "2-bit packed (16 B per 64 bases)" if packed_api else "ASCII", "seed_chars": int(info.seed_chars),
-                       "seed_table_MB": int(info.seed_table_mb),
+                       "seed_table_MB": int(info.seed_table_mb), "verification_records_MB": int(info.vrec_mb),
                        "index_device_MB": round(info.device_bytes / 1e6, 1), "index_load_s": round(load_s, 3)},
             "occurrences_per_s": (occ_all / (dev_ms_max / 1e3)) if locate else None,
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
@@ -725,10 +725,17 @@ def cpp_host_arm(prep, device):
     return json.loads(line[-1])
 
 
-def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind):
-    """roofline of the dominant kernel. This layout's contract (replaces SURVEY.md 8(d)'s table, which prices
-    the REFERENCE's five-to-seven-sector operations): 32 B per sector the kernel has to gather (rank sectors, pair-table entries,
-    sa / text / record gathers), 2 B x 2 per row streamed by the wildcard scan."""
+def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind, npat=0):
+    """Roofline of the dominant kernel. This layout's contract (it replaces SURVEY.md 8(d)'s table, which prices the
+    REFERENCE's five-to-seven-sector operations): 32 B per 32-byte sector the kernel has to gather (seed-table sectors, verification
+    records, rank sectors, sa / text / record gathers), 2 B x 2 per row streamed by the wildcard scan.
+
+    The ceiling of such a kernel is not the copy bandwidth but the RANDOM-GATHER rate of the part, measured on this box for a working
+    set of the index's size by e2fm_debug_gather_bench (47 G gathers/s from 1 GB up on a B200: every gather activates a DRAM row and,
+    without a hint, moves a whole 128-byte line, i.e. 6.0 TB/s of DRAM traffic = 0.92 of the copy peak; profiles/exp/). So:
+        achieved = 32 B x sectors / kernel time          peak = 32 B x measured gathers/s          frac = achieved / peak
+    and next to it the same against the HBM copy peak of MEASURED_PEAKS.json (hbm_copy_peak), with the ncu DRAM traffic of the
+    kernel (`traffic`, bytes per launch of `launch_patterns` patterns) when profiles/ holds a capture of this workload."""
     resident = info.device_bytes < L2_BYTES
     # random-gather rate of THIS box for a working set of the index's size (power of two >= the image, at least 16 MB)
     ws_buf = 16 << 20
@@ -741,23 +748,27 @@ def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, pea
         log(f"[bench] gather microbenchmark failed: {e}")
     seeded = ctr_sum.get("seeded", 0) > 0
     k3 = "seed_lookup_kernel" if seeded else "backward_search_kernel"
-    k4 = "seed_verify_kernel" if seeded else ("walk_kernel" if args.walk else "resolve_kernel")
+    k4 = ("seed_verify_rec_kernel" if info.vrec_mb else "seed_verify_kernel") if seeded else ("walk_kernel" if args.walk else "resolve_kernel")
     lay = {k3: 32.0 * ctr_sum.get("rank_sectors", 0), k4: 32.0 * ctr_sum.get("walk_gathers", 0),
            "firstcheck_kernel": 4.0 * ctr_sum.get("scan_rows", 0)}
     tms = {k3: ph_ms["backward_search"], k4: ph_ms["walk"], "firstcheck_kernel": ph_ms["firstcheck"]}
+    gpeak = gg * 32.0 if gg else None
     kern = {}
     for name in lay:
         t = tms[name]
-        kern[name] = {"ms_per_step": t / steps, "algorithmic_bytes_per_step": lay[name] / steps,
-                      "achieved_gbs": lay[name] / (t / 1e3) / 1e9 if t else 0.0}
+        ach = lay[name] / (t / 1e3) / 1e9 if t else 0.0
+        kern[name] = {"ms_per_step": t / steps, "algorithmic_bytes_per_step": lay[name] / steps, "achieved_gbs": ach,
+                      "frac_of_random_gather_rate": (ach / gpeak) if (gpeak and name != "firstcheck_kernel") else None,
+                      "frac_of_hbm_copy_peak": ach / peak}
     dom = max(tms, key=lambda n: tms[n])
+    # ncu DRAM traffic of the dominant kernel: one launch = one chunk of the device-resident batch
+    chunk = min(npat, 4 << 20) if npat else 0
     traffic = None
     short = {"ecoli": "ecoli", "collection25": "c25", "collection100": "c100", "config1": "config1"}.get(args.workload, args.workload)
     try:
         import glob
-        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
-        if tfiles:
-            with open(tfiles[-1]) as f:
+        for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json"))):
+            with open(tf) as f:
                 tj = json.load(f)
             for name, d in tj.items():
                 if name.startswith(f"prof_{short}_") and dom in d:
@@ -765,22 +776,29 @@ def make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, pea
     except Exception:
         traffic = None
     achieved = kern[dom]["achieved_gbs"]
+    per_launch = (chunk / npat) if npat else 1.0
+    t_launch_s = tms[dom] / steps / 1e3 * per_launch
     ref_bytes = 160.0 * ctr_sum.get("rank", 0) + 224.0 * ctr_sum.get("lf", 0) + 64.0 * ctr_sum.get("mark", 0)
-    return {"bound": "l2" if resident else "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-            "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes_per_step"],
-            "random_gather": None if not gg else {
-                "giga_gathers_per_s": gg, "peak_gbs": gg * 32.0, "frac": achieved / (gg * 32.0), "buffer_MB": ws_buf >> 20,
-                "frac_of_hbm_copy_peak": gg * 32.0 / peak,
-                "how": "independent 8-byte loads at hashed addresses of a buffer of the device image's size (next power of two), 2^29 "
-                       "gathers, best of 3 (e2fm_debug_gather_bench); one 32-byte sector per gather"},
-            "note": ("the device image fits the 126 MB L2: HBM fraction is low by construction, read random_gather.frac" if resident else
-                     "achieved = 32 B x sectors this layout must gather, per step, over the kernel's CUDA-event time; "
-                     "traffic = ncu dram read+write of the same kernel (profiles/)"),
+    use_gather = gpeak is not None and dom != "firstcheck_kernel"
+    roof = {"bound": "l2" if resident else "hbm", "kernel": dom, "achieved": achieved, "peak": gpeak if use_gather else peak, "unit": "GB/s",
+            "frac": achieved / (gpeak if use_gather else peak), "traffic": traffic,
+            "peak_source": ((f"measured in this run: {gg:.1f} G random 32-byte-sector gathers/s over a {ws_buf >> 20} MB buffer (e2fm_debug_gather_bench, "
+                             f"2^29 independent 8-byte loads at hashed addresses, best of 3) x 32 B; the HBM copy peak is in hbm_copy_peak")
+                            if use_gather else f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"),
+            "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes_per_step"] * per_launch, "launch_patterns": chunk,
+            "hbm_copy_peak": {"peak": peak, "source": "MEASURED_PEAKS.json hbm_gbs (" + peak_kind + ")", "frac_sectors": achieved / peak,
+                              "dram_traffic_gbs": (traffic / t_launch_s / 1e9) if (traffic and t_launch_s) else None,
+                              "frac_dram_traffic": (traffic / t_launch_s / 1e9 / peak) if (traffic and t_launch_s) else None,
+                              "random_gather_rate_as_frac": (gpeak / peak) if gpeak else None},
+            "random_gather": None if not gg else {"giga_gathers_per_s": gg, "buffer_MB": ws_buf >> 20},
+            "note": ("the device image fits the 126 MB L2: the gather rate is that of an L2-resident working set of the same size" if resident else
+                     "achieved = 32 B x sectors this layout must gather, per step, over the kernel's CUDA-event time; traffic = ncu dram read+write "
+                     "of one launch of the same kernel (profiles/traffic_*.json, launch_patterns patterns)"),
             "reference_model": {"bytes_per_step": ref_bytes / steps,
                                 "note": "SURVEY.md 8(d): 160 B/rank + 224 B/lf + 64 B/mark x the REFERENCE operations this batch stands for; "
-                                        "not a measure of this layout (one sector per rank, no walks)"},
+                                        "not a measure of this layout (seed table, verification records, one sector per rank, no walks)"},
             "kernels": kern}
+    return roof
 
 
 def shard_plan(w, world):

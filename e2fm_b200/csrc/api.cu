@@ -489,13 +489,13 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
         if (const char *ov = getenv("E2FM_SEED_CHARS")) j = (uint32_t)atoi(ov);
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        auto table_bytes = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi * d.seed_gph * 32.0; };
+        auto table_bytes = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi * d.seed_gph * 16.0; };
         auto hi_values = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi; };
         while (j >= 2 && (table_bytes(j) > 0.25 * (double)free_b || hi_values(j) > 2147483648.0)) j--;
         if (j >= 2 && j <= 8) {
             h = tm.begin(6);
             const uint64_t n_sectors = (uint64_t)hi_values(j) * d.seed_gph;
-            uint4 *tab = dev_keep<uint4>(ix, n_sectors * 2);
+            uint4 *tab = dev_keep<uint4>(ix, n_sectors);
             SeedBuildParams sp{img.n, img.A, j, d.seed_gph, sa, text, tab, d_status.p};
             launch_seed_build(sp, n_sectors, s);
             tm.end(h);
@@ -507,11 +507,11 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
                 // rows not in seed order (never seen on a reference-built index): search without the table
                 CK(cudaFree(tab));
                 ix->owned.pop_back();
-                ix->device_bytes -= n_sectors * 32;
+                ix->device_bytes -= n_sectors * 16;
             } else {
                 d.seed_tab = tab;
                 d.seed_chars = j;
-                ix->seed_bytes = n_sectors * 32;
+                ix->seed_bytes = n_sectors * 16;
             }
         }
     }
@@ -848,7 +848,7 @@ void seed_search(RunState &st, const Batch &b) {
                 tm.end(h);
             }
             SeedArgs sa{dix, packed, pflag, m, first, cnt, st.mode, st.counts, st.res_pat.p, st.res_pos.p, st.res_cap(), clist.p,
-                        tasks.p, cap, chunk_ctr.p + c, ix->d_stats};
+                        tasks.p, cap, chunk_ctr.p + c, ix->d_stats, getenv("E2FM_SEED_DEBUG") ? (uint32_t)atoi(getenv("E2FM_SEED_DEBUG")) : 0u};
             int h = tm.begin(1);
             launch_seed_lookup(sa, nw, ix->n_sm, s);
             tm.end(h);
@@ -1120,7 +1120,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
         if (trace) { tr_begin[c] = ix->events.get(true); CK(cudaEventRecord(tr_begin[c], s)); }
         if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
-        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st};
+        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st, 0u};
         launch_seed_lookup(sa, nw, ix->n_sm, s);
         launch_seed_verify(sa, nw, ix->n_sm, s);
         launches += 2;

@@ -66,7 +66,7 @@ struct DevIndex {
     // seed table (seed.cuh): the interval of the last seed_chars super-characters of a shift in one gather; nullptr = none
     const uint4 *seed_tab;
     uint32_t seed_chars;        // j
-    uint32_t seed_gph;          // sectors per value of the first j-1 super-characters = ceil(A / 56)
+    uint32_t seed_gph;          // 16-byte entries per value of the first j-1 super-characters = ceil(A / 24)
     // verification records (index_build.cu, vrec_build_kernel): [n] 32-byte sectors {sa[row], the VREC_LEFT super-characters before
     // that text position, the one seed_chars behind it}; nullptr = not built (HBM short): seed_verify_kernel reads sa[] / text[]
     const uint4 *vrec;

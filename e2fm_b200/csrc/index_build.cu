@@ -593,12 +593,10 @@ void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s) {
 
 // ---------------------------------------------------------------- seed table (seed.cuh)
 
-// every sector: base = n (no row at or beyond the group's first seed), all counters 0
+// every 16-byte entry: base = n (no row at or beyond the group's first seed), all counters 0
 __global__ void __launch_bounds__(256) seed_fill_kernel(uint4 *__restrict__ tab, uint64_t n_sectors, uint32_t n_rows) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sectors; i += (uint64_t)gridDim.x * blockDim.x) {
-        tab[2 * i] = make_uint4(n_rows, 0u, 0u, 0u);
-        tab[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sectors; i += (uint64_t)gridDim.x * blockDim.x)
+        tab[i] = make_uint4(n_rows, 0u, 0u, 0u);
 }
 
 // the first j super-characters of the rotation that row `row` stands for: all but the last packed in `hi`, the last in `cl`
@@ -645,14 +643,29 @@ __global__ void __launch_bounds__(256) seed_build_kernel(SeedBuildParams p) {
     }
     uint32_t *words = reinterpret_cast<uint32_t *>(p.tab);
     const uint32_t slot = cl % SEED_GROUP;
-    atomicOr(words + g * 8 + 1 + (slot >> 3), cnt << ((slot & 7u) * 4u));
-    for (uint64_t gg = g_first; gg <= g; gg++) words[gg * 8] = r;
+    atomicOr(words + g * 4 + 1 + (slot >> 3), cnt << ((slot & 7u) * 4u));
+    for (uint64_t gg = g_first; gg <= g; gg++) words[gg * 4] = r;
+}
+
+// last pass: bit 31 of an entry's base flags a saturated counter (rows are below 2^31, host_format.cpp), so that seed_decode
+// needs no per-counter test
+__global__ void __launch_bounds__(256) seed_flag_kernel(uint4 *__restrict__ tab, uint64_t n_sectors) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sectors; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 a = tab[i];
+        const uint32_t w[3] = {a.y, a.z, a.w};
+        uint32_t sat = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) sat |= w[q] & (w[q] >> 1) & (w[q] >> 2) & (w[q] >> 3);
+        if (sat & 0x11111111u) reinterpret_cast<uint32_t *>(tab)[i * 4] = a.x | 0x80000000u;
+    }
 }
 
 void launch_seed_build(const SeedBuildParams &p, uint64_t n_sectors, cudaStream_t s) {
     if (p.n == 0 || n_sectors == 0) return;
-    seed_fill_kernel<<<(uint32_t)std::min<uint64_t>((n_sectors + 255) / 256, 148 * 32), 256, 0, s>>>(p.tab, n_sectors, (uint32_t)p.n);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sectors + 255) / 256, 148 * 32);
+    seed_fill_kernel<<<grid, 256, 0, s>>>(p.tab, n_sectors, (uint32_t)p.n);
     seed_build_kernel<<<(uint32_t)((p.n + 255) / 256), 256, 0, s>>>(p);
+    seed_flag_kernel<<<grid, 256, 0, s>>>(p.tab, n_sectors);
 }
 
 }  // namespace e2fm

@@ -89,6 +89,7 @@ struct SeedArgs {
     unsigned long long task_cap;
     unsigned long long *task_cursor; // device-resident number of row tasks of the chunk
     unsigned long long *stats;
+    uint32_t debug;                  // measurement aid (E2FM_SEED_DEBUG): 1 = every lookup reads one of 64 entries (no DRAM gathers; wrong answers)
 };
 // true when every shift of an m-base pattern has at least seed_chars fixed super-characters (and the tables exist)
 bool seed_search_supported(const DevIndex &ix, uint32_t m);

@@ -7,14 +7,17 @@
 // of rows that start with exactly these j. Both are tabulated at load from the dense sa[] / text[] tables:
 //
 //   seed = (c_0, .., c_{j-2} | c_{j-1}):  hi = ((c_0 * A + c_1) * A + ..) + c_{j-2}   (all but the last super-character)
-//   group g = hi * gph + c_{j-1} / 56,  slot = c_{j-1} % 56,  gph = ceil(A / 56)
-//   sector g (32 bytes): w0 = rows whose seed is smaller than the group's first seed
-//                        w1..w7 = 56 4-bit counters: rows per seed of the group, 15 = "15 or more" (not exact)
+//   group g = hi * gph + c_{j-1} / 24,  slot = c_{j-1} % 24,  gph = ceil(A / 24)
+//   entry g (16 bytes): w0 = rows whose seed is smaller than the group's first seed (bit 31: a counter of the group is saturated)
+//                       w1..w3 = 24 4-bit counters: rows per seed of the group, 15 = "15 or more" (not exact)
 //   interval = [w0 + sum of the counters below the slot, + counter of the slot)
 //
-// A lookup that meets a saturated counter at or below its slot falls back to the backward steps it replaces. j is the
-// smallest number of super-characters with A^j >= n/2 (about one row per seed or fewer: for the 3.1 Gbp collection j = 4,
-// 2.75 GB), so that a shift that does not occur in the text is rejected by this one gather with probability 1 - n/A^j.
+// ONE 16-byte load answers a lookup (the DRAM moves a 64-byte burst for it either way; what the 16-byte entry saves against a
+// 32-byte sector of 56 counters is L2->SM traffic, decode work and four registers per gather in flight, which is what lets a thread
+// keep four lookups outstanding). A lookup in a group that holds a saturated counter falls back to the backward steps the table
+// replaces. j is the smallest number of super-characters with A^j >= n/2 (about one row per seed or fewer: for the 3.1 Gbp
+// collection j = 4, 3.0 GB), so that a shift that does not occur in the text is rejected by this one gather with probability
+// 1 - n/A^j.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -23,12 +26,12 @@
 
 namespace e2fm {
 
-constexpr uint32_t SEED_GROUP = 56;     // seeds per sector (7 words x 8 nibbles)
+constexpr uint32_t SEED_GROUP = 24;     // seeds per 16-byte entry (3 words x 8 nibbles)
 constexpr uint32_t SEED_SAT = 15;       // saturated counter
 
 struct SeedHit {
     uint32_t s, cnt;    // interval [s, s + cnt)
-    bool exact;         // false: a saturated counter was met, the interval is unknown
+    bool exact;         // false: a counter of the group is saturated, the interval is unknown
 };
 
 __device__ __forceinline__ size_t seed_sector(const DevIndex &ix, uint32_t hi, uint32_t c_last, uint32_t &slot) {
@@ -37,26 +40,29 @@ __device__ __forceinline__ size_t seed_sector(const DevIndex &ix, uint32_t hi, u
     return (size_t)hi * ix.seed_gph + q;
 }
 
-__device__ __forceinline__ Sector seed_load(const DevIndex &ix, size_t sector) {
-    return ld_sector(ix.seed_tab + sector * 2);
+__device__ __forceinline__ uint4 seed_load(const DevIndex &ix, size_t entry) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ix.seed_tab + entry));
+    return r;
 }
 
-__device__ __forceinline__ SeedHit seed_decode(const Sector &sec, uint32_t slot) {
-    const uint32_t w[7] = {sec.lo.y, sec.lo.z, sec.lo.w, sec.hi.x, sec.hi.y, sec.hi.z, sec.hi.w};
+__device__ __forceinline__ SeedHit seed_decode(const uint4 &e, uint32_t slot) {
+    const uint32_t w[3] = {e.y, e.z, e.w};
     const uint32_t wi = slot >> 3, sh = (slot & 7u) * 4u;
-    uint32_t acc = 0, sat = 0, own = 0;
+    uint32_t acc = 0, own = 0;
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
-        const uint32_t m = (uint32_t)i < wi ? 0xFFFFFFFFu : ((uint32_t)i == wi ? ((1u << sh) - 1u) : 0u);
-        const uint32_t x = w[i] & m;
-        sat |= x & (x >> 1) & (x >> 2) & (x >> 3);
-        acc += (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);     // byte sums: at most 7 words x 30
-        if ((uint32_t)i == wi) own = w[i];
+    for (int i = 0; i < 3; i++) {
+        // the counters of word i that lie below the slot: all of them when i < wi, the low ones when i == wi
+        uint32_t x = w[i];
+        if ((uint32_t)i == wi) { own = x; x &= (1u << sh) - 1u; }
+        else if ((uint32_t)i > wi) x = 0u;
+        acc = __dp4a(x & 0x0F0F0F0Fu, 0x01010101u, acc);           // sum of the four low nibbles
+        acc = __dp4a((x >> 4) & 0x0F0F0F0Fu, 0x01010101u, acc);    // ... and of the four high ones
     }
     SeedHit h;
     h.cnt = (own >> sh) & 15u;
-    h.s = sec.lo.x + (acc & 0xFFu) + ((acc >> 8) & 0xFFu) + ((acc >> 16) & 0xFFu) + (acc >> 24);
-    h.exact = (sat & 0x11111111u) == 0u && h.cnt != SEED_SAT;
+    h.s = (e.x & 0x7FFFFFFFu) + acc;
+    h.exact = (e.x >> 31) == 0u;           // bit 31 of the base (rows are below 2^31): a counter of this group is saturated
     return h;
 }
 

@@ -116,6 +116,20 @@ struct PatRegs {
         }
         return r;
     }
+    // WN words of the bit string starting at bit offset `off`, which may be negative (bits before the string read as zero): the
+    // caller then picks its fields at compile-time offsets of `out` — one round of selects instead of one per field
+    template <int WN>
+    __device__ __forceinline__ void window(int off, uint32_t (&out)[WN]) const {
+        const int wi = off >> 5;                       // floor
+        const uint32_t sh = (uint32_t)off & 31u;
+        uint32_t prev = word((uint32_t)wi);
+#pragma unroll
+        for (int i = 0; i < WN; i++) {
+            const uint32_t next = word((uint32_t)(wi + i + 1));
+            out[i] = __funnelshift_r(prev, next, sh);
+            prev = next;
+        }
+    }
     __device__ __forceinline__ uint32_t bits(uint32_t off, uint32_t mask) const {
         const uint32_t wi = off >> 5;
         return __funnelshift_r(word(wi), word(wi + 1), off & 31u) & mask;
@@ -164,8 +178,8 @@ __device__ __forceinline__ void seed_interval_slow(const DevIndex &ix, const uin
 // The kernel is bound by instruction issue as much as by the gathers (ncu, profiles/): a lane loads only the three words of the
 // pattern that hold its seed (where they are depends on the shift alone), the row tasks are staged per WARP (no CTA barrier in the
 // loop, one reservation per SL_FLUSH tasks), and the loads of SEED_U tiles are in flight together.
-template <int KT, int NW>
-__global__ void __launch_bounds__(256, 4) seed_lookup_kernel(SeedArgs a) {
+template <int KT, int NW, int JT>                      // JT = compile-time seed length (0: read it from the index)
+__global__ void __launch_bounds__(256, 5) seed_lookup_kernel(SeedArgs a) {
     extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code
     __shared__ uint2 st_task[8][SL_WCAP];
     const DevIndex &ix = a.ix;
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(256, 4) seed_lookup_kernel(SeedArgs a) {
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const uint32_t pl = lane / k, sa = lane - pl * k;
-    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A;
+    const uint32_t m = a.m, j = JT ? (uint32_t)JT : ix.seed_chars, A = ix.A;
     uint32_t L;
     bool last_var;
     int l, lo;
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(256, 4) seed_lookup_kernel(SeedArgs a) {
             flag[u] = nflag[u];
             x0[u] = nx0[u]; x1[u] = nx1[u]; x2[u] = nx2[u];
         }
-        Sector sec[U];
+        uint4 sec[U];
         unsigned long long window[U];
         uint32_t slot[U];
         bool look[U];
@@ -245,13 +259,16 @@ __global__ void __launch_bounds__(256, 4) seed_lookup_kernel(SeedArgs a) {
             if (valid[u] && live && flag[u] == 0) {
                 uint32_t hi = 0, cl = 0;
                 bool absent = false;
+#pragma unroll
                 for (uint32_t q = 0; q < j; q++) {
                     const uint32_t code = ctab[(uint32_t)(window[u] >> (2 * KT * q)) & KMASK];
                     absent |= code == 0xFFFFu;
                     if (q + 1 < j) hi = hi * A + code; else cl = code;
                 }
                 if (!absent) {
-                    sec[u] = seed_load(ix, seed_sector(ix, hi, cl, slot[u]));
+                    size_t entry = seed_sector(ix, hi, cl, slot[u]);
+                    if (a.debug & 1u) entry &= 63;
+                    sec[u] = seed_load(ix, entry);
                     look[u] = true;
                     n_sect++;
                 }
@@ -578,11 +595,25 @@ __global__ void __launch_bounds__(256, 4) seed_verify_rec_kernel(SeedArgs a) {
             tp[u] = pos >= d ? pos - d : pos + (n - d);
             bool good = true;
             uint32_t first_code = 0xFFFFFFFFu;                                 // text code at tp, when the record holds it
-            // text[pos - r] against super-character d - r, r = 1 .. d - lo (the fixed ones, right to left)
+            // text[pos - r] against super-character d - r, r = 1 .. d - lo (the fixed ones, right to left). The VREC_LEFT super-
+            // characters left of the seed are cut out of the pattern once, so that the r-th sits at a compile-time offset.
+            constexpr int WN = (2 * KT * (int)VREC_LEFT + 31) / 32;
+            uint32_t win[WN + 1];
+            {
+                uint32_t wtmp[WN];
+                pat[u].template window<WN>((int)bit0 - 32 * WN, wtmp);
+#pragma unroll
+                for (int i = 0; i < WN; i++) win[i] = wtmp[i];
+                win[WN] = 0;
+            }
 #pragma unroll
             for (uint32_t r = 1; r <= VREC_LEFT; r++) {
                 const uint32_t tv = (left[(r - 1) >> 1] >> (((r - 1) & 1u) * 16u)) & 0xFFFFu;
-                if (r + lo <= d) good &= ctab[pat[u].bits(bit0 - 2u * r * k, KMASK)] == tv;
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int at = 32 * WN - 2 * KT * (int)r;                       // bit offset of super-character d - r in the window
+                const uint32_t kmer = __funnelshift_r(win[at >> 5], win[(at >> 5) + 1], (uint32_t)(at & 31)) & KMASK;
+                if (r + lo <= d) good &= ctab[kmer] == tv;
                 if (r == d) first_code = tv;
             }
             for (uint32_t r = VREC_LEFT + 1; r + lo <= d && good; r++) {       // long patterns: the rest from text[]
@@ -667,12 +698,18 @@ static void launch_seed_nw(const SeedArgs &a, int n_sm, bool verify, cudaStream_
     constexpr uint32_t PPC = 8 * (32 / KT);
     const size_t smem = (size_t)2 << (2 * KT);
     // persistent grids: as many CTAs as the SMs hold (a multiple of the SM count)
-    static const uint32_t lookup_max = resident_ctas(seed_lookup_kernel<KT, NW>, smem, n_sm);
+    static const uint32_t lookup_max = resident_ctas(seed_lookup_kernel<KT, NW, 0>, smem, n_sm);
     static const uint32_t verify_max = resident_ctas(seed_verify_kernel<KT, NW>, smem, n_sm);
     static const uint32_t verify_rec_max = resident_ctas(seed_verify_rec_kernel<KT, NW>, smem, n_sm);
     if (!verify) {
         const uint32_t groups = ((a.count + PPC - 1) / PPC + SEED_U - 1) / SEED_U;
-        seed_lookup_kernel<KT, NW><<<std::max(1u, std::min(groups, lookup_max)), 256, smem, s>>>(a);
+        const uint32_t blocks = std::max(1u, std::min(groups, lookup_max));
+        switch (a.ix.seed_chars) {                    // the usual seed lengths get their own instance (unrolled code loop)
+            case 2: seed_lookup_kernel<KT, NW, 2><<<blocks, 256, smem, s>>>(a); break;
+            case 3: seed_lookup_kernel<KT, NW, 3><<<blocks, 256, smem, s>>>(a); break;
+            case 4: seed_lookup_kernel<KT, NW, 4><<<blocks, 256, smem, s>>>(a); break;
+            default: seed_lookup_kernel<KT, NW, 0><<<blocks, 256, smem, s>>>(a); break;
+        }
     } else if (a.ix.vrec) {
         seed_verify_rec_kernel<KT, NW><<<verify_rec_max, 256, smem, s>>>(a);
     } else {
