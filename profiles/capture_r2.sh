@@ -21,4 +21,11 @@ timeout 900 $NCU -k regex:"scan_block_sums|scan_sums|scan_apply|scatter_kernel|s
 timeout 900 $NCU -k regex:"hits_" -c 5 -o $OUT/prof_${W}_hits_r2 $B > $OUT/n3.log 2>&1; echo "hits rc=$?"
 # 5. load pipeline
 timeout 1200 $NCU -k regex:"salsa20|bucket_decode|sb_parse|rank_|dense_build|bwt16_build|pair_build|seed_fill|seed_build" -c 16 -o $OUT/prof_${W}_load_r2 $B > $OUT/n4.log 2>&1; echo "load rc=$?"
-ls -la $OUT/*_r2.ncu-rep
+# only 64 MiB travel back: keep the raw-page CSV of every capture, and the report itself only when it is small
+for r in $OUT/prof_${W}_*_r2.ncu-rep; do
+    ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2> /dev/null
+    if [ $(stat -c %s $r) -gt 12000000 ]; then rm -f $r; fi
+done
+rm -f $OUT/*.tmp
+ls -la $OUT/ | tail -30
+du -sh $OUT

@@ -34,7 +34,11 @@ KEYS = [
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        with open(rep) as f:
+            out = f.read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     return rows[0], rows[1], rows[2:]
 
@@ -42,8 +46,12 @@ def raw_rows(rep):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     traffic = {}
+    reps = {}
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"*_{tag}.ncu-rep"))):
-        name = os.path.basename(rep)[:-8]
+        reps[os.path.basename(rep)[:-8]] = rep
+    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"*_{tag}.raw.csv"))):     # exported on the GPU box (capture_r2.sh)
+        reps[os.path.basename(rep)[:-8]] = rep
+    for name, rep in sorted(reps.items()):
         hdr, units, rows = raw_rows(rep)
         idx = {h: i for i, h in enumerate(hdr)}
         with open(os.path.join(OUT, name + ".txt"), "w") as f:
