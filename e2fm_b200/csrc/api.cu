@@ -156,6 +156,7 @@ struct e2fm_index {
     std::vector<void *> owned;  // device allocations that live as long as the index
     uint64_t device_bytes = 0;
     uint64_t seed_bytes = 0, vrec_bytes = 0;
+    const uint4 *seed_tabs[9] = {nullptr};   // seed table per seed length (2 .. dix.seed_chars); dix.seed_tab is the longest
     uint64_t max_seq_len = 0;   // longest span between terminators (a 32-bit offset in the sequence fits when it is below 2^32)
     float load_ms[8] = {0};
     float batch_ms[8] = {0};
@@ -243,6 +244,15 @@ struct WsBuf {
     }
     void zero(size_t count) { if (count) CK(cudaMemsetAsync(p, 0, count * sizeof(T), s)); }
 };
+
+// E2FM_DEBUG_SYNC=1: synchronise after every launch of the search paths and name the kernel that faulted
+void dbg_sync(cudaStream_t s, const char *what) {
+    static const bool on = getenv("E2FM_DEBUG_SYNC") && atoi(getenv("E2FM_DEBUG_SYNC")) != 0;
+    if (!on) return;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) throw CudaError(std::string("after ") + what + ": " + cudaGetErrorString(e));
+}
 
 void read_stats(e2fm_index *ix) {
     CK(cudaMemcpyAsync(ix->h_stats, ix->d_stats, ST_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ix->stream));
@@ -396,6 +406,7 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
             h = tm.begin(6);
             sa = dev_keep<uint32_t>(ix, img.n);
             text = dev_keep<uint16_t>(ix, img.n + 32);   // seed_verify_kernel reads whole 32-byte sectors
+            CK(cudaMemsetAsync(text + img.n, 0, 64, s));
             launch_dense_build(rec, mark_tab, mrn, img.rate, img.n, sa, text, d_status.p, s);
             bwt16 = dev_keep<uint16_t>(ix, img.n + 16);   // firstcheck_kernel reads aligned 16-byte groups
             launch_bwt16_build(rec, img.n, bwt16, s);
@@ -492,11 +503,13 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
         auto table_bytes = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi * d.seed_gph * 16.0; };
         auto hi_values = [&](uint32_t jj) { double hi = 1; for (uint32_t i = 0; i + 1 < jj; i++) hi *= img.A; return hi; };
         while (j >= 2 && (table_bytes(j) > 0.25 * (double)free_b || hi_values(j) > 2147483648.0)) j--;
-        if (j >= 2 && j <= 8) {
+        // the main table (seed length j) and the smaller ones below it (a few MB: short patterns are searched with a shorter seed,
+        // seed_plan): the same build for every length
+        for (uint32_t jj = 2; jj <= j && j <= 8; jj++) {
             h = tm.begin(6);
-            const uint64_t n_sectors = (uint64_t)hi_values(j) * d.seed_gph;
+            const uint64_t n_sectors = (uint64_t)hi_values(jj) * d.seed_gph;
             uint4 *tab = dev_keep<uint4>(ix, n_sectors);
-            SeedBuildParams sp{img.n, img.A, j, d.seed_gph, sa, text, tab, d_status.p};
+            SeedBuildParams sp{img.n, img.A, jj, d.seed_gph, sa, text, tab, d_status.p};
             launch_seed_build(sp, n_sectors, s);
             tm.end(h);
             uint32_t st = 0;
@@ -504,15 +517,20 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
             CK(cudaStreamSynchronize(s));
             CK(cudaGetLastError());
             if (st & BUILD_ERR_SEED) {
-                // rows not in seed order (never seen on a reference-built index): search without the table
+                // rows not in seed order (never seen on a reference-built index): search without the tables
                 CK(cudaFree(tab));
                 ix->owned.pop_back();
                 ix->device_bytes -= n_sectors * 16;
-            } else {
-                d.seed_tab = tab;
-                d.seed_chars = j;
-                ix->seed_bytes = n_sectors * 16;
+                for (auto &t : ix->seed_tabs) t = nullptr;
+                d.seed_tab = nullptr;
+                d.seed_chars = 0;
+                ix->seed_bytes = 0;
+                break;
             }
+            ix->seed_tabs[jj] = tab;
+            d.seed_tab = tab;
+            d.seed_chars = jj;
+            ix->seed_bytes += n_sectors * 16;
         }
     }
     // ---- verification records for the seed search: 32 bytes per row, when HBM allows (E2FM_VREC=0: never)
@@ -523,7 +541,7 @@ void build_device_index(e2fm_index *ix, const uint8_t *file, size_t size) {
         if ((double)img.n * 32.0 < 0.3 * (double)free_b) {
             h = tm.begin(6);
             uint4 *vr = dev_keep<uint4>(ix, (size_t)img.n * 2);
-            launch_vrec_build(img.n, d.seed_chars, sa, text, vr, s);
+            launch_vrec_build(img.n, sa, text, vr, s);
             tm.end(h);
             d.vrec = vr;
             ix->vrec_bytes = (uint64_t)img.n * 32;
@@ -658,6 +676,7 @@ void generic_search(RunState &st, const Batch &b, bool allow_fast) {
         launch_encode_patterns(dix, all, 0, b.total_bytes, b.total_bytes, codes.p, ix->n_sm, s);
         launches++;
         tm.end(h);
+        dbg_sync(s, "encode_patterns_kernel");
     }
 
     // counts of a finished chunk go back to the host on the D2H stream while the next chunk searches
@@ -707,19 +726,23 @@ void generic_search(RunState &st, const Batch &b, bool allow_fast) {
             launch_backward_search(sa, ix->n_sm, s);
             launches++;
             tm.end(h);
+            dbg_sync(s, "backward_search_kernel (fast path)");
             h = tm.begin(2);
             launch_scan_expand(iv.p, cnt * k, scratch.p, tasks.p, cap, chunk_ctr.p + chunk_no, s);   // sets the chunk's task count
             launches += 2;
             tm.end(h);
+            dbg_sync(s, "scan_expand");
             h = tm.begin(7);
             launch_firstcheck(sa, ix->n_sm, s);                                                      // appends the wildcard survivors
             launches++;
             tm.end(h);
+            dbg_sync(s, "firstcheck_kernel");
             h = tm.begin(3);
             WalkArgs wa{dix, pv, mode, tasks.p, firstw.p, hatw.p, (uint32_t)cap, chunk_ctr.p + chunk_no, counts, st.res_pat.p, st.res_pos.p, st.res_cap(), ix->d_stats};
             launch_resolve(wa, ix->n_sm, s);
             launches++;
             tm.end(h);
+            dbg_sync(s, "resolve_kernel (fast path)");
             stream_counts_back(first, cnt);
         }
         if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_ctr.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
@@ -797,14 +820,23 @@ void generic_search(RunState &st, const Batch &b, bool allow_fast) {
     if (b.h_counts) CK(cudaStreamSynchronize(ix->d2h_stream));
 }
 
+// the seed length for a batch of m-base patterns, from the tables this index holds
+bool plan_seed(const e2fm_index *ix, uint32_t m, SeedPlan &plan) {
+    uint32_t mask = 0;
+    for (uint32_t j = 2; j <= 8; j++) if (ix->seed_tabs[j]) mask |= 1u << j;
+    return seed_plan(ix->dix, m, mask, plan);
+}
+
 // The seed path (seed_search.cu): fixed-length batches whose every shift holds a whole seed; ASCII input is packed on the
 // device first. Patterns it cannot finish (several rows left at the end of a shift, a saturated seed counter, an index symbol
 // outside ACGT) are searched by the generic path as a sub-batch.
-void seed_search(RunState &st, const Batch &b) {
+void seed_search(RunState &st, const Batch &b, const SeedPlan &plan) {
     e2fm_index *ix = st.ix;
     cudaStream_t s = st.s;
     EventTimer &tm = st.tm;
-    const DevIndex &dix = ix->dix;
+    DevIndex dix = ix->dix;                       // the kernels see the table of this batch's seed length
+    dix.seed_tab = ix->seed_tabs[plan.j];
+    dix.seed_chars = plan.j;
     const uint32_t m = b.fixed_len, nw = (m + 63) / 64;
     const bool locate = st.mode == E2FM_MODE_LOCATE;
 
@@ -848,13 +880,16 @@ void seed_search(RunState &st, const Batch &b) {
                 tm.end(h);
             }
             SeedArgs sa{dix, packed, pflag, m, first, cnt, st.mode, st.counts, st.res_pat.p, st.res_pos.p, st.res_cap(), clist.p,
-                        tasks.p, cap, chunk_ctr.p + c, ix->d_stats, getenv("E2FM_SEED_DEBUG") ? (uint32_t)atoi(getenv("E2FM_SEED_DEBUG")) : 0u};
+                        tasks.p, cap, chunk_ctr.p + c, ix->d_stats, getenv("E2FM_SEED_DEBUG") ? (uint32_t)atoi(getenv("E2FM_SEED_DEBUG")) : 0u,
+                        plan.enumerate ? plan.lookups : 0u};
             int h = tm.begin(1);
             launch_seed_lookup(sa, nw, ix->n_sm, s);
             tm.end(h);
+            dbg_sync(s, plan.enumerate ? "seed_lookup_enum_kernel" : "seed_lookup_kernel");
             h = tm.begin(3);
             launch_seed_verify(sa, nw, ix->n_sm, s);
             tm.end(h);
+            dbg_sync(s, "seed_verify kernel");
             st.launches += 2;
         }
         if (n_chunks) CK(cudaMemcpyAsync(h_chunk_tasks.data(), chunk_ctr.p, n_chunks * 8, cudaMemcpyDeviceToHost, s));
@@ -916,10 +951,11 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[10] = ix->batch_ctr[12] = ix->batch_ctr[13] = 0;
 
     RunState st(ix, mode, tm, counts.p);
-    const bool seeded = ix->use_seed && ix->use_dense && !b.d_off && !b.h_off && b.n > 0 && seed_search_supported(dix, b.fixed_len);
+    SeedPlan plan{0, false, 0};
+    const bool seeded = ix->use_seed && ix->use_dense && !b.d_off && !b.h_off && b.n > 0 && plan_seed(ix, b.fixed_len, plan);
     if (b.packed_in && !seeded && b.n > 0) throw std::runtime_error("packed patterns need the seed search: dense tables and seed table built, k <= 7, "
                                                          "pattern length <= 128 with a whole seed in every shift (use the ASCII entry points)");
-    if (seeded) seed_search(st, b);        // writes every count itself
+    if (seeded) seed_search(st, b, plan);  // writes every count itself
     else {
         counts.zero();
         generic_search(st, b, true);
@@ -1009,9 +1045,11 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
 // running occurrence total, and each stage reports {first occurrence, occurrences, trouble} into page-locked host memory, which is
 // all the host needs to queue the stage's D2H copies. Returns false when a store sized from earlier batches was too small or a
 // pattern needs the generic path (an index symbol outside ACGT): the caller then runs the plain path, which sizes exactly.
-bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, bool packed_in, int mode, e2fm_hits *hits) {
+bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, bool packed_in, int mode, e2fm_hits *hits, const SeedPlan &plan) {
     cudaStream_t s = ix->stream;
-    const DevIndex &dix = ix->dix;
+    DevIndex dix = ix->dix;                       // the kernels see the table of this batch's seed length
+    dix.seed_tab = ix->seed_tabs[plan.j];
+    dix.seed_chars = plan.j;
     const bool locate = mode == E2FM_MODE_LOCATE;
     const uint32_t nw = (m + 63) / 64;
     Batch b{nullptr, nullptr, m, n, 0};
@@ -1120,7 +1158,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
         if (trace) { tr_begin[c] = ix->events.get(true); CK(cudaEventRecord(tr_begin[c], s)); }
         if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
-        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st, 0u};
+        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st, 0u, plan.enumerate ? plan.lookups : 0u};
         launch_seed_lookup(sa, nw, ix->n_sm, s);
         launch_seed_verify(sa, nw, ix->n_sm, s);
         launches += 2;
@@ -1556,10 +1594,11 @@ int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32
     if (locate && ix->max_seq_len >= (1ull << 32)) return fail(E2FM_ERR_ARG, "a sequence is longer than 2^32-1: use e2fm_result_fetch");
     hits->total = 0;
     bool piped = false;
-    if (n && ix->use_seed && ix->use_dense && seed_search_supported(ix->dix, length)) {
+    SeedPlan plan{0, false, 0};
+    if (n && ix->use_seed && ix->use_dense && plan_seed(ix, length, plan)) {
         try {
             CK(cudaSetDevice(ix->device));
-            piped = hits_pipeline(ix, patterns, n, length, packed != 0, mode, hits);
+            piped = hits_pipeline(ix, patterns, n, length, packed != 0, mode, hits, plan);
         } catch (const CudaError &e) {
             quiesce(ix);
             return fail(E2FM_ERR_CUDA, e.what());

@@ -33,7 +33,7 @@
 namespace e2fm {
 
 constexpr uint64_t REC_MARKED = 1ull << 63;
-constexpr uint32_t VREC_LEFT = 12;      // super-characters before the row's text position held by a verification record
+constexpr uint32_t VREC_LEFT = 10;      // super-characters before the row's text position held by a verification record
 constexpr int SECTOR_SLOTS = 14;
 constexpr int SECTOR_INLINE_OVF = 12;
 
@@ -68,7 +68,7 @@ struct DevIndex {
     uint32_t seed_chars;        // j
     uint32_t seed_gph;          // 16-byte entries per value of the first j-1 super-characters = ceil(A / 24)
     // verification records (index_build.cu, vrec_build_kernel): [n] 32-byte sectors {sa[row], the VREC_LEFT super-characters before
-    // that text position, the one seed_chars behind it}; nullptr = not built (HBM short): seed_verify_kernel reads sa[] / text[]
+    // that text position, the ones 2, 3 and 4 behind it}; nullptr = not built (HBM short): seed_verify_kernel reads sa[] / text[]
     const uint4 *vrec;
     // 2-bit packed patterns (A C G T = 0 1 2 3, base i of a k-mer at bits 2i): packed k-mer -> compact code, 0xFFFF when the
     // k-mer does not occur in the text or one of its symbols is not in the index's alphabet; nullptr when k > 7

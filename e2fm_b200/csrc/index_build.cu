@@ -537,21 +537,25 @@ void launch_dense_build(const uint64_t *rec, const uint2 *mark_tab, uint64_t mrn
     dense_build_kernel<<<(uint32_t)((mrn + 255) / 256), 256, 0, s>>>(rec, mark_tab, mrn, rate, n, sa, text, status);
 }
 
+// bwt16 has 16 entries of padding (firstcheck_kernel reads aligned groups of 8 rows and looks every code up in a table before it
+// masks the rows outside the interval): they are zeroed, a code must never be garbage
 __global__ void __launch_bounds__(256) bwt16_build_kernel(const uint64_t *__restrict__ rec, uint64_t n, uint16_t *__restrict__ bwt16) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) bwt16[i] = (uint16_t)rec_code(rec[i]);
+    else if (i < n + 16) bwt16[i] = 0;
 }
 void launch_bwt16_build(const uint64_t *rec, uint64_t n, uint16_t *bwt16, cudaStream_t s) {
-    if (n) bwt16_build_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rec, n, bwt16);
+    if (n) bwt16_build_kernel<<<(uint32_t)((n + 16 + 255) / 256), 256, 0, s>>>(rec, n, bwt16);
 }
 
 // Verification records (device_index.cuh): one 32-byte sector per row with everything seed_verify_rec_kernel needs to finish
 // EFMIndex::exactMatch for a row the seed table produced — the row's text position and the super-characters around it — so that
 // a row task costs ONE gather instead of sa[row] + one or two sectors of text[].
 //   w0      sa[row]
-//   w1..w6  text[sa - 1], text[sa - 2], .., text[sa - 12]   (indexes mod n; 16 bits each, the nearer one in the low half)
-//   w7      low half: text[sa + j] (the super-character behind the j of the seed: the '?'-suffixed last one), 0xFFFF beyond the text
-__global__ void __launch_bounds__(256) vrec_build_kernel(uint64_t n, uint32_t j, const uint32_t *__restrict__ sa, const uint16_t *__restrict__ text,
+//   w1..w5  text[sa - 1], text[sa - 2], .., text[sa - 10]   (indexes mod n; 16 bits each, the nearer one in the low half)
+//   w6, w7  text[sa + 2], text[sa + 3], text[sa + 4], 0: the super-character behind a seed of 2, 3 or 4 (the '?'-suffixed last one);
+//           0xFFFF beyond the end of the text
+__global__ void __launch_bounds__(256) vrec_build_kernel(uint64_t n, const uint32_t *__restrict__ sa, const uint16_t *__restrict__ text,
                                                           uint4 *__restrict__ vrec) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
@@ -559,18 +563,24 @@ __global__ void __launch_bounds__(256) vrec_build_kernel(uint64_t n, uint32_t j,
     uint32_t w[8];
     w[0] = pos;
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
+    for (int q = 0; q < 5; q++) {
         const uint32_t r0 = 2 * q + 1, r1 = 2 * q + 2;
         const uint32_t a = pos >= r0 ? pos - r0 : pos + (nn - r0), b = pos >= r1 ? pos - r1 : pos + (nn - r1);
         w[1 + q] = (uint32_t)__ldg(text + a) | ((uint32_t)__ldg(text + b) << 16);
     }
-    const uint64_t ph = (uint64_t)pos + j;
-    w[7] = ph < n ? (uint32_t)__ldg(text + ph) : 0xFFFFu;
+    uint32_t right[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const uint64_t ph = (uint64_t)pos + 2 + q;
+        right[q] = ph < n ? (uint32_t)__ldg(text + ph) : 0xFFFFu;
+    }
+    w[6] = right[0] | (right[1] << 16);
+    w[7] = right[2];
     vrec[2 * row] = make_uint4(w[0], w[1], w[2], w[3]);
     vrec[2 * row + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-void launch_vrec_build(uint64_t n, uint32_t j, const uint32_t *sa, const uint16_t *text, uint4 *vrec, cudaStream_t s) {
-    if (n) vrec_build_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(n, j, sa, text, vrec);
+void launch_vrec_build(uint64_t n, const uint32_t *sa, const uint16_t *text, uint4 *vrec, cudaStream_t s) {
+    if (n) vrec_build_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(n, sa, text, vrec);
 }
 
 __global__ void __launch_bounds__(256) pair_build_kernel(DevIndex ix, uint2 *__restrict__ pair_tab) {

@@ -78,8 +78,8 @@ void launch_bwt16_build(const uint64_t *rec, uint64_t n, uint16_t *bwt16, cudaSt
 // pair_tab[a*A + b] = {s,e}: [C[a], C[a+1]) after one backward step with b
 void launch_pair_build(const DevIndex &ix, uint2 *pair_tab, cudaStream_t s);
 
-// verification records: 32 bytes per row (sa[row], the 12 super-characters before that position, the one behind the seed)
-void launch_vrec_build(uint64_t n, uint32_t j, const uint32_t *sa, const uint16_t *text, uint4 *vrec, cudaStream_t s);
+// verification records: 32 bytes per row (sa[row], the 10 super-characters before that position, the ones 2, 3 and 4 behind it)
+void launch_vrec_build(uint64_t n, const uint32_t *sa, const uint16_t *text, uint4 *vrec, cudaStream_t s);
 
 // seed table (seed.cuh) from the dense tables: fill + one thread per row
 void launch_seed_build(const SeedBuildParams &p, uint64_t n_sectors, cudaStream_t s);

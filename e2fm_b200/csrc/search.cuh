@@ -90,9 +90,12 @@ struct SeedArgs {
     unsigned long long *task_cursor; // device-resident number of row tasks of the chunk
     unsigned long long *stats;
     uint32_t debug;                  // measurement aid (E2FM_SEED_DEBUG): 1 = every lookup reads one of 64 entries (no DRAM gathers; wrong answers)
+    uint32_t lookups;                // SeedPlan::lookups when some shift is enumerated (seed_lookup_enum_kernel), else 0
 };
-// true when every shift of an m-base pattern has at least seed_chars fixed super-characters (and the tables exist)
-bool seed_search_supported(const DevIndex &ix, uint32_t m);
+// the seed length that serves a batch of m-base patterns (tables_mask: bit j set = a table of seed length j is built), whether some
+// shift needs the completions of its last super-character enumerated, and the lookups per pattern; false: the generic path
+struct SeedPlan { uint32_t j; bool enumerate; uint32_t lookups; };
+bool seed_plan(const DevIndex &ix, uint32_t m, uint32_t tables_mask, SeedPlan &out);
 void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t first, uint32_t count, uint32_t m, uint32_t nw,
                           uint4 *packed, uint8_t *pflag, cudaStream_t s);
 void launch_seed_lookup(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s);

@@ -341,6 +341,169 @@ __global__ void __launch_bounds__(256, 5) seed_lookup_kernel(SeedArgs a) {
     if (lane == 0 && n_sect) atomicAdd(a.stats + ST_SECT_BS, n_sect);
 }
 
+// K_a for short patterns: one LANE per (pattern, lookup). A shift with one fixed super-character fewer than a seed is looked up
+// once for every k-mer that completes its '?'-suffixed last super-character (EFMIndex::findWholePatternMatches, :1862-1899, checks
+// that character row by row AFTER the search; rows of a suffix-array interval are sorted by what follows, so the rows that pass
+// are the union of the intervals of the completed seeds). The lookups of a pattern are laid out behind one another (a small table
+// in shared memory says which shift and which completion lookup t is), so that lanes stay busy whatever the shift: for m = 12,
+// k = 4 a pattern has 1 + 64 + 16 + 4 of them, all in a seed table of a few MB that lives in the L2.
+// The rows of an interval are pre-filtered with the '?'-prefixed first super-character where there is one
+// (EFMIndex::backwardStepIfMatch, :2011-2041: the BWT symbol of a row is the character before its suffix, so bwt16[row] is tested
+// against the pattern's first bases); seed_verify_rec_kernel repeats that test from the record, so the filter only saves tasks.
+static constexpr uint32_t SE_DIRECT = 14;                        // every exact counter is staged
+static constexpr uint32_t SE_FLUSH = 128, SE_WCAP = SE_FLUSH + 32 * SE_DIRECT;
+static constexpr uint32_t SE_MAX_LOOKUPS = 8192;
+
+template <int KT, int NW>
+__global__ void __launch_bounds__(256) seed_lookup_enum_kernel(SeedArgs a) {
+    extern __shared__ uint16_t ctab[];                 // [4^k] packed k-mer -> compact code, then tmap[lookups]
+    __shared__ uint2 st_task[8][SE_WCAP];
+    const DevIndex &ix = a.ix;
+    constexpr uint32_t k = KT;
+    constexpr uint32_t KMASK = (1u << (2 * KT)) - 1u;
+    uint32_t *tmap = reinterpret_cast<uint32_t *>(ctab + (1u << (2 * KT)));   // lookup t of a pattern: shift << 16 | completion
+    const uint32_t m = a.m, j = ix.seed_chars, A = ix.A, T = a.lookups;
+    for (uint32_t i = threadIdx.x; i < (1u << (2 * KT)); i += blockDim.x) ctab[i] = ix.packed_code[i];
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (uint32_t sa = 0; sa < k; sa++) {
+            uint32_t L;
+            bool last_var;
+            int l, lo;
+            shift_geometry(m, k, sa, L, last_var, l, lo);
+            if (l <= 0) continue;
+            const uint32_t nfix = (uint32_t)(l - lo);
+            const uint32_t cand = nfix >= j ? 1u : 1u << (2 * (k - (m + sa) % k));
+            for (uint32_t c = 0; c < cand && t < T; c++) tmap[t++] = (sa << 16) | c;
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    uint2 *stage = st_task[warp];
+    uint32_t wcnt = 0;
+    unsigned long long n_sect = 0;
+    auto flush = [&]() {                               // whole warp
+        unsigned long long b0 = 0;
+        if (lane == 0) b0 = atomicAdd(a.task_cursor, (unsigned long long)wcnt);
+        b0 = __shfl_sync(FULL, b0, 0);
+        __syncwarp();
+        for (uint32_t i = lane; i < wcnt; i += 32)
+            if (b0 + i < a.task_cap) a.tasks[b0 + i] = stage[i];
+        __syncwarp();
+        wcnt = 0;
+    };
+    const unsigned long long n_items = (unsigned long long)a.count * T;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    // whole warps run the loop (the ballots below need every lane)
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + warp * 32u; base < n_items; base += stride) {
+        const unsigned long long it = base + lane;
+        uint32_t cnt = 0, s = 0, big = 0, item = 0;
+        if (it < n_items) {
+            const uint32_t p_local = (uint32_t)(it / T), t = (uint32_t)(it - (unsigned long long)p_local * T);
+            const uint64_t p = a.first + p_local;
+            const uint32_t flag = a.pflag ? a.pflag[p] : 0;
+            if (t == 0) {
+                a.counts[p] = 0;                       // seed_verify_rec_kernel (and the generic path for list members) add to it
+                if (flag == 1) {                       // an index symbol outside ACGT: the generic path searches this pattern
+                    const unsigned long long at = atomicAdd(a.stats + ST_COMPLEX, 1ull);
+                    a.complex_list[at] = (uint32_t)p;
+                }
+            }
+            if (flag == 0) {
+                const uint32_t tm_ = tmap[t], sa = tm_ >> 16, c = tm_ & 0xFFFFu;
+                uint32_t L;
+                bool last_var;
+                int l, lo;
+                shift_geometry(m, k, sa, L, last_var, l, lo);
+                const bool en = (uint32_t)(l - lo) < j;                              // the hat's completion c is the seed's last character
+                const uint32_t nf = en ? j - 1 : j;                                 // fixed super-characters of the seed: l - nf .. l - 1
+                PatRegs<NW> pat;
+                pat.load(a.packed + p * NW);
+                unsigned long long window = 0;
+                for (uint32_t q = 0; q < nf; q++)
+                    window |= (unsigned long long)pat.bits(2u * (((uint32_t)l - nf + q) * k - sa), KMASK) << (2 * KT * q);
+                if (en) {
+                    const uint32_t fh = (m + sa) % k;                               // known (first) bases of the last super-character
+                    const uint32_t known = pat.bits(2u * ((uint32_t)l * k - sa), (1u << (2 * fh)) - 1u);
+                    window |= (unsigned long long)(known | (c << (2 * fh))) << (2 * KT * nf);
+                }
+                uint32_t hi = 0, cl = 0;
+                bool absent = false;
+                for (uint32_t q = 0; q < j; q++) {
+                    const uint32_t code = ctab[(uint32_t)(window >> (2 * KT * q)) & KMASK];
+                    absent |= code == 0xFFFFu;
+                    if (q + 1 < j) hi = hi * A + code; else cl = code;
+                }
+                item = p_local * k + sa;
+                if (!absent) {
+                    uint32_t slot;
+                    const size_t entry = seed_sector(ix, hi, cl, slot);
+                    const SeedHit h = seed_decode(seed_load(ix, entry), slot);
+                    n_sect++;
+                    if (h.exact) { s = h.s; cnt = h.cnt; }
+                    else {
+                        uint32_t e;
+                        seed_interval_slow<KT>(ix, ctab, window, j, s, e);
+                        cnt = e > s ? e - s : 0u;
+                    }
+                    if (cnt > SE_DIRECT) { big = cnt; cnt = 0; }
+                    else if (cnt && sa > 0 && ix.bwt16) {
+                        // '?'-prefixed first super-character: keep the rows whose BWT symbol ends with the pattern's first bases.
+                        // The survivors of a short interval are re-packed as (first surviving row, bitmap of the others).
+                        const uint32_t f = k - sa;
+                        const uint32_t want = pat.natural(ix, 0, f);
+                        uint32_t keep = 0;
+                        if (want != 0xFFFFFFFFu)
+                            for (uint32_t q = 0; q < cnt; q++)
+                                if (__ldg(ix.kmer_low + (f - 1) * A + (uint32_t)__ldg(ix.bwt16 + s + q)) == want) keep |= 1u << q;
+                        n_sect++;
+                        big = 0;
+                        cnt = __popc(keep);
+                        cnt |= keep << 8;                                           // the bitmap rides in the high bits to the staging below
+                    }
+                }
+            }
+        }
+        // long intervals (repeats) are written by the whole warp, straight to the task list (unfiltered: the verification decides)
+        unsigned bigm = __ballot_sync(FULL, big != 0);
+        while (bigm) {
+            const int src = __ffs(bigm) - 1;
+            bigm &= bigm - 1;
+            const uint32_t r0 = __shfl_sync(FULL, s, src), ln = __shfl_sync(FULL, big, src), im = __shfl_sync(FULL, item, src);
+            unsigned long long b0 = 0;
+            if (lane == 0) b0 = atomicAdd(a.task_cursor, (unsigned long long)ln);
+            b0 = __shfl_sync(FULL, b0, 0);
+            for (uint32_t q = lane; q < ln; q += 32)
+                if (b0 + q < a.task_cap) a.tasks[b0 + q] = make_uint2(r0 + q, im);
+        }
+        const uint32_t keep = cnt >> 8;                // 0: all rows s .. s + cnt - 1
+        cnt &= 0xFFu;
+        const unsigned any = __ballot_sync(FULL, cnt != 0);
+        if (any) {
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const uint32_t excl = incl - cnt, wtot = __shfl_sync(FULL, incl, 31);
+            if (keep) {
+                uint32_t q = 0;
+                for (uint32_t bits = keep; bits; bits &= bits - 1) stage[wcnt + excl + q++] = make_uint2(s + (uint32_t)__ffs(bits) - 1u, item);
+            } else {
+                for (uint32_t q = 0; q < cnt; q++) stage[wcnt + excl + q] = make_uint2(s + q, item);
+            }
+            wcnt += wtot;
+            if (wcnt >= SE_FLUSH) flush();
+        }
+        (void)lt;
+    }
+    if (wcnt) flush();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_sect += __shfl_xor_sync(FULL, n_sect, d);
+    if (lane == 0 && n_sect) atomicAdd(a.stats + ST_SECT_BS, n_sect);
+}
+
 // text[] is read as whole aligned sectors (one 32-byte load each): with narrower loads a sector is requested from L2 once per load,
 // because thousands of gathers in flight per SM thrash the L1
 struct Sec8 { uint32_t w[8]; };
@@ -588,9 +751,13 @@ __global__ void __launch_bounds__(256, 4) seed_verify_rec_kernel(SeedArgs a) {
             bool last_var;
             int l, lo_i;
             shift_geometry(m, k, sa[u], L, last_var, l, lo_i);
-            const uint32_t d = (uint32_t)(l - (int)j), lo = (uint32_t)lo_i;   // super-characters 0 .. d-1 lie at text positions pos - d .. pos - 1
+            const uint32_t lo = (uint32_t)lo_i;
+            // a shift with one fixed super-character fewer than a seed was looked up with every completion of its '?'-suffixed last
+            // one (seed_lookup_enum_kernel): the seed then ends with that character, nothing is left to check behind it
+            const bool hat_in_seed = last_var && (uint32_t)(l - lo_i) + 1u == j;
+            const uint32_t d = hat_in_seed ? lo : (uint32_t)(l - (int)j);     // super-characters 0 .. d-1 lie at text positions pos - d .. pos - 1
             const uint32_t pos = rec[u].lo.x;
-            const uint32_t left[6] = {rec[u].lo.y, rec[u].lo.z, rec[u].lo.w, rec[u].hi.x, rec[u].hi.y, rec[u].hi.z};
+            const uint32_t left[5] = {rec[u].lo.y, rec[u].lo.z, rec[u].lo.w, rec[u].hi.x, rec[u].hi.y};
             const uint32_t bit0 = 2u * (d * k - sa[u]);                        // bit offset of super-character d (the seed's first)
             tp[u] = pos >= d ? pos - d : pos + (n - d);
             bool good = true;
@@ -627,8 +794,9 @@ __global__ void __launch_bounds__(256, 4) seed_verify_rec_kernel(SeedArgs a) {
                 const uint32_t code = d <= VREC_LEFT ? first_code : (uint32_t)__ldg(ix.text + tp[u]);
                 good = want != 0xFFFFFFFFu && __ldg(ix.kmer_low + (f - 1) * A + code) == want;
             }
-            if (good && last_var) {                                            // '?'-suffixed last super-character: text[pos + j]
-                const uint32_t code = rec[u].hi.w & 0xFFFFu;
+            if (good && last_var && !hat_in_seed) {                            // '?'-suffixed last super-character: text[pos + j]
+                uint32_t code = j == 2 ? (rec[u].hi.z & 0xFFFFu) : (j == 3 ? (rec[u].hi.z >> 16) : (rec[u].hi.w & 0xFFFFu));
+                if (j > 4) code = (unsigned long long)pos + j < ix.n ? (uint32_t)__ldg(ix.text + pos + j) : 0xFFFFu;
                 if (code == 0xFFFFu) good = false;                             // beyond the end of the text
                 else {
                     const uint32_t from = (L - 1) * k - sa[u], f = m - from;
@@ -669,21 +837,43 @@ __global__ void __launch_bounds__(256, 4) seed_verify_rec_kernel(SeedArgs a) {
     if (lane == 0 && n_sect) atomicAdd(a.stats + ST_GATHER, n_sect);
 }
 
-bool seed_search_supported(const DevIndex &ix, uint32_t m) {
-    if (!ix.seed_tab || !ix.packed_code || !ix.sa || !ix.text || ix.k < 2 || ix.k > 7 || m == 0 || m > 128) return false;
-    const uint32_t k = ix.k, j = ix.seed_chars;
-    if (2 * k * j > 64) return false;                              // seed_lookup_kernel reads a seed as one 64-bit window of the pattern
-    for (uint32_t sa = 0; sa < k; sa++) {
-        const uint32_t L = (m + sa + k - 1) / k;
-        const bool last_var = (m + sa) % k != 0;
-        int l = -1;
-        if (!last_var) { if (!(L == 1 && sa > 0)) l = (int)L; }
-        else if (L > 1 && (L > 2 || sa == 0)) l = (int)L - 1;
-        if (l <= 0) continue;                                  // the shift yields nothing (quirk 1)
-        const int lo = sa > 0 ? 1 : 0;
-        if (l - lo < (int)j) return false;                     // fewer fixed super-characters than a seed
+// Which seed length serves a batch of m-base patterns, and which shifts need their '?'-suffixed last super-character enumerated.
+// A shift with nfix fixed super-characters is looked up as it is when nfix >= j (the hat is then checked against the row's record);
+// when nfix == j - 1 and it ends with a partial super-character, every k-mer that completes that one is looked up (4^(k - fh)
+// candidates for fh known bases), which needs the verification records. Among the seed lengths that serve every shift the
+// cheapest wins: lookups (a table beyond the L2 costs four times one inside it) plus the rows they are expected to return.
+bool seed_plan(const DevIndex &ix, uint32_t m, uint32_t tables_mask, SeedPlan &out) {
+    out = SeedPlan{0, false, 0};
+    if (!ix.packed_code || !ix.sa || !ix.text || ix.k < 2 || ix.k > 7 || m == 0 || m > 128) return false;
+    const uint32_t k = ix.k;
+    double best = 0;
+    for (uint32_t j = 2; j <= 8; j++) {
+        if (!(tables_mask & (1u << j)) || 2 * k * j > 64) continue;   // seed_lookup_kernel reads a seed as one 64-bit window of the pattern
+        bool ok = true, enumerate = false;
+        uint64_t cand = 0;
+        for (uint32_t sa = 0; sa < k && ok; sa++) {
+            uint32_t L;
+            bool last_var;
+            int l, lo;
+            shift_geometry(m, k, sa, L, last_var, l, lo);
+            if (l <= 0) continue;                                  // the shift yields nothing (quirk 1)
+            const uint32_t nfix = (uint32_t)(l - lo);
+            if (nfix >= j) cand += 1;
+            else if (last_var && nfix + 1 == j && ix.vrec) {
+                const uint32_t fh = (m + sa) % k;
+                cand += 1ull << (2 * (k - fh));
+                enumerate = true;
+            } else ok = false;
+        }
+        if (!ok || cand == 0 || cand > 8192) continue;
+        double seeds = 1, entries = (double)ix.seed_gph * 16.0;
+        for (uint32_t i = 0; i < j; i++) seeds *= ix.A;
+        for (uint32_t i = 0; i + 1 < j; i++) entries *= ix.A;
+        const double rows = (double)ix.n / seeds;                  // expected rows per looked-up seed
+        const double cost = (double)cand * ((entries > 64e6 ? 4.0 : 1.0) + 1.5 * rows);
+        if (out.j == 0 || cost < best) { best = cost; out = SeedPlan{j, enumerate, (uint32_t)cand}; }
     }
-    return true;
+    return out.j != 0;
 }
 
 template <class Kern>
@@ -701,7 +891,14 @@ static void launch_seed_nw(const SeedArgs &a, int n_sm, bool verify, cudaStream_
     static const uint32_t lookup_max = resident_ctas(seed_lookup_kernel<KT, NW, 0>, smem, n_sm);
     static const uint32_t verify_max = resident_ctas(seed_verify_kernel<KT, NW>, smem, n_sm);
     static const uint32_t verify_rec_max = resident_ctas(seed_verify_rec_kernel<KT, NW>, smem, n_sm);
-    if (!verify) {
+    if (!verify && a.lookups) {
+        const size_t smem_e = smem + (size_t)a.lookups * 4;
+        static const bool opted = cudaFuncSetAttribute(seed_lookup_enum_kernel<KT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024) == cudaSuccess;
+        (void)opted;
+        static const uint32_t enum_max = resident_ctas(seed_lookup_enum_kernel<KT, NW>, smem + 4096, n_sm);
+        const unsigned long long want = ((unsigned long long)a.count * a.lookups + 255) / 256;
+        seed_lookup_enum_kernel<KT, NW><<<(uint32_t)std::max<unsigned long long>(1, std::min<unsigned long long>(want, enum_max)), 256, smem_e, s>>>(a);
+    } else if (!verify) {
         const uint32_t groups = ((a.count + PPC - 1) / PPC + SEED_U - 1) / SEED_U;
         const uint32_t blocks = std::max(1u, std::min(groups, lookup_max));
         switch (a.ix.seed_chars) {                    // the usual seed lengths get their own instance (unrolled code loop)

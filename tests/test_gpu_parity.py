@@ -467,6 +467,53 @@ def test_config1_short_patterns_take_the_wildcard_scan(config1, key64, oracle_mo
     dev.close()
 
 
+@pytest.mark.gpu
+def test_config1_short_fixed_length_batches_through_the_seed_tables(config1, key64, oracle_mod):
+    """fixed-length batches of SHORT patterns (BASELINE configs[4]'s shape: fewer fixed super-characters than the index's own seed
+    length) are searched with a shorter seed table, the '?'-suffixed last super-character of a shift enumerated where it is the
+    seed's last one: same counts and positions as the oracle, through the two-call form and through e2fm_search_hits"""
+    dev = capi.DeviceIndex(config1["index"], key64)
+    orc = oracle_mod.OracleIndex(config1["index"], key64)
+    try:
+        assert dev.info.seed_chars >= 3 and dev.info.vrec_mb > 0
+        rng = np.random.default_rng(5)
+        seq = config1["seqs"][0]
+        seeded_lengths = []
+        for L in (8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 23):
+            st = rng.integers(0, len(seq) - L, 150)
+            pats = [seq[s:s + L].tobytes() for s in st] + [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L)) for _ in range(30)]
+            pats += [b"ACGTACGTACGTACGTACGTACGTACGT"[:L], b"A" * L]
+            arr = np.frombuffer(b"".join(pats), dtype=np.uint8).reshape(len(pats), L).copy()
+            want = [orc.search(p, True) for p in pats]
+            for locate in (True, False):
+                r = dev.search_fixed(arr, locate)
+                c = dev.last_batch_counters()
+                out = r.fetch()
+                for i, (cnt, pos) in enumerate(want):
+                    assert int(out["counts"][i]) == cnt, (L, pats[i], locate, c["seeded"])
+                    if locate:
+                        a, b = int(out["pos_offsets"][i]), int(out["pos_offsets"][i + 1])
+                        assert np.array_equal(out["positions"][a:b], pos), (L, pats[i], c["seeded"])
+                r.free()
+            if c["seeded"]:
+                seeded_lengths.append(L)
+                total = sum(w[0] for w in want)
+                packed, bad = capi.pack_patterns(arr)
+                assert bad == 0
+                o32 = np.zeros(len(pats) + 1, dtype=np.uint32)
+                s32 = np.zeros(total + 4, dtype=np.uint32)
+                f32 = np.zeros(total + 4, dtype=np.uint32)
+                got = dev.search_hits(packed, len(pats), L, True, True, None, o32, s32, f32)
+                assert got == total and np.array_equal(np.diff(o32.astype(np.int64)), [w[0] for w in want]), L
+                for i in (0, 17, 151, len(pats) - 1):
+                    a, b = int(o32[i]), int(o32[i + 1])
+                    assert [orc.map_position(int(x)) for x in want[i][1]] == list(zip(s32[a:b].tolist(), f32[a:b].tolist())), (L, i)
+        assert 12 in seeded_lengths and 16 in seeded_lengths, seeded_lengths
+    finally:
+        dev.close()
+        orc.close()
+
+
 # ---------------------------------------------------------------- extract (SURVEY.md 8(f) row 1)
 
 @pytest.mark.parametrize("name", ["col3_k4", "one_k3"])
@@ -597,7 +644,10 @@ def test_seed_search_matches_reference(gpu, golden, key64, name, seed_chars):
             arr = np.frombuffer(b"".join(g["patterns"][i] for i in idxs), dtype=np.uint8).reshape(len(idxs), L).copy()
             want = _subset(g["res"], idxs)
             for locate in (False, True):
-                r = dev.search_fixed(arr, locate)
+                try:
+                    r = dev.search_fixed(arr, locate)
+                except capi.E2FMError as e:
+                    raise AssertionError(f"search_fixed failed for length {L}, {len(idxs)} patterns, locate={locate}: {e}")
                 seeded = dev.last_batch_counters()["seeded"]
                 _check_out(r.fetch(), want, locate, (name, L, "seed" if seeded else "generic"))
                 r.free()
