@@ -482,6 +482,15 @@ def gpu_arm(args, rank, world, local_rank):
         assert bad == 0, "the synthetic batch holds only A C G T"
     else:
         h_pats[lo:hi] = mine
+    # what travels over PCIe in the end-to-end call: the same 2-bit codes without the padding (ceil(L / 4) bytes per pattern,
+    # E2FM_PACKED_TIGHT; the device widens them stage by stage)
+    tight_api = packed_api and args.e2e_api == "hits" and not args.no_tight
+    h_tight = None
+    if tight_api:
+        tstride = capi.packed_tight_stride(L)
+        h_tight = shm.array("patterns_tight", (npat_all, tstride), np.uint8)
+        _, bad = capi.pack_patterns_tight(mine, h_tight[lo:hi].reshape(-1))
+        assert bad == 0
     # result buffers of the whole batch, ONE host buffer per array (every rank writes its own region of it): what
     # EFMCollection::search returns, in 32 bits. Region r holds rank r's occurrences; its offsets index that region.
     per_rank = -(-npat_all // world)
@@ -523,7 +532,8 @@ def gpu_arm(args, rank, world, local_rank):
         t0 = time.perf_counter()
         if args.e2e_api == "hits":
             # locate: a pattern's count is its number of occurrences (every match is located), so only the offsets travel back
-            total = ix.search_hits(h_pats[lo:hi].reshape(-1), npat, L, packed_api, locate, None if locate else h_counts[lo:hi],
+            total = ix.search_hits((h_tight if tight_api else h_pats)[lo:hi].reshape(-1), npat, L, 2 if tight_api else int(packed_api), locate,
+                                   None if locate else h_counts[lo:hi],
                                    h_noff[rank][:npat + 1] if locate else None, h_seq[rank] if locate else None,
                                    h_off[rank] if locate else None)
         else:
@@ -651,7 +661,7 @@ def gpu_arm(args, rank, world, local_rank):
         roofline = make_roofline(args, capi, info, local_rank, ctr_sum, ph_ms, steps, peak, peak_kind, npat)
         if sharded_obj is not None:
             roofline["note"] += "; the gather microbenchmark ran after the sharded leg freed the replica"
-        h2d = int(npat * unit)
+        h2d = int(npat * (tstride if tight_api else unit))
         d2h = int(((npat + 1) * 4 + (occ_total // max(steps, 1)) * 8) if locate else npat * 4)
         line = {
             "metric": "patterns/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -670,7 +680,8 @@ def gpu_arm(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                     "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e2e_ms_max / steps,
                     "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None,
-                    "what": (("2-bit packed patterns (e2fm_search_batch_packed, 16 B per 64 bases)" if packed_api else "ASCII patterns") +
+                    "what": ((f"2-bit packed patterns without padding (E2FM_PACKED_TIGHT, {tstride} B per pattern)" if tight_api else
+                              "2-bit packed patterns (e2fm_search_batch_packed, 16 B per 64 bases)" if packed_api else "ASCII patterns") +
                              " from page-locked host memory; " +
                              ("per-pattern occurrence offsets, sequence index and offset in the sequence of every occurrence (what "
                               "EFMCollection::search returns, FMCollection.h:23-44), 32 bits each" if locate else "32-bit counts") +
@@ -991,6 +1002,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")
     ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
+    ap.add_argument("--no-tight", action="store_true", help="end-to-end call on the 16-byte-word packing instead of the tight one")
     ap.add_argument("--ascii", action="store_true", help="ASCII patterns through e2fm_search_batch_fixed even when the packed entry point would take the batch")
     ap.add_argument("--e2e-api", default="hits", choices=["hits", "fetch"], help="end-to-end leg: the pipelined one-call form or search + fetch")
     ap.add_argument("--walk", action="store_true", help="locate / verify by per-query walks from the marked rows instead of the dense tables")

@@ -38,7 +38,7 @@ EXPORTS = [
     "e2fm_packed_stride", "e2fm_pack_patterns", "e2fm_search_batch_packed", "e2fm_search_batch_packed_device",
     "e2fm_result_fetch_compact", "e2fm_debug_seed",
     "e2fm_shardset_unique_id", "e2fm_shardset_create", "e2fm_shardset_destroy", "e2fm_shardset_slice", "e2fm_shardset_search",
-    "e2fm_shardset_last_ms", "e2fm_search_hits", "e2fm_debug_gather_bench_ex",
+    "e2fm_shardset_last_ms", "e2fm_search_hits", "e2fm_debug_gather_bench_ex", "e2fm_packed_tight_stride", "e2fm_pack_patterns_tight",
 ]
 
 
@@ -99,6 +99,9 @@ def lib():
     L.e2fm_packed_stride.restype = u32
     L.e2fm_packed_stride.argtypes = [u32]
     L.e2fm_pack_patterns.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
+    L.e2fm_packed_tight_stride.argtypes = [u32]
+    L.e2fm_packed_tight_stride.restype = u32
+    L.e2fm_pack_patterns_tight.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
     L.e2fm_search_batch_packed.argtypes = [vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
     L.e2fm_search_batch_packed_device.argtypes = [vp, vp, u64, u32, i32, C.POINTER(vp)]
     L.e2fm_result_fetch_compact.argtypes = [vp, vp, vp, vp, vp]
@@ -348,8 +351,8 @@ class DeviceIndex:
 
     def search_hits(self, patterns: np.ndarray, n: int, length: int, packed: bool, locate: bool, counts: np.ndarray = None,
                     occ_offsets: np.ndarray = None, seq_index: np.ndarray = None, seq_offset: np.ndarray = None) -> int:
-        """e2fm_search_hits: host patterns (ASCII n x length, or packed) -> 32-bit results in the caller's host arrays, pipelined.
-        Returns the number of occurrences written (locate)."""
+        """e2fm_search_hits: host patterns (packed: 0/False ASCII n x length, 1/True 16-byte words, 2 tight) -> 32-bit results in
+        the caller's host arrays, pipelined. Returns the number of occurrences written (locate)."""
         assert patterns.dtype == np.uint8 and patterns.flags.c_contiguous
         for a in (counts, occ_offsets, seq_index, seq_offset):
             assert a is None or (a.dtype == np.uint32 and a.flags.c_contiguous)
@@ -360,7 +363,7 @@ class DeviceIndex:
         h.seq_offset = seq_offset.ctypes.data if seq_offset is not None else None
         h.capacity = min(seq_index.size, seq_offset.size) if (seq_index is not None and seq_offset is not None) else 0
         self.last_hits_total = 0
-        rc = lib().e2fm_search_hits(self._h, patterns.ctypes.data if patterns.size else None, n, length, 1 if packed else 0,
+        rc = lib().e2fm_search_hits(self._h, patterns.ctypes.data if patterns.size else None, n, length, int(packed),
                                     MODE_LOCATE if locate else MODE_COUNT, C.byref(h))
         self.last_hits_total = int(h.total)
         check(rc)
@@ -491,6 +494,21 @@ def pack_patterns(pats: np.ndarray, out: np.ndarray = None):
         out = np.zeros(n * packed_stride(L), dtype=np.uint8)
     bad = C.c_uint64(0)
     check(lib().e2fm_pack_patterns(pats.ctypes.data if pats.size else None, n, L, out.ctypes.data if out.size else None, C.byref(bad)))
+    return out, int(bad.value)
+
+
+def packed_tight_stride(length: int) -> int:
+    return int(lib().e2fm_packed_tight_stride(length))
+
+
+def pack_patterns_tight(pats: np.ndarray, out: np.ndarray = None):
+    """(n, L) ASCII uint8 -> (n * ceil(L / 4) bytes without padding, number of patterns with a byte outside ACGT)"""
+    assert pats.dtype == np.uint8 and pats.ndim == 2 and pats.flags.c_contiguous
+    n, L = pats.shape
+    if out is None:
+        out = np.zeros(n * packed_tight_stride(L), dtype=np.uint8)
+    bad = C.c_uint64(0)
+    check(lib().e2fm_pack_patterns_tight(pats.ctypes.data if pats.size else None, n, L, out.ctypes.data if out.size else None, C.byref(bad)))
     return out, int(bad.value)
 
 

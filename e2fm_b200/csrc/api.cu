@@ -148,6 +148,7 @@ struct e2fm_index {
     int n_sm = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-buffer pipeline
+    cudaStream_t res_stream = nullptr;                         // result kernels of e2fm_search_hits stages (beside the next stage's search)
     int phase_timers = 2;                                         // 0 never, 1 always, 2 device-resident batches only
     bool pipe_taper = false;                                      // host batches: stage sizes halve towards the end of the batch
     uint64_t pipe_patterns = 1u << 18;                          // patterns per pipeline stage when the batch comes from the host
@@ -177,6 +178,10 @@ struct e2fm_index {
     HitsStageInfo *h_stage_info = nullptr;   // pinned, written by hits_tail_kernel
     size_t h_stage_cap = 0;
     uint64_t hits_stage_patterns = 1u << 20;   // patterns per (full) pipeline stage of e2fm_search_hits
+    // the kernels of a pipeline stage as ONE graph launch (slot = 3 * locate + packing): re-captured per stage, the instantiated
+    // graph is updated in place (same topology, other arguments)
+    cudaGraphExec_t hits_exec[12] = {};        // [0..5] search part, [6..11] result part
+    bool hits_graph = true;                    // E2FM_HITS_GRAPH=0: plain launches
 };
 
 struct e2fm_result {
@@ -1045,7 +1050,7 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
 // running occurrence total, and each stage reports {first occurrence, occurrences, trouble} into page-locked host memory, which is
 // all the host needs to queue the stage's D2H copies. Returns false when a store sized from earlier batches was too small or a
 // pattern needs the generic path (an index symbol outside ACGT): the caller then runs the plain path, which sizes exactly.
-bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, bool packed_in, int mode, e2fm_hits *hits, const SeedPlan &plan) {
+bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, int packing, int mode, e2fm_hits *hits, const SeedPlan &plan) {
     cudaStream_t s = ix->stream;
     DevIndex dix = ix->dix;                       // the kernels see the table of this batch's seed length
     dix.seed_tab = ix->seed_tabs[plan.j];
@@ -1053,8 +1058,11 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     const bool locate = mode == E2FM_MODE_LOCATE;
     const uint32_t nw = (m + 63) / 64;
     Batch b{nullptr, nullptr, m, n, 0};
+    const bool packed_in = packing == E2FM_PACKED_WORDS;     // already in the 16-byte form the kernels load
+    const bool tight_in = packing == E2FM_PACKED_TIGHT;      // ceil(m / 4) bytes each: widened on the device, stage by stage
     b.packed_in = packed_in;
-    b.total_bytes = n * b.unit();
+    const uint64_t unit = tight_in ? e2fm_packed_tight_stride(m) : b.unit();   // input bytes per pattern
+    b.total_bytes = n * unit;
     b.h_bytes = h_in;
     memset(ix->batch_ms, 0, sizeof(ix->batch_ms));
     memset(ix->batch_ctr, 0, sizeof(ix->batch_ctr));
@@ -1073,9 +1081,11 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     WsBuf<uint8_t> pflag_ws(ix, WS_PFLAG, s);
     if (!packed_in) {
         packed_ws.alloc(n * nw + 1);
-        pflag_ws.alloc(n + 1);
         packed = packed_ws.p;
-        pflag = pflag_ws.p;
+        if (!tight_in) {
+            pflag_ws.alloc(n + 1);
+            pflag = pflag_ws.p;
+        }
     }
     WsBuf<unsigned long long> counts(ix, WS_HCOUNTS, n, s);
     WsBuf<uint32_t> clist(ix, WS_CLIST, stage, s);
@@ -1094,8 +1104,8 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         seq32(ix, WS_OUT_SEQ, s), soff32(ix, WS_OUT_SOFF, s);
     WsBuf<uint64_t> res_pos(ix, WS_RES_POS, s), st_off(ix, WS_STAGE_OFF, s), st_pos(ix, WS_STAGE_POS, s), scratch(ix, WS_SCRATCH, s);
     if (locate) {
-        res_pat.alloc(res_cap);
-        res_pos.alloc(res_cap);
+        res_pat.alloc(2 * res_cap);                          // two halves: stage c uses half c & 1
+        res_pos.alloc(2 * res_cap);
         st_off.alloc(stage + 1);
         st_pos.alloc(res_cap);
         cursor.alloc(stage);
@@ -1136,7 +1146,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         CK(cudaStreamWaitEvent(ix->h2d_stream, ready, 0));
         const int hh = tm.begin(0, ix->h2d_stream);
         for (uint64_t c = 0; c < S; c++) {                   // every H2D copy queued up front, one event per stage
-            const uint64_t lo = sg.bounds[c] * b.unit(), hi = sg.bounds[c + 1] * b.unit();
+            const uint64_t lo = sg.bounds[c] * unit, hi = sg.bounds[c + 1] * unit;
             CK(cudaMemcpyAsync(d_in.p + lo, h_in + lo, hi - lo, cudaMemcpyHostToDevice, ix->h2d_stream));
             cudaEvent_t e = ix->events.get(false);
             sg.h2d_ev.push_back(e);
@@ -1146,34 +1156,106 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     }
     std::vector<cudaEvent_t> done(S);
     // E2FM_HITS_TRACE=1: per-stage timeline (CUDA events on the three streams) on stderr
-    static const bool trace = getenv("E2FM_HITS_TRACE") && atoi(getenv("E2FM_HITS_TRACE")) != 0;
+    // (2: also an event after every kernel group of a stage; E2FM_HITS_SERIAL=1: the search starts when the whole batch has arrived)
+    static const int trace_level = getenv("E2FM_HITS_TRACE") ? atoi(getenv("E2FM_HITS_TRACE")) : 0;
+    static const bool serial = getenv("E2FM_HITS_SERIAL") && atoi(getenv("E2FM_HITS_SERIAL")) != 0;
+    const bool trace = trace_level != 0, trace_k = trace_level >= 2;
     std::vector<cudaEvent_t> tr_begin(trace ? S : 0), tr_search(trace ? S : 0), tr_out(trace ? S : 0);
+    std::vector<cudaEvent_t> tr_k(trace_k ? S * 4 : 0);
+    // two compute streams: the search kernels of stage c + 1 (s) run beside the result kernels of stage c (rs); the lists of located
+    // occurrences between them are double-buffered (E2FM_HITS_OVERLAP=0: one stream)
+    static const bool overlap_env = !(getenv("E2FM_HITS_OVERLAP") && atoi(getenv("E2FM_HITS_OVERLAP")) == 0);
+    cudaStream_t rs = overlap_env ? ix->res_stream : s;
+    auto mark = [&](uint64_t c, int which, cudaStream_t on) {
+        if (!trace_k) return;
+        tr_k[c * 4 + which] = ix->events.get(true);
+        CK(cudaEventRecord(tr_k[c * 4 + which], on));
+    };
+    if (serial) CK(cudaStreamWaitEvent(s, sg.h2d_ev[S - 1], 0));
+    static const bool graph_env = !(getenv("E2FM_HITS_GRAPH") && atoi(getenv("E2FM_HITS_GRAPH")) == 0);
+    const bool use_graph = graph_env && ix->hits_graph && !trace_k;
     cudaEvent_t tr_zero = nullptr;
     if (trace) { tr_zero = ix->events.get(true); CK(cudaEventRecord(tr_zero, s)); }
+    if (rs != s) {                                             // the buffers were allocated (and zeroed) in order on s
+        cudaEvent_t ready = ix->events.get(false);
+        CK(cudaEventRecord(ready, s));
+        CK(cudaStreamWaitEvent(rs, ready, 0));
+    }
     uint64_t launches = 0;
+    // The kernels of a part go down as ONE graph launch: while the batch is still arriving the PCIe link is full of H2D traffic, and
+    // every command the GPU front end fetches from the host waits behind it (profiles/exp/logs/hits_trace2_*: the gap between two
+    // launches grows from 3 to 25 us). The graph is re-captured per stage and the instantiated one updated in place.
+    auto graph_part = [&](cudaStream_t on, int slot, auto &&body) {
+        if (!use_graph) { body(); return; }
+        CK(cudaStreamBeginCapture(on, cudaStreamCaptureModeRelaxed));
+        try {
+            body();
+        } catch (...) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(on, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamEndCapture(on, &g));
+        cudaGraphExec_t &ge = ix->hits_exec[slot];
+        if (ge) {
+            cudaGraphExecUpdateResultInfo upd;
+            if (cudaGraphExecUpdate(ge, g, &upd) != cudaSuccess) {          // another topology: instantiate anew
+                cudaGetLastError();
+                cudaGraphExecDestroy(ge);
+                ge = nullptr;
+            }
+        }
+        if (!ge) {
+            const cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+            if (e != cudaSuccess) { ge = nullptr; cudaGraphDestroy(g); CK(e); }
+        }
+        cudaGraphDestroy(g);
+        CK(cudaGraphLaunch(ge, on));
+    };
+    std::vector<cudaEvent_t> searched(S);
     auto enqueue = [&](uint64_t c) {
         const uint64_t first = sg.bounds[c];
         const uint32_t cnt = (uint32_t)(sg.bounds[c + 1] - first);
         unsigned long long *st = stage_stats.p + c * ST_N;
+        uint32_t *rpat = res_pat.p ? res_pat.p + (c & 1) * res_cap : nullptr;
+        uint64_t *rpos = res_pos.p ? res_pos.p + (c & 1) * res_cap : nullptr;
+        const int slot = (locate ? 3 : 0) + packing;
+        // search part: [widen | pack], seed lookup, verification
         CK(cudaStreamWaitEvent(s, sg.h2d_ev[c], 0));
+        if (c >= 2 && rs != s) CK(cudaStreamWaitEvent(s, done[c - 2], 0));     // the results of stage c - 2 have left this half of the lists
         if (trace) { tr_begin[c] = ix->events.get(true); CK(cudaEventRecord(tr_begin[c], s)); }
-        if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
-        SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, res_pat.p, res_pos.p, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st, 0u, plan.enumerate ? plan.lookups : 0u};
-        launch_seed_lookup(sa, nw, ix->n_sm, s);
-        launch_seed_verify(sa, nw, ix->n_sm, s);
-        launches += 2;
-        if (trace) { tr_search[c] = ix->events.get(true); CK(cudaEventRecord(tr_search[c], s)); }
-        if (locate) {
-            launch_hits_scan(counts.p + first, cnt, st_off.p, cursor.p, reinterpret_cast<unsigned long long *>(scratch.p), s);
-            launch_hits_scatter(res_pat.p, res_pos.p, st, res_cap, first, st_off.p, cursor.p, st_pos.p, ix->n_sm, s);
-            launches += 3;
-        }
-        HitsOut ho{counts.p, first, cnt, locate ? st_off.p : nullptr, st_pos.p, run.p, out_cap, res_cap, task_cap, cnt32.p, off32.p, seq32.p, soff32.p,
-                   big_list.p, locate && c + 1 == S ? off32.p + n : nullptr, st, task_ctr.p + c, info + c};
-        launch_hits_finish(dix, ho, ix->n_sm, s);
-        launches += 2;
+        graph_part(s, slot, [&]() {
+            if (tight_in) { launch_widen_packed(b.d_bytes, first, cnt, m, nw, packed_ws.p, s); launches++; }
+            else if (!packed_in) { launch_pack_patterns(dix, b.d_bytes, first, cnt, m, nw, packed_ws.p, pflag_ws.p, s); launches++; }
+            SeedArgs sa{dix, packed, pflag, m, first, cnt, mode, counts.p, rpat, rpos, res_cap, clist.p, tasks.p, task_cap, task_ctr.p + c, st, 0u, plan.enumerate ? plan.lookups : 0u};
+            mark(c, 0, s);
+            launch_seed_lookup(sa, nw, ix->n_sm, s);
+            mark(c, 1, s);
+            launch_seed_verify(sa, nw, ix->n_sm, s);
+            launches += 2;
+        });
+        searched[c] = ix->events.get(trace);
+        CK(cudaEventRecord(searched[c], s));
+        if (trace) tr_search[c] = searched[c];
+        // result part: the stage's CSR, scatter, sort + (sequence, offset), report
+        if (rs != s) CK(cudaStreamWaitEvent(rs, searched[c], 0));
+        graph_part(rs, 6 + slot, [&]() {
+            if (locate) {
+                launch_hits_scan(counts.p + first, cnt, st_off.p, cursor.p, reinterpret_cast<unsigned long long *>(scratch.p), rs);
+                mark(c, 2, rs);
+                launch_hits_scatter(rpat, rpos, st, res_cap, first, st_off.p, cursor.p, st_pos.p, ix->n_sm, rs);
+                launches += 3;
+            }
+            mark(c, 3, rs);
+            HitsOut ho{counts.p, first, cnt, locate ? st_off.p : nullptr, st_pos.p, run.p, out_cap, res_cap, task_cap, cnt32.p, off32.p, seq32.p, soff32.p,
+                       big_list.p, locate && c + 1 == S ? off32.p + n : nullptr, st, task_ctr.p + c, info + c};
+            launch_hits_finish(dix, ho, ix->n_sm, rs);
+            launches += 2;
+        });
         done[c] = ix->events.get(trace);
-        CK(cudaEventRecord(done[c], s));
+        CK(cudaEventRecord(done[c], rs));
     };
     bool trouble = false;
     uint64_t total = 0;
@@ -1196,13 +1278,17 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
         if (trace) { tr_out[c] = ix->events.get(true); CK(cudaEventRecord(tr_out[c], ix->d2h_stream)); }
     };
     const uint64_t ahead = 2;                                  // stages queued on the compute stream beyond the one being drained
+    uint64_t enqueued = 0;
     for (uint64_t c = 0; c < S && !trouble; c++) {
         enqueue(c);
+        enqueued = c + 1;
         if (c >= ahead) drain(c - ahead);
     }
     for (uint64_t c = S > ahead ? S - ahead : 0; c < S && !trouble; c++) drain(c);
+    if (rs != s && enqueued) CK(cudaStreamWaitEvent(s, done[enqueued - 1], 0));
     tm.end(whole);
     CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(rs));
     CK(cudaStreamSynchronize(ix->d2h_stream));
     CK(cudaStreamSynchronize(ix->h2d_stream));
     CK(cudaGetLastError());
@@ -1215,6 +1301,17 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
             cudaEventElapsedTime(&t3, tr_zero, tr_out[c]);
             fprintf(stderr, "[hits] stage %2llu: %8llu patterns  search starts %7.3f  seed kernels done %7.3f  results done %7.3f  D2H done %7.3f ms\n",
                     (unsigned long long)c, (unsigned long long)(sg.bounds[c + 1] - sg.bounds[c]), t0, t1, t2, t3);
+            if (trace_k && locate) {
+                float k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
+                cudaEventElapsedTime(&k0, tr_begin[c], tr_k[c * 4 + 0]);        // widen / pack
+                cudaEventElapsedTime(&k1, tr_k[c * 4 + 0], tr_k[c * 4 + 1]);    // lookup
+                cudaEventElapsedTime(&k2, tr_k[c * 4 + 1], tr_search[c]);       // verify
+                cudaEventElapsedTime(&k3, tr_search[c], tr_k[c * 4 + 2]);       // scan (2 kernels)
+                cudaEventElapsedTime(&k4, tr_k[c * 4 + 2], tr_k[c * 4 + 3]);    // scatter
+                cudaEventElapsedTime(&k5, tr_k[c * 4 + 3], done[c]);            // sort + finish, tail + report
+                fprintf(stderr, "[hits]           us: widen %5.1f  lookup %6.1f  verify %6.1f  scan %5.1f  scatter %5.1f  sortfin+tail %5.1f\n",
+                        1e3f * k0, 1e3f * k1, 1e3f * k2, 1e3f * k3, 1e3f * k4, 1e3f * k5);
+            }
         }
     }
     // what the stages report: trouble flags (count mode reads them only now), densities for the next batch's stores
@@ -1249,6 +1346,7 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
 void quiesce(e2fm_index *ix) {
     if (ix->h2d_stream) cudaStreamSynchronize(ix->h2d_stream);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->res_stream) cudaStreamSynchronize(ix->res_stream);
     if (ix->d2h_stream) cudaStreamSynchronize(ix->d2h_stream);
     cudaGetLastError();
 }
@@ -1435,6 +1533,7 @@ int e2fm_index_open(const uint8_t *file, size_t size, const uint8_t key64[64], i
         ix->life->stream = ix->stream;
         CK(cudaStreamCreateWithFlags(&ix->h2d_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ix->d2h_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ix->res_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = ~0ull;   // keep freed blocks in the pool: batches reuse their work buffers
@@ -1467,8 +1566,10 @@ void e2fm_index_close(e2fm_index *ix) {
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->h_stats) cudaFreeHost(ix->h_stats);
     if (ix->h_stage_info) cudaFreeHost(ix->h_stage_info);
+    for (auto &ge : ix->hits_exec) if (ge) cudaGraphExecDestroy(ge);
     if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);
     if (ix->d2h_stream) cudaStreamDestroy(ix->d2h_stream);
+    if (ix->res_stream) cudaStreamDestroy(ix->res_stream);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     if (ix->life) {
         ix->life->alive = false;                 // results that are still around free their arrays synchronously from now on
@@ -1543,6 +1644,32 @@ int e2fm_search_batch_device_fixed(e2fm_index *ix, const uint8_t *d_bytes, uint6
 }
 
 uint32_t e2fm_packed_stride(uint32_t length) { return 16u * ((length + 63u) / 64u); }
+uint32_t e2fm_packed_tight_stride(uint32_t length) { return (length + 3u) / 4u; }
+
+int e2fm_pack_patterns_tight(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable) {
+    if ((n && (!ascii || !packed_out)) || length == 0) return fail(E2FM_ERR_ARG, "bad argument");
+    static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
+    const uint32_t tb = e2fm_packed_tight_stride(length);
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *src = ascii + i * length;
+        uint8_t *dst = packed_out + i * tb;
+        uint32_t worst = 0;
+        for (uint32_t b = 0; b < tb; b++) {
+            uint32_t cur = 0;
+            const uint32_t end = std::min<uint32_t>(length, 4 * b + 4);
+            for (uint32_t j = 4 * b, sh = 0; j < end; j++, sh += 2) {
+                const uint32_t c = lut.v[src[j]];
+                worst |= c;
+                cur |= (c & 3u) << sh;
+            }
+            dst[b] = (uint8_t)cur;
+        }
+        if (worst & 4u) bad++;
+    }
+    if (n_unpackable) *n_unpackable = bad;
+    return E2FM_OK;
+}
 
 int e2fm_pack_patterns(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable) {
     if ((n && (!ascii || !packed_out)) || length == 0) return fail(E2FM_ERR_ARG, "bad argument");
@@ -1587,6 +1714,7 @@ int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32
     if (!ix || !hits || length == 0 || (mode != E2FM_MODE_COUNT && mode != E2FM_MODE_LOCATE)) return fail(E2FM_ERR_ARG, "bad argument");
     if (n && !patterns) return fail(E2FM_ERR_ARG, "pattern bytes missing");
     if (n >= (1ull << 32)) return fail(E2FM_ERR_ARG, "more than 2^32-1 patterns in one batch");
+    if (packed < 0 || packed > E2FM_PACKED_TIGHT) return fail(E2FM_ERR_ARG, "packed must be E2FM_ASCII, E2FM_PACKED_WORDS or E2FM_PACKED_TIGHT");
     const bool locate = mode == E2FM_MODE_LOCATE;
     if (locate && (!hits->occ_offsets || ((!hits->seq_index || !hits->seq_offset) && hits->capacity)))
         return fail(E2FM_ERR_ARG, "locate needs occ_offsets, seq_index and seq_offset");
@@ -1598,7 +1726,7 @@ int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32
     if (n && ix->use_seed && ix->use_dense && plan_seed(ix, length, plan)) {
         try {
             CK(cudaSetDevice(ix->device));
-            piped = hits_pipeline(ix, patterns, n, length, packed != 0, mode, hits, plan);
+            piped = hits_pipeline(ix, patterns, n, length, packed, mode, hits, plan);
         } catch (const CudaError &e) {
             quiesce(ix);
             return fail(E2FM_ERR_CUDA, e.what());
@@ -1615,6 +1743,17 @@ int e2fm_search_hits(e2fm_index *ix, const uint8_t *patterns, uint64_t n, uint32
     e2fm_result *r = nullptr;
     const uint64_t unit = packed ? e2fm_packed_stride(length) : length;
     const uint64_t gave_up = ix->batch_ctr[13];
+    std::vector<uint8_t> widened;                            // tight input: the plain path takes the 16-byte form
+    if (packed == E2FM_PACKED_TIGHT) {
+        try { widened.assign(n * unit, 0); } catch (const std::bad_alloc &) { return fail(E2FM_ERR_OOM, "out of host memory"); }
+        const uint32_t tb = e2fm_packed_tight_stride(length);
+        const uint32_t tail_bits = 2 * (length & 3u);        // bits of the last byte that belong to the pattern (0: all 8)
+        for (uint64_t i = 0; i < n; i++) {
+            memcpy(widened.data() + i * unit, patterns + i * tb, tb);
+            if (tail_bits) widened[i * unit + tb - 1] &= (uint8_t)((1u << tail_bits) - 1u);
+        }
+        patterns = widened.data();
+    }
     int rc = search_common(ix, patterns, nullptr, length, n, n * unit, false, mode, &r, nullptr, packed != 0);
     if (rc != E2FM_OK) return rc;
     ix->batch_ctr[13] = gave_up;

@@ -98,6 +98,7 @@ struct SeedPlan { uint32_t j; bool enumerate; uint32_t lookups; };
 bool seed_plan(const DevIndex &ix, uint32_t m, uint32_t tables_mask, SeedPlan &out);
 void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t first, uint32_t count, uint32_t m, uint32_t nw,
                           uint4 *packed, uint8_t *pflag, cudaStream_t s);
+void launch_widen_packed(const uint8_t *tight, uint64_t first, uint32_t count, uint32_t m, uint32_t nw, uint4 *packed, cudaStream_t s);
 void launch_seed_lookup(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s);
 void launch_seed_verify(const SeedArgs &a, uint32_t nw, int n_sm, cudaStream_t s);
 void launch_materialize(const uint32_t *sel, uint32_t n_sel, uint32_t m, uint32_t nw, const uint8_t *ascii, const uint4 *packed,

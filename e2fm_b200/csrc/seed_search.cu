@@ -81,6 +81,33 @@ void launch_pack_patterns(const DevIndex &ix, const uint8_t *bytes, uint64_t fir
                                                                reinterpret_cast<unsigned long long *>(packed), pflag);
 }
 
+// ---------------------------------------------------------------- tight 2-bit packing -> 16-byte words
+
+// Patterns that travelled over PCIe as ceil(m / 4) bytes each (the first bytes of the 16-byte form: base i at bits 2i) are widened
+// to the 16 bytes per 64 bases the search kernels load with one instruction. A thread per pattern; consecutive threads read
+// consecutive byte runs, so the warp's loads cover a contiguous span.
+__global__ void __launch_bounds__(256) widen_packed_kernel(const uint8_t *__restrict__ tight, uint64_t first, uint32_t count, uint32_t m,
+                                                            uint32_t nw, unsigned long long *__restrict__ packed) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t p = first + i;
+    const uint32_t tb = (m + 3) / 4;
+    const uint8_t *src = tight + p * tb;
+    for (uint32_t w = 0; w < 2 * nw; w++) {
+        unsigned long long cur = 0;
+        const uint32_t b0 = w * 8, b1 = min(tb, b0 + 8);
+        for (uint32_t b = b0; b < b1; b++) cur |= (unsigned long long)__ldg(src + b) << (8 * (b - b0));
+        const uint32_t lo = w * 32;                       // bases [lo, lo + 32) live in this word; those from m on are zero
+        if (m < lo + 32) cur &= m > lo ? (~0ull >> (64 - 2 * (m - lo))) : 0ull;
+        packed[p * 2 * nw + w] = cur;
+    }
+}
+
+void launch_widen_packed(const uint8_t *tight, uint64_t first, uint32_t count, uint32_t m, uint32_t nw, uint4 *packed, cudaStream_t s) {
+    if (count == 0) return;
+    widen_packed_kernel<<<(count + 255) / 256, 256, 0, s>>>(tight, first, count, m, nw, reinterpret_cast<unsigned long long *>(packed));
+}
+
 // ---------------------------------------------------------------- the search: seed lookup, then verification
 
 // which super-characters of shift sa are searched: l = their end (exclusive), lo = the first fixed one, or l <= 0 when the shift

@@ -110,6 +110,14 @@ uint32_t e2fm_packed_stride(uint32_t length);
 /* host helper: ASCII (n x length) -> packed; *n_unpackable = patterns holding a byte other than A C G T (packed as if it were A:
  * send such batches through the ASCII entry points, which handle every symbol of the index's alphabet) */
 int e2fm_pack_patterns(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable);
+/* The same bit string without the padding, for the PCIe-bound host-to-host call (e2fm_search_hits with packed =
+ * E2FM_PACKED_TIGHT): ceil(length / 4) bytes per pattern, base i at bits 2(i mod 4) of byte i / 4 — i.e. the first bytes of the
+ * 16-byte form. A length-50 pattern travels as 13 bytes instead of 16 (or 50 as ASCII); the device widens it stage by stage. */
+#define E2FM_ASCII 0
+#define E2FM_PACKED_WORDS 1
+#define E2FM_PACKED_TIGHT 2
+uint32_t e2fm_packed_tight_stride(uint32_t length);
+int e2fm_pack_patterns_tight(const uint8_t *ascii, uint64_t n, uint32_t length, uint8_t *packed_out, uint64_t *n_unpackable);
 int e2fm_search_batch_packed(e2fm_index *ix, const uint8_t *packed, uint64_t n, uint32_t length, int mode, uint64_t *counts_out,
                              e2fm_result **out);
 int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uint64_t n, uint32_t length, int mode,
@@ -117,7 +125,8 @@ int e2fm_search_batch_packed_device(e2fm_index *ix, const uint8_t *d_packed, uin
 /* Host to host in ONE pipelined call: the batched replacement of the loop around EFMCollection::search (Main.cpp:1055-1079) that hands
  * back what that loop collects — per pattern the number of matches (EFMIndex::countOccurrences) and, in locate mode, the
  * (Occurrence::sequenceIndex, Occurrence::patternPosition) pairs of FMCollection.h:23-44 — in 32 bits, straight into the caller's
- * host arrays. Fixed-length patterns, ASCII (packed == 0, n x length bytes) or 2-bit packed (e2fm_packed_stride bytes each). The batch
+ * host arrays. Fixed-length patterns, ASCII (packed == E2FM_ASCII, n x length bytes), 2-bit packed in 16-byte words (E2FM_PACKED_WORDS,
+ * e2fm_packed_stride bytes each) or 2-bit packed without padding (E2FM_PACKED_TIGHT, e2fm_packed_tight_stride bytes each). The batch
  * is cut into stages; stage c travels to the device while stage c-1 is searched and the results of stage c-2 travel back, so the call
  * takes about as long as the slower of the two PCIe directions. Page-locked buffers (e2fm_host_alloc) are needed for the overlap.
  *   counts        [n]      may be NULL

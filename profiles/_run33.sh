@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "search_hits or seed_search" > gpurun_out/t20.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/t20.log
+E2FM_HITS_TRACE=1 E2FM_TRACE_MULT=2 timeout 600 python profiles/exp/hits_trace.py mid50 > gpurun_out/trace1_graph.log 2>&1; echo "rc=$?"
+E2FM_HITS_TRACE=1 E2FM_TRACE_MULT=2 E2FM_HITS_GRAPH=0 timeout 600 python profiles/exp/hits_trace.py mid50 > gpurun_out/trace1_nograph.log 2>&1; echo "rc=$?"
+E2FM_HITS_TRACE=0 E2FM_TRACE_MULT=2 timeout 600 python profiles/exp/hits_trace.py mid50 > gpurun_out/trace0_graph.log 2>&1; echo "rc=$?"
+E2FM_HITS_TRACE=0 E2FM_TRACE_MULT=2 E2FM_HITS_GRAPH=0 timeout 600 python profiles/exp/hits_trace.py mid50 > gpurun_out/trace0_nograph.log 2>&1; echo "rc=$?"
+tail -14 gpurun_out/trace1_graph.log; tail -14 gpurun_out/trace1_nograph.log; grep wall gpurun_out/trace0_graph.log gpurun_out/trace0_nograph.log

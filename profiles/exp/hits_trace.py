@@ -5,7 +5,7 @@ import time
 
 import numpy as np
 
-os.environ["E2FM_HITS_TRACE"] = "1"
+os.environ.setdefault("E2FM_HITS_TRACE", "1")     # 2: an event after every kernel group; E2FM_HITS_SERIAL=1: search after the whole H2D
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
@@ -19,14 +19,19 @@ ix = capi.DeviceIndex(open(prep["efm"], "rb").read(), synth.test_key(), 0)
 if len(sys.argv) > 2:
     ix.set_option(capi.OPT_HITS_STAGE, int(sys.argv[2]))
 pats = np.ascontiguousarray(bench.load_patterns(prep)[:n])
-stride = capi.packed_stride(L)
+mult = int(os.environ.get("E2FM_TRACE_MULT", "1"))          # the batch repeated: more pipeline stages
+if mult > 1:
+    pats = np.ascontiguousarray(np.tile(pats, (mult, 1)))
+    n *= mult
+tight = os.environ.get("E2FM_TRACE_TIGHT", "0") != "0"    # ceil(L / 4) bytes per pattern instead of 16-byte words
+stride = capi.packed_tight_stride(L) if tight else capi.packed_stride(L)
 h_in = capi.PinnedArray((n, stride), np.uint8)
-capi.pack_patterns(pats, h_in.array.reshape(-1))
+(capi.pack_patterns_tight if tight else capi.pack_patterns)(pats, h_in.array.reshape(-1))
 cap = 2 * n + 4096
 h_off, h_seq, h_so = (capi.PinnedArray(s, np.uint32) for s in (n + 1, cap, cap))
 for rep in range(4):
     print(f"--- call {rep}", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
-    ix.search_hits(h_in.array.reshape(-1), n, L, True, True, None, h_off.array, h_seq.array, h_so.array)
+    ix.search_hits(h_in.array.reshape(-1), n, L, 2 if tight else 1, True, None, h_off.array, h_seq.array, h_so.array)
     print(f"--- wall {1e3 * (time.perf_counter() - t0):.3f} ms", file=sys.stderr, flush=True)
 ix.close()

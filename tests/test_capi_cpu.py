@@ -114,3 +114,21 @@ def test_header_parse_never_reads_outside_the_buffer(tmp_path):
                            timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
         assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
         assert "parsed=" in r.stdout
+
+
+def test_tight_packing_is_the_prefix_of_the_word_packing():
+    """e2fm_pack_patterns_tight writes the first ceil(L / 4) bytes of what e2fm_pack_patterns writes (base i at bits 2i), and both
+    count the patterns that hold a byte outside ACGT"""
+    rng = np.random.default_rng(7)
+    for L in (1, 3, 4, 5, 12, 31, 32, 33, 50, 64, 65, 130):
+        n = 37
+        pats = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, L))].copy()
+        words, bad_w = capi.pack_patterns(pats)
+        tight, bad_t = capi.pack_patterns_tight(pats)
+        tb = capi.packed_tight_stride(L)
+        assert tb == (L + 3) // 4 and bad_w == 0 and bad_t == 0
+        assert np.array_equal(words.reshape(n, capi.packed_stride(L))[:, :tb], tight.reshape(n, tb)), L
+        assert not words.reshape(n, capi.packed_stride(L))[:, tb:].any()
+        pats[5, L // 2] = ord("N")
+        pats[9, L - 1] = ord("$")
+        assert capi.pack_patterns_tight(pats)[1] == 2 and capi.pack_patterns(pats)[1] == 2

@@ -742,7 +742,7 @@ def _hits_call(dev, arr, L, packed, locate, cap):
     n = len(arr)
     pats = arr
     if packed:
-        pats, bad = capi.pack_patterns(arr)
+        pats, bad = capi.pack_patterns_tight(arr) if packed == 2 else capi.pack_patterns(arr)
         assert bad == 0
     c32 = np.full(n, 0xDEADBEEF, dtype=np.uint32)
     o32 = np.full(n + 1, 0xDEADBEEF, dtype=np.uint32) if locate else None
@@ -758,7 +758,8 @@ def _hits_call(dev, arr, L, packed, locate, cap):
 def test_search_hits_matches_reference(gpu, golden, key64, name, stage, vrec):
     """e2fm_search_hits (pipeline stages of 2^20, 64 and 7 patterns; candidate rows verified through the 32-byte verification
     records and, with E2FM_VREC=0, through sa[] / text[]): counts, occurrence offsets, sequence index and offset in the sequence of
-    every occurrence equal the reference's, from ASCII and from packed patterns, count and locate"""
+    every occurrence equal the reference's, from ASCII, from packed (16-byte words) and from tightly packed patterns (ceil(L / 4)
+    bytes each, widened on the device), count and locate"""
     g = golden[name]
     os.environ["E2FM_VREC"] = str(vrec)
     try:
@@ -775,7 +776,7 @@ def test_search_hits_matches_reference(gpu, golden, key64, name, stage, vrec):
             arr = np.frombuffer(b"".join(g["patterns"][i] for i in idxs), dtype=np.uint8).reshape(len(idxs), L).copy()
             want = _subset(g["res"], idxs)
             acgt = all(all(ch in b"ACGT" for ch in g["patterns"][i]) for i in idxs)
-            for packed in ((False, True) if acgt else (False,)):
+            for packed in ((0, 1, 2) if acgt else (0,)):
                 for locate in (False, True):
                     try:
                         total, c32, o32, s32, f32 = _hits_call(dev, arr, L, packed, locate, len(want["seq"]) + 3)
@@ -819,6 +820,12 @@ def test_search_hits_undersized_stores_and_capacity(gpu, golden, key64):
         assert dev.last_batch_counters()["hits_stages"] == 0, "the call must have fallen back"
         assert total == len(want["seq"]) and np.array_equal(c32, want["counts"].astype(np.uint32))
         assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)) and np.array_equal(s32[:total], want["seq"])
+        # the same through the tight packing: its fallback widens on the host
+        dev.set_option(capi.OPT_DENSITY, 1)
+        total, c32, o32, s32, f32 = _hits_call(dev, big, L, 2, True, len(want["seq"]) + 8)
+        assert dev.last_batch_counters()["hits_stages"] == 0
+        assert total == len(want["seq"]) and np.array_equal(c32, want["counts"].astype(np.uint32))
+        assert np.array_equal(o32, want["pos_offsets"].astype(np.uint32)) and np.array_equal(f32[:total], want["off"].astype(np.uint32))
         # now the densities are learned: the same call is pipelined
         total, c32, o32, s32, f32 = _hits_call(dev, big, L, False, True, len(want["seq"]) + 8)
         c = dev.last_batch_counters()
