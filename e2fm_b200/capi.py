@@ -39,6 +39,7 @@ EXPORTS = [
     "e2fm_result_fetch_compact", "e2fm_debug_seed",
     "e2fm_shardset_unique_id", "e2fm_shardset_create", "e2fm_shardset_destroy", "e2fm_shardset_slice", "e2fm_shardset_search",
     "e2fm_shardset_last_ms", "e2fm_search_hits", "e2fm_debug_gather_bench_ex", "e2fm_packed_tight_stride", "e2fm_pack_patterns_tight",
+    "e2fm_encode_buckets",
 ]
 
 
@@ -100,6 +101,8 @@ def lib():
     L.e2fm_packed_stride.argtypes = [u32]
     L.e2fm_pack_patterns.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
     L.e2fm_packed_tight_stride.argtypes = [u32]
+    L.e2fm_encode_buckets.argtypes = [i32, C.c_char_p, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp, u64, C.POINTER(u64), vp,
+                                      C.POINTER(C.c_float)]
     L.e2fm_packed_tight_stride.restype = u32
     L.e2fm_pack_patterns_tight.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
     L.e2fm_search_batch_packed.argtypes = [vp, vp, u64, u32, i32, vp, C.POINTER(vp)]
@@ -510,6 +513,31 @@ def pack_patterns_tight(pats: np.ndarray, out: np.ndarray = None):
     bad = C.c_uint64(0)
     check(lib().e2fm_pack_patterns_tight(pats.ctypes.data if pats.size else None, n, L, out.ctypes.data if out.size else None, C.byref(bad)))
     return out, int(bad.value)
+
+
+def encode_buckets(key64: bytes, codes: np.ndarray, bucket_size: int, first_bucket: int, per_super_bucket: int, total_buckets: int,
+                   alpha: np.ndarray, want_sequence: bool = False, payload_cap: int = None, device: int = 0) -> dict:
+    """e2fm_encode_buckets: Bucket::encodeText + the symbol loop of Bucket::writeText for consecutive buckets.
+    -> {"clen": [n_buckets], "offsets": [n_buckets + 1], "payload": bytes-like, "sequence": [n_rows] or None, "device_ms": float}"""
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    alpha = np.ascontiguousarray(alpha, dtype=np.uint32)
+    nb = len(alpha)
+    clen = np.zeros(max(nb, 1), dtype=np.uint64)
+    off = np.zeros(nb + 1, dtype=np.uint64)
+    cap = payload_cap if payload_cap is not None else 2 * len(codes) + 8 * nb + 64    # <= 16 bits per symbol, 8-byte slots
+    payload = np.zeros(max(cap, 8), dtype=np.uint8)
+    seq = np.zeros(max(len(codes), 1), dtype=np.uint32) if want_sequence else None
+    need = C.c_uint64(0)
+    ms = C.c_float(0)
+    rc = lib().e2fm_encode_buckets(device, key64, codes.ctypes.data if codes.size else None, len(codes), bucket_size, first_bucket, nb,
+                                   per_super_bucket, total_buckets, alpha.ctypes.data if nb else None, clen.ctypes.data, off.ctypes.data,
+                                   payload.ctypes.data, cap, C.byref(need), seq.ctypes.data if want_sequence else None, C.byref(ms))
+    if rc != 0:
+        e = E2FMError(rc, lib().e2fm_last_error().decode(errors="replace"))
+        e.payload_bytes = int(need.value)
+        raise e
+    return {"clen": clen[:nb], "offsets": off, "payload": payload[:int(need.value)], "sequence": seq[:len(codes)] if want_sequence else None,
+            "device_ms": float(ms.value), "payload_bytes": int(need.value)}
 
 
 def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count: int, device: int = 0) -> np.ndarray:

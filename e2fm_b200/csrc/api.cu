@@ -17,6 +17,7 @@
 
 #include "bits.h"
 #include "device_index.cuh"
+#include "encode.cuh"
 #include "host_format.h"
 #include "index_build.cuh"
 #include "internal.h"
@@ -1975,6 +1976,102 @@ int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, ui
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
     } catch (const std::exception &e) {
+        return fail(E2FM_ERR_CUDA, e.what());
+    }
+    return E2FM_OK;
+}
+
+int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *bucket_codes, uint64_t n_rows, uint64_t bucket_size,
+                        uint64_t first_bucket, uint64_t n_buckets, uint64_t buckets_per_super_bucket, uint64_t total_buckets,
+                        const uint32_t *bucket_alpha_size, uint64_t *compressed_length, uint64_t *payload_offset, uint8_t *payload,
+                        uint64_t payload_cap, uint64_t *payload_bytes, uint32_t *sequence, float *device_ms) {
+    if (!key64 || bucket_size == 0 || buckets_per_super_bucket == 0 || (n_buckets && (!bucket_codes || !bucket_alpha_size || !compressed_length)))
+        return fail(E2FM_ERR_ARG, "bad argument");
+    if (n_rows > n_buckets * bucket_size || (n_buckets && n_rows <= (n_buckets - 1) * bucket_size))
+        return fail(E2FM_ERR_ARG, "n_rows does not fit n_buckets buckets of bucket_size rows (only the last one may be shorter)");
+    if (first_bucket + n_buckets > total_buckets) return fail(E2FM_ERR_ARG, "first_bucket + n_buckets exceeds total_buckets");
+    if (payload && !payload_offset) return fail(E2FM_ERR_ARG, "payload needs payload_offset");
+    if (payload_bytes) *payload_bytes = 0;
+    if (device_ms) *device_ms = 0;
+    cudaStream_t s;
+    int rc = with_device(device, &s);
+    if (rc) return rc;
+    if (n_buckets == 0) { if (payload_offset) payload_offset[0] = 0; return E2FM_OK; }
+    try {
+        uint32_t a_max = 0;
+        for (uint64_t b = 0; b < n_buckets; b++) a_max = std::max(a_max, bucket_alpha_size[b]);
+        if (a_max == 0 || a_max > 65535) return fail(E2FM_ERR_ARG, "bucket alphabet sizes must be in 1..65535");
+        EncodeParams p{};
+        p.n_rows = n_rows;
+        p.b_size = bucket_size;
+        p.first_bucket = first_bucket;
+        p.n_buckets = n_buckets;
+        p.per = buckets_per_super_bucket;
+        p.total_buckets = total_buckets;
+        p.list_elems = (a_max + 1) / 2 * 2;
+        const int wpc = 4;
+        const size_t smem = (size_t)wpc * 2 * p.list_elems * sizeof(uint16_t);
+        if (smem > 200 * 1024) return fail(E2FM_ERR_UNSUPPORTED, "bucket alphabet too large for the encode kernel");
+        CK(configure_bucket_encode(smem));
+        uint32_t kw[8];
+        key_words(key64 + 32, kw);                              // EncryptionManager: the poly-alphabetic key is bytes 32..63
+        DBuf<uint32_t> d_codes(n_rows, s), d_alpha(n_buckets, s), d_status(1, s), d_seq(sequence ? n_rows : 0, s);
+        DBuf<uint16_t> d_vals(n_rows + 8, s);
+        DBuf<uint64_t> d_clen(n_buckets, s), d_off(n_buckets + 1, s);
+        DBuf<uint8_t> d_payload(payload ? payload_cap + 8 : 0, s);
+        d_status.zero();
+        CK(cudaMemcpyAsync(d_codes.p, bucket_codes, n_rows * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_alpha.p, bucket_alpha_size, n_buckets * 4, cudaMemcpyHostToDevice, s));
+        p.codes = d_codes.p;
+        p.alpha = d_alpha.p;
+        p.vals = d_vals.p;
+        p.clen = d_clen.p;
+        p.payload_off = d_off.p;
+        p.payload = d_payload.p;
+        p.payload_cap = payload ? payload_cap / 8 * 8 : 0;
+        p.sequence = d_seq.p;
+        p.status = d_status.p;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, s));
+        launch_bucket_mtf_rle(p, wpc, smem, s);
+        launch_payload_offsets(p, s);
+        // key stream + substitution + packing, in batches of buckets (the key stream of a batch stays below 256 MB)
+        const uint32_t kbits_max = int_log2((uint64_t)a_max + 1);
+        const uint32_t blocks_per_bucket = (uint32_t)((bucket_size * kbits_max + 511) / 512 + 2);
+        const uint32_t ks_stride = blocks_per_bucket * 64;
+        const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n_buckets, (256ull << 20) / ks_stride));
+        DBuf<uint8_t> d_ks((size_t)batch * ks_stride + 64, s);
+        for (uint64_t b0 = 0; b0 < n_buckets; b0 += batch) {
+            const uint64_t nb = std::min(batch, n_buckets - b0);
+            launch_keystream(kw, first_bucket + b0, nb, blocks_per_bucket, 0, reinterpret_cast<uint4 *>(d_ks.p), s);
+            launch_bucket_substitute_pack(p, b0, nb, d_ks.p, ks_stride, s);
+        }
+        CK(cudaEventRecord(e1, s));
+        uint32_t status = 0;
+        std::vector<uint64_t> off(n_buckets + 1);
+        CK(cudaMemcpyAsync(&status, d_status.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(compressed_length, d_clen.p, n_buckets * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(off.data(), d_off.p, (n_buckets + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (device_ms) *device_ms = ms;
+        if (payload_offset) memcpy(payload_offset, off.data(), (n_buckets + 1) * 8);
+        if (payload_bytes) *payload_bytes = off[n_buckets];
+        if (status & ENCODE_ERR_ALPHABET) return fail(E2FM_ERR_ARG, "a bucket alphabet size is 0");
+        if (status & ENCODE_ERR_CODE) return fail(E2FM_ERR_ARG, "a row holds a code that is not below its bucket's alphabet size");
+        if (status & ENCODE_ERR_BOUNDS) return fail(E2FM_ERR_FORMAT, "key stream too short for a bucket (internal)");
+        if (status & ENCODE_ERR_CAPACITY) return fail(E2FM_ERR_ARG, "payload_cap is too small (see payload_bytes)");
+        if (payload && off[n_buckets]) CK(cudaMemcpyAsync(payload, d_payload.p, off[n_buckets], cudaMemcpyDeviceToHost, s));
+        if (sequence) CK(cudaMemcpyAsync(sequence, d_seq.p, n_rows * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    } catch (const std::exception &e) {
+        cudaGetLastError();
         return fail(E2FM_ERR_CUDA, e.what());
     }
     return E2FM_OK;

@@ -236,6 +236,29 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
                                     Same results either way. */
 int e2fm_set_option(e2fm_index *ix, int option, uint64_t value);
 
+/* ---- build side: the bucket text encoder ----
+ * EFMIndex::encodeBuckets (EFMIndex.cpp:751-773) -> Bucket::encodeText (Bucket.cpp:442-536) for a run of consecutive buckets, and
+ * the symbol loop of Bucket::writeText (Bucket.cpp:232-246): move-to-front, RLE0 of the runs of rank 0, poly-alphabetic substitution
+ * with the bucket's Salsa20 key stream (EFMIndex::getCryptoParams, EFMIndex.cpp:1668; key = bytes 32..63 of key64, nonce = bucket
+ * number), int_log2(bucketAlphaSize) bits per symbol, most significant bit first. BWT construction, the two remappings and the
+ * bucket headers stay in the reference builder; this is its per-bucket step, a warp per bucket on the GPU.
+ *   bucket_codes        host, n_rows: sbwt[] of the rows of buckets [first_bucket, first_bucket + n_buckets) AFTER the super-bucket
+ *                       and bucket remappings (EFMIndex.cpp:841-858); every bucket holds bucket_size rows, the last may be shorter
+ *   buckets_per_super_bucket, total_buckets   which buckets are encoded last row first (EFMIndex.cpp:898-901)
+ *   bucket_alpha_size   [n_buckets] Bucket::bucketAlphaSize
+ *   compressed_length   out [n_buckets]: EncodingResult::realLength (0 for a single-character bucket: Bucket::write writes no text)
+ *   payload_offset      out [n_buckets + 1] (may be NULL without payload): byte offset of each bucket's packed text in `payload`
+ *                       (8-byte aligned slots; the text is (compressed_length * int_log2(alpha) + 7) / 8 bytes, zero padded like
+ *                       BitWriter::flush) — what Bucket::writeText writes after the sequenceLength field
+ *   payload             out, payload_cap bytes (may be NULL); *payload_bytes = bytes needed (E2FM_ERR_ARG when the cap is too small)
+ *   sequence            optional out [n_rows]: EncodingResult::sequence of each bucket at its row offset (what the reference's own
+ *                       writeText would be handed instead of the packed bytes)
+ *   device_ms           optional out: CUDA-event time of the kernels */
+int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *bucket_codes, uint64_t n_rows, uint64_t bucket_size,
+                        uint64_t first_bucket, uint64_t n_buckets, uint64_t buckets_per_super_bucket, uint64_t total_buckets,
+                        const uint32_t *bucket_alpha_size, uint64_t *compressed_length, uint64_t *payload_offset, uint8_t *payload,
+                        uint64_t payload_cap, uint64_t *payload_bytes, uint32_t *sequence, float *device_ms);
+
 /* ---- test hooks (parity of the individual kernels against the oracle) ---- */
 /* K1: Salsa20 keystream kernel. Replaces RandomGenerator::populateKeyStreamBuffer + nextInt over salsa20.S
  * (RandomGenerator.cpp:125,60): `count` values of int_log2(max_value+1) bits starting at value `start`

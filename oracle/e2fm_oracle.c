@@ -736,3 +736,85 @@ void orc_map_position(const orc_index *ix, uint64_t p, uint32_t *seq, uint64_t *
     *seq = (uint32_t)s;
     *off = p - (s > 0 ? (uint64_t)ix->term[s - 1] + ix->k : 0);
 }
+
+/* ------------------------------------------------------------------ build side: bucket text encoder */
+
+/* What the builder wrote for bucket bn: [0] length, [1] bucketAlphaSize, [2] isOdd, [3] isFirstInSuperBucket, [4] compressedLength
+ * (0 for a single-character bucket: Bucket.cpp:166-170 writes no text), [5] bit offset of the text in the file, [6] bits per text symbol */
+void orc_bucket_info(const orc_index *ix, uint64_t bn, uint64_t out[8]) {
+    const bucket_t *b = &ix->bk[bn];
+    out[0] = b->length; out[1] = b->alpha; out[2] = (uint64_t)b->is_odd; out[3] = (uint64_t)b->is_first;
+    out[4] = b->alpha > 1 ? b->clen : 0; out[5] = b->text_bit; out[6] = b->tbits; out[7] = 0;
+}
+
+/* The rows of bucket bn as the builder saw them when it encoded the bucket: sbwt[] after the super-bucket and the bucket
+ * remapping (EFMIndex.cpp:841-858: SuperBucket::charactersRemappings, then Bucket::charactersRemappings), in row order.
+ * Both remappings are order preserving, so a bucket code is the rank of the row's compact code among the bucket's symbols. */
+void orc_bucket_codes(const orc_index *ix, uint64_t bn, uint32_t *out) {
+    const bucket_t *b = &ix->bk[bn];
+    uint64_t sn = bn / ix->per;
+    uint32_t A = ix->A;
+    int64_t *code_of = (int64_t *)malloc(sizeof(int64_t) * A);
+    for (uint32_t j = 0; j < A; j++) code_of[j] = -1;
+    for (uint32_t j = 0, sbc = 0, c = 0; j < A; j++) {
+        if (!ix->sb_bits[sn * A + j]) continue;
+        if (b->bits[sbc]) code_of[j] = c++;
+        sbc++;
+    }
+    const uint32_t *bwt = ix->bwt + bn * ix->b_size;
+    for (uint64_t i = 0; i < b->length; i++) out[i] = (uint32_t)code_of[bwt[i]];
+    free(code_of);
+}
+
+/* Bucket::encodeText (Bucket.cpp:442-536): single-pass move-to-front, RLE0 of the runs of rank 0 and poly-alphabetic
+ * substitution with the bucket's key stream (EFMIndex::getCryptoParams :1668 -> computeBucketKeyStream(bucketNumber, 0,
+ * length - 1, bucketAlphaSize)). codes: the bucket's rows as bucket codes (orc_bucket_codes); odd buckets are encoded from
+ * their last row to their first (:446-448). seq_out: `length` entries; returns EncodingResult::realLength. */
+uint64_t orc_encode_bucket(const uint8_t key32[32], uint64_t bucket_number, const uint32_t *codes, uint64_t length, uint32_t alpha,
+                           int is_odd, uint32_t *seq_out) {
+    uint32_t *key = (uint32_t *)malloc(sizeof(uint32_t) * (length + 1));
+    orc_keystream_ints(key32, bucket_number, alpha, 0, length, key);
+    uint32_t *text = (uint32_t *)malloc(sizeof(uint32_t) * (length + 1));
+    for (uint64_t j = 0; j < length; j++) text[is_odd ? length - j - 1 : j] = codes[j];
+    uint32_t *mtf = (uint32_t *)malloc(sizeof(uint32_t) * alpha);              /* ArrayMTFList(bucketAlphaSize) */
+    for (uint32_t i = 0; i < alpha; i++) mtf[i] = i;
+    const uint64_t mod = (uint64_t)alpha + 1;
+    uint64_t n_out = 0, i = 0;
+    while (i < length) {
+        uint32_t pos = 0;
+        while (mtf[pos] != text[i]) pos++;                                     /* ArrayMTFList::indexOf */
+        if (pos > 0) {
+            uint32_t e = mtf[pos];
+            memmove(mtf + 1, mtf, sizeof(uint32_t) * pos);                     /* moveToFront */
+            mtf[0] = e;
+            seq_out[n_out] = (uint32_t)(((uint64_t)pos + 1 + key[n_out % length]) % mod);   /* :480-481, keyStartOffset = 0 */
+            n_out++;
+            i++;
+        } else {
+            uint64_t m = 1;                                                     /* run of rank 0 (:499-506) */
+            while (i + m < length && text[i + m] == mtf[0]) m++;
+            uint32_t nb = 0;                                                    /* floor(log2(m + 1)) (:508) */
+            while (((m + 1) >> (nb + 1)) != 0) nb++;
+            const uint64_t N = m + 1 - (1ull << nb);
+            for (int64_t j = (int64_t)nb - 1; j >= 0; j--) {                    /* digits, most significant first (:512-519) */
+                const uint64_t digit = (N >> j) & 1u;
+                seq_out[n_out] = (uint32_t)((digit + key[n_out % length]) % mod);
+                n_out++;
+            }
+            i += m;
+        }
+    }
+    free(key); free(text); free(mtf);
+    return n_out;
+}
+
+/* the symbol loop of Bucket::writeText (Bucket.cpp:232-246) + BitWriter::flush: n symbols of `bits` bits each, most significant
+ * bit first, the last byte padded with zeros. out: (n * bits + 7) / 8 bytes. */
+void orc_pack_sequence(const uint32_t *seq, uint64_t n, uint32_t bits, uint8_t *out) {
+    memset(out, 0, (size_t)((n * bits + 7) / 8));
+    uint64_t bit = 0;
+    for (uint64_t i = 0; i < n; i++)
+        for (int32_t b = (int32_t)bits - 1; b >= 0; b--, bit++)
+            if ((seq[i] >> b) & 1u) out[bit >> 3] |= (uint8_t)(0x80u >> (bit & 7));
+}
+

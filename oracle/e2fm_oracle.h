@@ -70,6 +70,17 @@ void orc_rank_rows(orc_index *ix, const uint32_t *codes, const uint64_t *rows, u
 void orc_get_counters(const orc_index *ix, uint64_t *n_rank, uint64_t *n_lf, uint64_t *n_mark);
 void orc_reset_counters(orc_index *ix);
 
+/* ---- build side: the bucket text encoder, pinned against the bytes the reference builder wrote ---- */
+/* [0] length [1] bucketAlphaSize [2] isOdd [3] isFirstInSuperBucket [4] compressedLength [5] text bit offset in the file [6] bits per symbol */
+void orc_bucket_info(const orc_index *ix, uint64_t bucket, uint64_t out[8]);
+/* rows of the bucket as bucket codes, i.e. sbwt[] after both remappings (EFMIndex.cpp:841-858) */
+void orc_bucket_codes(const orc_index *ix, uint64_t bucket, uint32_t *out);
+/* Bucket::encodeText (Bucket.cpp:442-536); seq_out has `length` entries; returns EncodingResult::realLength */
+uint64_t orc_encode_bucket(const uint8_t key32[32], uint64_t bucket_number, const uint32_t *codes, uint64_t length, uint32_t alpha,
+                           int is_odd, uint32_t *seq_out);
+/* symbol loop of Bucket::writeText (Bucket.cpp:232-246) + flush */
+void orc_pack_sequence(const uint32_t *seq, uint64_t n, uint32_t bits, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

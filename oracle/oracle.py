@@ -68,6 +68,11 @@ def lib():
         L.orc_rank_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_get_counters.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
         L.orc_reset_counters.argtypes = [C.c_void_p]
+        L.orc_bucket_info.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_bucket_codes.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_encode_bucket.restype = C.c_uint64
+        L.orc_encode_bucket.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_pack_sequence.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -221,6 +226,18 @@ class OracleIndex:
         lib().orc_rank_rows(self._h, codes.ctypes.data, rows.ctypes.data, len(rows), out.ctypes.data)
         return out
 
+    # ---- build side (bucket text encoder)
+    def bucket_info(self, bucket: int) -> dict:
+        out = np.zeros(8, dtype=np.uint64)
+        lib().orc_bucket_info(self._h, bucket, out.ctypes.data)
+        return dict(zip(["length", "alpha", "is_odd", "is_first", "clen", "text_bit", "tbits"], [int(x) for x in out[:7]]))
+
+    def bucket_codes(self, bucket: int) -> np.ndarray:
+        """rows of the bucket as bucket codes (sbwt[] after both remappings, EFMIndex.cpp:841-858)"""
+        out = np.zeros(self.bucket_info(bucket)["length"], dtype=np.uint32)
+        lib().orc_bucket_codes(self._h, bucket, out.ctypes.data)
+        return out
+
     def counters(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         lib().orc_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c))
@@ -288,3 +305,20 @@ def ref_extract(index: str, keyfile: str, queries_file: str, out_file: str):
 def ref_kat() -> dict:
     r = subprocess.run([REF_BIN, "kat"], capture_output=True, text=True, check=True)
     return dict(l.split("=", 1) for l in r.stdout.splitlines() if "=" in l)
+
+
+def encode_bucket(key64: bytes, bucket_number: int, codes: np.ndarray, alpha: int, is_odd: bool) -> np.ndarray:
+    """Bucket::encodeText (Bucket.cpp:442-536): the encrypted MTF/RLE0 sequence of one bucket"""
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    out = np.zeros(max(len(codes), 1), dtype=np.uint32)
+    n = lib().orc_encode_bucket(key64[32:64], bucket_number, codes.ctypes.data, len(codes), alpha, 1 if is_odd else 0, out.ctypes.data)
+    return out[:int(n)]
+
+
+def pack_sequence(seq: np.ndarray, bits: int) -> bytes:
+    """the symbol loop of Bucket::writeText (Bucket.cpp:232-246) + flush"""
+    seq = np.ascontiguousarray(seq, dtype=np.uint32)
+    out = np.zeros((len(seq) * bits + 7) // 8 + 1, dtype=np.uint8)
+    lib().orc_pack_sequence(seq.ctypes.data, len(seq), bits, out.ctypes.data)
+    return out[:(len(seq) * bits + 7) // 8].tobytes()
+
