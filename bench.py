@@ -342,10 +342,14 @@ class SharedHost:
     with cudaHostRegister, so that each GPU copies its slice of the patterns straight out of it and its slice of the result
     straight into it. With one rank it is plain pinned memory from the library."""
 
-    def __init__(self, tag: str, world: int, rank: int, capi):
+    def __init__(self, tag: str, world: int, rank: int, capi, defer: bool = False):
         self.tag, self.world, self.rank, self.capi = tag, world, rank, capi
         self.arrays = {}
         self._keep = []
+        # defer: the shared files are page-locked by pin(), AFTER every rank has written its own part — a tmpfs page lives on the
+        # NUMA node of the CPU that touches it first, and page-locking touches every page
+        self.defer = defer
+        self._pending = []
 
     def array(self, name: str, shape, dtype):
         dtype = np.dtype(dtype)
@@ -365,13 +369,24 @@ class SharedHost:
         else:
             wait_for(path, 600)
         mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nbytes,))
-        rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, nbytes, 0)
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaHostRegister({name}) failed: {rc}")
+        if self.defer:
+            self._pending.append((name, mm, nbytes))
+        else:
+            rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister({name}) failed: {rc}")
         self._keep.append(mm)
         a = mm[:int(np.prod(shape, dtype=np.int64)) * dtype.itemsize].view(dtype).reshape(shape)
         self.arrays[name] = a
         return a
+
+    def pin(self):
+        import torch
+        for name, mm, nbytes in self._pending:
+            rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister({name}) failed: {rc}")
+        self._pending = []
 
     def close(self):
         if self.world > 1:
@@ -423,6 +438,33 @@ def compare_with_reference(ref_res, slices, got, n_checked):
     return {"checked": int(n_checked), "mismatches": int(mism), "first_mismatch": first_bad}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off, so that the host buffers it first touches (its slice of the
+    shared batch, its result region) are local to that GPU's PCIe root: with every rank on node 0 the copy rate of the far GPUs
+    halves (round-1 SCALE). Returns (affinity to restore, description) or (None, why not)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, "no NUMA node reported for the GPU"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        before = os.sched_getaffinity(0)
+        allowed = before & cpus
+        if not allowed:
+            return None, f"NUMA node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return before, f"NUMA node {node} ({len(allowed)} CPUs) of GPU {bus}"
+    except Exception as e:   # noqa: BLE001  (affinity is an optimisation, never a reason to fail)
+        return None, f"not bound: {type(e).__name__}: {e}"[:120]
+
+
 def gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -457,6 +499,9 @@ def gpu_arm(args, rank, world, local_rank):
     log(f"[bench r{rank}] index loaded in {load_s:.2f}s: n={info.text_length} buckets={info.n_buckets} "
         f"device_bytes={info.device_bytes / 1e6:.1f} MB load_ms={[round(x, 2) for x in info.load_ms]}")
 
+    # host buffers are first touched from here on: on the CPUs next to this rank's GPU
+    restore_affinity, affinity_note = (None, "off") if args.no_numa else bind_to_gpu_numa(local_rank)
+    log(f"[bench r{rank}] cpu affinity: {affinity_note}")
     # strong scaling: the ONE batch is partitioned by pattern; rank r owns the contiguous slice [lo, hi)
     npat_all, L = w["n_patterns"], w["pat_len"]
     lo, npat = capi.shardset_slice(npat_all, world, rank)     # contiguous slices of ceil(n / world) patterns
@@ -472,7 +517,7 @@ def gpu_arm(args, rank, world, local_rank):
         except capi.E2FMError:
             packed_api = False
     unit = stride if packed_api else L
-    shm = SharedHost(f"{os.environ.get('MASTER_PORT', '0')}_{args.workload}", world, rank, capi)
+    shm = SharedHost(f"{os.environ.get('MASTER_PORT', '0')}_{args.workload}", world, rank, capi, defer=True)
     h_pats = shm.array("patterns", (npat_all, unit), np.uint8)
     if world > 1:
         dist.barrier()
@@ -499,6 +544,15 @@ def gpu_arm(args, rank, world, local_rank):
     h_noff = shm.array("occ_offsets", (world, per_rank + 2), np.uint32) if locate else None
     h_seq = shm.array("seq", (world, occ_cap), np.uint32) if locate else None
     h_off = shm.array("off", (world, occ_cap), np.uint32) if locate else None
+    if world > 1:                              # every rank touches its own regions, then all page-lock the shared buffers
+        h_counts[lo:hi] = 0
+        if locate:
+            h_noff[rank] = 0
+            h_seq[rank] = 0
+            h_off[rank] = 0
+        dist.barrier()
+        shm.pin()
+        dist.barrier()
     d_pats = torch.from_numpy(np.array(h_pats[lo:hi])).to(dev_t)
     del mine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)   # > 126 MB L2
@@ -593,6 +647,34 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     clocks = sampler.stop()
 
+    # what the host link gives this rank: the H2D copy of its own slice alone (rank 0) and with every rank copying at once —
+    # GPUs behind one PCIe switch share its uplink, which bounds the end-to-end figure at N > 1 whatever the kernels do
+    def h2d_rate():
+        src = torch.from_numpy((h_tight if tight_api else h_pats)[lo:hi].reshape(-1))
+        dst = torch.empty(src.numel(), dtype=torch.uint8, device=dev_t)
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return src.numel() / best / 1e9
+    pcie = {}
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            pcie["h2d_gbs_rank0_alone"] = round(h2d_rate(), 1)
+        dist.barrier()
+        mine_gbs = torch.tensor([h2d_rate()], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(mine_gbs, op=dist.ReduceOp.MIN)
+        pcie["h2d_gbs_slowest_rank_all_copying"] = round(float(mine_gbs[0]), 1)
+    else:
+        pcie["h2d_gbs_rank0_alone"] = round(h2d_rate(), 1)
+    if restore_affinity is not None:           # the reference processes of the parity / CPU-baseline leg and the shard builds use every core
+        os.sched_setaffinity(0, restore_affinity)
+
     # max over ranks (times), sum over ranks (work)
     t = torch.tensor([ph_ms["total"], e2e_s * 1e3, ph_ms["backward_search"], ph_ms["walk"]], dtype=torch.float64, device=dev_t)
     cnt = torch.tensor([occ_total, ctr_sum.get("launches", 0)], dtype=torch.int64, device=dev_t)
@@ -671,7 +753,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "patterns": npat_all, "pattern_len": L,
                        "parallelism": (f"{world} index replicas, the one batch partitioned by pattern ({npat} per GPU), results gathered in one "
                                        f"shared host buffer" if world > 1 else "one index replica, whole batch"),
-                       "l2": "256 MB flush between timed iterations",
+                       "l2": "256 MB flush between timed iterations", "cpu_affinity_rank0": affinity_note,
                        "locate_tables": "per-query walks from marked rows" if args.walk else "dense sa[]/text[] built at load",
                        "patterns_in": "2-bit packed (16 B per 64 bases)" if packed_api else "ASCII", "seed_chars": int(info.seed_chars),
                        "seed_table_MB": int(info.seed_table_mb), "verification_records_MB": int(info.vrec_mb),
@@ -680,6 +762,7 @@ def gpu_arm(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "patterns/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                     "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e2e_ms_max / steps,
                     "device_timeline_ms_per_step": float(np.mean(e2e_dev_ms[-steps:])) if e2e_dev_ms else None,
+                    "host_link": pcie,
                     "what": ((f"2-bit packed patterns without padding (E2FM_PACKED_TIGHT, {tstride} B per pattern)" if tight_api else
                               "2-bit packed patterns (e2fm_search_batch_packed, 16 B per 64 bases)" if packed_api else "ASCII patterns") +
                              " from page-locked host memory; " +
@@ -1002,6 +1085,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="patterns per internal chunk (0 = library default)")
     ap.add_argument("--taper", action="store_true", help="halving pipeline stages for host batches")
     ap.add_argument("--pipe", type=int, default=0, help="patterns per pipeline stage of host batches (0 = library default)")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-tight", action="store_true", help="end-to-end call on the 16-byte-word packing instead of the tight one")
     ap.add_argument("--ascii", action="store_true", help="ASCII patterns through e2fm_search_batch_fixed even when the packed entry point would take the batch")
     ap.add_argument("--e2e-api", default="hits", choices=["hits", "fetch"], help="end-to-end leg: the pipelined one-call form or search + fetch")

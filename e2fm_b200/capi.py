@@ -39,7 +39,7 @@ EXPORTS = [
     "e2fm_result_fetch_compact", "e2fm_debug_seed",
     "e2fm_shardset_unique_id", "e2fm_shardset_create", "e2fm_shardset_destroy", "e2fm_shardset_slice", "e2fm_shardset_search",
     "e2fm_shardset_last_ms", "e2fm_search_hits", "e2fm_debug_gather_bench_ex", "e2fm_packed_tight_stride", "e2fm_pack_patterns_tight",
-    "e2fm_encode_buckets",
+    "e2fm_encode_buckets", "e2fm_debug_hits_stages",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.e2fm_packed_stride.argtypes = [u32]
     L.e2fm_pack_patterns.argtypes = [vp, u64, u32, vp, C.POINTER(u64)]
     L.e2fm_packed_tight_stride.argtypes = [u32]
+    L.e2fm_debug_hits_stages.argtypes = [u64, u64, vp, u64, C.POINTER(u64)]
     L.e2fm_encode_buckets.argtypes = [i32, C.c_char_p, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp, u64, C.POINTER(u64), vp,
                                       C.POINTER(C.c_float)]
     L.e2fm_packed_tight_stride.restype = u32
@@ -538,6 +539,14 @@ def encode_buckets(key64: bytes, codes: np.ndarray, bucket_size: int, first_buck
         raise e
     return {"clen": clen[:nb], "offsets": off, "payload": payload[:int(need.value)], "sequence": seq[:len(codes)] if want_sequence else None,
             "device_ms": float(ms.value), "payload_bytes": int(need.value)}
+
+
+def hits_stages(n: int, stage_option: int = 0) -> np.ndarray:
+    """stage bounds of an e2fm_search_hits batch of n patterns (host-only helper)"""
+    out = np.zeros(n // max(1, stage_option or 131072) + 64, dtype=np.uint64)
+    cnt = C.c_uint64(0)
+    check(lib().e2fm_debug_hits_stages(n, stage_option, out.ctypes.data, len(out), C.byref(cnt)))
+    return out[:int(cnt.value)]
 
 
 def debug_keystream(key64: bytes, nonce: int, max_value: int, start: int, count: int, device: int = 0) -> np.ndarray:

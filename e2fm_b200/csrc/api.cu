@@ -179,6 +179,7 @@ struct e2fm_index {
     HitsStageInfo *h_stage_info = nullptr;   // pinned, written by hits_tail_kernel
     size_t h_stage_cap = 0;
     uint64_t hits_stage_patterns = 1u << 20;   // patterns per (full) pipeline stage of e2fm_search_hits
+    bool hits_stage_auto = true;               // no E2FM_OPT_HITS_STAGE given: small batches get smaller stages, long ones a short head
     // the kernels of a pipeline stage as ONE graph launch (slot = 3 * locate + packing): re-captured per stage, the instantiated
     // graph is updated in place (same topology, other arguments)
     cudaGraphExec_t hits_exec[12] = {};        // [0..5] search part, [6..11] result part
@@ -1045,6 +1046,33 @@ void run_batch(e2fm_index *ix, const Batch &b, int mode, e2fm_result *res, Event
     ix->batch_ctr[11] = seeded ? 1 : 0;
 }
 
+// The stages of an e2fm_search_hits batch of n patterns: bounds[c] .. bounds[c + 1] is stage c; *stage_out = patterns of a full stage.
+// Full stages of `opt_stage` patterns; automatic mode (no E2FM_OPT_HITS_STAGE given): a batch shorter than four stages is cut into
+// quarters (>= 2^17 patterns: a stage costs ~60 us of launches and kernel tails whatever its size), a long one starts with 1/4, 1/4,
+// 1/2 of a stage so that the search begins early. The last stage is cut into 1/2, 1/4, 1/4: what the call takes is the H2D time of
+// the whole batch plus search and D2H of the LAST stage (measured: profiles/exp/e2e_stages.py).
+std::vector<uint64_t> hits_stage_plan(uint64_t n, uint64_t opt_stage, bool auto_stage, uint64_t *stage_out) {
+    uint64_t stage = std::max<uint64_t>(1, std::min<uint64_t>(opt_stage, n));
+    if (auto_stage && n < 4 * stage) stage = std::min<uint64_t>(n, std::max<uint64_t>(131072, (n / 4 + 65535) / 65536 * 65536));
+    std::vector<uint64_t> bounds(1, 0);
+    if (auto_stage && n >= 8 * stage) {
+        bounds.push_back(stage / 4);
+        bounds.push_back(stage / 2);
+        bounds.push_back(stage);
+    }
+    while (bounds.back() < n) {
+        const uint64_t left = n - bounds.back();
+        if (left > stage) { bounds.push_back(bounds.back() + stage); continue; }
+        if (left >= (auto_stage ? 262144u : 65536u)) {
+            bounds.push_back(bounds.back() + left / 2);
+            bounds.push_back(bounds.back() + left / 4);
+        }
+        bounds.push_back(n);
+    }
+    if (stage_out) *stage_out = stage;
+    return bounds;
+}
+
 // e2fm_search_hits, the pipelined path: host patterns in, host results out, stage by stage. Stage c is copied in on the H2D stream
 // while stage c-1 runs on the compute stream (seed lookup, verification, the stage's result pipeline of hits.cu) and the results of
 // stage c-2 leave on the D2H stream. Nothing on the compute stream needs the host: counts stay on the device, the device carries the
@@ -1071,8 +1099,10 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     EventTimer tm(s, &ix->events);
     tm.phases = false;
     const int whole = tm.begin(6);
-    const uint64_t stage = std::max<uint64_t>(1, std::min<uint64_t>(ix->hits_stage_patterns, n));
-    const uint64_t S_max = (n + stage - 1) / stage + 24;      // stages (the tapered tail adds a few): sizes the per-stage arrays
+    uint64_t stage = 1;
+    Staging sg;
+    sg.bounds = hits_stage_plan(n, ix->hits_stage_patterns, ix->hits_stage_auto, &stage);
+    const uint64_t S_max = sg.bounds.size() + 8;              // sizes the per-stage arrays
 
     WsBuf<uint8_t> d_in(ix, WS_BYTES, b.total_bytes + 16, s);
     b.d_bytes = d_in.p;
@@ -1126,20 +1156,6 @@ bool hits_pipeline(e2fm_index *ix, const uint8_t *h_in, uint64_t n, uint32_t m, 
     HitsStageInfo *info = ix->h_stage_info;
     memset(info, 0, S_max * sizeof(HitsStageInfo));
 
-    // stage sizes: equal stages, the last one cut into 1/2, 1/4, 1/4: what the call takes is the H2D time of the whole batch plus
-    // search and D2H of the LAST stage, so the last stages are small; more than that does not pay (every stage costs ~40 us of
-    // launch latencies on the compute stream, measured: profiles/exp/e2e_stages.py)
-    Staging sg;
-    sg.bounds.assign(1, 0);
-    while (sg.bounds.back() < n) {
-        const uint64_t left = n - sg.bounds.back();
-        if (left > stage) { sg.bounds.push_back(sg.bounds.back() + stage); continue; }
-        if (left >= 65536 && S_max > 1) {
-            sg.bounds.push_back(sg.bounds.back() + left / 2);
-            sg.bounds.push_back(sg.bounds.back() + left / 4);
-        }
-        sg.bounds.push_back(n);
-    }
     const uint64_t S = sg.bounds.size() - 1;
     {
         cudaEvent_t ready = ix->events.get(false);
@@ -1943,7 +1959,10 @@ int e2fm_set_option(e2fm_index *ix, int option, uint64_t value) {
             return E2FM_OK;
         case E2FM_OPT_PIPE: ix->pipe_patterns = value ? value : (1u << 18); return E2FM_OK;
         case E2FM_OPT_TAPER: ix->pipe_taper = value != 0; return E2FM_OK;
-        case E2FM_OPT_HITS_STAGE: ix->hits_stage_patterns = value ? value : (1u << 20); return E2FM_OK;
+        case E2FM_OPT_HITS_STAGE:
+            ix->hits_stage_patterns = value ? value : (1u << 20);
+            ix->hits_stage_auto = value == 0;
+            return E2FM_OK;
         case E2FM_OPT_PHASE_TIMERS: ix->phase_timers = (int)std::min<uint64_t>(value, 2); return E2FM_OK;
         case E2FM_OPT_SEED:
             if (value && !(ix->dix.seed_tab && ix->dix.packed_code)) return fail(E2FM_ERR_UNSUPPORTED, "the seed table was not built for this index");
@@ -2074,6 +2093,15 @@ int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *buc
         cudaGetLastError();
         return fail(E2FM_ERR_CUDA, e.what());
     }
+    return E2FM_OK;
+}
+
+int e2fm_debug_hits_stages(uint64_t n, uint64_t stage_option, uint64_t *bounds_out, uint64_t cap, uint64_t *n_bounds) {
+    if (!n_bounds || (cap && !bounds_out)) return fail(E2FM_ERR_ARG, "bad argument");
+    const std::vector<uint64_t> b = hits_stage_plan(n, stage_option ? stage_option : (1u << 20), stage_option == 0, nullptr);
+    *n_bounds = b.size();
+    if (b.size() > cap) return fail(E2FM_ERR_ARG, "bounds_out is too small (see n_bounds)");
+    memcpy(bounds_out, b.data(), b.size() * 8);
     return E2FM_OK;
 }
 

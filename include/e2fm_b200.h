@@ -228,8 +228,9 @@ int e2fm_last_batch_counters(const e2fm_index *ix, uint64_t out[16]);
 #define E2FM_OPT_SEED 9          /* 1 (default when the seed table was built): fixed-length batches whose every shift holds a whole seed
                                     go through seed_search_kernel (seed table + dense tables); 0: always the generic backward search.
                                     Same results either way. */
-#define E2FM_OPT_HITS_STAGE 10   /* patterns per full pipeline stage of e2fm_search_hits (0 = default 2^20); the last stage of a batch is cut
-                                    into 1/2, 1/4, 1/4 */
+#define E2FM_OPT_HITS_STAGE 10   /* patterns per full pipeline stage of e2fm_search_hits; the last stage of a batch is cut into 1/2, 1/4, 1/4.
+                                    0 = default: 2^20, a quarter of the batch (>= 2^17) when the batch is shorter than four stages, and
+                                    the first stage cut into 1/4, 1/4, 1/2 so that the search starts early */
 #define E2FM_OPT_DENSE 4         /* 1 (default when the tables were built): locate and hat verification read the dense sa[] / text[]
                                     tables that the load pipeline fills by walking LF from every marked row once (6 bytes per row
                                     of HBM); 0: walk from the marked rows per query (EFMIndex::getRowPosition, EFMIndex.cpp:2468).
@@ -265,6 +266,9 @@ int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *buc
  * of the stream (key = bytes 32..63 of key64, nonce = `nonce`). */
 int e2fm_debug_keystream(int device, const uint8_t key64[64], uint64_t nonce, uint32_t max_value,
                          uint64_t start, uint64_t count, uint32_t *out);
+/* host only: the pipeline stages e2fm_search_hits cuts a batch of n patterns into (stage_option as E2FM_OPT_HITS_STAGE, 0 = automatic):
+ * bounds_out[c] .. bounds_out[c + 1] is stage c; *n_bounds = entries written (stages + 1) */
+int e2fm_debug_hits_stages(uint64_t n, uint64_t stage_option, uint64_t *bounds_out, uint64_t cap, uint64_t *n_bounds);
 /* HBM random-gather roofline: independent 8-byte loads at hashed addresses of a buffer_bytes buffer (make it much larger than
  * L2); returns 10^9 gathers per second (best of 3). Every gather moves one 32-byte sector over the memory system. */
 int e2fm_debug_gather_bench(int device, uint64_t buffer_bytes, uint64_t n_gathers, double *giga_gathers_per_s);

@@ -132,3 +132,24 @@ def test_tight_packing_is_the_prefix_of_the_word_packing():
         pats[5, L // 2] = ord("N")
         pats[9, L - 1] = ord("$")
         assert capi.pack_patterns_tight(pats)[1] == 2 and capi.pack_patterns(pats)[1] == 2
+
+
+def test_hits_stage_plan_covers_every_batch():
+    """the stages e2fm_search_hits cuts a batch into: contiguous, non-empty, covering; automatic mode gives a small batch (a GPU's
+    share of a partitioned batch) several stages and a long one a short head; an explicit stage size is kept"""
+    for n in (1, 7, 100_000, 131_072, 500_000, 1_250_000, 2_500_000, 4_000_000, 10_000_000, 33_554_433):
+        for opt in (0, 7, 64, 8192, 1 << 20):
+            if opt and n // opt > 100_000:
+                continue
+            b = capi.hits_stages(n, opt)
+            assert b[0] == 0 and b[-1] == n and np.all(np.diff(b.astype(np.int64)) > 0), (n, opt, b[:8])
+            sizes = np.diff(b.astype(np.int64))
+            if opt:
+                assert sizes.max() <= max(opt, 1) and len(sizes) >= -(-n // opt)
+            else:
+                assert sizes.max() <= 1 << 20
+                if n >= 1_000_000:
+                    assert len(sizes) >= 4, (n, sizes)              # copies and search of a small batch overlap
+                if n >= 8 << 20:
+                    assert sizes[0] == (1 << 20) // 4              # the search starts after a quarter stage
+                assert np.all(sizes[:-1] >= min(n, 65_536)), (n, sizes)       # (only the remainder may be tiny)
