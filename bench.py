@@ -605,7 +605,8 @@ def gpu_arm(args, rank, world, local_rank):
             r.free()
         dt = time.perf_counter() - t0
         e2e_dev_ms.append(ix.last_batch_ms()["total"])
-        e2e_state.update(total=total, stages=ix.last_batch_counters().get("hits_stages", 0))
+        ctr = ix.last_batch_counters()
+        e2e_state.update(total=total, stages=ctr.get("hits_stages", 0), launches=ctr.get("launches", 0))
         return dt, total
 
     for _ in range(args.warmup):
@@ -636,12 +637,14 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     wall_dev = time.perf_counter() - wall0
     e2e_s = 0.0
+    e2e_launches = 0
     for _ in range(args.steps):
         l2_flush()
         if world > 1:
             dist.barrier()     # a step = the whole batch: all ranks start it together
         dt, _tot = step_e2e()
         e2e_s += dt
+        e2e_launches += e2e_state.get("launches", 0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -677,12 +680,12 @@ def gpu_arm(args, rank, world, local_rank):
 
     # max over ranks (times), sum over ranks (work)
     t = torch.tensor([ph_ms["total"], e2e_s * 1e3, ph_ms["backward_search"], ph_ms["walk"]], dtype=torch.float64, device=dev_t)
-    cnt = torch.tensor([occ_total, ctr_sum.get("launches", 0)], dtype=torch.int64, device=dev_t)
+    cnt = torch.tensor([occ_total, ctr_sum.get("launches", 0), e2e_launches], dtype=torch.int64, device=dev_t)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    occ_all, launches_all = int(cnt[0]), int(cnt[1])
+    occ_all, launches_all, e2e_launches_all = int(cnt[0]), int(cnt[1]), int(cnt[2])
     steps = args.steps
 
     # ---- parity of the TIMED batch + CPU baseline (rank 0, outside the timed region): the unmodified reference searches the first
@@ -772,7 +775,8 @@ def gpu_arm(args, rank, world, local_rank):
                              (f"one call, e2fm_search_hits, {e2e_state.get('stages', 0)} pipeline stages" if args.e2e_api == "hits"
                               else "two calls: search, then e2fm_result_fetch_compact")),
                     "api": "e2fm_search_hits" if args.e2e_api == "hits" else "e2fm_search_batch_* + e2fm_result_fetch_compact"},
-            "gpu_launches": launches_all,
+            "gpu_launches": launches_all + e2e_launches_all,
+            "gpu_launches_by_leg": {"device_resident": launches_all, "end_to_end": e2e_launches_all},
             "roofline": roofline,
             "parity": parity,
             "ops_per_pattern": {k_: ctr_sum.get(k_, 0) / (npat * steps) for k_ in ("rank", "lf", "mark", "rank_sectors", "walk_gathers",

@@ -2050,10 +2050,13 @@ int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *buc
         p.payload_cap = payload ? payload_cap / 8 * 8 : 0;
         p.sequence = d_seq.p;
         p.status = d_status.p;
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, s));
+        struct EventPair {                                     // destroyed on every way out
+            cudaEvent_t a = nullptr, b = nullptr;
+            ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+        } ev;
+        CK(cudaEventCreate(&ev.a));
+        CK(cudaEventCreate(&ev.b));
+        CK(cudaEventRecord(ev.a, s));
         launch_bucket_mtf_rle(p, wpc, smem, s);
         launch_payload_offsets(p, s);
         // key stream + substitution + packing, in batches of buckets (the key stream of a batch stays below 256 MB)
@@ -2067,7 +2070,7 @@ int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *buc
             launch_keystream(kw, first_bucket + b0, nb, blocks_per_bucket, 0, reinterpret_cast<uint4 *>(d_ks.p), s);
             launch_bucket_substitute_pack(p, b0, nb, d_ks.p, ks_stride, s);
         }
-        CK(cudaEventRecord(e1, s));
+        CK(cudaEventRecord(ev.b, s));
         uint32_t status = 0;
         std::vector<uint64_t> off(n_buckets + 1);
         CK(cudaMemcpyAsync(&status, d_status.p, 4, cudaMemcpyDeviceToHost, s));
@@ -2076,9 +2079,7 @@ int e2fm_encode_buckets(int device, const uint8_t key64[64], const uint32_t *buc
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
         float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
         if (device_ms) *device_ms = ms;
         if (payload_offset) memcpy(payload_offset, off.data(), (n_buckets + 1) * 8);
         if (payload_bytes) *payload_bytes = off[n_buckets];
