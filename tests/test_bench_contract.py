@@ -35,3 +35,47 @@ def test_reference_arm_on_other_ranks_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_affinity_helper_never_fails_and_restores():
+    """bench.bind_to_gpu_numa is an optimisation: without a GPU (or without a NUMA node for it) it reports why and changes nothing"""
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    restore, note = bench.bind_to_gpu_numa(0)
+    try:
+        assert isinstance(note, str) and note
+        if restore is None:
+            assert os.sched_getaffinity(0) == before
+        else:
+            assert os.sched_getaffinity(0) <= before and restore == before
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_shared_host_buffers_defer_page_locking(tmp_path):
+    """SharedHost(defer=True) hands out the shared arrays unlocked, so that every rank can first-touch its own part; world 1 uses the
+    library's pinned allocator, which needs the CUDA runtime — here only the bookkeeping of the deferred mode is checked"""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+
+    import bench
+
+    class NoCapi:
+        pass
+    sh = bench.SharedHost(f"pytest_{os.getpid()}", 2, 0, NoCapi(), defer=True)
+    try:
+        a = sh.array("x", (4, 8), np.uint32)
+        assert a.shape == (4, 8) and a.dtype == np.uint32 and len(sh._pending) == 1
+        a[1] = 7                                           # writable before it is page-locked
+        other = bench.SharedHost(f"pytest_{os.getpid()}", 2, 1, NoCapi(), defer=True)
+        b = other.array("x", (4, 8), np.uint32)
+        assert b[1, 3] == 7                                # the same pages
+    finally:
+        for s_ in (sh,):
+            s_._pending = []
+            for name in list(s_.arrays):
+                try:
+                    os.remove(f"/dev/shm/e2fm_bench_{s_.tag}_{name}")
+                except OSError:
+                    pass
