@@ -25,7 +25,18 @@ if mult > 1:
     n *= mult
 tight = os.environ.get("E2FM_TRACE_TIGHT", "0") != "0"    # ceil(L / 4) bytes per pattern instead of 16-byte words
 stride = capi.packed_tight_stride(L) if tight else capi.packed_stride(L)
-h_in = capi.PinnedArray((n, stride), np.uint8)
+if os.environ.get("E2FM_TRACE_WC", "0") != "0":            # experiment: write-combined page-locked memory for the input
+    import ctypes
+
+    from cuda import cudart
+    err, ptr = cudart.cudaHostAlloc(n * stride, cudart.cudaHostAllocWriteCombined)
+    assert int(err) == 0, err
+
+    class _WC:
+        array = np.ctypeslib.as_array((ctypes.c_uint8 * (n * stride)).from_address(int(ptr))).reshape(n, stride)
+    h_in = _WC()
+else:
+    h_in = capi.PinnedArray((n, stride), np.uint8)
 (capi.pack_patterns_tight if tight else capi.pack_patterns)(pats, h_in.array.reshape(-1))
 cap = 2 * n + 4096
 h_off, h_seq, h_so = (capi.PinnedArray(s, np.uint32) for s in (n + 1, cap, cap))
