@@ -19,6 +19,9 @@ ix = capi.DeviceIndex(open(prep["efm"], "rb").read(), synth.test_key(), 0)
 if len(sys.argv) > 2:
     ix.set_option(capi.OPT_HITS_STAGE, int(sys.argv[2]))
 pats = np.ascontiguousarray(bench.load_patterns(prep)[:n])
+if os.environ.get("E2FM_TRACE_N"):                           # a shorter batch (a GPU's share of a partitioned one)
+    n = min(n, int(os.environ["E2FM_TRACE_N"]))
+    pats = np.ascontiguousarray(pats[:n])
 mult = int(os.environ.get("E2FM_TRACE_MULT", "1"))          # the batch repeated: more pipeline stages
 if mult > 1:
     pats = np.ascontiguousarray(np.tile(pats, (mult, 1)))
@@ -40,7 +43,7 @@ else:
 (capi.pack_patterns_tight if tight else capi.pack_patterns)(pats, h_in.array.reshape(-1))
 cap = 2 * n + 4096
 h_off, h_seq, h_so = (capi.PinnedArray(s, np.uint32) for s in (n + 1, cap, cap))
-for rep in range(4):
+for rep in range(int(os.environ.get("E2FM_TRACE_REPS", "4"))):
     print(f"--- call {rep}", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
     ix.search_hits(h_in.array.reshape(-1), n, L, 2 if tight else 1, True, None, h_off.array, h_seq.array, h_so.array)
