@@ -818,3 +818,38 @@ void orc_pack_sequence(const uint32_t *seq, uint64_t n, uint32_t bits, uint8_t *
             if ((seq[i] >> b) & 1u) out[bit >> 3] |= (uint8_t)(0x80u >> (bit & 7));
 }
 
+/* The inverse, for round-trip properties: Bucket::readTextUntilTo (Bucket.cpp:288-403) over a sequence held in memory instead of
+ * the file's bit stream — invertPoly (:406), RLE0^-1 (:377), ArrayMTFList::moveToFront (ArrayMTFList.cpp:32), odd buckets written
+ * back last row first. Returns the number of rows produced (== length for a well-formed sequence). */
+uint64_t orc_decode_sequence(const uint8_t key32[32], uint64_t bucket_number, const uint32_t *seq, uint64_t clen, uint64_t length,
+                             uint32_t alpha, int is_odd, uint32_t *codes_out) {
+    uint32_t *key = (uint32_t *)malloc(sizeof(uint32_t) * (clen + 1));
+    orc_keystream_ints(key32, bucket_number, alpha, 0, clen, key);
+    uint32_t *mtf = (uint32_t *)malloc(sizeof(uint32_t) * alpha);
+    for (uint32_t i = 0; i < alpha; i++) mtf[i] = i;
+    const int64_t mod = (int64_t)alpha + 1;
+    uint64_t p = 0, i = 0;
+    while (p < length && i < clen) {
+        int64_t c = (((int64_t)seq[i] - (int64_t)key[i]) % mod + mod) % mod;
+        if (c > 1) {
+            uint32_t pos = (uint32_t)(c - 1), e = mtf[pos];
+            memmove(mtf + 1, mtf, sizeof(uint32_t) * pos);
+            mtf[0] = e;
+            codes_out[is_odd ? length - p - 1 : p] = e;
+            p++; i++;
+        } else {
+            uint64_t x = 0, N = 0;
+            while (i + x < clen) {
+                int64_t d = (((int64_t)seq[i + x] - (int64_t)key[i + x]) % mod + mod) % mod;
+                if (d >= 2) break;
+                N = 2 * N + (uint64_t)d; x++;
+            }
+            uint64_t m = (1ull << x) + N - 1;
+            for (uint64_t j = 0; j < m && p < length; j++) { codes_out[is_odd ? length - p - 1 : p] = mtf[0]; p++; }
+            i += x;
+        }
+    }
+    free(key); free(mtf);
+    return p;
+}
+

@@ -6,7 +6,7 @@
  * Parity status: PINNED. Every function is checked against the compiled, unmodified reference
  * (oracle/_ref/e2fm_ref, built by oracle/Makefile from /root/reference) — known-answer vectors
  * (tests/golden/kat.txt), byte-identical internal dumps (`e2fm_ref dump` vs orc_dump) and search
- * results (tests/golden/*.res) — and against naive string search.
+ * results (the .res files under tests/golden) — and against naive string search.
  */
 #ifndef E2FM_ORACLE_H_
 #define E2FM_ORACLE_H_
@@ -80,6 +80,9 @@ uint64_t orc_encode_bucket(const uint8_t key32[32], uint64_t bucket_number, cons
                            int is_odd, uint32_t *seq_out);
 /* symbol loop of Bucket::writeText (Bucket.cpp:232-246) + flush */
 void orc_pack_sequence(const uint32_t *seq, uint64_t n, uint32_t bits, uint8_t *out);
+/* Bucket::readTextUntilTo (Bucket.cpp:288-403) over a sequence in memory: the inverse of orc_encode_bucket; returns rows produced */
+uint64_t orc_decode_sequence(const uint8_t key32[32], uint64_t bucket_number, const uint32_t *seq, uint64_t clen, uint64_t length,
+                             uint32_t alpha, int is_odd, uint32_t *codes_out);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ def lib():
         L.orc_encode_bucket.restype = C.c_uint64
         L.orc_encode_bucket.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.orc_pack_sequence.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.orc_decode_sequence.restype = C.c_uint64
+        L.orc_decode_sequence.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -321,4 +323,13 @@ def pack_sequence(seq: np.ndarray, bits: int) -> bytes:
     out = np.zeros((len(seq) * bits + 7) // 8 + 1, dtype=np.uint8)
     lib().orc_pack_sequence(seq.ctypes.data, len(seq), bits, out.ctypes.data)
     return out[:(len(seq) * bits + 7) // 8].tobytes()
+
+
+def decode_sequence(key64: bytes, bucket_number: int, seq: np.ndarray, length: int, alpha: int, is_odd: bool) -> np.ndarray:
+    """Bucket::readTextUntilTo (Bucket.cpp:288-403) over a sequence in memory: the rows (bucket codes) an encoded bucket decodes to"""
+    seq = np.ascontiguousarray(seq, dtype=np.uint32)
+    out = np.full(max(length, 1), 0xFFFFFFFF, dtype=np.uint32)
+    n = lib().orc_decode_sequence(key64[32:64], bucket_number, seq.ctypes.data, len(seq), length, alpha, 1 if is_odd else 0, out.ctypes.data)
+    assert int(n) == length, f"decoded {n} of {length} rows"
+    return out[:length]
 

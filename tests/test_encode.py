@@ -148,3 +148,59 @@ def test_gpu_encoder_config1_full_size(key64, oracle_mod, tmp_path):
         raw = f.read()
     buckets, meta = _gpu_check(oracle_mod, raw, key64, "config1", splits=(1,))
     assert meta["B"] > 600
+
+
+def random_bucket(rng, length, alpha, runs):
+    """bucket codes that use every symbol of the alphabet when the bucket is long enough; `runs`: long stretches of one symbol"""
+    if runs:
+        codes = np.repeat(rng.integers(0, alpha, size=max(1, length // 7)), rng.integers(1, 40, size=max(1, length // 7)))[:length]
+        codes = np.concatenate([codes, rng.integers(0, alpha, size=length - len(codes))]) if len(codes) < length else codes
+    else:
+        codes = rng.integers(0, alpha, size=length)
+    return np.ascontiguousarray(codes, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("alpha,length", [(2, 1), (2, 31), (2, 4096), (3, 33), (5, 128), (255, 4096), (256, 4095), (257, 4097), (1026, 8192), (4099, 8192)])
+@pytest.mark.parametrize("runs", [False, True])
+def test_oracle_encode_decode_round_trip(alpha, length, runs, key64, oracle_mod):
+    """size-independent property of the restatement: readTextUntilTo(encodeText(bucket)) == bucket, for even and reversed buckets, over
+    alphabets and bucket lengths the goldens do not reach"""
+    rng = np.random.default_rng(alpha * 100003 + length + (7 if runs else 0))
+    codes = random_bucket(rng, length, alpha, runs)
+    for bn, odd in ((0, False), (12, True), (2 ** 33 + 5, False)):
+        seq = oracle_mod.encode_bucket(key64, bn, codes, alpha, odd)
+        assert len(seq) <= length and (len(seq) == 0 or int(seq.max()) <= alpha)
+        back = oracle_mod.decode_sequence(key64, bn, seq, length, alpha, odd)
+        assert np.array_equal(back, codes), (alpha, length, runs, bn)
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_random_buckets_against_the_oracle(key64, oracle_mod):
+    """e2fm_encode_buckets on synthetic buckets (alphabets 1..4099, long runs, a short last bucket, bucket numbers that start far from
+    0): sequences and packed texts equal the oracle's, and the oracle decodes them back to the rows"""
+    if capi.device_count() == 0:
+        pytest.skip("no CUDA device")
+    rng = np.random.default_rng(99)
+    for bs, alphas, per, first, total in ((4096, [2, 3, 1, 17, 255, 256, 257, 1, 258, 100, 2, 258], 4, 6, 40),
+                                          (8192, [1026, 4099, 1000, 2, 4099], 2, 1000, 1005),
+                                          (100, [5, 1, 2, 7, 9, 3, 4], 3, 0, 7)):
+        nb = len(alphas)
+        lens = [bs] * (nb - 1) + [bs - 37 if first + nb == total else bs]
+        parts = [random_bucket(rng, L, a, runs=(i % 2 == 1)) for i, (L, a) in enumerate(zip(lens, alphas))]
+        r = capi.encode_buckets(key64, np.concatenate(parts), bs, first, per, total, np.array(alphas, dtype=np.uint32), want_sequence=True)
+        row = 0
+        for i, (codes, a) in enumerate(zip(parts, alphas)):
+            bn = first + i
+            odd = (bn % 2 == 0) and (bn % per != 0) and (bn != total - 1)          # EFMIndex.cpp:898-901
+            if a == 1:
+                assert int(r["clen"][i]) == 0
+            else:
+                want = oracle_mod.encode_bucket(key64, bn, codes, a, odd)
+                got = r["sequence"][row:row + int(r["clen"][i])]
+                assert np.array_equal(got, want), (bs, bn, a)
+                tb = oracle_mod.int_log2(a)
+                off = int(r["offsets"][i])
+                packed = oracle_mod.pack_sequence(want, tb)
+                assert r["payload"][off:off + len(packed)].tobytes() == packed, (bs, bn, a)
+                assert np.array_equal(oracle_mod.decode_sequence(key64, bn, got, len(codes), a, odd), codes)
+            row += len(codes)
